@@ -1,0 +1,176 @@
+/*
+ * scalesim_b200.h — C ABI of libscalesim_b200.so: the B200-native Time Warp core.
+ *
+ * This is the drop-in boundary for ONE path of masatoshihanai/ScaleSim: the optimistic PDES
+ * core that scalesim::runner<App> drives (reference include/scalesim/simulation/runner.hpp).
+ * The reference has no FFI; its boundary is the C++ template surface. The host-side mirror of
+ * that surface (include/scalesim/*.hpp in this repo) talks to the device engine only through
+ * the functions below. Plain C: int status returns (0 = ok), no exceptions cross the boundary,
+ * the engine owns all device memory, the caller owns every host buffer it passes, one host
+ * thread per engine. There is NO CPU fallback: ssb_create fails when no CUDA device is usable.
+ *
+ * Which reference interface each entry point replaces (file:line in the reference tree):
+ *   ssb_create / ssb_destroy      runner<App>::runner, lp_mngr::init_lps / delete_lps
+ *                                 (runner.hpp:31-35, logical_process.hpp:265-287, 305-313)
+ *   ssb_set_partition             lp_mngr::init_partition(App::init_partition_index(ranks))
+ *                                 (runner.hpp:98, logical_process.hpp:258-263)
+ *   ssb_set_model_data            App::init() — PHOLD's file-static tables (phold.hpp:144-164),
+ *                                 TrafficSim's routes carried inside events (traffic_sim.hpp:43)
+ *   ssb_load_states               App::init_states_in_this_rank -> lp::init_state (runner.hpp:108-118)
+ *   ssb_load_events               App::init_events -> shuffle -> lp::init_event = lp::buffer
+ *                                 (runner.hpp:131-147, logical_process.hpp:115-127)
+ *   ssb_run / ssb_step            runner::loop — run_lp/run_lp_aggr, GVT, std_out, clear
+ *                                 (runner.hpp:350-396, 517-583)
+ *   ssb_committed_digest,         eventq::std_out + sim_event::result_out — the "RE,..." lines
+ *   ssb_drain_committed           (queue.hpp:203-211, sim_obj.hpp:66-77)
+ *   ssb_get_stats                 runner::finish report (runner.hpp:482-507)
+ *   ssb_read_states               (no reference equivalent: sim_state::result_out is empty,
+ *                                 sim_obj.hpp:97; used by the parity tests for final LP states)
+ *   ssb_comm_*                    event_com / mpi_thr / mpi_gsync (com/*.hpp) — replaced by NCCL
+ *                                 all-to-all + allreduce-min between one-engine-per-GPU processes
+ */
+#ifndef SCALESIM_B200_H_
+#define SCALESIM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+typedef struct ssb_engine ssb_engine;
+
+/* device twins of the application handlers (App::event_handler) */
+enum ssb_model_id {
+  SSB_MODEL_PHOLD = 1,    /* src/phold/phold.hpp:256-281 */
+  SSB_MODEL_TRAFFIC = 2,  /* src/trafficsim/traffic_sim.hpp:279-342 */
+  SSB_MODEL_PHOLD_STATEFUL = 3 /* test model: PHOLD whose LP state mutates and feeds back into events */
+};
+
+/* status codes */
+enum ssb_status {
+  SSB_OK = 0,
+  SSB_ERR_INVALID = 1,      /* bad argument / call order */
+  SSB_ERR_CUDA = 2,         /* CUDA runtime failure (incl. no device) */
+  SSB_ERR_RANGE = 3,        /* a value does not fit the device record (see limits below) */
+  SSB_ERR_CAPACITY = 4,     /* a device pool overflowed (max_events / max_batch / ...) */
+  SSB_ERR_MODEL = 5,        /* model data missing or inconsistent */
+  SSB_ERR_COMM = 6          /* NCCL failure */
+};
+
+/*
+ * Device record limits (asserted at load and at every emit; violation -> SSB_ERR_RANGE):
+ *   0 <= time < 2^31, 0 <= event id < 2^32-1, 0 <= LP id < 2^32-1, source may be -1.
+ * The sort key is (receive_time, id) packed into one u64 — ScaleSim's timestamp order
+ * (util/timestamp.hpp:53-59).
+ */
+typedef struct ssb_config {
+  int32_t abi_version;      /* SSB_ABI_VERSION */
+  int32_t model;            /* ssb_model_id */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t rank, world;      /* this partition / number of partitions (one engine per GPU) */
+  int32_t window_buckets;   /* optimistic window, in calendar buckets (>= 1) */
+  int64_t n_lp;             /* global number of LPs; LP ids are [0, n_lp) */
+  int64_t finish_time;      /* App::finish_time() */
+  int64_t bucket_ticks;     /* calendar bucket width in simulation ticks (>= 1) */
+  int64_t max_events;       /* capacity of the device event pool (live + uncommitted events) */
+  int64_t max_batch;        /* max events integrated per round */
+  int64_t max_committed;    /* capacity of the device committed-record log; 0 = digest only */
+  int64_t max_snapshots;    /* capacity of the state-snapshot ring */
+  int32_t rounds_per_sync;  /* rounds enqueued between host checks of the done flag */
+  int32_t flags;            /* SSB_FLAG_* */
+} ssb_config;
+
+#define SSB_FLAG_DEBUG_CHECKS 1   /* extra device-side invariant checks */
+
+/* Host-side POD mirror of the App::Event accessors (sim_obj.hpp:50-59) + model payload. */
+typedef struct ssb_event {
+  int64_t id;            /* Event::id() */
+  int64_t src;           /* Event::source() (-1 = none) */
+  int64_t dst;           /* Event::destination() */
+  int64_t recv_time;     /* Event::receive_time() */
+  int64_t send_time;     /* Event::send_time() */
+  int64_t p0;            /* PHOLD: num_hops(); TrafficSim: offset of destination() in the route pool */
+  int64_t p1;            /* TrafficSim: number of route nodes left, including destination() */
+  int64_t flags;         /* bit 0: is_cancel() */
+} ssb_event;
+
+/* One committed result = one "RE,id,src,send,dst,recv[,START|,END]" line (sim_obj.hpp:66-77). */
+typedef struct ssb_record {
+  int64_t id, src, send_time, dst, recv_time;
+  int64_t tag;           /* 0 none, 1 START, 2 END */
+} ssb_record;
+
+typedef struct ssb_stats {
+  int64_t rounds;            /* windows executed */
+  int64_t processed;         /* handler invocations ("# of processing events", runner.hpp:495) */
+  int64_t rollbacks;         /* LP turns that rolled back */
+  int64_t undone;            /* processed events undone by rollbacks */
+  int64_t antis_sent;        /* anti-messages emitted ("# of cancels", runner.hpp:496) */
+  int64_t annihilated;       /* positive/anti pairs annihilated */
+  int64_t duplicates;        /* duplicate keys ignored (queue.hpp:92) */
+  int64_t committed;         /* "# of output events" (runner.hpp:497) */
+  int64_t beyond_finish;     /* events emitted with receive_time >= finish_time (never executed) */
+  int64_t remote_sent;       /* events sent to other partitions */
+  int64_t gvt_time, gvt_id;  /* final GVT */
+  int64_t pool_high_water;   /* peak event-pool slots in use */
+  int64_t log_dropped;       /* committed records not kept because max_committed was reached */
+  double loop_ms;            /* device time of the window loop (CUDA events) */
+} ssb_stats;
+
+int ssb_abi_version(void);
+const char* ssb_last_error(ssb_engine* e);      /* e may be NULL: error of the last failed ssb_create */
+
+int ssb_create(const ssb_config* cfg, ssb_engine** out);
+void ssb_destroy(ssb_engine* e);
+
+/* lp_to_part[lp] = owning partition in [0, world). NULL = PHOLD's default `lp % world` (phold.hpp:181-186). */
+int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp);
+
+/*
+ * Model data (host pointers, copied):
+ *   PHOLD   slot 0: LATENCY_TABLE  int64[n]   slot 1: REMOTE_COM_TABLE int32[n]   (phold.hpp:56-58)
+ *           slot 2: int64[2] = { LOOK_AHEAD, NUM_LP }
+ *   TRAFFIC slot 0: route pool int64[n] (all route nodes, concatenated; events index into it)
+ */
+int ssb_set_model_data(ssb_engine* e, int slot, const void* data, size_t bytes);
+
+/* states: n records of `ssb_state_words()` 32-bit words each, for LPs lp_ids[i] owned by this rank. */
+int ssb_state_words(ssb_engine* e);
+int ssb_load_states(ssb_engine* e, const int64_t* lp_ids, const uint32_t* words, int64_t n);
+int ssb_read_states(ssb_engine* e, const int64_t* lp_ids, uint32_t* words, int64_t n);
+
+/* initial (or injected) events; events whose destination is owned by another rank are forwarded at the next step. */
+int ssb_load_events(ssb_engine* e, const ssb_event* ev, int64_t n);
+
+/* Run windows until GVT.time >= finish_time (runner.hpp:392). */
+int ssb_run(ssb_engine* e, ssb_stats* stats);
+/* Run exactly one window (one round). *done = 1 when GVT.time >= finish_time. */
+int ssb_step(ssb_engine* e, int* done);
+
+int ssb_get_stats(ssb_engine* e, ssb_stats* stats);
+/* digest of the committed multiset: d[0]=count, d[1]=sum h, d[2]=xor h, d[3]=sum mix(h+K) */
+int ssb_committed_digest(ssb_engine* e, uint64_t d[4]);
+/* copy up to cap committed records to host memory and remove them from the device log */
+int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n);
+
+/* ---- multi-GPU: one engine per process/GPU, NCCL between them ---- */
+/* 128-byte NCCL unique id; created on rank 0 and distributed by the caller (torch.distributed, MPI, files, ...) */
+int ssb_comm_unique_id(void* id128);
+int ssb_comm_init(ssb_engine* e, const void* id128);
+
+/* ---- host helpers of the PHOLD app mirror (no device work) ---- */
+/* phold.hpp:144-164: the two 10M-entry tables, libstdc++ default_random_engine streams */
+int ssb_phold_build_tables(int64_t seed, double lambda, double remote_ratio, int64_t n,
+                           int64_t* latency, int32_t* remote);
+/* phold.hpp:197-209: initial events with id % stride == offset (id in [0, num_init_msg)) */
+int64_t ssb_phold_init_events(int64_t num_lp, int64_t num_init_msg, const int64_t* latency, int64_t table_size,
+                              int64_t offset, int64_t stride, ssb_event* out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCALESIM_B200_H_ */

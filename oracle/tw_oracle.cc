@@ -257,8 +257,12 @@ struct two_sim {
   int64_t n_committed = 0;
   int64_t stats[4] = {0, 0, 0, 0};
 
-  /* event handlers: return true and fill `out` if a new event is produced */
-  bool handle(const Ev& e, Ev& out) const {
+  long initial_state(long id) const { return stateful ? (long)((uint64_t)(uint32_t)id << 32) : id; }
+  bool stateful = false;   /* test model PHOLD_STATEFUL (csrc/ssb_models.cuh PholdStatefulModel); no reference app */
+  std::unordered_map<long, long> final_states;
+
+  /* event handlers: return true and fill `out` if a new event is produced; `state` may be updated */
+  bool handle(const Ev& e, long& state, Ev& out) const {
     if (kind == PHOLD) {
       /* phold.hpp:256-281 */
       long ev_id = e.id;
@@ -266,11 +270,22 @@ struct two_sim {
       long send_time = e.recv;
       int num_hops = 1 + e.hops;
       int rand_table_id = (int)(ev_id + (long)num_hops) % kRandTableSize;
+      uint32_t count = 0;
+      if (stateful) {
+        /* state = count | chain << 32; count' = count + 1; chain' = (u32) mix64(chain << 32 ^ key) */
+        count = (uint32_t)((uint64_t)state & 0xFFFFFFFFull) + 1u;
+        uint32_t chain = (uint32_t)((uint64_t)state >> 32);
+        uint64_t key = ((uint64_t)e.recv << 32) | (uint64_t)(uint32_t)e.id;
+        chain = (uint32_t)mix64(((uint64_t)chain << 32) ^ key);
+        state = (long)(((uint64_t)chain << 32) | count);
+        rand_table_id = (int)((ev_id + (long)num_hops + (long)(chain & 7u)) % kRandTableSize);
+      }
       long receive_time = send_time + latency[rand_table_id] + kLookAhead;
       long dst_id = (remote[rand_table_id] == 1) ? latency[rand_table_id] % num_lp : e.dst;
       out = Ev();
       out.id = ev_id; out.src = src_id; out.dst = dst_id; out.recv = receive_time; out.send = send_time;
       out.hops = num_hops;
+      out.rpos = stateful ? (long)count : 0;   /* p1 of the device record */
       return true;
     }
     /* traffic_sim.hpp:279-342 */
@@ -346,6 +361,12 @@ void two_lp_clear(two_lp* p, int64_t t, int64_t i) {
 }
 int64_t two_lp_size_ev(two_lp* p) { return (int64_t)p->lp.eventq_.map_.size(); }
 int64_t two_lp_size_can(two_lp* p) { return (int64_t)p->lp.eventq_.can_map_.size(); }
+
+uint64_t two_fnv_fold(const int64_t* v, int64_t n) {
+  uint64_t h = 1469598103934665603ULL;
+  for (int64_t i = 0; i < n; ++i) h = (h ^ (uint64_t)v[i]) * 1099511628211ULL;
+  return h;
+}
 
 void two_phold_tables(int64_t seed, double lambda, double ratio, int64_t n, int64_t* lat, int32_t* rem) {
   build_phold_tables(seed, lambda, ratio, n, lat, rem);
@@ -465,7 +486,7 @@ int64_t two_sim_run_timewarp(two_sim* s, int num_sched, int gsync_interval, int 
     return it->second;
   };
   /* runner::init (runner.hpp:79-176): states keyed null(), events buffered at destination() */
-  for (long id : s->state_ids) get_lp(id).stateq_.push_back_state(id, TS::null());
+  for (long id : s->state_ids) get_lp(id).stateq_.push_back_state(s->initial_state(id), TS::null());
   for (const Ev& e : s->init_events) get_lp(e.dst).buffer(e);
 
   long remote_sends = 0, gvt_rounds = 0;
@@ -482,9 +503,9 @@ int64_t two_sim_run_timewarp(two_sim* s, int num_sched, int gsync_interval, int 
       bool has_state = !lp.stateq_.state_map.empty();
       long state = has_state ? lp.stateq_.get_state() : -1;
       Ev out;
-      if (!s->handle(ev, out)) break;                                /* :552-553 */
+      if (!s->handle(ev, state, out)) break;                         /* :552-553 */
       lp.eventq_.set_cancel(out);                                    /* :556 */
-      lp.stateq_.push_back_state(state, TS{out.send, out.id});       /* :557-558 (handlers return the state unchanged) */
+      lp.stateq_.push_back_state(state, TS{out.send, out.id});       /* :557-558 */
       if (s->kind == two_sim::PHOLD && out.dst != ev.dst) ++remote_sends;
       send_event(out);                                               /* :566 */
     }
@@ -551,7 +572,8 @@ int64_t two_sim_run_closure(two_sim* s, int num_threads, int keep_records) {
         digest_add(d, r);
         if (keep_records) recs[t].push_back(r);
         Ev out;
-        if (!s->handle(e, out)) break;
+        long dummy = 0;
+        if (!s->handle(e, dummy, out)) break;
         if (s->kind == two_sim::PHOLD && out.dst != e.dst) ++remote[t];
         e = out;
       }
@@ -571,6 +593,63 @@ int64_t two_sim_run_closure(two_sim* s, int num_threads, int keep_records) {
   s->n_committed = (int64_t)s->digest[0];
   s->stats[0] = s->n_committed; s->stats[1] = 0; s->stats[2] = 0; s->stats[3] = rs;
   return s->n_committed;
+}
+
+/* ---------------- plain sequential discrete-event simulation (global (receive_time,id) order) ----------------
+ * The definition of correctness for any Time Warp execution: same committed records, same final states. */
+int64_t two_sim_run_sequential(two_sim* s, int keep_records) {
+  s->committed.clear();
+  s->digest[0] = s->digest[1] = s->digest[2] = s->digest[3] = 0;
+  s->final_states.clear();
+  struct Item { TS key; long dst; Ev ev; };
+  auto cmp = [](const Item& a, const Item& b) {
+    if (b.key < a.key) return true;
+    if (a.key < b.key) return false;
+    return b.dst < a.dst;
+  };
+  std::vector<Item> heap;
+  heap.reserve(s->init_events.size());
+  for (const Ev& e : s->init_events) heap.push_back(Item{e.key(), e.dst, e});
+  std::make_heap(heap.begin(), heap.end(), cmp);
+  for (long id : s->state_ids) s->final_states[id] = s->initial_state(id);
+  long processed = 0;
+  while (!heap.empty()) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    Item it = heap.back();
+    heap.pop_back();
+    if (it.ev.recv >= s->finish_time) continue;
+    two_record r = to_record(it.ev);
+    digest_add(s->digest, r);
+    if (keep_records) s->committed.push_back(r);
+    ++processed;
+    long& st = s->final_states[it.ev.dst];
+    long st_new = st;
+    Ev out;
+    if (!s->handle(it.ev, st_new, out)) continue;   /* no event: state update dropped (runner.hpp:552-558) */
+    st = st_new;
+    heap.push_back(Item{out.key(), out.dst, out});
+    std::push_heap(heap.begin(), heap.end(), cmp);
+  }
+  s->n_committed = (int64_t)s->digest[0];
+  s->stats[0] = processed; s->stats[1] = 0; s->stats[2] = 0; s->stats[3] = 0;
+  return s->n_committed;
+}
+
+void two_sim_set_stateful(two_sim* s, int on) { s->stateful = on != 0; }
+
+/* final LP states of the last run_sequential, as the device's two state words {lo, hi} */
+int64_t two_sim_final_states(two_sim* s, int64_t* ids, uint32_t* words, int64_t cap) {
+  int64_t n = 0;
+  std::vector<long> keys;
+  for (auto& kv : s->final_states) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  for (long id : keys) {
+    if (n >= cap) break;
+    uint64_t v = (uint64_t)s->final_states[id];
+    ids[n] = id; words[2 * n] = (uint32_t)v; words[2 * n + 1] = (uint32_t)(v >> 32);
+    ++n;
+  }
+  return n;
 }
 
 int64_t two_sim_num_committed(two_sim* s) { return s->n_committed; }

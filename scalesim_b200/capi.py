@@ -1,0 +1,295 @@
+"""ctypes binding of include/scalesim_b200.h (the C ABI of libscalesim_b200.so)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+MODEL_PHOLD = 1
+MODEL_TRAFFIC = 2
+MODEL_PHOLD_STATEFUL = 3
+ABI_VERSION = 1
+
+#: host mirror of ``ssb_event`` (8 x int64)
+EVENT_DTYPE = np.dtype([
+    ("id", "<i8"), ("src", "<i8"), ("dst", "<i8"), ("recv_time", "<i8"), ("send_time", "<i8"),
+    ("p0", "<i8"), ("p1", "<i8"), ("flags", "<i8"),
+])
+#: host mirror of ``ssb_record`` (6 x int64): one committed "RE,..." line
+RECORD_DTYPE = np.dtype([
+    ("id", "<i8"), ("src", "<i8"), ("send_time", "<i8"), ("dst", "<i8"), ("recv_time", "<i8"), ("tag", "<i8"),
+])
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"scalesim_b200 status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("model", C.c_int32), ("device", C.c_int32),
+        ("rank", C.c_int32), ("world", C.c_int32), ("window_buckets", C.c_int32),
+        ("n_lp", C.c_int64), ("finish_time", C.c_int64), ("bucket_ticks", C.c_int64),
+        ("max_events", C.c_int64), ("max_batch", C.c_int64), ("max_committed", C.c_int64),
+        ("max_snapshots", C.c_int64), ("rounds_per_sync", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+class _Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "rounds", "processed", "rollbacks", "undone", "antis_sent", "annihilated", "duplicates",
+        "committed", "beyond_finish", "remote_sent", "gvt_time", "gvt_id", "pool_high_water", "log_dropped",
+    )] + [("loop_ms", C.c_double)]
+
+
+@dataclass
+class Config:
+    model: int
+    n_lp: int
+    finish_time: int
+    bucket_ticks: int
+    window_buckets: int = 1
+    max_events: int = 1 << 20
+    max_batch: int = 1 << 18
+    max_committed: int = 0
+    max_snapshots: int = 1 << 16
+    rounds_per_sync: int = 4
+    device: int = 0
+    rank: int = 0
+    world: int = 1
+    flags: int = 0
+
+
+@dataclass
+class Stats:
+    rounds: int = 0
+    processed: int = 0
+    rollbacks: int = 0
+    undone: int = 0
+    antis_sent: int = 0
+    annihilated: int = 0
+    duplicates: int = 0
+    committed: int = 0
+    beyond_finish: int = 0
+    remote_sent: int = 0
+    gvt_time: int = 0
+    gvt_id: int = 0
+    pool_high_water: int = 0
+    log_dropped: int = 0
+    loop_ms: float = 0.0
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libscalesim_b200.so")
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libscalesim_b200.so (built in-tree by ``__graft_entry__.build()``). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise EngineError(-1, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.ssb_abi_version.restype = i32
+    lib.ssb_last_error.restype = C.c_char_p
+    lib.ssb_last_error.argtypes = [vp]
+    lib.ssb_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    lib.ssb_destroy.argtypes = [vp]
+    lib.ssb_destroy.restype = None
+    lib.ssb_set_partition.argtypes = [vp, vp, i64]
+    lib.ssb_set_model_data.argtypes = [vp, i32, vp, C.c_size_t]
+    lib.ssb_state_words.argtypes = [vp]
+    lib.ssb_load_states.argtypes = [vp, vp, vp, i64]
+    lib.ssb_read_states.argtypes = [vp, vp, vp, i64]
+    lib.ssb_load_events.argtypes = [vp, vp, i64]
+    lib.ssb_run.argtypes = [vp, C.POINTER(_Stats)]
+    lib.ssb_step.argtypes = [vp, C.POINTER(i32)]
+    lib.ssb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+    lib.ssb_committed_digest.argtypes = [vp, vp]
+    lib.ssb_drain_committed.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_comm_unique_id.argtypes = [vp]
+    lib.ssb_comm_init.argtypes = [vp, vp]
+    lib.ssb_phold_build_tables.argtypes = [i64, C.c_double, C.c_double, i64, vp, vp]
+    lib.ssb_phold_init_events.argtypes = [i64, i64, vp, i64, i64, i64, vp, i64]
+    lib.ssb_phold_init_events.restype = i64
+    if lib.ssb_abi_version() != ABI_VERSION:
+        raise EngineError(-1, "libscalesim_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One Time Warp engine = one partition on one GPU (``ssb_engine``)."""
+
+    def __init__(self, cfg: Config):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        c = _Config(ABI_VERSION, cfg.model, cfg.device, cfg.rank, cfg.world, cfg.window_buckets, cfg.n_lp,
+                    cfg.finish_time, cfg.bucket_ticks, cfg.max_events, cfg.max_batch, cfg.max_committed,
+                    cfg.max_snapshots, cfg.rounds_per_sync, cfg.flags)
+        rc = self._lib.ssb_create(C.byref(c), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.ssb_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise EngineError(rc, msg)
+        self.cfg = cfg
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.ssb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, self._lib.ssb_last_error(self._h).decode())
+
+    # -- setup --
+    def set_partition(self, lp_to_part=None):
+        if lp_to_part is None:
+            self._check(self._lib.ssb_set_partition(self._h, None, 0))
+        else:
+            a = np.ascontiguousarray(lp_to_part, dtype=np.int64)
+            self._check(self._lib.ssb_set_partition(self._h, _ptr(a), a.size))
+
+    def set_model_data(self, slot: int, data: np.ndarray):
+        a = np.ascontiguousarray(data)
+        self._check(self._lib.ssb_set_model_data(self._h, slot, _ptr(a), a.nbytes))
+
+    @property
+    def state_words(self) -> int:
+        return self._lib.ssb_state_words(self._h)
+
+    def load_states(self, lp_ids, words):
+        ids = np.ascontiguousarray(lp_ids, dtype=np.int64)
+        w = np.ascontiguousarray(words, dtype=np.uint32).reshape(ids.size, self.state_words)
+        self._check(self._lib.ssb_load_states(self._h, _ptr(ids), _ptr(w), ids.size))
+
+    def read_states(self, lp_ids) -> np.ndarray:
+        ids = np.ascontiguousarray(lp_ids, dtype=np.int64)
+        w = np.empty((ids.size, self.state_words), dtype=np.uint32)
+        self._check(self._lib.ssb_read_states(self._h, _ptr(ids), _ptr(w), ids.size))
+        return w
+
+    def load_events(self, events: np.ndarray):
+        assert events.dtype == EVENT_DTYPE
+        a = np.ascontiguousarray(events)
+        self._check(self._lib.ssb_load_events(self._h, _ptr(a), a.size))
+
+    def load_events_ptr(self, ptr: int, n: int):
+        """Load ``n`` ssb_event records from a raw host pointer (e.g. a pinned torch tensor)."""
+        self._check(self._lib.ssb_load_events(self._h, C.c_void_p(ptr), n))
+
+    # -- run --
+    def run(self) -> Stats:
+        s = _Stats()
+        self._check(self._lib.ssb_run(self._h, C.byref(s)))
+        return self._stats(s)
+
+    def step(self) -> bool:
+        done = C.c_int(0)
+        self._check(self._lib.ssb_step(self._h, C.byref(done)))
+        return bool(done.value)
+
+    def stats(self) -> Stats:
+        s = _Stats()
+        self._check(self._lib.ssb_get_stats(self._h, C.byref(s)))
+        return self._stats(s)
+
+    @staticmethod
+    def _stats(s: _Stats) -> Stats:
+        return Stats(**{n: getattr(s, n) for n, _ in _Stats._fields_})
+
+    def digest(self):
+        d = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.ssb_committed_digest(self._h, _ptr(d)))
+        return tuple(int(x) for x in d)
+
+    def drain_committed(self, cap: int | None = None) -> np.ndarray:
+        if cap is None:
+            cap = max(1, self.stats().committed)
+        out = np.empty(cap, dtype=RECORD_DTYPE)
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_committed(self._h, _ptr(out), cap, C.byref(n)))
+        return out[: n.value]
+
+    def drain_committed_ptr(self, ptr: int, cap: int) -> int:
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_committed(self._h, C.c_void_p(ptr), cap, C.byref(n)))
+        return n.value
+
+    # -- multi-GPU --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.ssb_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineError(rc, lib.ssb_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        assert len(unique_id) == 128
+        self._check(self._lib.ssb_comm_init(self._h, C.c_char_p(unique_id)))
+
+
+# ---------------------------------------------------------------------------------------
+# committed records -> the reference's output
+# ---------------------------------------------------------------------------------------
+def records_to_lines(rec: np.ndarray) -> list[str]:
+    """``RE,id,src,send,dst,recv[,START|,END]`` (reference sim_obj.hpp:66-77), one per record."""
+    suffix = ("", ",START", ",END")
+    return [f"RE,{r['id']},{r['src']},{r['send_time']},{r['dst']},{r['recv_time']}{suffix[int(r['tag'])]}" for r in rec]
+
+
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    z = z ^ (z >> np.uint64(30))
+    z = z * _M1
+    z = z ^ (z >> np.uint64(27))
+    z = z * _M2
+    return z ^ (z >> np.uint64(31))
+
+
+def digest_records(rec: np.ndarray):
+    """Order-independent digest of a multiset of committed records; same function as the device
+    digest (ssb_device.cuh record_hash) and the oracle's (tw_oracle.cc record_hash)."""
+    with np.errstate(over="ignore"):
+        h = np.full(rec.shape, 0x9E3779B97F4A7C15, dtype=np.uint64)
+        for f in ("id", "src", "send_time", "dst", "recv_time", "tag"):
+            h = _mix64(h ^ rec[f].astype(np.int64).view(np.uint64))
+        s1 = int(np.add.reduce(h, dtype=np.uint64)) if h.size else 0
+        x = int(np.bitwise_xor.reduce(h)) if h.size else 0
+        s2 = int(np.add.reduce(_mix64(h + np.uint64(0xD1B54A32D192ED03)), dtype=np.uint64)) if h.size else 0
+    return (int(rec.size), s1, x, s2)

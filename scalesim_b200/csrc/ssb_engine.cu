@@ -1,0 +1,663 @@
+// ssb_engine.cu — host side of libscalesim_b200.so: owns the device memory, enqueues the per-round kernel
+// sequence on one CUDA stream, and implements the C ABI of include/scalesim_b200.h.
+// There is no CPU fallback: every entry point that does work needs a CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "../../include/scalesim_b200.h"
+#include "ssb_kernels.cuh"
+
+using namespace ssb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t err__ = (call);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(err__));                  \
+      return SSB_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+// ---- NCCL, resolved at run time so that single-GPU use has no NCCL dependency ----
+struct Nccl {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void* Comm;
+  void* lib = nullptr;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  static constexpr int kUint8 = 1, kUint32 = 3, kUint64 = 5, kMin = 3;
+  bool load(std::string& why) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { why = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { why = "missing " name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+  }
+};
+Nccl g_nccl;
+
+template <class T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
+
+}  // namespace
+
+struct ssb_engine {
+  ssb_config cfg;
+  std::string error;
+  View v;
+  Ctl* h_ctl = nullptr;          // pinned host mirror
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int n_sm = 148;
+  u32 n_chunks = 0;
+  size_t route_smem = 0;
+  std::vector<void*> allocs;
+  // partition (host copies)
+  std::vector<u32> h_owner, h_local;
+  bool partition_set = false;
+  // model data
+  u32* d_phold_table = nullptr; u32 phold_table_size = 0;
+  long long h_phold_params[2] = {10000, 0};
+  std::vector<long long> h_lat; std::vector<int> h_rem;
+  bool have_lat = false, have_rem = false;
+  u32* d_route = nullptr; u32 route_len = 0;
+  // staging
+  HostEvent* d_stage = nullptr;
+  long long* d_unpack = nullptr; size_t unpack_cap = 0;
+  u64 log_drained = 0;
+  double loop_ms = 0.0;
+  long long rounds = 0;
+  // comm
+  Nccl::Comm comm = nullptr;
+
+  void set_error(const std::string& s) { error = s; }
+
+  PholdModel::Data phold_data() const {
+    PholdModel::Data d;
+    d.table = d_phold_table; d.table_size = phold_table_size;
+    d.lookahead = (u32)h_phold_params[0]; d.num_lp = (u32)h_phold_params[1];
+    return d;
+  }
+  TrafficModel::Data traffic_data() const { TrafficModel::Data d; d.route = d_route; d.route_len = route_len; return d; }
+
+  int grid(size_t n, int threads) const {
+    size_t b = (n + threads - 1) / threads;
+    size_t cap = (size_t)n_sm * 8;
+    return (int)std::max<size_t>(1, std::min(b, cap));
+  }
+
+  template <class T> int alloc(T** p, size_t n) {
+    CK(dalloc(p, n));
+    allocs.push_back(*p);
+    return SSB_OK;
+  }
+  int fill32(u32* p, u32 val, size_t n) {
+    if (n) k_fill_u32<<<grid(n, 256), 256, 0, stream>>>(p, val, n);
+    CK(cudaGetLastError());
+    return SSB_OK;
+  }
+  int fill64(u64* p, u64 val, size_t n) {
+    if (n) k_fill_u64<<<grid(n, 256), 256, 0, stream>>>(p, val, n);
+    CK(cudaGetLastError());
+    return SSB_OK;
+  }
+
+  int state_words() const {
+    switch (cfg.model) {
+      case SSB_MODEL_PHOLD: return PholdModel::kStateWords;
+      case SSB_MODEL_PHOLD_STATEFUL: return PholdStatefulModel::kStateWords;
+      case SSB_MODEL_TRAFFIC: return TrafficModel::kStateWords;
+    }
+    return 0;
+  }
+
+  int init();
+  int sync_ctl();
+  int check_device_error();
+  int model_ready();
+  int enqueue_round();
+  int exchange();
+  template <class M> void launch_model_kernels_commit(const typename M::Data& md);
+  template <class M> void launch_model_kernels_exec(const typename M::Data& md);
+  void launch_commit();
+  void launch_exec();
+  void launch_route(int which, u32 peer, u32 filter);
+  u32 owner_of(long long lp) const { return h_owner.empty() ? (u32)(lp % cfg.world) : h_owner[(size_t)lp]; }
+  u32 local_of(long long lp) const { return h_local.empty() ? (u32)(lp / cfg.world) : h_local[(size_t)lp]; }
+};
+
+int ssb_engine::init() {
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) { set_error("no CUDA device"); return SSB_ERR_CUDA; }
+  CK(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg.device));
+  n_sm = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&h_ctl), sizeof(Ctl), cudaHostAllocDefault));
+
+  std::memset(&v, 0, sizeof(v));
+  v.rank = (u32)cfg.rank; v.world = (u32)cfg.world;
+  v.n_lp = (u32)cfg.n_lp;
+  v.n_lp_local = (u32)((cfg.n_lp - cfg.rank + cfg.world - 1) / cfg.world);   // default modulo partition
+  v.part_mode = 0;
+  v.bucket_ticks = (u32)cfg.bucket_ticks;
+  v.finish_time = (u32)cfg.finish_time;
+  v.window = (u32)cfg.window_buckets;
+  v.nb = (u32)((cfg.finish_time + cfg.bucket_ticks - 1) / cfg.bucket_ticks);
+  if (v.nb == 0) v.nb = 1;
+  v.ch_log = cfg.max_events >= (1 << 22) ? 12 : (cfg.max_events >= (1 << 16) ? 8 : 4);
+  const u32 chs = 1u << v.ch_log;
+  n_chunks = (u32)((cfg.max_events + chs - 1) / chs) + 1;   // + the sacrificial chunk 0
+  // every non-empty bucket wastes at most one partly filled chunk
+  n_chunks += v.nb < 4096 ? v.nb : 4096;
+  v.maxc = n_chunks;
+  v.cap_batch = (u32)cfg.max_batch;
+  v.cap_aux = std::max<u32>(1024, v.cap_batch / 4);
+  v.cap_snap = (u32)std::max<int64_t>(cfg.max_snapshots, 1024);
+  v.cap_send = cfg.world > 1 ? v.cap_batch : 1;
+  v.cap_log = (u64)cfg.max_committed;
+  v.state_words = (u32)state_words();
+
+  const size_t n_slots = (size_t)n_chunks << v.ch_log;
+  int rc;
+  if ((rc = alloc(&v.ev, n_slots))) return rc;
+  if ((rc = alloc(&v.meta, n_slots))) return rc;
+  if ((rc = alloc(&v.sent_key, n_slots))) return rc;
+  if ((rc = alloc(&v.chunk_tab, (size_t)v.nb * v.maxc))) return rc;
+  if ((rc = alloc(&v.free_stack, n_chunks))) return rc;
+  if ((rc = alloc(&v.fill, v.nb))) return rc;
+  if ((rc = alloc(&v.consumed, v.nb))) return rc;
+  if ((rc = alloc(&v.min_key, v.nb))) return rc;
+  if ((rc = alloc(&v.cnt, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.seg_start, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.last_slot, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.last_time, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.state, (size_t)v.n_lp_local * v.state_words))) return rc;
+  if ((rc = alloc(&v.tmp_sorted, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.tmp_lp, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.sorted, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.active, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
+  if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
+  if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1)))) return rc;
+  if ((rc = alloc(&v.commit, v.nb))) return rc;
+  if ((rc = alloc(&v.sendbuf, (size_t)v.world * v.cap_send))) return rc;
+  if ((rc = alloc(&v.recvbuf, (size_t)v.world * v.cap_send))) return rc;
+  if ((rc = alloc(&v.log, (size_t)v.cap_log))) return rc;
+  if ((rc = alloc(&v.snap, (size_t)v.cap_snap * v.state_words))) return rc;
+  if ((rc = alloc(&v.ctl, 1))) return rc;
+  if ((rc = alloc(&d_stage, v.cap_batch))) return rc;
+
+  CK(cudaMemsetAsync(v.ctl, 0, sizeof(Ctl), stream));
+  Ctl init;
+  std::memset(&init, 0, sizeof(init));
+  init.local_min = KEY_MAX; init.gvt = 0; init.beyond_min = KEY_MAX;
+  init.free_top = n_chunks - 1; init.free_low = n_chunks - 1;
+  CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+  k_iota_u32<<<grid(n_chunks - 1, 256), 256, 0, stream>>>(v.free_stack, 1u, n_chunks - 1);   // chunks 1..n-1 are free
+  if ((rc = fill32(v.chunk_tab, NIL, (size_t)v.nb * v.maxc))) return rc;
+  CK(cudaMemsetAsync(v.fill, 0, sizeof(u32) * v.nb, stream));
+  CK(cudaMemsetAsync(v.consumed, 0, sizeof(u32) * v.nb, stream));
+  if ((rc = fill64(v.min_key, KEY_MAX, v.nb))) return rc;
+  CK(cudaMemsetAsync(v.cnt, 0, sizeof(u32) * v.n_lp_local, stream));
+  if ((rc = fill32(v.last_slot, NIL, v.n_lp_local))) return rc;
+  CK(cudaMemsetAsync(v.last_time, 0, sizeof(u32) * v.n_lp_local, stream));
+  CK(cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
+  route_smem = (size_t)(v.nb + 1 + v.world) * 16;
+  if (route_smem > 200 * 1024) { set_error("too many calendar buckets for the route kernel's shared memory: raise bucket_ticks"); return SSB_ERR_INVALID; }
+  CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  return SSB_OK;
+}
+
+int ssb_engine::sync_ctl() {
+  CK(cudaMemcpyAsync(h_ctl, v.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  return SSB_OK;
+}
+
+int ssb_engine::check_device_error() {
+  u32 e = h_ctl->error;
+  if (!e) return SSB_OK;
+  std::string s = "device error:";
+  if (e & E_POOL) s += " event pool exhausted (raise max_events)";
+  if (e & E_RANGE) s += " value out of device record range / destination not owned";
+  if (e & E_BATCH) s += " rollback outbox overflow (raise max_batch)";
+  if (e & E_SNAP) s += " snapshot ring overflow (raise max_snapshots)";
+  if (e & E_HORIZON) s += " calendar horizon exceeded";
+  if (e & E_SENDBUF) s += " send buffer overflow (raise max_batch)";
+  if (e & E_INTERNAL) s += " internal invariant violated";
+  set_error(s);
+  if (e & (E_POOL | E_BATCH | E_SNAP | E_SENDBUF)) return SSB_ERR_CAPACITY;
+  if (e & E_RANGE) return SSB_ERR_RANGE;
+  return SSB_ERR_INVALID;
+}
+
+int ssb_engine::model_ready() {
+  if (cfg.model == SSB_MODEL_PHOLD || cfg.model == SSB_MODEL_PHOLD_STATEFUL) {
+    if (!d_phold_table) {
+      if (!(have_lat && have_rem)) { set_error("PHOLD model data slots 0 and 1 not set"); return SSB_ERR_MODEL; }
+      u32 n = (u32)h_lat.size();
+      if (h_rem.size() != h_lat.size()) { set_error("PHOLD tables differ in length"); return SSB_ERR_MODEL; }
+      long long* d_lat = nullptr; int* d_rem = nullptr;
+      CK(dalloc(&d_lat, n)); CK(dalloc(&d_rem, n));
+      int rc = alloc(&d_phold_table, n);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(d_lat, h_lat.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(d_rem, h_rem.data(), sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+      k_pack_phold_table<<<grid(n, 256), 256, 0, stream>>>(d_lat, d_rem, d_phold_table, n, v.ctl);
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaFree(d_lat)); CK(cudaFree(d_rem));
+      phold_table_size = n;
+      h_lat.clear(); h_lat.shrink_to_fit(); h_rem.clear(); h_rem.shrink_to_fit();
+    }
+    if (h_phold_params[1] <= 0) h_phold_params[1] = cfg.n_lp;
+  } else if (cfg.model == SSB_MODEL_TRAFFIC) {
+    if (!d_route) { set_error("TrafficSim model data slot 0 (route pool) not set"); return SSB_ERR_MODEL; }
+  }
+  return SSB_OK;
+}
+
+void ssb_engine::launch_route(int which, u32 peer, u32 filter) {
+  k_route<<<n_sm * 4, kRouteThreads, route_smem, stream>>>(v, which, peer, filter);
+}
+
+void ssb_engine::launch_commit() {
+  const int g = n_sm * 8;
+  switch (cfg.model) {
+    case SSB_MODEL_PHOLD: k_commit<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_PHOLD_STATEFUL: k_commit<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_TRAFFIC: k_commit<TrafficModel><<<g, 256, 0, stream>>>(v, traffic_data()); break;
+  }
+}
+
+void ssb_engine::launch_exec() {
+  const int g = n_sm * 16;
+  switch (cfg.model) {
+    case SSB_MODEL_PHOLD: k_exec<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_PHOLD_STATEFUL: k_exec<PholdStatefulModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_TRAFFIC: k_exec<TrafficModel><<<g, 128, 0, stream>>>(v, traffic_data()); break;
+  }
+}
+
+// counts all-to-all, then payload all-to-all (grouped ncclSend/ncclRecv), then integrate what arrived
+int ssb_engine::exchange() {
+  if (cfg.world <= 1) return SSB_OK;
+  if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
+  Nccl& n = g_nccl;
+  int rc;
+#define NC(call) do { rc = (call); if (rc != 0) { set_error(std::string(#call) + ": " + n.GetErrorString(rc)); return SSB_ERR_COMM; } } while (0)
+  NC(n.GroupStart());
+  for (int r = 0; r < cfg.world; ++r) {
+    if (r == cfg.rank) continue;
+    NC(n.Send(&v.ctl->send_count[r], 1, Nccl::kUint32, r, comm, stream));
+    NC(n.Recv(&v.ctl->recv_count[r], 1, Nccl::kUint32, r, comm, stream));
+  }
+  NC(n.GroupEnd());
+  int s = sync_ctl();
+  if (s) return s;
+  NC(n.GroupStart());
+  for (int r = 0; r < cfg.world; ++r) {
+    if (r == cfg.rank) continue;
+    u32 ns = std::min(h_ctl->send_count[r], v.cap_send), nr = h_ctl->recv_count[r];
+    if (nr > v.cap_send) { set_error("receive buffer overflow (raise max_batch)"); return SSB_ERR_CAPACITY; }
+    if (ns) NC(n.Send(v.sendbuf + (size_t)r * v.cap_send, (size_t)ns * sizeof(Ev), Nccl::kUint8, r, comm, stream));
+    if (nr) NC(n.Recv(v.recvbuf + (size_t)r * v.cap_send, (size_t)nr * sizeof(Ev), Nccl::kUint8, r, comm, stream));
+  }
+  NC(n.GroupEnd());
+#undef NC
+  for (int pass = 1; pass <= 2; ++pass)
+    for (int r = 0; r < cfg.world; ++r)
+      if (r != cfg.rank && h_ctl->recv_count[r]) launch_route(2, (u32)r, (u32)pass);
+  CK(cudaGetLastError());
+  return SSB_OK;
+}
+
+int ssb_engine::enqueue_round() {
+  k_min<<<1, 1024, 0, stream>>>(v);
+  if (cfg.world > 1) {
+    if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
+    int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
+    if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
+  }
+  k_plan<<<1, 32, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
+  launch_commit();
+  k_free<<<64, 256, 0, stream>>>(v);
+  const int g = n_sm * 8;
+  k_hist<<<g, 256, 0, stream>>>(v);
+  k_segs<<<g, 256, 0, stream>>>(v);
+  k_scatter<<<g, 256, 0, stream>>>(v);
+  launch_exec();
+  launch_route(0, 0, 0);
+  launch_route(1, 0, 0);
+  CK(cudaGetLastError());
+  ++rounds;
+  return exchange();
+}
+
+// ======================================= C ABI =======================================
+extern "C" {
+
+int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+
+const char* ssb_last_error(ssb_engine* e) { return e ? e->error.c_str() : g_create_error.c_str(); }
+
+void ssb_destroy(ssb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->d_unpack) cudaFree(e->d_unpack);
+  if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int ssb_create(const ssb_config* cfg, ssb_engine** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return SSB_ERR_INVALID; }
+  *out = nullptr;
+  auto bad = [&](const char* m) { g_create_error = m; return SSB_ERR_INVALID; };
+  if (cfg->abi_version != SSB_ABI_VERSION) return bad("abi_version mismatch");
+  if (cfg->model != SSB_MODEL_PHOLD && cfg->model != SSB_MODEL_TRAFFIC && cfg->model != SSB_MODEL_PHOLD_STATEFUL) return bad("unknown model");
+  if (cfg->world < 1 || cfg->world > MAX_WORLD || cfg->rank < 0 || cfg->rank >= cfg->world) return bad("bad rank/world");
+  if (cfg->n_lp < 1 || cfg->n_lp >= 0xFFFFFFFFll) return bad("n_lp out of range");
+  if (cfg->finish_time < 1 || cfg->finish_time >= 0x7FFFFFFFll) return bad("finish_time out of range (must be < 2^31)");
+  if (cfg->bucket_ticks < 1 || cfg->window_buckets < 1) return bad("bucket_ticks and window_buckets must be >= 1");
+  if (cfg->max_events < 1 || cfg->max_events > 0xF0000000ll) return bad("max_events out of range");
+  if (cfg->max_batch < 1 || cfg->max_batch > 0x7FFFFFFFll) return bad("max_batch out of range");
+  if (cfg->max_committed < 0) return bad("max_committed out of range");
+  ssb_engine* e = new ssb_engine();
+  e->cfg = *cfg;
+  if (e->cfg.rounds_per_sync < 1) e->cfg.rounds_per_sync = 4;
+  int rc = e->init();
+  if (rc != SSB_OK) {
+    g_create_error = e->error;
+    ssb_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return SSB_OK;
+}
+
+int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
+  if (!e) return SSB_ERR_INVALID;
+  if (e->partition_set) { e->set_error("partition already set"); return SSB_ERR_INVALID; }
+  cudaSetDevice(e->cfg.device);
+  if (!lp_to_part) { e->partition_set = true; return SSB_OK; }   // default: lp % world
+  if (n_lp != e->cfg.n_lp) { e->set_error("partition length != n_lp"); return SSB_ERR_INVALID; }
+  bool modulo = true;
+  for (int64_t i = 0; i < n_lp; ++i) {
+    if (lp_to_part[i] < 0 || lp_to_part[i] >= e->cfg.world) { e->set_error("partition value out of [0, world) (reference quirk Q12)"); return SSB_ERR_INVALID; }
+    if (lp_to_part[i] != i % e->cfg.world) modulo = false;
+  }
+  e->partition_set = true;
+  if (modulo) return SSB_OK;
+  e->h_owner.resize((size_t)n_lp); e->h_local.resize((size_t)n_lp);
+  std::vector<u32> counts((size_t)e->cfg.world, 0);
+  for (int64_t i = 0; i < n_lp; ++i) {
+    u32 o = (u32)lp_to_part[i];
+    e->h_owner[(size_t)i] = o;
+    e->h_local[(size_t)i] = counts[o]++;
+  }
+  u32 mine = counts[(size_t)e->cfg.rank];
+  if (mine > e->v.n_lp_local) {
+    // per-LP arrays were sized for the modulo partition: grow them
+    auto& v = e->v;
+    auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
+    if (regrow(&v.cnt, mine) || regrow(&v.seg_start, mine) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
+        regrow(&v.state, (size_t)mine * v.state_words)) { e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA; }
+    cudaMemsetAsync(v.cnt, 0, sizeof(u32) * mine, e->stream);
+    e->fill32(v.last_slot, NIL, mine);
+    cudaMemsetAsync(v.last_time, 0, sizeof(u32) * mine, e->stream);
+    cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)mine * v.state_words, e->stream);
+  }
+  e->v.n_lp_local = mine;
+  u32 *d_o = nullptr, *d_l = nullptr;
+  int rc;
+  if ((rc = e->alloc(&d_o, (size_t)n_lp))) return rc;
+  if ((rc = e->alloc(&d_l, (size_t)n_lp))) return rc;
+  cudaMemcpyAsync(d_o, e->h_owner.data(), sizeof(u32) * (size_t)n_lp, cudaMemcpyHostToDevice, e->stream);
+  cudaMemcpyAsync(d_l, e->h_local.data(), sizeof(u32) * (size_t)n_lp, cudaMemcpyHostToDevice, e->stream);
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) { e->set_error(cudaGetErrorString(ce)); return SSB_ERR_CUDA; }
+  e->v.part_mode = 1; e->v.part_owner = d_o; e->v.part_local = d_l;
+  return SSB_OK;
+}
+
+int ssb_set_model_data(ssb_engine* e, int slot, const void* data, size_t bytes) {
+  if (!e || !data) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  if (e->cfg.model == SSB_MODEL_PHOLD || e->cfg.model == SSB_MODEL_PHOLD_STATEFUL) {
+    if (slot == 0) { e->h_lat.assign((const long long*)data, (const long long*)data + bytes / 8); e->have_lat = true; return SSB_OK; }
+    if (slot == 1) { e->h_rem.assign((const int*)data, (const int*)data + bytes / 4); e->have_rem = true; return SSB_OK; }
+    if (slot == 2 && bytes == 16) { std::memcpy(e->h_phold_params, data, 16); return SSB_OK; }
+    set_error("PHOLD: unknown model data slot");
+    return SSB_ERR_MODEL;
+  }
+  if (e->cfg.model == SSB_MODEL_TRAFFIC) {
+    if (slot != 0) { set_error("TrafficSim: unknown model data slot"); return SSB_ERR_MODEL; }
+    size_t n = bytes / 8;
+    if (n >= 0xFFFFFFFFull) { set_error("route pool too large"); return SSB_ERR_RANGE; }
+    long long* d_in = nullptr;
+    CK(dalloc(&d_in, n));
+    int rc = e->alloc(&e->d_route, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_in, data, n * 8, cudaMemcpyHostToDevice, e->stream));
+    k_narrow_u32<<<e->grid(n, 256), 256, 0, e->stream>>>(d_in, e->d_route, n, e->v.ctl);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaFree(d_in));
+    e->route_len = (u32)n;
+    return SSB_OK;
+  }
+  return SSB_ERR_MODEL;
+}
+
+int ssb_state_words(ssb_engine* e) { return e ? e->state_words() : 0; }
+
+static int states_io(ssb_engine* e, const int64_t* lp_ids, uint32_t* words, int64_t n, bool write) {
+  if (!e || !lp_ids || !words || n < 0) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  const int sw = e->state_words();
+  // contiguous runs of local indices are copied with one memcpy each
+  int64_t i = 0;
+  while (i < n) {
+    if (lp_ids[i] < 0 || lp_ids[i] >= e->cfg.n_lp || e->owner_of(lp_ids[i]) != (u32)e->cfg.rank) {
+      set_error("state for an LP this rank does not own"); return SSB_ERR_INVALID;
+    }
+    u32 l0 = e->local_of(lp_ids[i]);
+    int64_t j = i + 1;
+    while (j < n && lp_ids[j] >= 0 && lp_ids[j] < e->cfg.n_lp && e->owner_of(lp_ids[j]) == (u32)e->cfg.rank &&
+           e->local_of(lp_ids[j]) == l0 + (u32)(j - i)) ++j;
+    size_t bytes = (size_t)(j - i) * sw * 4;
+    if (write) CK(cudaMemcpyAsync(e->v.state + (size_t)l0 * sw, words + (size_t)i * sw, bytes, cudaMemcpyHostToDevice, e->stream));
+    else CK(cudaMemcpyAsync(words + (size_t)i * sw, e->v.state + (size_t)l0 * sw, bytes, cudaMemcpyDeviceToHost, e->stream));
+    i = j;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return SSB_OK;
+}
+int ssb_load_states(ssb_engine* e, const int64_t* lp_ids, const uint32_t* words, int64_t n) {
+  return states_io(e, lp_ids, const_cast<uint32_t*>(words), n, true);
+}
+int ssb_read_states(ssb_engine* e, const int64_t* lp_ids, uint32_t* words, int64_t n) {
+  return states_io(e, lp_ids, words, n, false);
+}
+
+int ssb_load_events(ssb_engine* e, const ssb_event* ev, int64_t n) {
+  if (!e || (!ev && n) || n < 0) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  static_assert(sizeof(ssb_event) == sizeof(HostEvent), "ssb_event layout");
+  int64_t done = 0;
+  while (done < n) {
+    u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
+    CK(cudaMemcpyAsync(e->d_stage, ev + done, sizeof(HostEvent) * m, cudaMemcpyHostToDevice, e->stream));
+    k_pack<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, e->d_stage, m);
+    e->launch_route(3, 0, 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));   // the host buffer may be reused by the caller; staging is single-buffered
+    done += m;
+  }
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  return e->check_device_error();
+}
+
+int ssb_step(ssb_engine* e, int* done) {
+  if (!e) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  int rc = e->model_ready();
+  if (rc) return rc;
+  if ((rc = e->enqueue_round())) return rc;
+  if ((rc = e->sync_ctl())) return rc;
+  if (done) *done = (int)e->h_ctl->done;
+  return e->check_device_error();
+}
+
+int ssb_run(ssb_engine* e, ssb_stats* stats) {
+  if (!e) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  int rc = e->model_ready();
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (;;) {
+    for (int i = 0; i < e->cfg.rounds_per_sync; ++i)
+      if ((rc = e->enqueue_round())) return rc;
+    if ((rc = e->sync_ctl())) return rc;
+    if ((rc = e->check_device_error())) return rc;
+    if (e->h_ctl->done) break;
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaEventSynchronize(e->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->loop_ms += ms;
+  if (stats) return ssb_get_stats(e, stats);
+  return SSB_OK;
+}
+
+int ssb_get_stats(ssb_engine* e, ssb_stats* s) {
+  if (!e || !s) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  const Ctl& c = *e->h_ctl;
+  std::memset(s, 0, sizeof(*s));
+  s->rounds = c.round;
+  s->processed = (int64_t)c.n_processed;
+  s->rollbacks = (int64_t)c.n_rollbacks;
+  s->undone = (int64_t)c.n_undone;
+  s->antis_sent = (int64_t)c.n_antis;
+  s->annihilated = (int64_t)c.n_annihilated;
+  s->duplicates = (int64_t)c.n_dups;
+  s->committed = (int64_t)c.n_committed;
+  s->beyond_finish = (int64_t)c.n_beyond;
+  s->remote_sent = (int64_t)c.n_remote;
+  s->gvt_time = c.gvt == KEY_MAX ? INT64_MAX : (int64_t)(c.gvt >> 32);
+  s->gvt_id = c.gvt == KEY_MAX ? INT64_MAX : (int64_t)(c.gvt & 0xFFFFFFFFull);
+  s->pool_high_water = (int64_t)(e->n_chunks - 1 - c.free_low) << e->v.ch_log;
+  s->log_dropped = (int64_t)c.log_dropped;
+  s->loop_ms = e->loop_ms;
+  return SSB_OK;
+}
+
+int ssb_committed_digest(ssb_engine* e, uint64_t d[4]) {
+  if (!e || !d) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) d[i] = e->h_ctl->digest[i];
+  return SSB_OK;
+}
+
+int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n) {
+  if (!e || !n || (!out && cap) || cap < 0) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
+  u64 avail = have - e->log_drained;
+  u64 m = std::min<u64>(avail, (u64)cap);
+  *n = (int64_t)m;
+  const u64 kChunk = 1u << 22;
+  if (m && e->unpack_cap < std::min<u64>(m, kChunk)) {
+    if (e->d_unpack) cudaFree(e->d_unpack);
+    e->unpack_cap = std::min<u64>(std::max<u64>(m, 1 << 16), kChunk);
+    CK(dalloc(&e->d_unpack, e->unpack_cap * 6));
+  }
+  u64 done = 0;
+  while (done < m) {
+    u32 k = (u32)std::min<u64>(m - done, e->unpack_cap);
+    k_unpack_log<<<e->grid(k, 256), 256, 0, e->stream>>>(e->v.log, e->log_drained + done, k, e->d_unpack);
+    CK(cudaMemcpyAsync(out + done, e->d_unpack, (size_t)k * sizeof(ssb_record), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    done += k;
+  }
+  e->log_drained += m;
+  if (e->log_drained == have && have == e->h_ctl->log_count) {
+    // log fully drained: rewind so that the buffer can be reused by later windows
+    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->log_drained = 0;
+  }
+  return SSB_OK;
+}
+
+int ssb_comm_unique_id(void* id128) {
+  std::string why;
+  if (!id128) return SSB_ERR_INVALID;
+  if (!g_nccl.load(why)) { g_create_error = why; return SSB_ERR_COMM; }
+  Nccl::UniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc); return SSB_ERR_COMM; }
+  std::memcpy(id128, &id, 128);
+  return SSB_OK;
+}
+
+int ssb_comm_init(ssb_engine* e, const void* id128) {
+  if (!e || !id128) return SSB_ERR_INVALID;
+  if (e->cfg.world <= 1) return SSB_OK;
+  std::string why;
+  if (!g_nccl.load(why)) { e->set_error(why); return SSB_ERR_COMM; }
+  cudaSetDevice(e->cfg.device);
+  Nccl::UniqueId id;
+  std::memcpy(&id, id128, 128);
+  int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, id, e->cfg.rank);
+  if (rc != 0) { e->set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
+  return SSB_OK;
+}
+
+}  // extern "C"

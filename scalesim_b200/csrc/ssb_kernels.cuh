@@ -1,0 +1,707 @@
+// ssb_kernels.cuh — the Time Warp core as CUDA kernels (sm_100a).
+//
+// One round (= one optimistic window step) is, in stream order:
+//   k_min     block min-reduction of the calendar's per-bucket minima  -> local GVT candidate
+//   [ncclAllReduce(min) when world > 1]
+//   k_plan    GVT, window bounds, gather list, commit list
+//   k_commit  stream-compaction of every bucket that fell below GVT into the committed log + digest
+//   k_free    fossil collection: the committed buckets' chunks go back to the pool
+//   k_hist    arrivals of the window: per-LP histogram (rank inside the LP's segment)
+//   k_segs    per-LP segment allocation (warp-aggregated) + active-LP list
+//   k_scatter arrivals -> per-LP segments
+//   k_exec    one thread per active LP: sort the segment, annihilate, detect stragglers, roll back,
+//             execute the handler in key order, record sent-log / snapshots, write the outbox
+//   k_route   outbox -> calendar buckets / per-destination-partition send buffers
+//             (block-aggregated atomics; anti-messages first, then positives)
+//   [exchange + k_route of the receive buffer when world > 1]
+// Reference semantics restated per kernel; rule numbers R1..R10 refer to SURVEY.md Appendix A.
+#pragma once
+#include "ssb_device.cuh"
+#include "ssb_models.cuh"
+
+namespace ssb {
+
+constexpr int kRouteThreads = 256;
+constexpr int kRouteItems = 4;
+constexpr int kRouteTile = kRouteThreads * kRouteItems;
+
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ u64 warp_xor_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_min — GVT candidate (R7): min over the unconsumed tails of all calendar buckets and over the
+// events dropped beyond finish_time. Replaces scheduler::min_locals (process_scheduler.hpp:83-90) +
+// the local half of mpi_gsync::check_sync (global_sync.hpp:95-150). Warp-shuffle + block reduction.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_min(View v) {
+  __shared__ u64 sm[32];
+  u64 m = KEY_MAX;
+  for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x) {
+    u64 k = v.min_key[b];
+    m = k < m ? k : m;
+  }
+  m = warp_min_u64(m);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : KEY_MAX;
+    m = warp_min_u64(m);
+    if (threadIdx.x == 0) {
+      u64 bm = v.ctl->beyond_min;
+      v.ctl->local_min = bm < m ? bm : m;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_plan — one thread. GVT := (all-reduced) local_min. Finish test of runner.hpp:392. Commit list =
+// buckets entirely below GVT (R8/R9). Gather list = unconsumed tails of the buckets inside the
+// optimistic window [bucket(GVT), bucket(GVT) + window).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_plan(View v, int use_global_gvt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Ctl* c = v.ctl;
+  u64 gvt = use_global_gvt ? c->gvt : c->local_min;
+  c->gvt = gvt;
+  u32 t = gvt == KEY_MAX ? 0xFFFFFFFFu : key_time(gvt);
+  bool done = t >= v.finish_time;
+  u32 fin_b = (v.finish_time + v.bucket_ticks - 1) / v.bucket_ticks;   // buckets [0, fin_b) hold times < finish
+  if (fin_b > v.nb) fin_b = v.nb;
+  u32 cur = done ? fin_b : t / v.bucket_ticks;
+  if (cur > fin_b) cur = fin_b;
+  c->cur_abs = cur;
+  // commit list
+  u32 nc = 0, tot = 0;
+  for (u32 b = c->commit_next; b < cur; ++b) {
+    u32 f = v.fill[b];
+    if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
+  }
+  c->commit_next = cur > c->commit_next ? cur : c->commit_next;
+  c->n_commit = nc;
+  c->commit_total = tot;
+  // snapshot ring: rounds whose window lies below GVT are dead (their snapshots can be reused)
+  while (c->rq_tail != c->rq_head && c->rq_bound[c->rq_tail % RQ_LEN] <= cur) c->rq_tail++;
+  c->snap_tail = c->rq_tail == c->rq_head ? c->snap_head : c->rq_snap[c->rq_tail % RQ_LEN];
+  // gather list
+  u32 ng = 0, total = 0;
+  u32 bound = cur;
+  if (!done) {
+    bound = cur + v.window < fin_b ? cur + v.window : fin_b;
+    for (u32 b = cur; b < bound; ++b) {
+      u32 avail = v.fill[b] - v.consumed[b];
+      if (!avail) continue;
+      u32 take = avail < v.cap_batch - total ? avail : v.cap_batch - total;
+      if (take) {
+        v.gather[ng++] = make_uint4(b, v.consumed[b], take, total);
+        total += take;
+        v.consumed[b] += take;
+      }
+      if (take < avail) {
+        // batch capacity reached: the rest of this bucket stays pending; a conservative minimum keeps GVT valid
+        v.min_key[b] = make_key(b * v.bucket_ticks, 0);
+        bound = b + 1;
+        break;
+      }
+      v.min_key[b] = KEY_MAX;
+    }
+    if (c->rq_head - c->rq_tail < RQ_LEN) {
+      c->rq_bound[c->rq_head % RQ_LEN] = bound;
+      c->rq_snap[c->rq_head % RQ_LEN] = c->snap_head;
+      c->rq_head++;
+    } else {
+      c->rq_bound[(c->rq_head - 1) % RQ_LEN] = bound;
+    }
+  }
+  c->bound_abs = bound;
+  c->n_gather = ng;
+  c->n_arr = total;
+  c->n_active = 0;
+  c->seg_cursor = 0;
+  c->n_anti = 0;
+  c->n_extra = 0;
+  c->done = done ? 1u : 0u;
+  c->round++;
+  for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_commit — R8: every event with receive_time < finish_time that survived (not annihilated) is output
+// exactly once, when its bucket falls below GVT. Stream compaction into the committed log, plus the
+// order-independent digest. Replaces eventq::std_out + sim_event::result_out (queue.hpp:203-211,
+// sim_obj.hpp:66-77), which print one line per event serially on the main thread.
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_commit(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  const u32 total = c->commit_total;
+  const u32 nc = c->n_commit;
+  u64 cnt = 0, hsum = 0, hxor = 0, hsum2 = 0;
+  const u32 lane = threadIdx.x & 31;
+  const u32 nthreads = gridDim.x * blockDim.x;
+  // every warp iterates the same number of times so that the ballots below are full-warp
+  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads) {
+    u32 i = base + lane;
+    bool keep = false;
+    Ev e;
+    u32 tg = 0;
+    if (i < total) {
+      // locate the bucket: binary search over the commit list offsets
+      u32 lo = 0, hi = nc;
+      while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (v.commit[mid].z <= i) lo = mid; else hi = mid;
+      }
+      uint4 ce = v.commit[lo];
+      u32 slot = slot_of(v, ce.x, i - ce.z);
+      e = load_ev(v.ev + slot);
+      keep = !(e.flags & (F_CANCEL | F_DEAD)) && key_time(e.key) < v.finish_time;
+      if (keep) {
+        if (!(e.flags & F_PROCESSED)) atomicOr(&c->error, E_INTERNAL);
+        tg = M::tag(md, e);
+        u64 h = record_hash(e, tg);
+        cnt += 1; hsum += h; hxor ^= h; hsum2 += mix64(h + 0xD1B54A32D192ED03ULL);
+      }
+    }
+    if (v.cap_log) {
+      u32 bal = __ballot_sync(0xffffffffu, keep);
+      if (bal) {
+        u64 pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&c->log_count, (u64)__popc(bal));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (keep) {
+          u64 pos = pos0 + __popc(bal & ((1u << lane) - 1u));
+          if (pos < v.cap_log) { e.flags = tg; store_ev(v.log + pos, e); }
+          else atomicAdd(&c->log_dropped, 1ull);
+        }
+      }
+    }
+  }
+  cnt = warp_sum_u64(cnt); hsum = warp_sum_u64(hsum); hxor = warp_xor_u64(hxor); hsum2 = warp_sum_u64(hsum2);
+  if (lane == 0 && cnt) {
+    atomicAdd(&c->digest[0], cnt);
+    atomicAdd(&c->digest[1], hsum);
+    atomicXor(&c->digest[2], hxor);
+    atomicAdd(&c->digest[3], hsum2);
+    atomicAdd(&c->n_committed, cnt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_free — R9 fossil collection: chunks of committed buckets return to the free stack. Replaces
+// eventq::release / release_cancel / stateq::release (queue.hpp:159-177, 292-302).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_free(View v) {
+  Ctl* c = v.ctl;
+  const u32 nc = c->n_commit;
+  const u32 chs = 1u << v.ch_log;
+  for (u32 k = blockIdx.x; k < nc; k += gridDim.x) {
+    uint4 ce = v.commit[k];
+    u32 b = ce.x;
+    u32 nch = (ce.y + chs - 1) >> v.ch_log;
+    for (u32 j = threadIdx.x; j < nch; j += blockDim.x) {
+      u32* entry = &v.chunk_tab[(size_t)b * v.maxc + j];
+      u32 ch = *entry;
+      *entry = NIL;
+      u32 pos = atomicAdd(&c->free_top, 1u);
+      v.free_stack[pos] = ch;
+    }
+    if (threadIdx.x == 0) { v.fill[b] = 0; v.consumed[b] = 0; v.min_key[b] = KEY_MAX; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_hist — arrivals of this window, in calendar order. Replaces the inbox append of lp::buffer
+// (logical_process.hpp:115-127): rank = position inside the LP's inbox.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hist(View v) {
+  Ctl* c = v.ctl;
+  const u32 n = c->n_arr;
+  const u32 ng = c->n_gather;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    u32 g = 0;
+    while (g + 1 < ng && v.gather[g + 1].w <= i) ++g;
+    uint4 ge = v.gather[g];
+    u32 slot = slot_of(v, ge.x, ge.y + (i - ge.w));
+    Ev e = load_ev(v.ev + slot);
+    u32 lp = part_local(v, e.dst);
+    u32 rank = atomicAdd(&v.cnt[lp], 1u);
+    Sorted s;
+    s.key = e.key; s.slot = slot; s.seq = i | ((e.flags & F_CANCEL) ? 0x80000000u : 0u);
+    v.tmp_sorted[i] = s;
+    v.tmp_lp[i] = lp;
+    v.tmp_rank[i] = rank;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_segs — one thread per LP: allocate the LP's segment of this round (warp-aggregated atomic on the
+// cursor) and append the LP to the active list. Replaces scheduler::queue/dequeue
+// (process_scheduler.hpp:55-81): "which LPs have work in this window".
+// ------------------------------------------------------------------------------------------------
+__global__ void k_segs(View v) {
+  Ctl* c = v.ctl;
+  if (c->n_arr == 0) return;
+  const u32 lane = threadIdx.x & 31;
+  const u32 nthreads = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < v.n_lp_local; base += nthreads) {
+    u32 lp = base + lane;
+    u32 n = lp < v.n_lp_local ? v.cnt[lp] : 0u;
+    u32 incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+    u32 bal = __ballot_sync(0xffffffffu, n != 0);
+    if (tot == 0) continue;
+    u32 seg0 = 0, act0 = 0;
+    if (lane == 0) {
+      seg0 = atomicAdd(&c->seg_cursor, tot);
+      act0 = atomicAdd(&c->n_active, (u32)__popc(bal));
+    }
+    seg0 = __shfl_sync(0xffffffffu, seg0, 0);
+    act0 = __shfl_sync(0xffffffffu, act0, 0);
+    if (n) {
+      u32 start = seg0 + incl - n;
+      v.seg_start[lp] = start;
+      v.cnt[lp] = 0;
+      v.active[act0 + __popc(bal & ((1u << lane) - 1u))] = make_uint4(lp, start, n, 0);
+    }
+  }
+}
+
+__global__ void k_scatter(View v) {
+  const u32 n = v.ctl->n_arr;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    u32 pos = v.seg_start[v.tmp_lp[i]] + v.tmp_rank[i];
+    v.sorted[pos] = v.tmp_sorted[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lp_turn — one LP's turn in a round: what runner::run_lp_aggr does (runner.hpp:530-570) for every event
+// of the window instead of switch_lp_interval() of them.
+//   1. sort the inbox segment by (key, arrival order)                      — R1
+//   2. straggler test against the newest processed event; roll back: walk the processed chain, emit the
+//      anti-message of every undone event's output, restore the pre-state from the snapshot ring,
+//      put the undone events back in front of the merge                  — R5 (queue.hpp:98-105, 286-290)
+//   3. merge inbox and undone events in key order; per key apply the inbox items in arrival order:
+//      positive = insert unless present, anti = erase if present           — R4/R6 (queue.hpp:82-96)
+//   4. execute survivors in key order; record sent-log + snapshot          — R2 (runner.hpp:544-568)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sorted_less(const Sorted& a, const Sorted& b) {
+  return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
+}
+
+template <class M>
+struct Turn {
+  const View& v;
+  const typename M::Data& md;
+  u32 lp_global_hint;
+  u32 last_slot, last_time;
+  u32 st[M::kStateWords];
+  bool st_dirty;
+  u32 err;
+  u32 n_proc, n_undone, n_anti, n_annih, n_dup;
+
+  __device__ Turn(const View& v_, const typename M::Data& md_) : v(v_), md(md_) {}
+
+  __device__ __forceinline__ void emit_anti(u64 key, u32 dst, u32 src, u32 send) {
+    u32 pos = atomicAdd(&v.ctl->n_anti, 1u);
+    if (pos >= v.cap_aux) { err |= E_BATCH; return; }
+    Ev a;
+    a.key = key; a.dst = dst; a.src = src; a.send = send; a.p0 = 0; a.p1 = 0; a.flags = F_CANCEL;
+    store_ev(v.anti_box + pos, a);
+    ++n_anti;
+  }
+
+  // run the handler on the event in `slot`; out_idx = outbox position for its output
+  __device__ __forceinline__ void process(u32 slot, u32 out_idx) {
+    Ev e = load_ev(v.ev + slot);
+    u32 pre[M::kStateWords];
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) pre[w] = st[w];
+    Ev out;
+    bool has = M::handle(md, e, st, out, err);
+    Meta m;
+    m.link = last_slot;
+    m.prevtime = last_time;
+    m.sent_dst = NIL;
+    m.snap = NIL;
+    if (has) {
+      bool changed = false;
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) changed |= (pre[w] != st[w]);
+      if (changed) {
+        // state saving: the pre-state goes to the snapshot ring (copy-on-change)
+        u32 s = atomicAdd(&v.ctl->snap_head, 1u);
+        if (s - v.ctl->snap_tail >= v.cap_snap) err |= E_SNAP;
+        u32 si = s % v.cap_snap;
+#pragma unroll
+        for (int w = 0; w < M::kStateWords; ++w) v.snap[(size_t)si * M::kStateWords + w] = pre[w];
+        m.snap = si;
+        st_dirty = true;
+      }
+      m.sent_dst = out.dst;
+      v.sent_key[slot] = out.key;
+      store_ev(v.outbox + out_idx, out);
+    } else {
+      // no event produced: nothing recorded, state update dropped (runner.hpp:552-553, quirk Q2)
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) st[w] = pre[w];
+      v.outbox[out_idx].key = KEY_MAX;
+    }
+    v.meta[slot] = m;
+    v.ev[slot].flags = (e.flags & ~F_DEAD) | F_PROCESSED;
+    last_slot = slot;
+    last_time = key_time(e.key);
+    ++n_proc;
+  }
+
+  __device__ __forceinline__ u32 extra_idx() {
+    u32 pos = atomicAdd(&v.ctl->n_extra, 1u);
+    if (pos >= v.cap_aux) { err |= E_BATCH; pos = v.cap_aux - 1; }
+    return v.cap_batch + pos;
+  }
+
+  __device__ void run(u32 lp, u32 s0, u32 n) {
+    err = 0; n_proc = n_undone = n_anti = n_annih = n_dup = 0;
+    st_dirty = false;
+    Sorted* seg = v.sorted + s0;
+    // 1. insertion sort (segments are short; long ones are handled by the heavy path)
+    for (u32 i = 1; i < n; ++i) {
+      Sorted x = seg[i];
+      u32 j = i;
+      while (j > 0) {
+        Sorted y = seg[j - 1];
+        if (!sorted_less(x, y)) break;
+        seg[j] = y;
+        --j;
+      }
+      if (j != i) seg[j] = x;
+    }
+    last_slot = v.last_slot[lp];
+    last_time = v.last_time[lp];
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) st[w] = v.state[(size_t)lp * M::kStateWords + w];
+
+    // 2. rollback
+    u32 U = NIL;   // undone events, ascending key order, linked through Meta::link
+    const u64 m = seg[0].key;
+    const u32 mtime = key_time(m);
+    if (last_slot != NIL && last_time >= mtime) {
+      u32 cur = last_slot, curtime = last_time;
+      bool any = false;
+      while (cur != NIL && curtime >= mtime) {
+        Ev e = load_ev(v.ev + cur);
+        if (e.key < m) break;
+        Meta mt = v.meta[cur];
+        if (mt.sent_dst != NIL) emit_anti(v.sent_key[cur], mt.sent_dst, e.dst, key_time(e.key));
+        if (mt.snap != NIL) {
+#pragma unroll
+          for (int w = 0; w < M::kStateWords; ++w) st[w] = v.snap[(size_t)mt.snap * M::kStateWords + w];
+          st_dirty = true;
+        }
+        v.ev[cur].flags = e.flags & ~F_PROCESSED;
+        v.meta[cur].link = U;
+        U = cur;
+        cur = mt.link;
+        curtime = mt.prevtime;
+        ++n_undone;
+        any = true;
+      }
+      last_slot = cur;
+      last_time = curtime;
+      if (any) atomicAdd(&v.ctl->n_rollbacks, 1ull);
+    }
+
+    // 3 + 4. merge and execute
+    u32 ia = 0;
+    while (ia < n || U != NIL) {
+      u64 ka = ia < n ? seg[ia].key : KEY_MAX;
+      u64 ku = KEY_MAX;
+      if (U != NIL) ku = v.ev[U].key;
+      u64 k = ka < ku ? ka : ku;
+      u32 present = NIL;      // slot of the event currently in the queue under key k
+      u32 out_idx = NIL;
+      if (ku == k) {
+        present = U;
+        U = v.meta[present].link;
+      }
+      while (ia < n && seg[ia].key == k) {
+        Sorted a = seg[ia];
+        if (a.seq & 0x80000000u) {
+          v.ev[a.slot].flags |= F_DEAD;                 // the anti-message itself is consumed
+          v.outbox[s0 + ia].key = KEY_MAX;
+          if (present != NIL) {                         // erase (queue.hpp:87-90)
+            v.ev[present].flags |= F_DEAD;
+            present = NIL;
+            if (out_idx != NIL) { v.outbox[out_idx].key = KEY_MAX; out_idx = NIL; }
+            ++n_annih;
+          }
+        } else if (present == NIL) {
+          present = a.slot;                             // insert (queue.hpp:92)
+          out_idx = s0 + ia;
+        } else {
+          v.ev[a.slot].flags |= F_DEAD;                 // duplicate key: second insert ignored
+          v.outbox[s0 + ia].key = KEY_MAX;
+          ++n_dup;
+        }
+        ++ia;
+      }
+      if (present != NIL) {
+        // a re-executed (rolled back) event has no inbox position: its output goes to the extra region
+        process(present, out_idx != NIL ? out_idx : extra_idx());
+      }
+    }
+
+    v.last_slot[lp] = last_slot;
+    v.last_time[lp] = last_time;
+    if (st_dirty) {
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) v.state[(size_t)lp * M::kStateWords + w] = st[w];
+    }
+  }
+};
+
+template <class M>
+__global__ void k_exec(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  const u32 na = c->n_active;
+  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0;
+  u32 err = 0;
+  const u32 lane = threadIdx.x & 31;
+  const u32 nthreads = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < na; base += nthreads) {
+    u32 k = base + lane;
+    if (k < na) {
+      uint4 a = v.active[k];
+      Turn<M> t(v, md);
+      t.run(a.x, a.y, a.z);
+      n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
+      err |= t.err;
+    }
+  }
+  __syncwarp();
+  n_proc = warp_sum_u64(n_proc);
+  n_undone = warp_sum_u64(n_undone);
+  n_anti = warp_sum_u64(n_anti);
+  n_annih = warp_sum_u64(n_annih);
+  n_dup = warp_sum_u64(n_dup);
+  if (lane == 0) {
+    if (n_proc) atomicAdd(&c->n_processed, n_proc);
+    if (n_undone) atomicAdd(&c->n_undone, n_undone);
+    if (n_anti) atomicAdd(&c->n_antis, n_anti);
+    if (n_annih) atomicAdd(&c->n_annihilated, n_annih);
+    if (n_dup) atomicAdd(&c->n_dups, n_dup);
+  }
+  if (err) atomicOr(&c->error, err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_route — emit: outbox -> calendar buckets (local destination) or per-partition send buffers.
+// Replaces event_com::send_event (event_communicator.hpp:90-103) + lp::buffer. Per tile of 1024 events the
+// block builds a shared-memory histogram over targets, claims one range per target with a single global
+// atomic (block-aggregated), and updates the bucket's unconsumed minimum (R3: the destination's local time
+// drops at once, so GVT sees the event). Events at or beyond finish_time are never executed nor committed
+// (R8), so they are counted and dropped; only their minimum key is kept for GVT.
+//   which: 0 = anti box, 1 = main + extra outbox, 2 = receive buffer, 3 = host-loaded staging (outbox[0..load_count))
+//   filter: 0 = all, 1 = anti-messages only, 2 = positives only (the receive side keeps antis ahead of positives)
+// Targets: [0, nb) buckets, nb = "beyond", nb+1+r = partition r.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 peer, u32 filter) {
+  extern __shared__ u64 smem64[];
+  Ctl* c = v.ctl;
+  const u32 nt = v.nb + 1 + v.world;
+  u64* s_min = smem64;                                  // [nt]
+  u32* s_cnt = reinterpret_cast<u32*>(smem64 + nt);     // [nt]
+  u32* s_base = s_cnt + nt;                             // [nt]
+  const Ev* src;
+  u32 n0, n1 = 0;        // main count, extra count (extra region starts at cap_batch)
+  if (which == 0) { src = v.anti_box; n0 = c->n_anti < v.cap_aux ? c->n_anti : v.cap_aux; }
+  else if (which == 1) { src = v.outbox; n0 = c->n_arr; n1 = c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux; }
+  else if (which == 2) { src = v.recvbuf + (size_t)peer * v.cap_send; n0 = c->recv_count[peer]; }
+  else { src = v.outbox; n0 = c->load_count; }
+  const u32 total = n0 + n1;
+  const u32 chm = (1u << v.ch_log) - 1u;
+  for (u32 tile = blockIdx.x * kRouteTile; tile < total; tile += gridDim.x * kRouteTile) {
+    for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) { s_cnt[t] = 0; s_min[t] = KEY_MAX; }
+    __syncthreads();
+    Ev e[kRouteItems];
+    u32 tgt[kRouteItems], rnk[kRouteItems];
+#pragma unroll
+    for (int it = 0; it < kRouteItems; ++it) {
+      u32 i = tile + it * kRouteThreads + threadIdx.x;
+      tgt[it] = NIL;
+      if (i < total) {
+        u32 idx = i < n0 ? i : v.cap_batch + (i - n0);
+        e[it] = load_ev(src + idx);
+        bool take = e[it].key != KEY_MAX;
+        if (filter == 1u) take = take && (e[it].flags & F_CANCEL);
+        if (filter == 2u) take = take && !(e[it].flags & F_CANCEL);
+        if (take) {
+          u32 tm = key_time(e[it].key);
+          u32 t;
+          u32 owner = v.world > 1 ? part_owner(v, e[it].dst) : v.rank;
+          if (e[it].dst >= v.n_lp) { atomicOr(&c->error, E_RANGE); continue; }
+          if (owner != v.rank) t = v.nb + 1 + owner;
+          else if (tm >= v.finish_time) t = v.nb;
+          else {
+            t = tm / v.bucket_ticks;
+            if (t < c->commit_next) { atomicOr(&c->error, E_INTERNAL); continue; }   // causality: nothing may arrive below GVT
+          }
+          if (which == 3 && owner != v.rank) { atomicOr(&c->error, E_RANGE); continue; }
+          tgt[it] = t;
+          rnk[it] = atomicAdd(&s_cnt[t], 1u);
+          atomicMin(&s_min[t], e[it].key);
+        }
+      }
+    }
+    __syncthreads();
+    for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) {
+      u32 n = s_cnt[t];
+      if (!n) continue;
+      if (t < v.nb) {
+        s_base[t] = atomicAdd(&v.fill[t], n);
+        atomicMin(&v.min_key[t], s_min[t]);
+      } else if (t == v.nb) {
+        atomicAdd(&c->n_beyond, (u64)n);
+        atomicMin(&c->beyond_min, s_min[t]);
+      } else {
+        s_base[t] = atomicAdd(&c->send_count[t - v.nb - 1], n);
+        atomicAdd(&c->n_remote, (u64)n);
+      }
+    }
+    __syncthreads();
+    // chunk allocation: the owner of a chunk's first position allocates and publishes it
+#pragma unroll
+    for (int it = 0; it < kRouteItems; ++it) {
+      u32 t = tgt[it];
+      if (t < v.nb) {
+        u32 p = s_base[t] + rnk[it];
+        if ((p & chm) == 0) {
+          u32 top = atomicSub(&c->free_top, 1u);
+          u32 ch;
+          if (top == 0 || top > 0x7FFFFFFFu) {
+            atomicAdd(&c->free_top, 1u);
+            atomicOr(&c->error, E_POOL);
+            ch = 0;   // chunk 0 is a sacrificial chunk: keeps everyone moving after an overflow
+          } else {
+            ch = v.free_stack[top - 1];
+            atomicMin(&c->free_low, top - 1);
+          }
+          if ((p >> v.ch_log) >= v.maxc) { atomicOr(&c->error, E_POOL); }
+          else atomicExch(&v.chunk_tab[(size_t)t * v.maxc + (p >> v.ch_log)], ch);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kRouteItems; ++it) {
+      u32 t = tgt[it];
+      if (t == NIL || t == v.nb) continue;
+      u32 p = s_base[t] + rnk[it];
+      e[it].flags &= F_CANCEL;
+      if (t < v.nb) {
+        if ((p >> v.ch_log) >= v.maxc) continue;
+        volatile u32* entry = &v.chunk_tab[(size_t)t * v.maxc + (p >> v.ch_log)];
+        u32 ch = *entry;
+        while (ch == NIL) ch = *entry;     // allocated by another block: wait for the publish
+        store_ev(v.ev + (((size_t)ch << v.ch_log) | (p & chm)), e[it]);
+      } else {
+        u32 r = t - v.nb - 1;
+        if (p < v.cap_send) store_ev(v.sendbuf + (size_t)r * v.cap_send + p, e[it]);
+        else atomicOr(&c->error, E_SENDBUF);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pack — host events (ssb_event, 64 B) -> device records in the outbox staging area, with range checks.
+// ------------------------------------------------------------------------------------------------
+struct HostEvent { long long id, src, dst, recv, send, p0, p1, flags; };
+
+__global__ void k_pack(View v, const HostEvent* in, u32 n) {
+  Ctl* c = v.ctl;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    HostEvent h = in[i];
+    bool ok = h.id >= 0 && h.id < 0xFFFFFFFFll && h.dst >= 0 && h.dst < (long long)v.n_lp &&
+              h.recv >= 0 && h.recv < 0x80000000ll && h.send >= 0 && h.send < 0x100000000ll &&
+              h.src >= -1 && h.src < 0xFFFFFFFFll && h.p0 >= 0 && h.p0 < 0x100000000ll &&
+              h.p1 >= 0 && h.p1 < 0x100000000ll;
+    Ev e;
+    if (!ok) {
+      atomicOr(&c->error, E_RANGE);
+      e.key = KEY_MAX; e.dst = 0; e.src = 0; e.send = 0; e.p0 = 0; e.p1 = 0; e.flags = 0;
+    } else {
+      e.key = make_key((u32)h.recv, (u32)h.id);
+      e.dst = (u32)h.dst;
+      e.src = h.src < 0 ? NIL : (u32)h.src;
+      e.send = (u32)h.send;
+      e.p0 = (u32)h.p0; e.p1 = (u32)h.p1;
+      e.flags = (h.flags & 1) ? F_CANCEL : 0u;
+    }
+    store_ev(v.outbox + i, e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = n;
+}
+
+// committed log record (device Ev with flags = tag) -> ssb_record (6 x int64)
+__global__ void k_unpack_log(const Ev* log, u64 first, u32 n, long long* out) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ev e = load_ev(log + first + i);
+    long long* o = out + (size_t)i * 6;
+    o[0] = key_id(e.key);
+    o[1] = e.src == NIL ? -1ll : (long long)e.src;
+    o[2] = e.send;
+    o[3] = e.dst;
+    o[4] = key_time(e.key);
+    o[5] = e.flags;
+  }
+}
+
+__global__ void k_fill_u32(u32* p, u32 val, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
+}
+__global__ void k_fill_u64(u64* p, u64 val, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
+}
+__global__ void k_iota_u32(u32* p, u32 start, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = start + (u32)i;
+}
+// PHOLD table packing: latency << 1 | remote
+__global__ void k_pack_phold_table(const long long* lat, const int* rem, u32* out, u32 n, Ctl* c) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long l = lat[i];
+    if (l < 0 || l >= 0x7FFFFFFFll) { atomicOr(&c->error, E_RANGE); l = 0; }
+    out[i] = ((u32)l << 1) | (rem[i] == 1 ? 1u : 0u);
+  }
+}
+__global__ void k_narrow_u32(const long long* in, u32* out, size_t n, Ctl* c) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    long long x = in[i];
+    if (x < 0 || x >= 0xFFFFFFFFll) { atomicOr(&c->error, E_RANGE); x = 0; }
+    out[i] = (u32)x;
+  }
+}
+
+}  // namespace ssb

@@ -1,0 +1,134 @@
+// ssb_models.cuh — device twins of the application event handlers.
+//
+// A model provides
+//   kStateWords              size of the LP state in 32-bit words
+//   struct Data              read-only model data (device pointers)
+//   handle(d, e, state, out) App::event_handler: returns true and fills `out` when one new event is
+//                            produced; may modify `state` (kept only when an event is produced, which
+//                            is what runner.hpp:552-558 does — quirk Q2 of SURVEY.md)
+//   tag(e)                   START / END suffix of the committed line (sim_obj.hpp:73-75)
+// Both shipped ScaleSim applications produce at most one event per handled event.
+#pragma once
+#include "ssb_device.cuh"
+
+namespace ssb {
+
+// ---------------------------------------------------------------------------------------------
+// PHOLD — src/phold/phold.hpp:256-281
+//   hops' = hops + 1; idx = (int)(id + hops') % RAND_TABLE_SIZE
+//   recv' = recv + LATENCY[idx] + LOOK_AHEAD; dst' = REMOTE[idx] == 1 ? LATENCY[idx] % NUM_LP : dst
+//   src' = dst; send' = recv; id' = id.   State {long id} is returned unchanged.
+// The two host tables are packed into one u32 table: latency << 1 | remote (latency < 2^31 is
+// checked when the tables are uploaded).
+// ---------------------------------------------------------------------------------------------
+struct PholdModel {
+  static constexpr int kStateWords = 2;
+  struct Data {
+    const u32* table;
+    u32 table_size;
+    u32 lookahead;
+    u32 num_lp;
+  };
+  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
+    (void)state;
+    u32 hops = e.p0 + 1u;
+    // (int)(ev_id + (long)num_hops) % RAND_TABLE_SIZE — id + hops < 2^31 is asserted at load (quirk Q8)
+    u32 idx = (key_id(e.key) + hops) % d.table_size;
+    u32 t = __ldg(d.table + idx);
+    u32 lat = t >> 1;
+    u64 recv = (u64)key_time(e.key) + lat + d.lookahead;
+    if (recv >= 0x80000000ull) { err |= E_RANGE; recv = 0x7FFFFFFFull; }
+    out.key = make_key((u32)recv, key_id(e.key));
+    out.dst = (t & 1u) ? lat % d.num_lp : e.dst;
+    out.src = e.dst;
+    out.send = key_time(e.key);
+    out.p0 = hops;
+    out.p1 = 0;
+    out.flags = 0;
+    return true;
+  }
+  __device__ static __forceinline__ u32 tag(const Data&, const Ev& e) {
+    return e.src == NIL ? TAG_START : TAG_END;   // phold::Event::end() is always true (phold.hpp:89)
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// PHOLD with mutable LP state — a test model (no reference application behaves like this; the
+// parity target is the oracle's sequential execution). The LP state {count, chain} changes with
+// every event and feeds back into the produced event, so any ordering or rollback mistake
+// changes the committed records.
+//   count' = count + 1; chain' = mix(chain ^ id ^ recv)
+//   as PHOLD, except idx = (id + hops' + (chain' & 7)) % RAND_TABLE_SIZE and p1' = count'
+// ---------------------------------------------------------------------------------------------
+struct PholdStatefulModel {
+  static constexpr int kStateWords = 2;
+  typedef PholdModel::Data Data;
+  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
+    u32 count = state[0] + 1u;
+    u32 chain = (u32)mix64(((u64)state[1] << 32) ^ e.key);
+    state[0] = count;
+    state[1] = chain;
+    u32 hops = e.p0 + 1u;
+    u32 idx = (key_id(e.key) + hops + (chain & 7u)) % d.table_size;
+    u32 t = __ldg(d.table + idx);
+    u32 lat = t >> 1;
+    u64 recv = (u64)key_time(e.key) + lat + d.lookahead;
+    if (recv >= 0x80000000ull) { err |= E_RANGE; recv = 0x7FFFFFFFull; }
+    out.key = make_key((u32)recv, key_id(e.key));
+    out.dst = (t & 1u) ? lat % d.num_lp : e.dst;
+    out.src = e.dst;
+    out.send = key_time(e.key);
+    out.p0 = hops;
+    out.p1 = count;
+    out.flags = 0;
+    return true;
+  }
+  __device__ static __forceinline__ u32 tag(const Data&, const Ev& e) { return e.src == NIL ? TAG_START : TAG_END; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// TrafficSim — src/trafficsim/traffic_sim.hpp:279-342
+// Event payload: p0 = offset of destination() in the route pool, p1 = route nodes left (>= 1).
+// LP state words: [0] = id, [1] = number of out-roads n (<= kMaxRoads), then n x {dst, speed km/h, length m}.
+//   no event when the route is exhausted (p1 == 1) or no road leads to the next node (:286-306)
+//   arrival' = len*3600/speed/1000 + arrival + 5   (speed != 0, left-to-right truncating division, :314-316)
+//            = len*3600 + arrival                   (speed == 0, :318-319)
+//   departure' = arrival; source' = this node; the state is returned unchanged.
+// ---------------------------------------------------------------------------------------------
+struct TrafficModel {
+  static constexpr int kMaxRoads = 4;
+  static constexpr int kStateWords = 2 + 3 * kMaxRoads;
+  struct Data {
+    const u32* route;   // route pool
+    u32 route_len;
+  };
+  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
+    if (e.p1 <= 1u) return false;
+    if (e.p0 + 1u >= d.route_len) { err |= E_INTERNAL; return false; }
+    u32 next = __ldg(d.route + e.p0 + 1u);
+    u32 n = state[1];
+    int i = -1;
+#pragma unroll
+    for (int r = kMaxRoads - 1; r >= 0; --r)
+      if ((u32)r < n && state[2 + 3 * r] == next) i = r;   // first match, as std::find
+    if (i < 0) return false;
+    u64 speed = state[2 + 3 * i + 1], len = state[2 + 3 * i + 2];
+    u64 arrival = key_time(e.key);
+    u64 recv = speed != 0 ? len * 60ull * 60ull / speed / 1000ull + arrival + 5ull : len * 60ull * 60ull + arrival;
+    if (recv >= 0x80000000ull) { err |= E_RANGE; recv = 0x7FFFFFFFull; }
+    out.key = make_key((u32)recv, key_id(e.key));
+    out.dst = next;
+    out.src = e.dst;          // destinations_.front() == this LP
+    out.send = (u32)arrival;
+    out.p0 = e.p0 + 1u;
+    out.p1 = e.p1 - 1u;
+    out.flags = 0;
+    return true;
+  }
+  __device__ static __forceinline__ u32 tag(const Data&, const Ev& e) {
+    if (e.src == NIL) return TAG_START;
+    return e.p1 == 1u ? TAG_END : 0u;   // end() == (destinations_.size() == 1), traffic_sim.hpp:77
+  }
+};
+
+}  // namespace ssb

@@ -1,0 +1,233 @@
+"""Host-side mirror of ScaleSim's TrafficSim application (reference src/trafficsim/traffic_sim.hpp):
+the file readers, a synthetic grid generator, and the packing into the engine's records.
+The handler runs on the GPU (``TrafficModel`` in csrc/ssb_models.cuh).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .capi import EVENT_DTYPE, MODEL_TRAFFIC, Config, Engine
+
+FINISH_TIME = 10800      # traffic_sim.hpp:240-247
+MAX_ROADS = 4            # TrafficModel::kMaxRoads
+STATE_WORDS = 2 + 3 * MAX_ROADS
+
+
+@dataclass
+class Scenario:
+    """Road network + trips in flat arrays."""
+    n_lp: int
+    state_ids: np.ndarray     # LP id of each state record (quirk Q10: field 2 of the LAST road on the line)
+    road_start: np.ndarray    # CSR over state records
+    road_dst: np.ndarray
+    road_speed: np.ndarray
+    road_len: np.ndarray
+    trip_id: np.ndarray
+    trip_dep: np.ndarray
+    route_start: np.ndarray   # CSR over trips
+    route_nodes: np.ndarray
+    partition: np.ndarray | None = None
+
+
+def _atol(s: str) -> int:
+    """C atol: optional whitespace, sign, digits; anything else ends the number; no digits = 0."""
+    s = s.lstrip(" \t\n\v\f\r")
+    i, sign = 0, 1
+    if s[:1] in "+-" and s[:1]:
+        sign = -1 if s[0] == "-" else 1
+        i = 1
+    j = i
+    while j < len(s) and s[j].isdigit():
+        j += 1
+    return sign * int(s[i:j]) if j > i else 0
+
+
+def read_partition(path: str) -> np.ndarray:
+    """traffic_reader::graph_read (traffic_sim.hpp:345-362): one partition number per line, line index = LP id."""
+    with open(path) as f:
+        return np.array([_atol(line) for line in f.read().splitlines()], dtype=np.int64)
+
+
+def read_roads(path: str):
+    """traffic_reader::road_read (traffic_sim.hpp:364-408), all partitions. One line per LP; roads split on ';',
+    fields on ','; state id = field 2 of the last road; length 0 -> 1; lanes ignored by the handler."""
+    state_ids, start, dst, speed, length = [], [0], [], [], []
+    with open(path) as f:
+        for line in f.read().splitlines():
+            sid = -1
+            for road in line.split(";"):
+                fld = road.split(",")
+                if len(fld) < 7:
+                    continue
+                sid = _atol(fld[2])
+                dst.append(_atol(fld[3]))
+                speed.append(_atol(fld[4]))
+                ln = _atol(fld[5])
+                length.append(ln if ln != 0 else 1)
+            state_ids.append(sid)
+            start.append(len(dst))
+    return (np.array(state_ids, dtype=np.int64), np.array(start, dtype=np.int64), np.array(dst, dtype=np.int64),
+            np.array(speed, dtype=np.int64), np.array(length, dtype=np.int64))
+
+
+def read_trips(path: str):
+    """traffic_reader::trip_read (traffic_sim.hpp:410-451): vehicle id = field 1, arrival = departure = field 3,
+    route = fields 4.., source = -1 (field 2 ignored)."""
+    tid, dep, start, nodes = [], [], [0], []
+    with open(path) as f:
+        for line in f.read().splitlines():
+            fld = line.split(",")
+            if len(fld) < 5:
+                continue
+            tid.append(_atol(fld[1]))
+            dep.append(_atol(fld[3]))
+            nodes.extend(_atol(x) for x in fld[4:])
+            start.append(len(nodes))
+    return (np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
+            np.array(nodes, dtype=np.int64))
+
+
+def read_scenario(road_csv: str, trip_csv: str, partition_file: str | None = None) -> Scenario:
+    sid, rs, rd, sp, ln = read_roads(road_csv)
+    tid, dep, ts, nodes = read_trips(trip_csv)
+    part = read_partition(partition_file) if partition_file else None
+    n_lp = int(max(sid.max(initial=-1), rd.max(initial=-1), nodes.max(initial=-1))) + 1
+    if part is not None:
+        n_lp = max(n_lp, part.size)
+    return Scenario(n_lp, sid, rs, rd, sp, ln, tid, dep, ts, nodes, part)
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic grid (BASELINE.json config 3; the reference ships no generator — SURVEY.md §8d freezes this one)
+# ---------------------------------------------------------------------------------------
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def synthetic_grid(width: int = 1024, height: int = 1024, n_trips: int = 10_000_000, seed: int = 1,
+                   min_hops: int = 8, max_hops: int = 64, max_departure: int = 7200) -> Scenario:
+    """Torus grid: node = r*W + c, two out-roads per node (right, down, with wrap), road id = 2*node + {0,1};
+    speed in {10..60} km/h and length in {100..1000} m from splitmix64(road_id ^ seed); trip t: departure =
+    h % 7200, start = h' % (W*H), hop count in [8, 64], each hop right/down from hash bits."""
+    n = width * height
+    node = np.arange(n, dtype=np.int64)
+    r, c = node // width, node % width
+    right = r * width + (c + 1) % width
+    down = ((r + 1) % height) * width + c
+    road_dst = np.stack([right, down], axis=1).reshape(-1)
+    rid = np.arange(2 * n, dtype=np.uint64)
+    h = _splitmix64(rid ^ np.uint64(seed))
+    road_speed = (10 + (h % np.uint64(51))).astype(np.int64)
+    road_len = (100 + ((h >> np.uint64(20)) % np.uint64(901))).astype(np.int64)
+    road_start = np.arange(0, 2 * n + 1, 2, dtype=np.int64)
+
+    t = np.arange(n_trips, dtype=np.uint64)
+    h1 = _splitmix64(t ^ (np.uint64(seed) << np.uint64(32)))
+    h2 = _splitmix64(h1)
+    h3 = _splitmix64(h2)
+    dep = (h1 % np.uint64(max_departure)).astype(np.int64)
+    start = (h2 % np.uint64(n)).astype(np.int64)
+    hops = (min_hops + (h3 % np.uint64(max_hops - min_hops + 1))).astype(np.int64)   # number of moves
+    lens = hops + 1
+    route_start = np.zeros(n_trips + 1, dtype=np.int64)
+    np.cumsum(lens, out=route_start[1:])
+    nodes = np.empty(int(route_start[-1]), dtype=np.int64)
+    # direction bits: bit k of splitmix64(h3 + k // 64)
+    cur_r, cur_c = start // width, start % width
+    alive = np.ones(n_trips, dtype=bool)
+    bits = _splitmix64(h3)
+    for k in range(int(max_hops) + 1):
+        idx = np.nonzero(alive)[0]
+        if idx.size == 0:
+            break
+        nodes[route_start[idx] + k] = cur_r[idx] * width + cur_c[idx]
+        if k % 64 == 0 and k > 0:
+            bits = _splitmix64(bits)
+        go_down = ((bits >> np.uint64(k % 64)) & np.uint64(1)).astype(bool)
+        mv = alive & (k < hops)
+        cur_r = np.where(mv & go_down, (cur_r + 1) % height, cur_r)
+        cur_c = np.where(mv & ~go_down, (cur_c + 1) % width, cur_c)
+        alive = alive & (k + 1 < lens)
+    part = None
+    return Scenario(n, node.copy(), road_start, road_dst, road_speed, road_len, t.astype(np.int64), dep,
+                    route_start, nodes, part)
+
+
+def stripe_partition(width: int, height: int, world: int) -> np.ndarray:
+    """Row-stripe partition of the grid (METIS is not available): rows [k*H/world, (k+1)*H/world) -> k."""
+    rows = np.arange(height, dtype=np.int64) * world // height
+    return np.repeat(rows, width)
+
+
+# ---------------------------------------------------------------------------------------
+# packing
+# ---------------------------------------------------------------------------------------
+def pack_states(sc: Scenario):
+    """LP state words: [id, n_roads, (dst, speed, length) x n_roads], padded to MAX_ROADS."""
+    n = sc.state_ids.size
+    deg = np.diff(sc.road_start)
+    if deg.size and deg.max() > MAX_ROADS:
+        raise ValueError(f"an LP has {int(deg.max())} out-roads; the device model supports {MAX_ROADS}")
+    words = np.zeros((n, STATE_WORDS), dtype=np.uint32)
+    words[:, 0] = sc.state_ids.astype(np.uint32)
+    words[:, 1] = deg.astype(np.uint32)
+    for k in range(MAX_ROADS):
+        has = deg > k
+        j = sc.road_start[:-1][has] + k
+        words[has, 2 + 3 * k] = sc.road_dst[j].astype(np.uint32)
+        words[has, 3 + 3 * k] = sc.road_speed[j].astype(np.uint32)
+        words[has, 4 + 3 * k] = sc.road_len[j].astype(np.uint32)
+    return sc.state_ids.astype(np.int64), words
+
+
+def pack_events(sc: Scenario) -> np.ndarray:
+    """One initial event per trip: source -1, destination = first route node, p0 = offset of that node in the
+    route pool, p1 = route length."""
+    n = sc.trip_id.size
+    ev = np.zeros(n, dtype=EVENT_DTYPE)
+    ev["id"] = sc.trip_id
+    ev["src"] = -1
+    ev["dst"] = sc.route_nodes[sc.route_start[:-1]]
+    ev["recv_time"] = sc.trip_dep
+    ev["send_time"] = sc.trip_dep
+    ev["p0"] = sc.route_start[:-1]
+    ev["p1"] = np.diff(sc.route_start)
+    return ev
+
+
+def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1, keep_records: bool = False,
+                rank: int = 0, world: int = 1, device: int = 0, max_events: int | None = None,
+                max_batch: int | None = None, max_committed: int | None = None, finish_time: int = FINISH_TIME,
+                rounds_per_sync: int = 8) -> Engine:
+    """Build a TrafficSim engine the way runner<traffic_sim>::init does (runner.hpp:79-176)."""
+    n_trips = sc.trip_id.size
+    n_nodes = sc.route_nodes.size
+    if max_events is None:
+        max_events = int(n_trips * 1.5) + (1 << 16) + 4096 * 8
+    if max_batch is None:
+        max_batch = max(1 << 14, n_trips // 2 + (1 << 14))
+    if max_committed is None:
+        max_committed = n_nodes + 1024 if keep_records else 0
+    cfg = Config(model=MODEL_TRAFFIC, n_lp=sc.n_lp, finish_time=finish_time, bucket_ticks=bucket_ticks,
+                 window_buckets=window_buckets, max_events=max_events, max_batch=max_batch,
+                 max_committed=max_committed, rank=rank, world=world, device=device, rounds_per_sync=rounds_per_sync)
+    eng = Engine(cfg)
+    part = sc.partition
+    if part is not None and part.size < sc.n_lp:
+        part = np.concatenate([part, np.zeros(sc.n_lp - part.size, dtype=np.int64)])
+    eng.set_partition(part % world if part is not None else None)
+    eng.set_model_data(0, sc.route_nodes.astype(np.int64))
+    ids, words = pack_states(sc)
+    owner = (part[ids] % world) if part is not None else (ids % world)
+    mine = owner == rank
+    eng.load_states(ids[mine], words[mine])
+    ev = pack_events(sc)
+    ev_owner = (part[ev["dst"]] % world) if part is not None else (ev["dst"] % world)
+    eng.load_events(ev[ev_owner == rank])
+    return eng
