@@ -89,6 +89,7 @@ struct View {
   u32 n_lp, n_lp_local;
   u32 nb;                 // calendar buckets (absolute index, no wrap: nb*bucket_ticks >= finish_time)
   u32 ch_log, maxc;       // chunk size log2, chunk-table row length
+  u32 route_slots;        // buckets covered by k_route's shared-memory table
   u32 bucket_ticks, finish_time, window;
   u32 cap_batch, cap_aux, cap_snap, cap_send;
   u64 cap_log;

@@ -168,11 +168,16 @@ int ssb_engine::init() {
   v.window = (u32)cfg.window_buckets;
   v.nb = (u32)((cfg.finish_time + cfg.bucket_ticks - 1) / cfg.bucket_ticks);
   if (v.nb == 0) v.nb = 1;
-  v.ch_log = cfg.max_events >= (1 << 22) ? 12 : (cfg.max_events >= (1 << 16) ? 8 : 4);
+  // chunk size: as large as possible while the per-bucket tail waste (one partly filled chunk per bucket) stays
+  // below half of the pool
+  v.ch_log = 12;
+  while (v.ch_log > 4 && ((size_t)v.nb << v.ch_log) > (size_t)cfg.max_events / 2) --v.ch_log;
   const u32 chs = 1u << v.ch_log;
-  n_chunks = (u32)((cfg.max_events + chs - 1) / chs) + 1;   // + the sacrificial chunk 0
-  // every non-empty bucket wastes at most one partly filled chunk
-  n_chunks += v.nb < 4096 ? v.nb : 4096;
+  n_chunks = (u32)((cfg.max_events + chs - 1) / chs) + v.nb + 1;   // + tail waste + the sacrificial chunk 0
+  if ((size_t)v.nb * n_chunks * sizeof(u32) > ((size_t)4 << 30)) {
+    set_error("calendar chunk table would exceed 4 GiB: raise bucket_ticks");
+    return SSB_ERR_INVALID;
+  }
   v.maxc = n_chunks;
   v.cap_batch = (u32)cfg.max_batch;
   v.cap_aux = std::max<u32>(1024, v.cap_batch / 4);
@@ -228,8 +233,8 @@ int ssb_engine::init() {
   if ((rc = fill32(v.last_slot, NIL, v.n_lp_local))) return rc;
   CK(cudaMemsetAsync(v.last_time, 0, sizeof(u32) * v.n_lp_local, stream));
   CK(cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
-  route_smem = (size_t)(v.nb + 1 + v.world) * 16;
-  if (route_smem > 200 * 1024) { set_error("too many calendar buckets for the route kernel's shared memory: raise bucket_ticks"); return SSB_ERR_INVALID; }
+  v.route_slots = std::min<u32>(v.nb, 2048);
+  route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
@@ -552,12 +557,17 @@ int ssb_run(ssb_engine* e, ssb_stats* stats) {
   int rc = e->model_ready();
   if (rc) return rc;
   CK(cudaEventRecord(e->ev0, e->stream));
+  u64 last_gvt = ~0ull;
+  long long stalled = 0;
   for (;;) {
     for (int i = 0; i < e->cfg.rounds_per_sync; ++i)
       if ((rc = e->enqueue_round())) return rc;
     if ((rc = e->sync_ctl())) return rc;
     if ((rc = e->check_device_error())) return rc;
     if (e->h_ctl->done) break;
+    // GVT must keep advancing (every round commits or integrates something); bail out instead of spinning forever
+    if (e->h_ctl->gvt == last_gvt) stalled += e->cfg.rounds_per_sync; else { stalled = 0; last_gvt = e->h_ctl->gvt; }
+    if (stalled > 100000) { e->set_error("no GVT progress in 100000 rounds"); return SSB_ERR_INVALID; }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   CK(cudaEventSynchronize(e->ev1));

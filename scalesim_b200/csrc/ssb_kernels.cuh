@@ -234,8 +234,11 @@ __global__ void k_hist(View v) {
   const u32 n = c->n_arr;
   const u32 ng = c->n_gather;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    u32 g = 0;
-    while (g + 1 < ng && v.gather[g + 1].w <= i) ++g;
+    u32 g = 0, hi = ng;            // binary search: last gather entry whose offset is <= i
+    while (hi - g > 1) {
+      u32 mid = (g + hi) >> 1;
+      if (v.gather[mid].w <= i) g = mid; else hi = mid;
+    }
     uint4 ge = v.gather[g];
     u32 slot = slot_of(v, ge.x, ge.y + (i - ge.w));
     Ev e = load_ev(v.ev + slot);
@@ -524,12 +527,15 @@ __global__ void k_exec(View v, typename M::Data md) {
 // (R8), so they are counted and dropped; only their minimum key is kept for GVT.
 //   which: 0 = anti box, 1 = main + extra outbox, 2 = receive buffer, 3 = host-loaded staging (outbox[0..load_count))
 //   filter: 0 = all, 1 = anti-messages only, 2 = positives only (the receive side keeps antis ahead of positives)
-// Targets: [0, nb) buckets, nb = "beyond", nb+1+r = partition r.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 peer, u32 filter) {
   extern __shared__ u64 smem64[];
   Ctl* c = v.ctl;
-  const u32 nt = v.nb + 1 + v.world;
+  // shared-memory targets: [0, rs) = buckets base .. base+rs-1, rs = "beyond", rs+1+r = partition r.
+  // Buckets further ahead than the table (tiny bucket_ticks) take one global atomic per event instead.
+  const u32 rs = v.route_slots;
+  const u32 nt = rs + 1 + v.world;
+  const u32 base = c->commit_next;
   u64* s_min = smem64;                                  // [nt]
   u32* s_cnt = reinterpret_cast<u32*>(smem64 + nt);     // [nt]
   u32* s_base = s_cnt + nt;                             // [nt]
@@ -541,15 +547,18 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   else { src = v.outbox; n0 = c->load_count; }
   const u32 total = n0 + n1;
   const u32 chm = (1u << v.ch_log) - 1u;
+  const u32 T_NONE = NIL, T_DIRECT = NIL - 1u;
   for (u32 tile = blockIdx.x * kRouteTile; tile < total; tile += gridDim.x * kRouteTile) {
     for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) { s_cnt[t] = 0; s_min[t] = KEY_MAX; }
     __syncthreads();
     Ev e[kRouteItems];
-    u32 tgt[kRouteItems], rnk[kRouteItems];
+    u32 tgt[kRouteItems], rnk[kRouteItems], bkt[kRouteItems];
 #pragma unroll
     for (int it = 0; it < kRouteItems; ++it) {
       u32 i = tile + it * kRouteThreads + threadIdx.x;
-      tgt[it] = NIL;
+      tgt[it] = T_NONE;
+      bkt[it] = 0;
+      rnk[it] = 0;
       if (i < total) {
         u32 idx = i < n0 ? i : v.cap_batch + (i - n0);
         e[it] = load_ev(src + idx);
@@ -557,20 +566,29 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         if (filter == 1u) take = take && (e[it].flags & F_CANCEL);
         if (filter == 2u) take = take && !(e[it].flags & F_CANCEL);
         if (take) {
-          u32 tm = key_time(e[it].key);
-          u32 t;
-          u32 owner = v.world > 1 ? part_owner(v, e[it].dst) : v.rank;
           if (e[it].dst >= v.n_lp) { atomicOr(&c->error, E_RANGE); continue; }
-          if (owner != v.rank) t = v.nb + 1 + owner;
-          else if (tm >= v.finish_time) t = v.nb;
-          else {
-            t = tm / v.bucket_ticks;
-            if (t < c->commit_next) { atomicOr(&c->error, E_INTERNAL); continue; }   // causality: nothing may arrive below GVT
+          u32 tm = key_time(e[it].key);
+          u32 owner = v.world > 1 ? part_owner(v, e[it].dst) : v.rank;
+          u32 t;
+          if (owner != v.rank) {
+            if (which == 3) { atomicOr(&c->error, E_RANGE); continue; }   // loaded events must be owned by this rank
+            t = rs + 1 + owner;
+          } else if (tm >= v.finish_time) {
+            t = rs;
+          } else {
+            u32 b = tm / v.bucket_ticks;
+            if (b < base) { atomicOr(&c->error, E_INTERNAL); continue; }   // causality: nothing may arrive below GVT
+            bkt[it] = b;
+            t = b - base < rs ? b - base : T_DIRECT;
           }
-          if (which == 3 && owner != v.rank) { atomicOr(&c->error, E_RANGE); continue; }
           tgt[it] = t;
-          rnk[it] = atomicAdd(&s_cnt[t], 1u);
-          atomicMin(&s_min[t], e[it].key);
+          if (t == T_DIRECT) {
+            rnk[it] = atomicAdd(&v.fill[bkt[it]], 1u);       // final position
+            atomicMin(&v.min_key[bkt[it]], e[it].key);
+          } else {
+            rnk[it] = atomicAdd(&s_cnt[t], 1u);
+            atomicMin(&s_min[t], e[it].key);
+          }
         }
       }
     }
@@ -578,24 +596,26 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
     for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) {
       u32 n = s_cnt[t];
       if (!n) continue;
-      if (t < v.nb) {
-        s_base[t] = atomicAdd(&v.fill[t], n);
-        atomicMin(&v.min_key[t], s_min[t]);
-      } else if (t == v.nb) {
+      if (t < rs) {
+        s_base[t] = atomicAdd(&v.fill[base + t], n);
+        atomicMin(&v.min_key[base + t], s_min[t]);
+      } else if (t == rs) {
         atomicAdd(&c->n_beyond, (u64)n);
         atomicMin(&c->beyond_min, s_min[t]);
       } else {
-        s_base[t] = atomicAdd(&c->send_count[t - v.nb - 1], n);
+        s_base[t] = atomicAdd(&c->send_count[t - rs - 1], n);
         atomicAdd(&c->n_remote, (u64)n);
       }
     }
     __syncthreads();
-    // chunk allocation: the owner of a chunk's first position allocates and publishes it
+    // final positions; chunk allocation: the owner of a chunk's first position allocates and publishes it
 #pragma unroll
     for (int it = 0; it < kRouteItems; ++it) {
       u32 t = tgt[it];
-      if (t < v.nb) {
-        u32 p = s_base[t] + rnk[it];
+      if (t == T_NONE || t == rs) continue;
+      if (t != T_DIRECT) rnk[it] += s_base[t];
+      if (t < rs || t == T_DIRECT) {
+        u32 p = rnk[it];
         if ((p & chm) == 0) {
           u32 top = atomicSub(&c->free_top, 1u);
           u32 ch;
@@ -607,8 +627,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
             ch = v.free_stack[top - 1];
             atomicMin(&c->free_low, top - 1);
           }
-          if ((p >> v.ch_log) >= v.maxc) { atomicOr(&c->error, E_POOL); }
-          else atomicExch(&v.chunk_tab[(size_t)t * v.maxc + (p >> v.ch_log)], ch);
+          if ((p >> v.ch_log) >= v.maxc) atomicOr(&c->error, E_POOL);
+          else atomicExch(&v.chunk_tab[(size_t)bkt[it] * v.maxc + (p >> v.ch_log)], ch);
         }
       }
     }
@@ -616,17 +636,19 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
 #pragma unroll
     for (int it = 0; it < kRouteItems; ++it) {
       u32 t = tgt[it];
-      if (t == NIL || t == v.nb) continue;
-      u32 p = s_base[t] + rnk[it];
+      if (t == T_NONE || t == rs) continue;
+      u32 p = rnk[it];
       e[it].flags &= F_CANCEL;
-      if (t < v.nb) {
+      if (t < rs || t == T_DIRECT) {
         if ((p >> v.ch_log) >= v.maxc) continue;
-        volatile u32* entry = &v.chunk_tab[(size_t)t * v.maxc + (p >> v.ch_log)];
+        volatile u32* entry = &v.chunk_tab[(size_t)bkt[it] * v.maxc + (p >> v.ch_log)];
         u32 ch = *entry;
-        while (ch == NIL) ch = *entry;     // allocated by another block: wait for the publish
+        // allocated by another block: wait for the publish (bounded, so a logic error cannot hang the GPU)
+        for (u32 spin = 0; ch == NIL && spin < (1u << 24); ++spin) ch = *entry;
+        if (ch == NIL) { atomicOr(&c->error, E_INTERNAL); continue; }
         store_ev(v.ev + (((size_t)ch << v.ch_log) | (p & chm)), e[it]);
       } else {
-        u32 r = t - v.nb - 1;
+        u32 r = t - rs - 1;
         if (p < v.cap_send) store_ev(v.sendbuf + (size_t)r * v.cap_send + p, e[it]);
         else atomicOr(&c->error, E_SENDBUF);
       }

@@ -79,7 +79,7 @@ def make_engine(num_lp: int, num_init_msg: int, remote_ratio: float, lam: float,
     if max_events is None:
         max_events = default_capacity(num_init_msg, world)
     if max_batch is None:
-        max_batch = max(1 << 14, int(per * 0.25 * window_buckets) + (1 << 14))
+        max_batch = max(1 << 14, min(per, int(per * 0.25 * window_buckets)) + (1 << 14))
     if max_committed is None:
         max_committed = int(per * 6) if keep_records else 0
     cfg = Config(model=MODEL_PHOLD_STATEFUL if stateful else MODEL_PHOLD, n_lp=num_lp, finish_time=finish_time,

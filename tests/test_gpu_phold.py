@@ -45,7 +45,7 @@ def test_phold_shapes_equal_reference(name, window):
     eng.close()
 
 
-@pytest.mark.parametrize("bucket,window", [(10000, 1), (10000, 4), (2500, 2), (25000, 1), (7, 3000)])
+@pytest.mark.parametrize("bucket,window", [(10000, 1), (10000, 4), (2500, 2), (25000, 1), (50, 400)])
 def test_phold_10000_digest_equal_reference(phold_tables_01, bucket, window):
     """Optimism invariance: the committed result does not depend on the bucket width or the window."""
     g = golden("phold_10000_160000")
@@ -87,44 +87,94 @@ def test_stateful_model_equals_sequential_oracle(phold_tables_01, window):
     eng.close()
 
 
-def test_injected_straggler_and_antimessage(phold_tables_01):
-    """LP-level rules R4-R6 on the device: a straggler rolls the LP back, an anti-message annihilates a processed
-    event, a duplicate key is ignored, an unmatched anti-message is dropped."""
-    lat, rem = phold_tables_01
-    cfg = ssb.Config(model=ssb.MODEL_PHOLD, n_lp=4, finish_time=1000, bucket_ticks=1000, window_buckets=1,
+def _crafted_engine(window=1):
+    """PHOLD kernels with hand-made tables (16 entries, LOOK_AHEAD 0) so that every hop is chosen by the test.
+    idx = (id + hops') % 16;  remote entry: dst = latency % NUM_LP."""
+    lat = np.full(16, 5000, dtype=np.int64)       # default: local, lands beyond finish_time (dropped, never executed)
+    rem = np.zeros(16, dtype=np.int32)
+    lat[3], rem[3] = 24, 1                        # id 2, first hop: LP1@5 -> LP0@29
+    lat[5], rem[5] = 1, 1                         # id 4, first hop: LP2@1 -> LP1@2
+    cfg = ssb.Config(model=ssb.MODEL_PHOLD, n_lp=4, finish_time=1000, bucket_ticks=100, window_buckets=window,
                      max_events=1 << 12, max_batch=1 << 10, max_committed=1 << 12)
     eng = ssb.Engine(cfg)
     eng.set_partition(None)
     eng.set_model_data(0, lat)
     eng.set_model_data(1, rem)
-    eng.set_model_data(2, np.array([10000, 4], dtype=np.int64))
+    eng.set_model_data(2, np.array([0, 4], dtype=np.int64))
     ids, words = phold.init_states(4)
     eng.load_states(ids, words)
+    return eng
 
-    def ev(i, t, dst=0, cancel=False):
-        e = np.zeros(1, dtype=ssb.EVENT_DTYPE)
-        e[0] = (i, dst, dst, t, t, 0, 0, 1 if cancel else 0)
-        return e
 
-    eng.load_events(np.concatenate([ev(0, 10), ev(1, 20), ev(3, 40)]))
-    assert not eng.step()                   # processes 0, 1, 3 (outputs land beyond finish)
+def _ev(i, t, dst, cancel=False):
+    e = np.zeros(1, dtype=ssb.EVENT_DTYPE)
+    e[0] = (i, dst, dst, t, t, 0, 0, 1 if cancel else 0)
+    return e
+
+
+def test_crafted_straggler_and_antimessage_cascade():
+    """Rules R4-R6 on the device, step by step (the device counterpart of logical_process_test.cc:472-784).
+    round 1: LP0 runs 10,20,40; LP1 runs id2@5 (-> LP0@29); LP2 runs id4@1 (-> LP1@2)
+    round 2: LP0 gets straggler 29 < 40: undo 40 (+ its anti), run 29, 40 again.
+             LP1 gets straggler 2 < 5 : undo 5, anti-message for (29,id2) to LP0, run 2, run 5 again (re-sends 29)
+    round 3: LP0 gets anti(29,id2) then the re-sent (29,id2): undo 29 and 40, annihilate the old 29, run the new 29, 40."""
+    eng = _crafted_engine()
+    eng.load_events(np.concatenate([_ev(0, 10, 0), _ev(1, 20, 0), _ev(3, 40, 0), _ev(2, 5, 1), _ev(4, 1, 2)]))
+    assert not eng.step()
     st = eng.stats()
-    assert st.processed == 3 and st.rollbacks == 0
-    eng.load_events(ev(2, 30))              # straggler
-    eng.step()
+    assert (st.processed, st.rollbacks, st.undone, st.antis_sent) == (5, 0, 0, 0)
+    assert not eng.step()
     st = eng.stats()
-    assert st.rollbacks == 1 and st.undone == 1 and st.antis_sent == 1 and st.processed == 5
-    eng.load_events(np.concatenate([ev(1, 20, cancel=True), ev(3, 40), ev(9, 50, cancel=True)]))
-    eng.step()                              # anti for processed 1 -> rollback to 1; duplicate of 3; unmatched anti
+    assert (st.processed, st.rollbacks, st.undone, st.antis_sent) == (5 + 4, 2, 2, 2)
+    assert st.annihilated == 0
+    assert not eng.step()
     st = eng.stats()
-    assert st.annihilated == 1 and st.duplicates == 1
-    assert st.undone == 1 + 3 and st.antis_sent == 1 + 3
+    assert (st.processed, st.rollbacks, st.undone) == (9 + 2, 3, 4)
+    assert st.annihilated == 1 and st.duplicates == 0
+    assert st.antis_sent == 2 + 2
+    done = False
     for _ in range(4):
-        if eng.step():
+        done = eng.step()
+        if done:
             break
+    assert done
     rec = eng.drain_committed()
-    assert sorted(int(r["id"]) for r in rec) == [0, 2, 3]
-    assert eng.stats().committed == 3
+    got = sorted((int(r["dst"]), int(r["recv_time"]), int(r["id"]), int(r["src"]), int(r["send_time"])) for r in rec)
+    assert got == [(0, 10, 0, 0, 10), (0, 20, 1, 0, 20), (0, 29, 2, 1, 5), (0, 40, 3, 0, 40),
+                   (1, 2, 4, 2, 1), (1, 5, 2, 1, 5), (2, 1, 4, 2, 1)]
+    assert eng.stats().committed == 7
+    eng.close()
+
+
+def test_crafted_duplicate_and_unmatched_anti():
+    """queue.hpp:92 (second insert of a key ignored), queue.hpp:87-90 (anti without a match is dropped; anti in the
+    same batch erases the positive: logical_process_test.cc:142-198)."""
+    eng = _crafted_engine()
+    eng.load_events(np.concatenate([
+        _ev(0, 10, 0), _ev(0, 10, 0),                         # duplicate key: one survives
+        _ev(7, 15, 0),
+        _ev(9, 50, 3, cancel=True),                           # unmatched anti-message: dropped
+    ]))
+    # ev, cancel, ev -> exactly one survives. Arrival order matters here, and it is only defined across calls
+    # (inside one ssb_load_events call equal keys may be appended in any order).
+    eng.load_events(_ev(7, 15, 0, cancel=True))          # annihilated inside the batch
+    eng.load_events(_ev(8, 16, 0))
+    eng.load_events(_ev(8, 16, 0, cancel=True))
+    eng.load_events(_ev(8, 16, 0))
+    eng.run()
+    st = eng.stats()
+    assert st.duplicates == 1 and st.annihilated == 2
+    rec = eng.drain_committed()
+    assert sorted((int(r["dst"]), int(r["recv_time"]), int(r["id"])) for r in rec) == [(0, 10, 0), (0, 16, 8)]
+    eng.close()
+
+
+@pytest.mark.parametrize("window", [1, 10])
+def test_crafted_scenario_result_is_window_invariant(window):
+    eng = _crafted_engine(window)
+    eng.load_events(np.concatenate([_ev(0, 10, 0), _ev(1, 20, 0), _ev(3, 40, 0), _ev(2, 5, 1), _ev(4, 1, 2)]))
+    eng.run()
+    assert eng.stats().committed == 7
     eng.close()
 
 
