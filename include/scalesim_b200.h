@@ -23,7 +23,9 @@
  *                                 (runner.hpp:350-396, 517-583)
  *   ssb_committed_digest,         eventq::std_out + sim_event::result_out — the "RE,..." lines
  *   ssb_drain_committed           (queue.hpp:203-211, sim_obj.hpp:66-77)
- *   ssb_get_stats                 runner::finish report (runner.hpp:482-507)
+ *   ssb_get_stats, ssb_kernel_times  runner::finish report + the stopwatch phases (runner.hpp:482-507,
+ *                                 util/stopwatch.hpp)
+ *   ssb_reset                     (no reference equivalent: the reference is one simulation per process)
  *   ssb_read_states               (no reference equivalent: sim_state::result_out is empty,
  *                                 sim_obj.hpp:97; used by the parity tests for final LP states)
  *   ssb_comm_*                    event_com / mpi_thr / mpi_gsync (com/*.hpp) — replaced by NCCL
@@ -85,6 +87,7 @@ typedef struct ssb_config {
 } ssb_config;
 
 #define SSB_FLAG_DEBUG_CHECKS 1   /* extra device-side invariant checks */
+#define SSB_FLAG_KERNEL_TIMING 2  /* bracket every kernel launch with CUDA events (see ssb_kernel_times) */
 
 /* Host-side POD mirror of the App::Event accessors (sim_obj.hpp:50-59) + model payload. */
 typedef struct ssb_event {
@@ -103,6 +106,13 @@ typedef struct ssb_record {
   int64_t id, src, send_time, dst, recv_time;
   int64_t tag;           /* 0 none, 1 START, 2 END */
 } ssb_record;
+
+/* Compact committed record as it sits in the device log (32 bytes; what ssb_drain_committed_raw copies).
+ * recv_time = key >> 32, id = key & 0xffffffff; src 0xffffffff = -1; tag as in ssb_record. */
+typedef struct ssb_raw_record {
+  uint64_t key;
+  uint32_t dst, src, send_time, p0, p1, tag;
+} ssb_raw_record;
 
 typedef struct ssb_stats {
   int64_t rounds;            /* windows executed */
@@ -156,6 +166,20 @@ int ssb_get_stats(ssb_engine* e, ssb_stats* stats);
 int ssb_committed_digest(ssb_engine* e, uint64_t d[4]);
 /* copy up to cap committed records to host memory and remove them from the device log */
 int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n);
+
+/* same, without widening: n raw 32-byte records straight from the device log (one D2H copy; `out` may be pinned) */
+int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int64_t* n);
+
+/* Back to the state right after ssb_load_states: empty calendar, zero statistics; model data, partition and the
+ * loaded initial states are kept. Lets one engine run many simulations (bench steps) without re-allocating. */
+int ssb_reset(ssb_engine* e);
+
+/* change ssb_config.flags after creation (e.g. switch SSB_FLAG_KERNEL_TIMING on for one profiled run) */
+int ssb_set_flags(ssb_engine* e, int32_t flags);
+
+/* With SSB_FLAG_KERNEL_TIMING: per-kernel device time since create/reset. names[i] points to a static string.
+ * Returns the number of kernels written (<= cap). */
+int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap);
 
 /* ---- multi-GPU: one engine per process/GPU, NCCL between them ---- */
 /* 128-byte NCCL unique id; created on rank 0 and distributed by the caller (torch.distributed, MPI, files, ...) */

@@ -13,6 +13,9 @@ from .capi import (  # noqa: F401
     Stats,
     EVENT_DTYPE,
     RECORD_DTYPE,
+    RAW_RECORD_DTYPE,
+    FLAG_KERNEL_TIMING,
+    raw_to_records,
     MODEL_PHOLD,
     MODEL_TRAFFIC,
     MODEL_PHOLD_STATEFUL,
@@ -24,7 +27,7 @@ from .capi import (  # noqa: F401
 from . import phold, traffic  # noqa: F401
 
 __all__ = [
-    "Engine", "EngineError", "Config", "Stats", "EVENT_DTYPE", "RECORD_DTYPE",
+    "Engine", "EngineError", "Config", "Stats", "EVENT_DTYPE", "RECORD_DTYPE", "RAW_RECORD_DTYPE", "FLAG_KERNEL_TIMING", "raw_to_records",
     "MODEL_PHOLD", "MODEL_TRAFFIC", "MODEL_PHOLD_STATEFUL", "library_path", "load_library",
     "records_to_lines", "digest_records", "phold", "traffic",
 ]

@@ -23,6 +23,28 @@ RECORD_DTYPE = np.dtype([
 ])
 
 
+#: host mirror of ``ssb_raw_record`` (32 bytes): the committed log as it sits in HBM
+RAW_RECORD_DTYPE = np.dtype([
+    ("key", "<u8"), ("dst", "<u4"), ("src", "<u4"), ("send_time", "<u4"), ("p0", "<u4"), ("p1", "<u4"), ("tag", "<u4"),
+])
+FLAG_DEBUG_CHECKS = 1
+FLAG_KERNEL_TIMING = 2
+
+
+def raw_to_records(raw: np.ndarray) -> np.ndarray:
+    """ssb_raw_record -> ssb_record (widening; src 0xffffffff -> -1)."""
+    rec = np.empty(raw.shape, dtype=RECORD_DTYPE)
+    rec["id"] = (raw["key"] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    rec["recv_time"] = (raw["key"] >> np.uint64(32)).astype(np.int64)
+    src = raw["src"].astype(np.int64)
+    src[raw["src"] == 0xFFFFFFFF] = -1
+    rec["src"] = src
+    rec["send_time"] = raw["send_time"]
+    rec["dst"] = raw["dst"]
+    rec["tag"] = raw["tag"]
+    return rec
+
+
 class EngineError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"scalesim_b200 status {status}: {message}")
@@ -119,6 +141,10 @@ def load_library() -> C.CDLL:
     lib.ssb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     lib.ssb_committed_digest.argtypes = [vp, vp]
     lib.ssb_drain_committed.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_drain_committed_raw.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_reset.argtypes = [vp]
+    lib.ssb_set_flags.argtypes = [vp, C.c_int32]
+    lib.ssb_kernel_times.argtypes = [vp, vp, vp, vp, i32]
     lib.ssb_comm_unique_id.argtypes = [vp]
     lib.ssb_comm_init.argtypes = [vp, vp]
     lib.ssb_phold_build_tables.argtypes = [i64, C.c_double, C.c_double, i64, vp, vp]
@@ -245,6 +271,35 @@ class Engine:
         n = C.c_int64(0)
         self._check(self._lib.ssb_drain_committed(self._h, C.c_void_p(ptr), cap, C.byref(n)))
         return n.value
+
+    def drain_committed_raw(self, cap: int | None = None) -> np.ndarray:
+        """Committed records in the compact 32-byte device layout (``ssb_raw_record``)."""
+        if cap is None:
+            cap = max(1, self.stats().committed)
+        out = np.empty(cap, dtype=RAW_RECORD_DTYPE)
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_committed_raw(self._h, _ptr(out), cap, C.byref(n)))
+        return out[: n.value]
+
+    def drain_committed_raw_ptr(self, ptr: int, cap: int) -> int:
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_committed_raw(self._h, C.c_void_p(ptr), cap, C.byref(n)))
+        return n.value
+
+    def reset(self):
+        self._check(self._lib.ssb_reset(self._h))
+
+    def set_flags(self, flags: int):
+        self._check(self._lib.ssb_set_flags(self._h, flags))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total device ms, launches)}; needs FLAG_KERNEL_TIMING."""
+        cap = 16
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        ln = (C.c_int64 * cap)()
+        k = self._lib.ssb_kernel_times(self._h, names, ms, ln, cap)
+        return {names[i].decode(): (ms[i], ln[i]) for i in range(k)}
 
     # -- multi-GPU --
     @staticmethod

@@ -88,6 +88,37 @@ struct ssb_engine {
   long long rounds = 0;
   // comm
   Nccl::Comm comm = nullptr;
+  // initial states (for ssb_reset)
+  u32* d_state0 = nullptr;
+  // kernel timing
+  enum { K_MIN, K_PLAN, K_COMMIT, K_FREE, K_HIST, K_SEGS, K_SCATTER, K_EXEC, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
+  struct Timed { int id; cudaEvent_t a, b; };
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> event_pool;
+  double k_ms[K_COUNT] = {0};
+  long long k_launches[K_COUNT] = {0};
+  bool timing() const { return (cfg.flags & SSB_FLAG_KERNEL_TIMING) != 0; }
+  void t_begin(int id) {
+    if (!timing()) return;
+    Timed t; t.id = id;
+    cudaEvent_t* ev[2] = {&t.a, &t.b};
+    for (auto p : ev) {
+      if (!event_pool.empty()) { *p = event_pool.back(); event_pool.pop_back(); }
+      else cudaEventCreate(p);
+    }
+    cudaEventRecord(t.a, stream);
+    timed.push_back(t);
+  }
+  void t_end() { if (timing()) cudaEventRecord(timed.back().b, stream); }
+  void t_collect() {
+    for (auto& t : timed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { k_ms[t.id] += ms; k_launches[t.id]++; }
+      event_pool.push_back(t.a); event_pool.push_back(t.b);
+    }
+    timed.clear();
+  }
+  int reset_sim();
 
   void set_error(const std::string& s) { error = s; }
 
@@ -217,14 +248,28 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.ctl, 1))) return rc;
   if ((rc = alloc(&d_stage, v.cap_batch))) return rc;
 
-  CK(cudaMemsetAsync(v.ctl, 0, sizeof(Ctl), stream));
+  if ((rc = alloc(&d_state0, (size_t)v.n_lp_local * v.state_words))) return rc;
+  CK(cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
+  CK(cudaMemsetAsync(d_state0, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
+  if ((rc = reset_sim())) return rc;
+  v.route_slots = std::min<u32>(v.nb, 2048);
+  route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
+  CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  return SSB_OK;
+}
+
+int ssb_engine::reset_sim() {
   Ctl init;
   std::memset(&init, 0, sizeof(init));
   init.local_min = KEY_MAX; init.gvt = 0; init.beyond_min = KEY_MAX;
   init.free_top = n_chunks - 1; init.free_low = n_chunks - 1;
-  CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
   CK(cudaStreamSynchronize(stream));
+  CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));   // `init` lives on the stack
   k_iota_u32<<<grid(n_chunks - 1, 256), 256, 0, stream>>>(v.free_stack, 1u, n_chunks - 1);   // chunks 1..n-1 are free
+  int rc;
   if ((rc = fill32(v.chunk_tab, NIL, (size_t)v.nb * v.maxc))) return rc;
   CK(cudaMemsetAsync(v.fill, 0, sizeof(u32) * v.nb, stream));
   CK(cudaMemsetAsync(v.consumed, 0, sizeof(u32) * v.nb, stream));
@@ -232,12 +277,14 @@ int ssb_engine::init() {
   CK(cudaMemsetAsync(v.cnt, 0, sizeof(u32) * v.n_lp_local, stream));
   if ((rc = fill32(v.last_slot, NIL, v.n_lp_local))) return rc;
   CK(cudaMemsetAsync(v.last_time, 0, sizeof(u32) * v.n_lp_local, stream));
-  CK(cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
-  v.route_slots = std::min<u32>(v.nb, 2048);
-  route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
-  CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
+  CK(cudaMemcpyAsync(v.state, d_state0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, cudaMemcpyDeviceToDevice, stream));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
+  log_drained = 0;
+  loop_ms = 0.0;
+  rounds = 0;
+  t_collect();
+  for (int i = 0; i < K_COUNT; ++i) { k_ms[i] = 0; k_launches[i] = 0; }
   return SSB_OK;
 }
 
@@ -290,7 +337,9 @@ int ssb_engine::model_ready() {
 }
 
 void ssb_engine::launch_route(int which, u32 peer, u32 filter) {
+  t_begin(which == 0 ? K_ROUTE_ANTI : (which == 2 ? K_ROUTE_RECV : K_ROUTE));
   k_route<<<n_sm * 4, kRouteThreads, route_smem, stream>>>(v, which, peer, filter);
+  t_end();
 }
 
 void ssb_engine::launch_commit() {
@@ -345,20 +394,36 @@ int ssb_engine::exchange() {
 }
 
 int ssb_engine::enqueue_round() {
+  t_begin(K_MIN);
   k_min<<<1, 1024, 0, stream>>>(v);
+  t_end();
   if (cfg.world > 1) {
     if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
     int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
     if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
   }
+  t_begin(K_PLAN);
   k_plan<<<1, 32, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
+  t_end();
+  t_begin(K_COMMIT);
   launch_commit();
+  t_end();
+  t_begin(K_FREE);
   k_free<<<64, 256, 0, stream>>>(v);
+  t_end();
   const int g = n_sm * 8;
+  t_begin(K_HIST);
   k_hist<<<g, 256, 0, stream>>>(v);
+  t_end();
+  t_begin(K_SEGS);
   k_segs<<<g, 256, 0, stream>>>(v);
+  t_end();
+  t_begin(K_SCATTER);
   k_scatter<<<g, 256, 0, stream>>>(v);
+  t_end();
+  t_begin(K_EXEC);
   launch_exec();
+  t_end();
   launch_route(0, 0, 0);
   launch_route(1, 0, 0);
   CK(cudaGetLastError());
@@ -381,6 +446,8 @@ void ssb_destroy(ssb_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_unpack) cudaFree(e->d_unpack);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  e->t_collect();
+  for (cudaEvent_t x : e->event_pool) cudaEventDestroy(x);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -439,7 +506,10 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
     auto& v = e->v;
     auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
     if (regrow(&v.cnt, mine) || regrow(&v.seg_start, mine) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
-        regrow(&v.state, (size_t)mine * v.state_words)) { e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA; }
+        regrow(&v.state, (size_t)mine * v.state_words) || regrow(&e->d_state0, (size_t)mine * v.state_words)) {
+      e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA;
+    }
+    cudaMemsetAsync(e->d_state0, 0, sizeof(u32) * (size_t)mine * v.state_words, e->stream);
     cudaMemsetAsync(v.cnt, 0, sizeof(u32) * mine, e->stream);
     e->fill32(v.last_slot, NIL, mine);
     cudaMemsetAsync(v.last_time, 0, sizeof(u32) * mine, e->stream);
@@ -505,7 +575,10 @@ static int states_io(ssb_engine* e, const int64_t* lp_ids, uint32_t* words, int6
     while (j < n && lp_ids[j] >= 0 && lp_ids[j] < e->cfg.n_lp && e->owner_of(lp_ids[j]) == (u32)e->cfg.rank &&
            e->local_of(lp_ids[j]) == l0 + (u32)(j - i)) ++j;
     size_t bytes = (size_t)(j - i) * sw * 4;
-    if (write) CK(cudaMemcpyAsync(e->v.state + (size_t)l0 * sw, words + (size_t)i * sw, bytes, cudaMemcpyHostToDevice, e->stream));
+    if (write) {
+      CK(cudaMemcpyAsync(e->v.state + (size_t)l0 * sw, words + (size_t)i * sw, bytes, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(e->d_state0 + (size_t)l0 * sw, words + (size_t)i * sw, bytes, cudaMemcpyHostToDevice, e->stream));
+    }
     else CK(cudaMemcpyAsync(words + (size_t)i * sw, e->v.state + (size_t)l0 * sw, bytes, cudaMemcpyDeviceToHost, e->stream));
     i = j;
   }
@@ -644,6 +717,58 @@ int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n)
     e->log_drained = 0;
   }
   return SSB_OK;
+}
+
+int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int64_t* n) {
+  if (!e || !n || (!out && cap) || cap < 0) return SSB_ERR_INVALID;
+  static_assert(sizeof(ssb_raw_record) == sizeof(Ev), "raw record layout");
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
+  u64 m = std::min<u64>(have - e->log_drained, (u64)cap);
+  *n = (int64_t)m;
+  if (m) {
+    CK(cudaMemcpyAsync(out, e->v.log + e->log_drained, m * sizeof(Ev), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  e->log_drained += m;
+  if (e->log_drained == have && have == e->h_ctl->log_count) {
+    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->log_drained = 0;
+  }
+  return SSB_OK;
+}
+
+int ssb_reset(ssb_engine* e) {
+  if (!e) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  return e->reset_sim();
+}
+
+int ssb_set_flags(ssb_engine* e, int32_t flags) {
+  if (!e) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  e->t_collect();
+  e->cfg.flags = flags;
+  return SSB_OK;
+}
+
+int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap) {
+  if (!e || !names || !total_ms || !launches) return 0;
+  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_free", "k_hist", "k_segs",
+                                                    "k_scatter", "k_exec", "k_route(anti)", "k_route", "k_route(recv)"};
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  e->t_collect();
+  int k = 0;
+  for (int i = 0; i < ssb_engine::K_COUNT && k < cap; ++i) {
+    names[k] = kNames[i]; total_ms[k] = e->k_ms[i]; launches[k] = e->k_launches[i]; ++k;
+  }
+  return k;
 }
 
 int ssb_comm_unique_id(void* id128) {
