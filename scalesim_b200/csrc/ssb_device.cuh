@@ -65,7 +65,7 @@ struct Ctl {
   u64 beyond_min;     // min key of events dropped because receive_time >= finish_time
   u32 done, error;
   u32 cur_abs, bound_abs, commit_next;
-  u32 n_arr, n_active, seg_cursor, n_anti, n_extra;
+  u32 n_arr, n_active, seg_cursor, n_anti, n_extra, n_heavy, n_fix, commit_blocks;
   u32 n_gather, n_commit, commit_total;
   u32 free_top, free_low;
   u32 snap_head, snap_tail;
@@ -115,6 +115,9 @@ struct View {
   u32* tmp_rank;       // [cap_batch]
   Sorted* sorted;      // [cap_batch] grouped by LP
   uint4* active;       // [cap_batch] {lp, seg_start, cnt, 0}
+  uint4* prevlink;     // [cap_batch] at an LP's segment start: {old chain head slot, its time, n, flag}
+  uint4* fix;          // [cap_batch] LPs that need the sequential turn {lp, seg_start, n, 0}
+  u32* heavy;          // [cap_batch] indices into `active` of LPs with long segments
   Ev* outbox;          // [cap_batch + cap_aux]: main region aligned with `sorted`, then re-execution outputs
   Ev* anti_box;        // [cap_aux] anti-messages of this round
   uint4* gather;       // [window] {bucket, start, count, out_off}

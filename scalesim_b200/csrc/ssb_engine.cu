@@ -91,7 +91,7 @@ struct ssb_engine {
   // initial states (for ssb_reset)
   u32* d_state0 = nullptr;
   // kernel timing
-  enum { K_MIN, K_PLAN, K_COMMIT, K_FREE, K_HIST, K_SEGS, K_SCATTER, K_EXEC, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
+  enum { K_MIN, K_PLAN, K_COMMIT, K_HIST, K_SEGS, K_SCATTER, K_SORTSEG, K_SORTHEAVY, K_EXEC, K_FIXUP, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
   struct Timed { int id; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -119,6 +119,8 @@ struct ssb_engine {
     timed.clear();
   }
   int reset_sim();
+  static size_t heavy_smem() { return (size_t)kHeavyWarps * kHeavyCap * sizeof(Sorted); }
+  void launch_fixup();
 
   void set_error(const std::string& s) { error = s; }
 
@@ -237,6 +239,9 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
   if ((rc = alloc(&v.sorted, v.cap_batch))) return rc;
   if ((rc = alloc(&v.active, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.prevlink, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.fix, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.heavy, v.cap_batch))) return rc;
   if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
   if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
   if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1)))) return rc;
@@ -255,6 +260,7 @@ int ssb_engine::init() {
   v.route_slots = std::min<u32>(v.nb, 2048);
   route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
+  CK(cudaFuncSetAttribute(k_sortheavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   return SSB_OK;
@@ -352,11 +358,20 @@ void ssb_engine::launch_commit() {
 }
 
 void ssb_engine::launch_exec() {
-  const int g = n_sm * 16;
+  const int g = n_sm * 8;
   switch (cfg.model) {
-    case SSB_MODEL_PHOLD: k_exec<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_PHOLD_STATEFUL: k_exec<PholdStatefulModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_TRAFFIC: k_exec<TrafficModel><<<g, 128, 0, stream>>>(v, traffic_data()); break;
+    case SSB_MODEL_PHOLD: k_exec<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_PHOLD_STATEFUL: k_exec<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_TRAFFIC: k_exec<TrafficModel><<<g, 256, 0, stream>>>(v, traffic_data()); break;
+  }
+}
+
+void ssb_engine::launch_fixup() {
+  const int g = n_sm * 8;
+  switch (cfg.model) {
+    case SSB_MODEL_PHOLD: k_fixup<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_PHOLD_STATEFUL: k_fixup<PholdStatefulModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_TRAFFIC: k_fixup<TrafficModel><<<g, 128, 0, stream>>>(v, traffic_data()); break;
   }
 }
 
@@ -394,22 +409,19 @@ int ssb_engine::exchange() {
 }
 
 int ssb_engine::enqueue_round() {
-  t_begin(K_MIN);
-  k_min<<<1, 1024, 0, stream>>>(v);
-  t_end();
   if (cfg.world > 1) {
     if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
+    t_begin(K_MIN);
+    k_min<<<1, 1024, 0, stream>>>(v);
+    t_end();
     int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
     if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
   }
   t_begin(K_PLAN);
-  k_plan<<<1, 32, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
+  k_plan<<<1, 1024, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
   t_end();
   t_begin(K_COMMIT);
   launch_commit();
-  t_end();
-  t_begin(K_FREE);
-  k_free<<<64, 256, 0, stream>>>(v);
   t_end();
   const int g = n_sm * 8;
   t_begin(K_HIST);
@@ -421,8 +433,17 @@ int ssb_engine::enqueue_round() {
   t_begin(K_SCATTER);
   k_scatter<<<g, 256, 0, stream>>>(v);
   t_end();
+  t_begin(K_SORTSEG);
+  k_sortseg<<<g, 256, 0, stream>>>(v);
+  t_end();
+  t_begin(K_SORTHEAVY);
+  k_sortheavy<<<n_sm * 3, kHeavyWarps * 32, heavy_smem(), stream>>>(v);
+  t_end();
   t_begin(K_EXEC);
   launch_exec();
+  t_end();
+  t_begin(K_FIXUP);
+  launch_fixup();
   t_end();
   launch_route(0, 0, 0);
   launch_route(1, 0, 0);
@@ -759,8 +780,9 @@ int ssb_set_flags(ssb_engine* e, int32_t flags) {
 
 int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap) {
   if (!e || !names || !total_ms || !launches) return 0;
-  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_free", "k_hist", "k_segs",
-                                                    "k_scatter", "k_exec", "k_route(anti)", "k_route", "k_route(recv)"};
+  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_hist", "k_segs", "k_scatter",
+                                                    "k_sortseg", "k_sortheavy", "k_exec", "k_fixup", "k_route(anti)",
+                                                    "k_route", "k_route(recv)"};
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   e->t_collect();

@@ -1,18 +1,20 @@
 // ssb_kernels.cuh — the Time Warp core as CUDA kernels (sm_100a).
 //
 // One round (= one optimistic window step) is, in stream order:
-//   k_min     block min-reduction of the calendar's per-bucket minima  -> local GVT candidate
-//   [ncclAllReduce(min) when world > 1]
-//   k_plan    GVT, window bounds, gather list, commit list
-//   k_commit  stream-compaction of every bucket that fell below GVT into the committed log + digest
-//   k_free    fossil collection: the committed buckets' chunks go back to the pool
-//   k_hist    arrivals of the window: per-LP histogram (rank inside the LP's segment)
-//   k_segs    per-LP segment allocation (warp-aggregated) + active-LP list
-//   k_scatter arrivals -> per-LP segments
-//   k_exec    one thread per active LP: sort the segment, annihilate, detect stragglers, roll back,
-//             execute the handler in key order, record sent-log / snapshots, write the outbox
-//   k_route   outbox -> calendar buckets / per-destination-partition send buffers
-//             (block-aggregated atomics; anti-messages first, then positives)
+//   k_plan     GVT (block min-reduction over the calendar's per-bucket minima; k_min + ncclAllReduce(min) first
+//              when world > 1), window bounds, gather list, commit list
+//   k_commit   stream-compaction of every bucket that fell below GVT into the committed log + digest; the last
+//              block to finish does the fossil collection (chunks back to the pool)
+//   k_hist     arrivals of the window: per-LP histogram (rank inside the LP's segment)
+//   k_segs     per-LP segment allocation (block-aggregated) + active-LP list
+//   k_scatter  arrivals -> per-LP segments
+//   k_sortseg  one thread per active LP: sort its segment by (key, arrival order), classify the turn
+//   k_sortheavy one warp per LP with a long segment: bitonic sort in shared memory
+//   k_exec     one thread per EVENT: handler, processed-chain link, sent-log, outbox (speculative on the LP state)
+//   k_fixup    one thread per LP that is not plain (anti-message, duplicate, straggler, state-mutating handler):
+//              annihilate, roll back, re-execute sequentially, emit anti-messages
+//   k_route    outbox -> calendar buckets / per-destination-partition send buffers
+//              (block-aggregated atomics; anti-messages first, then positives)
 //   [exchange + k_route of the receive buffer when world > 1]
 // Reference semantics restated per kernel; rule numbers R1..R10 refer to SURVEY.md Appendix A.
 #pragma once
@@ -75,8 +77,28 @@ __global__ void k_min(View v) {
 // optimistic window [bucket(GVT), bucket(GVT) + window).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_plan(View v, int use_global_gvt) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ u64 sm[32];
   Ctl* c = v.ctl;
+  if (!use_global_gvt) {
+    // single partition: the GVT min-reduction is fused here (same code as k_min)
+    u64 m = KEY_MAX;
+    for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x) {
+      u64 k = v.min_key[b];
+      m = k < m ? k : m;
+    }
+    m = warp_min_u64(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : KEY_MAX;
+      m = warp_min_u64(m);
+      if (threadIdx.x == 0) {
+        u64 bm = c->beyond_min;
+        c->local_min = bm < m ? bm : m;
+      }
+    }
+  }
+  if (threadIdx.x != 0) return;
   u64 gvt = use_global_gvt ? c->gvt : c->local_min;
   c->gvt = gvt;
   u32 t = gvt == KEY_MAX ? 0xFFFFFFFFu : key_time(gvt);
@@ -135,6 +157,8 @@ __global__ void k_plan(View v, int use_global_gvt) {
   c->seg_cursor = 0;
   c->n_anti = 0;
   c->n_extra = 0;
+  c->n_heavy = 0;
+  c->n_fix = 0;
   c->done = done ? 1u : 0u;
   c->round++;
   for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
@@ -200,17 +224,19 @@ __global__ void k_commit(View v, typename M::Data md) {
     atomicAdd(&c->digest[3], hsum2);
     atomicAdd(&c->n_committed, cnt);
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_free — R9 fossil collection: chunks of committed buckets return to the free stack. Replaces
-// eventq::release / release_cancel / stateq::release (queue.hpp:159-177, 292-302).
-// ------------------------------------------------------------------------------------------------
-__global__ void k_free(View v) {
-  Ctl* c = v.ctl;
-  const u32 nc = c->n_commit;
+  // R9 fossil collection, by the last block to finish: chunks of the committed buckets return to the free stack.
+  // Replaces eventq::release / release_cancel / stateq::release (queue.hpp:159-177, 292-302).
+  if (nc == 0) return;
+  __shared__ u32 s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&c->commit_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
   const u32 chs = 1u << v.ch_log;
-  for (u32 k = blockIdx.x; k < nc; k += gridDim.x) {
+  for (u32 k = 0; k < nc; ++k) {
     uint4 ce = v.commit[k];
     u32 b = ce.x;
     u32 nch = (ce.y + chs - 1) >> v.ch_log;
@@ -223,6 +249,7 @@ __global__ void k_free(View v) {
     }
     if (threadIdx.x == 0) { v.fill[b] = 0; v.consumed[b] = 0; v.min_key[b] = KEY_MAX; }
   }
+  if (threadIdx.x == 0) c->commit_blocks = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,13 +284,13 @@ __global__ void k_hist(View v) {
 // cursor) and append the LP to the active list. Replaces scheduler::queue/dequeue
 // (process_scheduler.hpp:55-81): "which LPs have work in this window".
 // ------------------------------------------------------------------------------------------------
-__global__ void k_segs(View v) {
+__global__ void __launch_bounds__(256) k_segs(View v) {
   Ctl* c = v.ctl;
   if (c->n_arr == 0) return;
-  const u32 lane = threadIdx.x & 31;
-  const u32 nthreads = gridDim.x * blockDim.x;
-  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < v.n_lp_local; base += nthreads) {
-    u32 lp = base + lane;
+  __shared__ u32 w_seg[8], w_act[8], b_seg, b_act;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (u32 base = blockIdx.x * 256u; base < v.n_lp_local; base += gridDim.x * 256u) {
+    u32 lp = base + threadIdx.x;
     u32 n = lp < v.n_lp_local ? v.cnt[lp] : 0u;
     u32 incl = n;
 #pragma unroll
@@ -271,22 +298,28 @@ __global__ void k_segs(View v) {
       u32 t = __shfl_up_sync(0xffffffffu, incl, o);
       if ((int)lane >= o) incl += t;
     }
-    u32 tot = __shfl_sync(0xffffffffu, incl, 31);
     u32 bal = __ballot_sync(0xffffffffu, n != 0);
-    if (tot == 0) continue;
-    u32 seg0 = 0, act0 = 0;
-    if (lane == 0) {
-      seg0 = atomicAdd(&c->seg_cursor, tot);
-      act0 = atomicAdd(&c->n_active, (u32)__popc(bal));
+    if (lane == 31) w_seg[warp] = incl;
+    if (lane == 0) w_act[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 ts = 0, ta = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        u32 a = w_seg[w]; w_seg[w] = ts; ts += a;
+        u32 b = w_act[w]; w_act[w] = ta; ta += b;
+      }
+      b_seg = ts ? atomicAdd(&c->seg_cursor, ts) : 0u;     // one atomic per 256 LPs
+      b_act = ta ? atomicAdd(&c->n_active, ta) : 0u;
     }
-    seg0 = __shfl_sync(0xffffffffu, seg0, 0);
-    act0 = __shfl_sync(0xffffffffu, act0, 0);
+    __syncthreads();
     if (n) {
-      u32 start = seg0 + incl - n;
+      u32 start = b_seg + w_seg[warp] + incl - n;
       v.seg_start[lp] = start;
       v.cnt[lp] = 0;
-      v.active[act0 + __popc(bal & ((1u << lane) - 1u))] = make_uint4(lp, start, n, 0);
+      v.active[b_act + w_act[warp] + __popc(bal & ((1u << lane) - 1u))] = make_uint4(lp, start, n, 0);
     }
+    __syncthreads();
   }
 }
 
@@ -384,24 +417,13 @@ struct Turn {
     return v.cap_batch + pos;
   }
 
-  __device__ void run(u32 lp, u32 s0, u32 n) {
+  // the segment is already sorted (k_sortseg / k_sortheavy); old_slot/old_time = the LP's chain head before this round
+  __device__ void run(u32 lp, u32 s0, u32 n, u32 old_slot, u32 old_time) {
     err = 0; n_proc = n_undone = n_anti = n_annih = n_dup = 0;
     st_dirty = false;
     Sorted* seg = v.sorted + s0;
-    // 1. insertion sort (segments are short; long ones are handled by the heavy path)
-    for (u32 i = 1; i < n; ++i) {
-      Sorted x = seg[i];
-      u32 j = i;
-      while (j > 0) {
-        Sorted y = seg[j - 1];
-        if (!sorted_less(x, y)) break;
-        seg[j] = y;
-        --j;
-      }
-      if (j != i) seg[j] = x;
-    }
-    last_slot = v.last_slot[lp];
-    last_time = v.last_time[lp];
+    last_slot = old_slot;
+    last_time = old_time;
 #pragma unroll
     for (int w = 0; w < M::kStateWords; ++w) st[w] = v.state[(size_t)lp * M::kStateWords + w];
 
@@ -484,32 +506,239 @@ struct Turn {
   }
 };
 
-template <class M>
-__global__ void k_exec(View v, typename M::Data md) {
+// ------------------------------------------------------------------------------------------------
+// k_sortseg — one thread per active LP: sort the LP's inbox segment by (key, arrival order) (R1), note the LP's
+// chain head, and classify the turn:
+//   flag 0  plain: only positives, distinct keys, all later than everything the LP has processed
+//           -> the events are executed one thread per EVENT by k_exec (skew-free: a hot LP's events spread over
+//              many threads)
+//   flag 1  an anti-message, a duplicate key or a straggler is present -> the sequential lp_turn in k_fixup
+// Segments longer than kLightMax go to k_sortheavy (one warp per LP, bitonic sort in shared memory).
+// prevlink[s0] = {old chain head slot, its receive_time, n, flag}.
+// ------------------------------------------------------------------------------------------------
+constexpr u32 kLightMax = 16;
+constexpr u32 kHeavyCap = 2048;       // entries per warp in k_sortheavy's shared memory
+constexpr int kHeavyWarps = 2;
+
+__device__ __forceinline__ void classify_append(const View& v, u32 lp, u32 s0, u32 n, u32 old_slot, u32 old_time,
+                                                u32 flag) {
+  v.prevlink[s0] = make_uint4(old_slot, old_time, n, flag);
+  if (flag) {
+    u32 pos = atomicAdd(&v.ctl->n_fix, 1u);
+    v.fix[pos] = make_uint4(lp, s0, n, 0);
+  }
+}
+
+__global__ void k_sortseg(View v) {
   Ctl* c = v.ctl;
   const u32 na = c->n_active;
-  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0;
-  u32 err = 0;
+  u64 planned = 0;
   const u32 lane = threadIdx.x & 31;
   const u32 nthreads = gridDim.x * blockDim.x;
   for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < na; base += nthreads) {
     u32 k = base + lane;
-    if (k < na) {
-      uint4 a = v.active[k];
+    if (k >= na) continue;
+    uint4 a = v.active[k];
+    const u32 lp = a.x, s0 = a.y, n = a.z;
+    if (n > kLightMax) {
+      v.heavy[atomicAdd(&c->n_heavy, 1u)] = k;
+      continue;
+    }
+    const u32 old_slot = v.last_slot[lp], old_time = v.last_time[lp];
+    Sorted* seg = v.sorted + s0;
+    u32 flag = 0;
+    u64 kmin;
+    if (n == 1) {
+      Sorted x = seg[0];
+      kmin = x.key;
+      flag = x.seq >> 31;
+    } else {
+      Sorted loc[kLightMax];
+      for (u32 i = 0; i < n; ++i) loc[i] = seg[i];
+      bool moved = false;
+      for (u32 i = 1; i < n; ++i) {
+        Sorted x = loc[i];
+        u32 j = i;
+        while (j > 0 && sorted_less(x, loc[j - 1])) { loc[j] = loc[j - 1]; --j; }
+        if (j != i) { loc[j] = x; moved = true; }
+      }
+      kmin = loc[0].key;
+      for (u32 i = 0; i < n; ++i) {
+        flag |= loc[i].seq >> 31;
+        if (i && loc[i].key == loc[i - 1].key) flag = 1;
+      }
+      if (moved) for (u32 i = 0; i < n; ++i) seg[i] = loc[i];
+    }
+    if (old_slot != NIL && key_time(kmin) <= old_time) flag = 1;     // possible straggler (exact test in lp_turn)
+    classify_append(v, lp, s0, n, old_slot, old_time, flag);
+    if (!flag) planned += n;
+  }
+  __syncwarp();
+  planned = warp_sum_u64(planned);
+  if (lane == 0 && planned) atomicAdd(&c->n_processed, planned);
+}
+
+__global__ void __launch_bounds__(kHeavyWarps * 32) k_sortheavy(View v) {
+  extern __shared__ uint4 smem_heavy[];
+  Ctl* c = v.ctl;
+  const u32 nh = c->n_heavy;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kHeavyCap;
+  for (u32 h = blockIdx.x * kHeavyWarps + warp; h < nh; h += gridDim.x * kHeavyWarps) {
+    uint4 a = v.active[v.heavy[h]];
+    const u32 lp = a.x, s0 = a.y, n = a.z;
+    Sorted* seg = v.sorted + s0;
+    u32 flag = 0;
+    if (n <= kHeavyCap) {
+      u32 P = 1;
+      while (P < n) P <<= 1;
+      for (u32 i = lane; i < P; i += 32) {
+        Sorted x;
+        if (i < n) x = seg[i]; else { x.key = KEY_MAX; x.slot = NIL; x.seq = 0x7FFFFFFFu; }
+        buf[i] = x;
+      }
+      __syncwarp();
+      for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
+        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          for (u32 i = lane; i < P; i += 32) {
+            u32 ixj = i ^ j2;
+            if (ixj > i) {
+              Sorted x = buf[i], y = buf[ixj];
+              bool asc = (i & k2) == 0;
+              if (sorted_less(y, x) == asc) { buf[i] = y; buf[ixj] = x; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      for (u32 i = lane; i < n; i += 32) {
+        Sorted x = buf[i];
+        seg[i] = x;
+        flag |= x.seq >> 31;
+        if (i && buf[i - 1].key == x.key) flag = 1;
+      }
+    } else {
+      // longer than the shared-memory buffer: one lane sorts in place (slow, but correct)
+      if (lane == 0) {
+        for (u32 i = 1; i < n; ++i) {
+          Sorted x = seg[i];
+          u32 j = i;
+          while (j > 0) {
+            Sorted y = seg[j - 1];
+            if (!sorted_less(x, y)) break;
+            seg[j] = y;
+            --j;
+          }
+          if (j != i) seg[j] = x;
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      for (u32 i = lane; i < n; i += 32) {
+        Sorted x = seg[i];
+        flag |= x.seq >> 31;
+        if (i && seg[i - 1].key == x.key) flag = 1;
+      }
+    }
+    flag = __any_sync(0xffffffffu, flag != 0) ? 1u : 0u;
+    __syncwarp();
+    if (lane == 0) {
+      const u32 old_slot = v.last_slot[lp], old_time = v.last_time[lp];
+      u64 kmin = n <= kHeavyCap ? buf[0].key : seg[0].key;
+      if (old_slot != NIL && key_time(kmin) <= old_time) flag = 1;
+      classify_append(v, lp, s0, n, old_slot, old_time, flag);
+      if (!flag) atomicAdd(&c->n_processed, (u64)n);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_exec — one thread per EVENT of the window (in per-LP key order): run the handler on the LP's current state,
+// link the event into the LP's processed chain, record the sent-log entry, write the produced event to the outbox.
+// This is the speculative form of runner::run_lp_aggr (runner.hpp:530-570): all events of an LP are executed against
+// the same state. That is exactly the sequential result as long as no handler invocation changes the state (both
+// shipped applications never do). The moment one does, the LP is flagged (prevlink.w = 2) and k_fixup re-executes
+// its whole segment sequentially — so handlers that mutate state are still executed with exact semantics.
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_exec(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  const u32 n = c->n_arr;
+  u32 err = 0;
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    Sorted s = v.sorted[j];
+    Ev e = load_ev(v.ev + s.slot);
+    const u32 lp = part_local(v, e.dst);
+    const u32 s0 = v.seg_start[lp];
+    const uint4 pl = v.prevlink[s0];
+    if (pl.w != 0) continue;                        // handled by k_fixup
+    u32 st[M::kStateWords], pre[M::kStateWords];
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) { st[w] = v.state[(size_t)lp * M::kStateWords + w]; pre[w] = st[w]; }
+    Ev out;
+    bool has = M::handle(md, e, st, out, err);
+    bool changed = false;
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) changed |= (pre[w] != st[w]);
+    if (has && changed) {
+      // state-mutating handler: this LP needs the sequential path
+      u32 old = atomicExch(&v.prevlink[s0].w, 2u);
+      if (old == 0) v.fix[atomicAdd(&c->n_fix, 1u)] = make_uint4(lp, s0, pl.z, 0);
+      continue;
+    }
+    Meta m;
+    if (j == s0) { m.link = pl.x; m.prevtime = pl.y; }
+    else { Sorted sp = v.sorted[j - 1]; m.link = sp.slot; m.prevtime = key_time(sp.key); }
+    m.sent_dst = NIL;
+    m.snap = NIL;
+    if (has) {
+      m.sent_dst = out.dst;
+      v.sent_key[s.slot] = out.key;
+      store_ev(v.outbox + j, out);
+    } else {
+      v.outbox[j].key = KEY_MAX;
+    }
+    v.meta[s.slot] = m;
+    v.ev[s.slot].flags = e.flags | F_PROCESSED;
+    if (j == s0 + pl.z - 1) { v.last_slot[lp] = s.slot; v.last_time[lp] = key_time(s.key); }
+  }
+  if (err) atomicOr(&c->error, err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fixup — one thread per LP whose turn is not plain (flag 1: anti-message / duplicate / straggler; flag 2: a
+// handler changed the LP state): the exact sequential lp_turn.
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_fixup(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  const u32 nf = c->n_fix;
+  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0, n_redo = 0;
+  u32 err = 0;
+  const u32 lane = threadIdx.x & 31;
+  const u32 nthreads = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nf; base += nthreads) {
+    u32 k = base + lane;
+    if (k < nf) {
+      uint4 f = v.fix[k];
+      uint4 pl = v.prevlink[f.y];
+      if (pl.w == 2u) n_redo += f.z;               // k_sortseg had counted these as processed by k_exec
       Turn<M> t(v, md);
-      t.run(a.x, a.y, a.z);
+      t.run(f.x, f.y, f.z, pl.x, pl.y);
       n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
       err |= t.err;
     }
   }
   __syncwarp();
   n_proc = warp_sum_u64(n_proc);
+  n_redo = warp_sum_u64(n_redo);
   n_undone = warp_sum_u64(n_undone);
   n_anti = warp_sum_u64(n_anti);
   n_annih = warp_sum_u64(n_annih);
   n_dup = warp_sum_u64(n_dup);
   if (lane == 0) {
-    if (n_proc) atomicAdd(&c->n_processed, n_proc);
+    if (n_proc != n_redo) atomicAdd(&c->n_processed, n_proc - n_redo);
     if (n_undone) atomicAdd(&c->n_undone, n_undone);
     if (n_anti) atomicAdd(&c->n_antis, n_anti);
     if (n_annih) atomicAdd(&c->n_annihilated, n_annih);
