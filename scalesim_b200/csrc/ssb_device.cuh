@@ -6,7 +6,7 @@
 //                    (chunk_tab) and is append-only, so "pending set" == the unconsumed tail of the buckets.
 //   * per-slot meta: Meta[max_events] + sent_key[max_events] — the processed-chain link, the sent-log entry
 //                    (what set_cancel keeps in the reference, queue.hpp:151-157) and the snapshot index.
-//   * per-LP       : cnt / seg_start / last_slot / last_time / state words.
+//   * per-LP       : cnt / seg / last_slot / last_time / state words.
 //   * per-round    : arrival staging, per-LP sorted segments, outboxes.
 #pragma once
 #include <cstdint>
@@ -65,7 +65,7 @@ struct Ctl {
   u64 beyond_min;     // min key of events dropped because receive_time >= finish_time
   u32 done, error;
   u32 cur_abs, bound_abs, commit_next;
-  u32 n_arr, n_active, seg_cursor, n_anti, n_extra, n_heavy, n_fix, commit_blocks;
+  u32 n_arr, seg_cursor, n_anti, n_extra, n_heavy, n_fix, n_fixheavy, commit_blocks;
   u32 n_gather, n_commit, commit_total;
   u32 free_top, free_low;
   u32 snap_head, snap_tail;
@@ -102,10 +102,9 @@ struct View {
   u32* free_stack;  // [n_chunks]
   u32* fill;        // [nb] events appended
   u32* consumed;    // [nb] events already integrated
-  u64* min_key;     // [nb] min key of the unconsumed tail
   // per LP
   u32* cnt;
-  u32* seg_start;
+  uint2* seg;       // {start of the LP's segment in `sorted`, its length} for this round
   u32* last_slot;
   u32* last_time;
   u32* state;       // [n_lp_local * state_words]
@@ -114,10 +113,10 @@ struct View {
   u32* tmp_lp;         // [cap_batch]
   u32* tmp_rank;       // [cap_batch]
   Sorted* sorted;      // [cap_batch] grouped by LP
-  uint4* active;       // [cap_batch] {lp, seg_start, cnt, 0}
   uint4* prevlink;     // [cap_batch] at an LP's segment start: {old chain head slot, its time, n, flag}
   uint4* fix;          // [cap_batch] LPs that need the sequential turn {lp, seg_start, n, 0}
-  u32* heavy;          // [cap_batch] indices into `active` of LPs with long segments
+  uint4* fixheavy;     // [cap_batch / 16] same, segments that still need a warp-level sort
+  uint4* heavy;        // [cap_batch / 64] LPs with long segments {lp, seg_start, n, 0}
   Ev* outbox;          // [cap_batch + cap_aux]: main region aligned with `sorted`, then re-execution outputs
   Ev* anti_box;        // [cap_aux] anti-messages of this round
   uint4* gather;       // [window] {bucket, start, count, out_off}

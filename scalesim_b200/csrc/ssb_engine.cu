@@ -91,7 +91,7 @@ struct ssb_engine {
   // initial states (for ssb_reset)
   u32* d_state0 = nullptr;
   // kernel timing
-  enum { K_MIN, K_PLAN, K_COMMIT, K_HIST, K_SEGS, K_SCATTER, K_SORTSEG, K_SORTHEAVY, K_EXEC, K_FIXUP, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
+  enum { K_MIN, K_PLAN, K_COMMIT, K_HIST, K_SEGS, K_SCATTER, K_SORTHEAVY, K_EXEC, K_FIXUP, K_FIXUP_HEAVY, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
   struct Timed { int id; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -120,7 +120,7 @@ struct ssb_engine {
   }
   int reset_sim();
   static size_t heavy_smem() { return (size_t)kHeavyWarps * kHeavyCap * sizeof(Sorted); }
-  void launch_fixup();
+  void launch_fixup(bool heavy);
 
   void set_error(const std::string& s) { error = s; }
 
@@ -228,9 +228,8 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.free_stack, n_chunks))) return rc;
   if ((rc = alloc(&v.fill, v.nb))) return rc;
   if ((rc = alloc(&v.consumed, v.nb))) return rc;
-  if ((rc = alloc(&v.min_key, v.nb))) return rc;
   if ((rc = alloc(&v.cnt, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.seg_start, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.seg, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.last_slot, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.last_time, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.state, (size_t)v.n_lp_local * v.state_words))) return rc;
@@ -238,10 +237,10 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.tmp_lp, v.cap_batch))) return rc;
   if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
   if ((rc = alloc(&v.sorted, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.active, v.cap_batch))) return rc;
   if ((rc = alloc(&v.prevlink, v.cap_batch))) return rc;
   if ((rc = alloc(&v.fix, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.heavy, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.fixheavy, v.cap_batch / 16 + 64))) return rc;
+  if ((rc = alloc(&v.heavy, v.cap_batch / 64 + 64))) return rc;
   if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
   if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
   if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1)))) return rc;
@@ -257,10 +256,13 @@ int ssb_engine::init() {
   CK(cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
   CK(cudaMemsetAsync(d_state0, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
   if ((rc = reset_sim())) return rc;
-  v.route_slots = std::min<u32>(v.nb, 2048);
-  route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
+  v.route_slots = std::min<u32>(v.nb, 4096);
+  route_smem = (size_t)(v.route_slots + 1 + v.world) * 8;
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
   CK(cudaFuncSetAttribute(k_sortheavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
+  CK(cudaFuncSetAttribute(k_fixup_heavy<PholdModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
+  CK(cudaFuncSetAttribute(k_fixup_heavy<PholdStatefulModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
+  CK(cudaFuncSetAttribute(k_fixup_heavy<TrafficModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   return SSB_OK;
@@ -269,7 +271,7 @@ int ssb_engine::init() {
 int ssb_engine::reset_sim() {
   Ctl init;
   std::memset(&init, 0, sizeof(init));
-  init.local_min = KEY_MAX; init.gvt = 0; init.beyond_min = KEY_MAX;
+  init.local_min = KEY_MAX; init.gvt = 0;
   init.free_top = n_chunks - 1; init.free_low = n_chunks - 1;
   CK(cudaStreamSynchronize(stream));
   CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
@@ -279,7 +281,6 @@ int ssb_engine::reset_sim() {
   if ((rc = fill32(v.chunk_tab, NIL, (size_t)v.nb * v.maxc))) return rc;
   CK(cudaMemsetAsync(v.fill, 0, sizeof(u32) * v.nb, stream));
   CK(cudaMemsetAsync(v.consumed, 0, sizeof(u32) * v.nb, stream));
-  if ((rc = fill64(v.min_key, KEY_MAX, v.nb))) return rc;
   CK(cudaMemsetAsync(v.cnt, 0, sizeof(u32) * v.n_lp_local, stream));
   if ((rc = fill32(v.last_slot, NIL, v.n_lp_local))) return rc;
   CK(cudaMemsetAsync(v.last_time, 0, sizeof(u32) * v.n_lp_local, stream));
@@ -366,7 +367,17 @@ void ssb_engine::launch_exec() {
   }
 }
 
-void ssb_engine::launch_fixup() {
+void ssb_engine::launch_fixup(bool heavy) {
+  if (heavy) {
+    const int g = n_sm * 3, t = kHeavyWarps * 32;
+    const size_t sm = heavy_smem();
+    switch (cfg.model) {
+      case SSB_MODEL_PHOLD: k_fixup_heavy<PholdModel><<<g, t, sm, stream>>>(v, phold_data()); break;
+      case SSB_MODEL_PHOLD_STATEFUL: k_fixup_heavy<PholdStatefulModel><<<g, t, sm, stream>>>(v, phold_data()); break;
+      case SSB_MODEL_TRAFFIC: k_fixup_heavy<TrafficModel><<<g, t, sm, stream>>>(v, traffic_data()); break;
+    }
+    return;
+  }
   const int g = n_sm * 8;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_fixup<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
@@ -433,9 +444,6 @@ int ssb_engine::enqueue_round() {
   t_begin(K_SCATTER);
   k_scatter<<<g, 256, 0, stream>>>(v);
   t_end();
-  t_begin(K_SORTSEG);
-  k_sortseg<<<g, 256, 0, stream>>>(v);
-  t_end();
   t_begin(K_SORTHEAVY);
   k_sortheavy<<<n_sm * 3, kHeavyWarps * 32, heavy_smem(), stream>>>(v);
   t_end();
@@ -443,7 +451,10 @@ int ssb_engine::enqueue_round() {
   launch_exec();
   t_end();
   t_begin(K_FIXUP);
-  launch_fixup();
+  launch_fixup(false);
+  t_end();
+  t_begin(K_FIXUP_HEAVY);
+  launch_fixup(true);
   t_end();
   launch_route(0, 0, 0);
   launch_route(1, 0, 0);
@@ -526,7 +537,7 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
     // per-LP arrays were sized for the modulo partition: grow them
     auto& v = e->v;
     auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
-    if (regrow(&v.cnt, mine) || regrow(&v.seg_start, mine) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
+    if (regrow(&v.cnt, mine) || regrow((u32**)&v.seg, (size_t)mine * 2) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
         regrow(&v.state, (size_t)mine * v.state_words) || regrow(&e->d_state0, (size_t)mine * v.state_words)) {
       e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA;
     }
@@ -781,8 +792,8 @@ int ssb_set_flags(ssb_engine* e, int32_t flags) {
 int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap) {
   if (!e || !names || !total_ms || !launches) return 0;
   static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_hist", "k_segs", "k_scatter",
-                                                    "k_sortseg", "k_sortheavy", "k_exec", "k_fixup", "k_route(anti)",
-                                                    "k_route", "k_route(recv)"};
+                                                    "k_sortheavy", "k_exec", "k_fixup", "k_fixup_heavy",
+                                                    "k_route(anti)", "k_route", "k_route(recv)"};
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   e->t_collect();

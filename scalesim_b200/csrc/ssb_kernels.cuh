@@ -47,17 +47,19 @@ __device__ __forceinline__ u64 warp_xor_u64(u64 v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_min — GVT candidate (R7): min over the unconsumed tails of all calendar buckets and over the
-// events dropped beyond finish_time. Replaces scheduler::min_locals (process_scheduler.hpp:83-90) +
-// the local half of mpi_gsync::check_sync (global_sync.hpp:95-150). Warp-shuffle + block reduction.
+// GVT candidate (R7): the smallest key any unprocessed event of this partition can have. After a round every
+// integrated event has been executed, so the unprocessed events are exactly the unconsumed tails of the calendar
+// buckets; the start time of the first bucket with such a tail is a valid lower bound ("any value <= every LP's
+// local time") and gives the same commit frontier as the exact minimum, because commit works on whole
+// buckets. Events dropped beyond finish_time count as (finish_time, 0). Warp-shuffle + block min-reduction.
+// Replaces scheduler::min_locals (process_scheduler.hpp:83-90) + the local half of mpi_gsync::check_sync
+// (global_sync.hpp:95-150).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_min(View v) {
-  __shared__ u64 sm[32];
+__device__ __forceinline__ void block_local_min(const View& v, u64* sm) {
+  Ctl* c = v.ctl;
   u64 m = KEY_MAX;
-  for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x) {
-    u64 k = v.min_key[b];
-    m = k < m ? k : m;
-  }
+  for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x)
+    if (v.fill[b] != v.consumed[b]) { u64 k = make_key(b * v.bucket_ticks, 0); m = k < m ? k : m; }
   m = warp_min_u64(m);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -65,39 +67,26 @@ __global__ void k_min(View v) {
     m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : KEY_MAX;
     m = warp_min_u64(m);
     if (threadIdx.x == 0) {
-      u64 bm = v.ctl->beyond_min;
-      v.ctl->local_min = bm < m ? bm : m;
+      u64 bm = c->n_beyond ? make_key(v.finish_time, 0) : KEY_MAX;
+      c->local_min = bm < m ? bm : m;
     }
   }
 }
 
+__global__ void k_min(View v) {
+  __shared__ u64 sm[32];
+  block_local_min(v, sm);
+}
+
 // ------------------------------------------------------------------------------------------------
-// k_plan — one thread. GVT := (all-reduced) local_min. Finish test of runner.hpp:392. Commit list =
-// buckets entirely below GVT (R8/R9). Gather list = unconsumed tails of the buckets inside the
-// optimistic window [bucket(GVT), bucket(GVT) + window).
+// k_plan — GVT := (all-reduced) local_min. Finish test of runner.hpp:392. Commit list = buckets entirely below GVT
+// (R8/R9). Gather list = unconsumed tails of the buckets inside the optimistic window
+// [bucket(GVT), bucket(GVT) + window).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_plan(View v, int use_global_gvt) {
   __shared__ u64 sm[32];
   Ctl* c = v.ctl;
-  if (!use_global_gvt) {
-    // single partition: the GVT min-reduction is fused here (same code as k_min)
-    u64 m = KEY_MAX;
-    for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x) {
-      u64 k = v.min_key[b];
-      m = k < m ? k : m;
-    }
-    m = warp_min_u64(m);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : KEY_MAX;
-      m = warp_min_u64(m);
-      if (threadIdx.x == 0) {
-        u64 bm = c->beyond_min;
-        c->local_min = bm < m ? bm : m;
-      }
-    }
-  }
+  if (!use_global_gvt) block_local_min(v, sm);     // single partition: the min-reduction is fused here
   if (threadIdx.x != 0) return;
   u64 gvt = use_global_gvt ? c->gvt : c->local_min;
   c->gvt = gvt;
@@ -134,13 +123,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
         total += take;
         v.consumed[b] += take;
       }
-      if (take < avail) {
-        // batch capacity reached: the rest of this bucket stays pending; a conservative minimum keeps GVT valid
-        v.min_key[b] = make_key(b * v.bucket_ticks, 0);
-        bound = b + 1;
-        break;
-      }
-      v.min_key[b] = KEY_MAX;
+      if (take < avail) { bound = b + 1; break; }   // batch capacity reached: the rest of this bucket stays pending
     }
     if (c->rq_head - c->rq_tail < RQ_LEN) {
       c->rq_bound[c->rq_head % RQ_LEN] = bound;
@@ -153,12 +136,13 @@ __global__ void k_plan(View v, int use_global_gvt) {
   c->bound_abs = bound;
   c->n_gather = ng;
   c->n_arr = total;
-  c->n_active = 0;
+  c->n_processed += total;   // k_fixup corrects this for the LPs it re-executes
   c->seg_cursor = 0;
   c->n_anti = 0;
   c->n_extra = 0;
   c->n_heavy = 0;
   c->n_fix = 0;
+  c->n_fixheavy = 0;
   c->done = done ? 1u : 0u;
   c->round++;
   for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
@@ -171,16 +155,17 @@ __global__ void k_plan(View v, int use_global_gvt) {
 // sim_obj.hpp:66-77), which print one line per event serially on the main thread.
 // ------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void k_commit(View v, typename M::Data md) {
+__global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
   Ctl* c = v.ctl;
   const u32 total = c->commit_total;
   const u32 nc = c->n_commit;
   u64 cnt = 0, hsum = 0, hxor = 0, hsum2 = 0;
-  const u32 lane = threadIdx.x & 31;
-  const u32 nthreads = gridDim.x * blockDim.x;
-  // every warp iterates the same number of times so that the ballots below are full-warp
-  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += nthreads) {
-    u32 i = base + lane;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ u32 w_cnt[8];
+  __shared__ u64 s_pos;
+  // every thread of a block iterates the same number of times (block-level compaction inside the loop)
+  for (u32 base = blockIdx.x * 256u; base < total; base += gridDim.x * 256u) {
+    u32 i = base + threadIdx.x;
     bool keep = false;
     Ev e;
     u32 tg = 0;
@@ -203,17 +188,23 @@ __global__ void k_commit(View v, typename M::Data md) {
       }
     }
     if (v.cap_log) {
+      // stream compaction: warp ballot -> block offsets -> ONE atomic per 256 events on the log cursor
       u32 bal = __ballot_sync(0xffffffffu, keep);
-      if (bal) {
-        u64 pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(&c->log_count, (u64)__popc(bal));
-        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-        if (keep) {
-          u64 pos = pos0 + __popc(bal & ((1u << lane) - 1u));
-          if (pos < v.cap_log) { e.flags = tg; store_ev(v.log + pos, e); }
-          else atomicAdd(&c->log_dropped, 1ull);
-        }
+      if (lane == 0) w_cnt[warp] = __popc(bal);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u32 tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { u32 a = w_cnt[w]; w_cnt[w] = tot; tot += a; }
+        s_pos = tot ? atomicAdd(&c->log_count, (u64)tot) : 0ull;
       }
+      __syncthreads();
+      if (keep) {
+        u64 pos = s_pos + w_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
+        if (pos < v.cap_log) { e.flags = tg; store_ev(v.log + pos, e); }
+        else atomicAdd(&c->log_dropped, 1ull);
+      }
+      __syncthreads();
     }
   }
   cnt = warp_sum_u64(cnt); hsum = warp_sum_u64(hsum); hxor = warp_xor_u64(hxor); hsum2 = warp_sum_u64(hsum2);
@@ -247,7 +238,7 @@ __global__ void k_commit(View v, typename M::Data md) {
       u32 pos = atomicAdd(&c->free_top, 1u);
       v.free_stack[pos] = ch;
     }
-    if (threadIdx.x == 0) { v.fill[b] = 0; v.consumed[b] = 0; v.min_key[b] = KEY_MAX; }
+    if (threadIdx.x == 0) { v.fill[b] = 0; v.consumed[b] = 0; }
   }
   if (threadIdx.x == 0) c->commit_blocks = 0;
 }
@@ -280,14 +271,14 @@ __global__ void k_hist(View v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_segs — one thread per LP: allocate the LP's segment of this round (warp-aggregated atomic on the
-// cursor) and append the LP to the active list. Replaces scheduler::queue/dequeue
-// (process_scheduler.hpp:55-81): "which LPs have work in this window".
+// k_segs — one thread per LP: allocate the LP's segment of this round; 256 LPs share one atomic on the cursor
+// (warp scan + block scan). Replaces scheduler::queue/dequeue (process_scheduler.hpp:55-81): "which LPs have work in
+// this window".
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_segs(View v) {
   Ctl* c = v.ctl;
   if (c->n_arr == 0) return;
-  __shared__ u32 w_seg[8], w_act[8], b_seg, b_act;
+  __shared__ u32 w_seg[8], b_seg;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (u32 base = blockIdx.x * 256u; base < v.n_lp_local; base += gridDim.x * 256u) {
     u32 lp = base + threadIdx.x;
@@ -298,36 +289,57 @@ __global__ void __launch_bounds__(256) k_segs(View v) {
       u32 t = __shfl_up_sync(0xffffffffu, incl, o);
       if ((int)lane >= o) incl += t;
     }
-    u32 bal = __ballot_sync(0xffffffffu, n != 0);
     if (lane == 31) w_seg[warp] = incl;
-    if (lane == 0) w_act[warp] = __popc(bal);
     __syncthreads();
     if (threadIdx.x == 0) {
-      u32 ts = 0, ta = 0;
+      u32 ts = 0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        u32 a = w_seg[w]; w_seg[w] = ts; ts += a;
-        u32 b = w_act[w]; w_act[w] = ta; ta += b;
-      }
-      b_seg = ts ? atomicAdd(&c->seg_cursor, ts) : 0u;     // one atomic per 256 LPs
-      b_act = ta ? atomicAdd(&c->n_active, ta) : 0u;
+      for (int w = 0; w < 8; ++w) { u32 a = w_seg[w]; w_seg[w] = ts; ts += a; }
+      b_seg = ts ? atomicAdd(&c->seg_cursor, ts) : 0u;
     }
     __syncthreads();
     if (n) {
-      u32 start = b_seg + w_seg[warp] + incl - n;
-      v.seg_start[lp] = start;
+      v.seg[lp] = make_uint2(b_seg + w_seg[warp] + incl - n, n);
       v.cnt[lp] = 0;
-      v.active[b_act + w_act[warp] + __popc(bal & ((1u << lane) - 1u))] = make_uint4(lp, start, n, 0);
     }
     __syncthreads();
   }
 }
 
+// flag bits of prevlink[s0].w
+constexpr u32 PL_IRREGULAR = 1u;   // anti-message, duplicate key or possible straggler in the segment
+constexpr u32 PL_MUTATED = 2u;     // a handler invocation changed the LP state
+constexpr u32 PL_SORTED = 4u;      // the segment is sorted by (key, arrival order)
+constexpr u32 PL_FIX = PL_IRREGULAR | PL_MUTATED;
+constexpr u32 kScanMax = 96;       // longer segments are sorted by k_sortheavy instead of scanned per event
+constexpr u32 kLightMax = 16;      // k_fixup sorts segments up to this length in registers/local memory
+constexpr u32 kHeavyCap = 2048;    // entries per warp in the shared-memory bitonic sort
+constexpr int kHeavyWarps = 2;
+
+// first flagger of an LP puts it on the fix list (light or heavy by segment length)
+__device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 s0, u32 n, u32 bit) {
+  u32 old = atomicOr(&v.prevlink[s0].w, bit);
+  if ((old & PL_FIX) == 0) {
+    if (n <= kLightMax || (old & PL_SORTED)) v.fix[atomicAdd(&v.ctl->n_fix, 1u)] = make_uint4(lp, s0, n, 0);
+    else v.fixheavy[atomicAdd(&v.ctl->n_fixheavy, 1u)] = make_uint4(lp, s0, n, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scatter — arrivals -> per-LP segments (arrival order inside a segment). The first arrival of an LP also notes
+// the LP's processed-chain head: prevlink[s0] = {head slot, its receive_time, n, flags}.
+// ------------------------------------------------------------------------------------------------
 __global__ void k_scatter(View v) {
-  const u32 n = v.ctl->n_arr;
+  Ctl* c = v.ctl;
+  const u32 n = c->n_arr;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    u32 pos = v.seg_start[v.tmp_lp[i]] + v.tmp_rank[i];
-    v.sorted[pos] = v.tmp_sorted[i];
+    const u32 lp = v.tmp_lp[i], rank = v.tmp_rank[i];
+    const uint2 sg = v.seg[lp];
+    v.sorted[sg.x + rank] = v.tmp_sorted[i];
+    if (rank == 0) {
+      v.prevlink[sg.x] = make_uint4(v.last_slot[lp], v.last_time[lp], sg.y, 0);
+      if (sg.y > kScanMax) v.heavy[atomicAdd(&c->n_heavy, 1u)] = make_uint4(lp, sg.x, sg.y, 0);
+    }
   }
 }
 
@@ -507,77 +519,69 @@ struct Turn {
 };
 
 // ------------------------------------------------------------------------------------------------
-// k_sortseg — one thread per active LP: sort the LP's inbox segment by (key, arrival order) (R1), note the LP's
-// chain head, and classify the turn:
-//   flag 0  plain: only positives, distinct keys, all later than everything the LP has processed
-//           -> the events are executed one thread per EVENT by k_exec (skew-free: a hot LP's events spread over
-//              many threads)
-//   flag 1  an anti-message, a duplicate key or a straggler is present -> the sequential lp_turn in k_fixup
-// Segments longer than kLightMax go to k_sortheavy (one warp per LP, bitonic sort in shared memory).
-// prevlink[s0] = {old chain head slot, its receive_time, n, flag}.
+// warp-cooperative sort of one segment by (key, arrival order): bitonic network in shared memory (n <= kHeavyCap),
+// else one lane sorts in place. Returns true (warp-uniform) if the segment holds an anti-message or a duplicate key.
 // ------------------------------------------------------------------------------------------------
-constexpr u32 kLightMax = 16;
-constexpr u32 kHeavyCap = 2048;       // entries per warp in k_sortheavy's shared memory
-constexpr int kHeavyWarps = 2;
-
-__device__ __forceinline__ void classify_append(const View& v, u32 lp, u32 s0, u32 n, u32 old_slot, u32 old_time,
-                                                u32 flag) {
-  v.prevlink[s0] = make_uint4(old_slot, old_time, n, flag);
-  if (flag) {
-    u32 pos = atomicAdd(&v.ctl->n_fix, 1u);
-    v.fix[pos] = make_uint4(lp, s0, n, 0);
-  }
-}
-
-__global__ void k_sortseg(View v) {
-  Ctl* c = v.ctl;
-  const u32 na = c->n_active;
-  u64 planned = 0;
-  const u32 lane = threadIdx.x & 31;
-  const u32 nthreads = gridDim.x * blockDim.x;
-  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < na; base += nthreads) {
-    u32 k = base + lane;
-    if (k >= na) continue;
-    uint4 a = v.active[k];
-    const u32 lp = a.x, s0 = a.y, n = a.z;
-    if (n > kLightMax) {
-      v.heavy[atomicAdd(&c->n_heavy, 1u)] = k;
-      continue;
+__device__ __forceinline__ bool warp_sort_segment(Sorted* seg, u32 n, Sorted* buf, u32 lane) {
+  u32 flag = 0;
+  if (n <= kHeavyCap) {
+    u32 P = 1;
+    while (P < n) P <<= 1;
+    for (u32 i = lane; i < P; i += 32) {
+      Sorted x;
+      if (i < n) x = seg[i]; else { x.key = KEY_MAX; x.slot = NIL; x.seq = 0x7FFFFFFFu; }
+      buf[i] = x;
     }
-    const u32 old_slot = v.last_slot[lp], old_time = v.last_time[lp];
-    Sorted* seg = v.sorted + s0;
-    u32 flag = 0;
-    u64 kmin;
-    if (n == 1) {
-      Sorted x = seg[0];
-      kmin = x.key;
-      flag = x.seq >> 31;
-    } else {
-      Sorted loc[kLightMax];
-      for (u32 i = 0; i < n; ++i) loc[i] = seg[i];
-      bool moved = false;
+    __syncwarp();
+    for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
+      for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+        for (u32 i = lane; i < P; i += 32) {
+          u32 ixj = i ^ j2;
+          if (ixj > i) {
+            Sorted x = buf[i], y = buf[ixj];
+            bool asc = (i & k2) == 0;
+            if (sorted_less(y, x) == asc) { buf[i] = y; buf[ixj] = x; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (u32 i = lane; i < n; i += 32) {
+      Sorted x = buf[i];
+      seg[i] = x;
+      flag |= x.seq >> 31;
+      if (i && buf[i - 1].key == x.key) flag = 1;
+    }
+  } else {
+    if (lane == 0) {
       for (u32 i = 1; i < n; ++i) {
-        Sorted x = loc[i];
+        Sorted x = seg[i];
         u32 j = i;
-        while (j > 0 && sorted_less(x, loc[j - 1])) { loc[j] = loc[j - 1]; --j; }
-        if (j != i) { loc[j] = x; moved = true; }
+        while (j > 0) {
+          Sorted y = seg[j - 1];
+          if (!sorted_less(x, y)) break;
+          seg[j] = y;
+          --j;
+        }
+        if (j != i) seg[j] = x;
       }
-      kmin = loc[0].key;
-      for (u32 i = 0; i < n; ++i) {
-        flag |= loc[i].seq >> 31;
-        if (i && loc[i].key == loc[i - 1].key) flag = 1;
-      }
-      if (moved) for (u32 i = 0; i < n; ++i) seg[i] = loc[i];
     }
-    if (old_slot != NIL && key_time(kmin) <= old_time) flag = 1;     // possible straggler (exact test in lp_turn)
-    classify_append(v, lp, s0, n, old_slot, old_time, flag);
-    if (!flag) planned += n;
+    __threadfence_block();
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) {
+      Sorted x = seg[i];
+      flag |= x.seq >> 31;
+      if (i && seg[i - 1].key == x.key) flag = 1;
+    }
   }
   __syncwarp();
-  planned = warp_sum_u64(planned);
-  if (lane == 0 && planned) atomicAdd(&c->n_processed, planned);
+  return __any_sync(0xffffffffu, flag != 0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_sortheavy — one warp per LP whose segment is too long for the per-event scan of k_exec (> kScanMax, the hot
+// LPs): sort it (R1) and classify it.
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kHeavyWarps * 32) k_sortheavy(View v) {
   extern __shared__ uint4 smem_heavy[];
   Ctl* c = v.ctl;
@@ -585,94 +589,73 @@ __global__ void __launch_bounds__(kHeavyWarps * 32) k_sortheavy(View v) {
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kHeavyCap;
   for (u32 h = blockIdx.x * kHeavyWarps + warp; h < nh; h += gridDim.x * kHeavyWarps) {
-    uint4 a = v.active[v.heavy[h]];
+    uint4 a = v.heavy[h];
     const u32 lp = a.x, s0 = a.y, n = a.z;
     Sorted* seg = v.sorted + s0;
-    u32 flag = 0;
-    if (n <= kHeavyCap) {
-      u32 P = 1;
-      while (P < n) P <<= 1;
-      for (u32 i = lane; i < P; i += 32) {
-        Sorted x;
-        if (i < n) x = seg[i]; else { x.key = KEY_MAX; x.slot = NIL; x.seq = 0x7FFFFFFFu; }
-        buf[i] = x;
-      }
-      __syncwarp();
-      for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
-        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-          for (u32 i = lane; i < P; i += 32) {
-            u32 ixj = i ^ j2;
-            if (ixj > i) {
-              Sorted x = buf[i], y = buf[ixj];
-              bool asc = (i & k2) == 0;
-              if (sorted_less(y, x) == asc) { buf[i] = y; buf[ixj] = x; }
-            }
-          }
-          __syncwarp();
-        }
-      }
-      for (u32 i = lane; i < n; i += 32) {
-        Sorted x = buf[i];
-        seg[i] = x;
-        flag |= x.seq >> 31;
-        if (i && buf[i - 1].key == x.key) flag = 1;
-      }
-    } else {
-      // longer than the shared-memory buffer: one lane sorts in place (slow, but correct)
-      if (lane == 0) {
-        for (u32 i = 1; i < n; ++i) {
-          Sorted x = seg[i];
-          u32 j = i;
-          while (j > 0) {
-            Sorted y = seg[j - 1];
-            if (!sorted_less(x, y)) break;
-            seg[j] = y;
-            --j;
-          }
-          if (j != i) seg[j] = x;
-        }
-      }
-      __threadfence_block();
-      __syncwarp();
-      for (u32 i = lane; i < n; i += 32) {
-        Sorted x = seg[i];
-        flag |= x.seq >> 31;
-        if (i && seg[i - 1].key == x.key) flag = 1;
-      }
-    }
-    flag = __any_sync(0xffffffffu, flag != 0) ? 1u : 0u;
-    __syncwarp();
+    bool irregular = warp_sort_segment(seg, n, buf, lane);
     if (lane == 0) {
-      const u32 old_slot = v.last_slot[lp], old_time = v.last_time[lp];
-      u64 kmin = n <= kHeavyCap ? buf[0].key : seg[0].key;
-      if (old_slot != NIL && key_time(kmin) <= old_time) flag = 1;
-      classify_append(v, lp, s0, n, old_slot, old_time, flag);
-      if (!flag) atomicAdd(&c->n_processed, (u64)n);
+      uint4 pl = v.prevlink[s0];
+      if (pl.x != NIL && key_time(seg[0].key) <= pl.y) irregular = true;     // possible straggler
+      atomicOr(&v.prevlink[s0].w, PL_SORTED);
+      if (irregular) flag_lp(v, lp, s0, n, PL_IRREGULAR);
     }
     __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_exec — one thread per EVENT of the window (in per-LP key order): run the handler on the LP's current state,
-// link the event into the LP's processed chain, record the sent-log entry, write the produced event to the outbox.
+// k_exec — one thread per EVENT of the window: find the event's place in its LP's key order (R1), run the handler
+// on the LP's current state, link the event into the LP's processed chain, record the sent-log entry, write the
+// produced event to the outbox. Skew-free: a hot LP's events are spread over many threads.
+//
+// Place in key order: segments up to kScanMax events are scanned by each of their events (all threads of a segment
+// read the same few cache lines): predecessor = largest smaller key, "last" = no larger key. The scan also finds the
+// irregular turns — an anti-message, a duplicate key, or a key not later than the LP's newest processed event
+// (straggler, R5) — which are left to the sequential lp_turn of k_fixup. Longer segments were sorted by k_sortheavy.
+//
 // This is the speculative form of runner::run_lp_aggr (runner.hpp:530-570): all events of an LP are executed against
-// the same state. That is exactly the sequential result as long as no handler invocation changes the state (both
-// shipped applications never do). The moment one does, the LP is flagged (prevlink.w = 2) and k_fixup re-executes
-// its whole segment sequentially — so handlers that mutate state are still executed with exact semantics.
+// the same state. That is exactly the sequential result as long as no invocation changes the state (neither shipped
+// application ever does). The moment one does, the LP is flagged and k_fixup re-executes its whole segment
+// sequentially — handlers that mutate state keep exact semantics.
 // ------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void k_exec(View v, typename M::Data md) {
+__global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
   Ctl* c = v.ctl;
-  const u32 n = c->n_arr;
+  const u32 n_arr = c->n_arr;
   u32 err = 0;
-  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    Sorted s = v.sorted[j];
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n_arr; j += gridDim.x * blockDim.x) {
+    const Sorted s = v.sorted[j];
     Ev e = load_ev(v.ev + s.slot);
     const u32 lp = part_local(v, e.dst);
-    const u32 s0 = v.seg_start[lp];
+    const uint2 sg = v.seg[lp];
+    const u32 s0 = sg.x, n = sg.y;
     const uint4 pl = v.prevlink[s0];
-    if (pl.w != 0) continue;                        // handled by k_fixup
+    if (pl.w & PL_FIX) continue;                        // handled by k_fixup
+    u32 pred_slot = pl.x, pred_time = pl.y;
+    bool is_last;
+    if (pl.w & PL_SORTED) {
+      if (j != s0) { Sorted sp = v.sorted[j - 1]; pred_slot = sp.slot; pred_time = key_time(sp.key); }
+      is_last = (j == s0 + n - 1);
+    } else {
+      bool bad = (s.seq >> 31) != 0;
+      if (pl.x != NIL && key_time(s.key) <= pl.y) bad = true;
+      u64 pk = 0;
+      bool have = false;
+      u32 larger = 0;
+      for (u32 i = s0; i < s0 + n; ++i) {
+        if (i == j) continue;
+        const Sorted t = v.sorted[i];
+        if (t.seq >> 31) bad = true;
+        if (t.key == s.key) bad = true;
+        else if (t.key < s.key) {
+          if (!have || t.key > pk) { pk = t.key; pred_slot = t.slot; pred_time = key_time(t.key); have = true; }
+        } else {
+          ++larger;
+        }
+      }
+      is_last = larger == 0;
+      if (bad) { flag_lp(v, lp, s0, n, PL_IRREGULAR); continue; }
+    }
     u32 st[M::kStateWords], pre[M::kStateWords];
 #pragma unroll
     for (int w = 0; w < M::kStateWords; ++w) { st[w] = v.state[(size_t)lp * M::kStateWords + w]; pre[w] = st[w]; }
@@ -681,15 +664,10 @@ __global__ void k_exec(View v, typename M::Data md) {
     bool changed = false;
 #pragma unroll
     for (int w = 0; w < M::kStateWords; ++w) changed |= (pre[w] != st[w]);
-    if (has && changed) {
-      // state-mutating handler: this LP needs the sequential path
-      u32 old = atomicExch(&v.prevlink[s0].w, 2u);
-      if (old == 0) v.fix[atomicAdd(&c->n_fix, 1u)] = make_uint4(lp, s0, pl.z, 0);
-      continue;
-    }
+    if (has && changed) { flag_lp(v, lp, s0, n, PL_MUTATED); continue; }   // state-mutating handler
     Meta m;
-    if (j == s0) { m.link = pl.x; m.prevtime = pl.y; }
-    else { Sorted sp = v.sorted[j - 1]; m.link = sp.slot; m.prevtime = key_time(sp.key); }
+    m.link = pred_slot;
+    m.prevtime = pred_time;
     m.sent_dst = NIL;
     m.snap = NIL;
     if (has) {
@@ -701,15 +679,35 @@ __global__ void k_exec(View v, typename M::Data md) {
     }
     v.meta[s.slot] = m;
     v.ev[s.slot].flags = e.flags | F_PROCESSED;
-    if (j == s0 + pl.z - 1) { v.last_slot[lp] = s.slot; v.last_time[lp] = key_time(s.key); }
+    if (is_last) { v.last_slot[lp] = s.slot; v.last_time[lp] = key_time(s.key); }
   }
   if (err) atomicOr(&c->error, err);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_fixup — one thread per LP whose turn is not plain (flag 1: anti-message / duplicate / straggler; flag 2: a
-// handler changed the LP state): the exact sequential lp_turn.
+// k_fixup / k_fixup_heavy — the LPs whose turn is not plain (anti-message, duplicate, straggler, state-mutating
+// handler): sort the segment if it is not sorted yet, then the exact sequential lp_turn. k_fixup: one thread per LP
+// (short or already sorted segments); k_fixup_heavy: one warp per LP (bitonic sort, then lane 0 runs the turn).
 // ------------------------------------------------------------------------------------------------
+template <class M>
+__device__ __forceinline__ void fixup_stats(Ctl* c, u32 lane, u64 n_proc, u64 n_redo, u64 n_undone, u64 n_anti,
+                                            u64 n_annih, u64 n_dup, u32 err) {
+  n_proc = warp_sum_u64(n_proc);
+  n_redo = warp_sum_u64(n_redo);
+  n_undone = warp_sum_u64(n_undone);
+  n_anti = warp_sum_u64(n_anti);
+  n_annih = warp_sum_u64(n_annih);
+  n_dup = warp_sum_u64(n_dup);
+  if (lane == 0) {
+    if (n_proc != n_redo) atomicAdd(&c->n_processed, n_proc - n_redo);   // k_plan counted every arrival once
+    if (n_undone) atomicAdd(&c->n_undone, n_undone);
+    if (n_anti) atomicAdd(&c->n_antis, n_anti);
+    if (n_annih) atomicAdd(&c->n_annihilated, n_annih);
+    if (n_dup) atomicAdd(&c->n_dups, n_dup);
+  }
+  if (err) atomicOr(&c->error, err);
+}
+
 template <class M>
 __global__ void k_fixup(View v, typename M::Data md) {
   Ctl* c = v.ctl;
@@ -721,39 +719,68 @@ __global__ void k_fixup(View v, typename M::Data md) {
   for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nf; base += nthreads) {
     u32 k = base + lane;
     if (k < nf) {
-      uint4 f = v.fix[k];
-      uint4 pl = v.prevlink[f.y];
-      if (pl.w == 2u) n_redo += f.z;               // k_sortseg had counted these as processed by k_exec
+      const uint4 f = v.fix[k];
+      const u32 lp = f.x, s0 = f.y, n = f.z;
+      const uint4 pl = v.prevlink[s0];
+      if (!(pl.w & PL_SORTED) && n > 1) {
+        Sorted* seg = v.sorted + s0;
+        Sorted loc[kLightMax];
+        for (u32 i = 0; i < n; ++i) loc[i] = seg[i];
+        for (u32 i = 1; i < n; ++i) {
+          Sorted x = loc[i];
+          u32 j = i;
+          while (j > 0 && sorted_less(x, loc[j - 1])) { loc[j] = loc[j - 1]; --j; }
+          loc[j] = x;
+        }
+        for (u32 i = 0; i < n; ++i) seg[i] = loc[i];
+      }
+      n_redo += n;
       Turn<M> t(v, md);
-      t.run(f.x, f.y, f.z, pl.x, pl.y);
+      t.run(lp, s0, n, pl.x, pl.y);
       n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
       err |= t.err;
     }
   }
   __syncwarp();
-  n_proc = warp_sum_u64(n_proc);
-  n_redo = warp_sum_u64(n_redo);
-  n_undone = warp_sum_u64(n_undone);
-  n_anti = warp_sum_u64(n_anti);
-  n_annih = warp_sum_u64(n_annih);
-  n_dup = warp_sum_u64(n_dup);
-  if (lane == 0) {
-    if (n_proc != n_redo) atomicAdd(&c->n_processed, n_proc - n_redo);
-    if (n_undone) atomicAdd(&c->n_undone, n_undone);
-    if (n_anti) atomicAdd(&c->n_antis, n_anti);
-    if (n_annih) atomicAdd(&c->n_annihilated, n_annih);
-    if (n_dup) atomicAdd(&c->n_dups, n_dup);
+  fixup_stats<M>(c, lane, n_proc, n_redo, n_undone, n_anti, n_annih, n_dup, err);
+}
+
+template <class M>
+__global__ void __launch_bounds__(kHeavyWarps * 32) k_fixup_heavy(View v, typename M::Data md) {
+  extern __shared__ uint4 smem_heavy[];
+  Ctl* c = v.ctl;
+  const u32 nf = c->n_fixheavy;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kHeavyCap;
+  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0, n_redo = 0;
+  u32 err = 0;
+  for (u32 h = blockIdx.x * kHeavyWarps + warp; h < nf; h += gridDim.x * kHeavyWarps) {
+    const uint4 f = v.fixheavy[h];
+    const u32 lp = f.x, s0 = f.y, n = f.z;
+    warp_sort_segment(v.sorted + s0, n, buf, lane);
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+      const uint4 pl = v.prevlink[s0];
+      n_redo += n;
+      Turn<M> t(v, md);
+      t.run(lp, s0, n, pl.x, pl.y);
+      n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
+      err |= t.err;
+    }
+    __syncwarp();
   }
-  if (err) atomicOr(&c->error, err);
+  __syncwarp();
+  fixup_stats<M>(c, lane, n_proc, n_redo, n_undone, n_anti, n_annih, n_dup, err);
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_route — emit: outbox -> calendar buckets (local destination) or per-partition send buffers.
 // Replaces event_com::send_event (event_communicator.hpp:90-103) + lp::buffer. Per tile of 1024 events the
 // block builds a shared-memory histogram over targets, claims one range per target with a single global
-// atomic (block-aggregated), and updates the bucket's unconsumed minimum (R3: the destination's local time
-// drops at once, so GVT sees the event). Events at or beyond finish_time are never executed nor committed
-// (R8), so they are counted and dropped; only their minimum key is kept for GVT.
+// atomic (block-aggregated). The appended event is at once part of the bucket's unconsumed tail, which is what the GVT
+// reduction looks at (R3: the destination's local time drops at once). Events at or beyond finish_time are never
+// executed nor committed (R8), so they are counted and dropped (GVT treats them as (finish_time, 0)).
 //   which: 0 = anti box, 1 = main + extra outbox, 2 = receive buffer, 3 = host-loaded staging (outbox[0..load_count))
 //   filter: 0 = all, 1 = anti-messages only, 2 = positives only (the receive side keeps antis ahead of positives)
 // ------------------------------------------------------------------------------------------------
@@ -765,8 +792,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   const u32 rs = v.route_slots;
   const u32 nt = rs + 1 + v.world;
   const u32 base = c->commit_next;
-  u64* s_min = smem64;                                  // [nt]
-  u32* s_cnt = reinterpret_cast<u32*>(smem64 + nt);     // [nt]
+  u32* s_cnt = reinterpret_cast<u32*>(smem64);          // [nt]
   u32* s_base = s_cnt + nt;                             // [nt]
   const Ev* src;
   u32 n0, n1 = 0;        // main count, extra count (extra region starts at cap_batch)
@@ -778,7 +804,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   const u32 chm = (1u << v.ch_log) - 1u;
   const u32 T_NONE = NIL, T_DIRECT = NIL - 1u;
   for (u32 tile = blockIdx.x * kRouteTile; tile < total; tile += gridDim.x * kRouteTile) {
-    for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) { s_cnt[t] = 0; s_min[t] = KEY_MAX; }
+    for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) s_cnt[t] = 0;
     __syncthreads();
     Ev e[kRouteItems];
     u32 tgt[kRouteItems], rnk[kRouteItems], bkt[kRouteItems];
@@ -811,13 +837,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
             t = b - base < rs ? b - base : T_DIRECT;
           }
           tgt[it] = t;
-          if (t == T_DIRECT) {
-            rnk[it] = atomicAdd(&v.fill[bkt[it]], 1u);       // final position
-            atomicMin(&v.min_key[bkt[it]], e[it].key);
-          } else {
-            rnk[it] = atomicAdd(&s_cnt[t], 1u);
-            atomicMin(&s_min[t], e[it].key);
-          }
+          if (t == T_DIRECT) rnk[it] = atomicAdd(&v.fill[bkt[it]], 1u);       // final position
+          else rnk[it] = atomicAdd(&s_cnt[t], 1u);
         }
       }
     }
@@ -827,10 +848,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       if (!n) continue;
       if (t < rs) {
         s_base[t] = atomicAdd(&v.fill[base + t], n);
-        atomicMin(&v.min_key[base + t], s_min[t]);
       } else if (t == rs) {
         atomicAdd(&c->n_beyond, (u64)n);
-        atomicMin(&c->beyond_min, s_min[t]);
       } else {
         s_base[t] = atomicAdd(&c->send_count[t - rs - 1], n);
         atomicAdd(&c->n_remote, (u64)n);
