@@ -4,9 +4,11 @@
 //   * event pool   : Ev[max_events], 32-byte records = one DRAM sector each, carved into chunks of
 //                    2^ch_log slots; a calendar bucket (receive_time / bucket_ticks) owns a list of chunks
 //                    (chunk_tab) and is append-only, so "pending set" == the unconsumed tail of the buckets.
-//   * per-slot meta: Meta[max_events] + sent_key[max_events] — the processed-chain link, the sent-log entry
-//                    (what set_cancel keeps in the reference, queue.hpp:151-157) and the snapshot index.
-//   * per-LP       : cnt / seg / last_slot / last_time / state words.
+//                    Event records are immutable once routed.
+//   * per-slot meta: Meta[max_events] (32 B: processed-chain link, sent-log entry — what set_cancel keeps in the
+//                    reference, queue.hpp:151-157 — and snapshot index) + pflag[max_events] (1 B: processed / dead).
+//   * per-LP       : cnt / lpw {segment start, length, chain head slot, its time} / lpflag / last_slot / last_time /
+//                    state words.
 //   * per-round    : arrival staging, per-LP sorted segments, outboxes.
 #pragma once
 #include <cstdint>
@@ -20,8 +22,8 @@ typedef unsigned int u32;
 constexpr u32 NIL = 0xFFFFFFFFu;
 constexpr u64 KEY_MAX = ~0ull;
 constexpr u32 F_CANCEL = 1u;      // anti-message (sim_event_base::is_cancel_, sim_obj.hpp:30)
-constexpr u32 F_PROCESSED = 2u;   // handler has run and the result stands
-constexpr u32 F_DEAD = 4u;        // annihilated, duplicate, or a consumed anti-message
+constexpr unsigned char P_PROCESSED = 1;   // pflag: handler has run and the result stands
+constexpr unsigned char P_DEAD = 2;        // pflag: annihilated, duplicate, or a consumed anti-message
 constexpr u32 TAG_START = 1u, TAG_END = 2u;
 constexpr int MAX_WORLD = 16;
 constexpr int RQ_LEN = 64;
@@ -46,12 +48,15 @@ struct __align__(32) Ev {
 };
 static_assert(sizeof(Ev) == 32, "Ev must be one 32-byte sector");
 
-struct __align__(16) Meta {
-  u32 link;      // before processing: unused; after: previous processed event of this LP (slot) or NIL
+struct __align__(32) Meta {
+  u32 link;      // previous processed event of this LP (slot) or NIL
   u32 prevtime;  // receive_time of that previous event (so a stale link is never dereferenced)
   u32 sent_dst;  // sent-log: destination LP of the event this one produced, NIL = none
   u32 snap;      // index into the snapshot ring of the pre-state, NIL = handler left the state unchanged
+  u64 sent_key;  // sent-log: key of the produced event
+  u32 pad0, pad1;
 };
+static_assert(sizeof(Meta) == 32, "Meta must be one 32-byte sector");
 
 struct __align__(16) Sorted {
   u64 key;
@@ -97,23 +102,24 @@ struct View {
   // event pool
   Ev* ev;
   Meta* meta;
-  u64* sent_key;
+  unsigned char* pflag;   // [max_events] P_PROCESSED / P_DEAD
   u32* chunk_tab;   // [nb * maxc]
   u32* free_stack;  // [n_chunks]
   u32* fill;        // [nb] events appended
   u32* consumed;    // [nb] events already integrated
   // per LP
   u32* cnt;
-  uint2* seg;       // {start of the LP's segment in `sorted`, its length} for this round
+  uint4* lpw;       // this round: {segment start in `sorted`, segment length, chain head slot, its receive_time}
+  u32* lpflag;      // this round: PL_* bits
   u32* last_slot;
   u32* last_time;
   u32* state;       // [n_lp_local * state_words]
   // per round
-  Sorted* tmp_sorted;  // [cap_batch] arrival order
+  Ev* tmp_work;        // [cap_batch] work records (event, flags = arrival index | anti << 31), arrival order
   u32* tmp_lp;         // [cap_batch]
   u32* tmp_rank;       // [cap_batch]
-  Sorted* sorted;      // [cap_batch] grouped by LP
-  uint4* prevlink;     // [cap_batch] at an LP's segment start: {old chain head slot, its time, n, flag}
+  Ev* work;            // [cap_batch] work records grouped by LP (segments)
+  Sorted* sorted;      // [cap_batch] (key, slot, arrival) of a segment, sorted — only for long or irregular segments
   uint4* fix;          // [cap_batch] LPs that need the sequential turn {lp, seg_start, n, 0}
   uint4* fixheavy;     // [cap_batch / 16] same, segments that still need a warp-level sort
   uint4* heavy;        // [cap_batch / 64] LPs with long segments {lp, seg_start, n, 0}
@@ -146,6 +152,19 @@ __device__ __forceinline__ Ev load_ev(const Ev* p) {
   e.key = ((u64)a.y << 32) | a.x; e.dst = a.z; e.src = a.w;
   e.send = b.x; e.p0 = b.y; e.p1 = b.z; e.flags = b.w;
   return e;
+}
+__device__ __forceinline__ Meta load_meta(const Meta* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Meta m;
+  m.link = a.x; m.prevtime = a.y; m.sent_dst = a.z; m.snap = a.w;
+  m.sent_key = ((u64)b.y << 32) | b.x; m.pad0 = 0; m.pad1 = 0;
+  return m;
+}
+__device__ __forceinline__ void store_meta(Meta* p, const Meta& m) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(m.link, m.prevtime, m.sent_dst, m.snap);
+  q[1] = make_uint4((u32)m.sent_key, (u32)(m.sent_key >> 32), 0u, 0u);
 }
 __device__ __forceinline__ void store_ev(Ev* p, const Ev& e) {
   uint4* q = reinterpret_cast<uint4*>(p);

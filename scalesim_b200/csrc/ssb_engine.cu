@@ -148,12 +148,6 @@ struct ssb_engine {
     CK(cudaGetLastError());
     return SSB_OK;
   }
-  int fill64(u64* p, u64 val, size_t n) {
-    if (n) k_fill_u64<<<grid(n, 256), 256, 0, stream>>>(p, val, n);
-    CK(cudaGetLastError());
-    return SSB_OK;
-  }
-
   int state_words() const {
     switch (cfg.model) {
       case SSB_MODEL_PHOLD: return PholdModel::kStateWords;
@@ -223,21 +217,22 @@ int ssb_engine::init() {
   int rc;
   if ((rc = alloc(&v.ev, n_slots))) return rc;
   if ((rc = alloc(&v.meta, n_slots))) return rc;
-  if ((rc = alloc(&v.sent_key, n_slots))) return rc;
+  if ((rc = alloc(&v.pflag, n_slots))) return rc;
   if ((rc = alloc(&v.chunk_tab, (size_t)v.nb * v.maxc))) return rc;
   if ((rc = alloc(&v.free_stack, n_chunks))) return rc;
   if ((rc = alloc(&v.fill, v.nb))) return rc;
   if ((rc = alloc(&v.consumed, v.nb))) return rc;
   if ((rc = alloc(&v.cnt, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.seg, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.lpw, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.lpflag, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.last_slot, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.last_time, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.state, (size_t)v.n_lp_local * v.state_words))) return rc;
-  if ((rc = alloc(&v.tmp_sorted, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.tmp_work, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.work, v.cap_batch))) return rc;
   if ((rc = alloc(&v.tmp_lp, v.cap_batch))) return rc;
   if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
   if ((rc = alloc(&v.sorted, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.prevlink, v.cap_batch))) return rc;
   if ((rc = alloc(&v.fix, v.cap_batch))) return rc;
   if ((rc = alloc(&v.fixheavy, v.cap_batch / 16 + 64))) return rc;
   if ((rc = alloc(&v.heavy, v.cap_batch / 64 + 64))) return rc;
@@ -256,8 +251,8 @@ int ssb_engine::init() {
   CK(cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
   CK(cudaMemsetAsync(d_state0, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
   if ((rc = reset_sim())) return rc;
-  v.route_slots = std::min<u32>(v.nb, 4096);
-  route_smem = (size_t)(v.route_slots + 1 + v.world) * 8;
+  v.route_slots = std::min<u32>(v.nb, 2048);
+  route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
   CK(cudaFuncSetAttribute(k_sortheavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
   CK(cudaFuncSetAttribute(k_fixup_heavy<PholdModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
@@ -345,7 +340,7 @@ int ssb_engine::model_ready() {
 
 void ssb_engine::launch_route(int which, u32 peer, u32 filter) {
   t_begin(which == 0 ? K_ROUTE_ANTI : (which == 2 ? K_ROUTE_RECV : K_ROUTE));
-  k_route<<<n_sm * 4, kRouteThreads, route_smem, stream>>>(v, which, peer, filter);
+  k_route<<<n_sm * 2, kRouteThreads, route_smem, stream>>>(v, which, peer, filter);
   t_end();
 }
 
@@ -537,7 +532,7 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
     // per-LP arrays were sized for the modulo partition: grow them
     auto& v = e->v;
     auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
-    if (regrow(&v.cnt, mine) || regrow((u32**)&v.seg, (size_t)mine * 2) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
+    if (regrow(&v.cnt, mine) || regrow((u32**)&v.lpw, (size_t)mine * 4) || regrow(&v.lpflag, mine) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
         regrow(&v.state, (size_t)mine * v.state_words) || regrow(&e->d_state0, (size_t)mine * v.state_words)) {
       e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA;
     }
