@@ -1,6 +1,7 @@
 // Stand-in for <boost/algorithm/string.hpp>: split() + is_any_of() only, with
 // Boost's default token_compress_off behaviour (empty tokens are kept).
 #pragma once
+#include <algorithm>   // the real header pulls it in; traffic_sim.hpp relies on that for std::find
 #include <string>
 #include <vector>
 namespace boost {

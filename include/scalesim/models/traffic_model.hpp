@@ -1,0 +1,49 @@
+// device_model<traffic_sim> — adapter for ScaleSim's TrafficSim application (reference src/trafficsim/traffic_sim.hpp).
+// Include AFTER the unmodified traffic_sim.hpp. The application keeps the vehicle's remaining route and the
+// junction's road list in private vectors; the adapter reads them through the classes' own serialize() members
+// (traffic_sim.hpp:84-95, 130-141) with scalesim::field_capture. Routes go to one pool in device memory and events
+// carry (offset, nodes left) instead of a vector. Device twin of traffic_sim::event_handler: TrafficModel in
+// csrc/ssb_models.cuh.
+#ifndef SCALESIM_B200_MODELS_TRAFFIC_MODEL_HPP_
+#define SCALESIM_B200_MODELS_TRAFFIC_MODEL_HPP_
+#include <stdexcept>
+#include "scalesim/simulation/device_model.hpp"
+
+namespace scalesim {
+template <>
+struct device_model<traffic_sim> {
+  static const int kMaxRoads = 4;   // TrafficModel::kMaxRoads
+  struct context { std::vector<int64_t> route_pool; };
+  static int model_id() { return SSB_MODEL_TRAFFIC; }
+  // shortest possible hop: length >= 1 m, so len*3600/speed/1000 >= 0, plus the fixed 5 s (traffic_sim.hpp:314-316)
+  static long default_bucket_ticks() { return 5; }
+  static long n_lp(const parti_ptr& partition) { return (long)partition->size(); }
+  static void pack_event(const traffic_sim::Event& e, ssb_event& out, context& cx) {
+    // serialize order: vehicle_id, arrival_time, departure_time, source_, destinations_, base_{white, cancel}
+    field_capture fc = capture_fields(e);
+    const std::vector<long>& route = fc.vectors.at(0);
+    out.id = e.id(); out.src = e.source(); out.dst = e.destination();
+    out.recv_time = e.receive_time(); out.send_time = e.send_time();
+    out.p0 = (int64_t)cx.route_pool.size(); out.p1 = (int64_t)route.size();
+    out.flags = e.is_cancel() ? 1 : 0;
+    cx.route_pool.insert(cx.route_pool.end(), route.begin(), route.end());
+  }
+  static int state_words() { return 2 + 3 * kMaxRoads; }
+  static void pack_state(const traffic_sim::State& s, uint32_t* w) {
+    // serialize order: id_, destinations_, speed_limit_, num_lanes_, road_length_
+    field_capture fc = capture_fields(s);
+    const std::vector<long>&dst = fc.vectors.at(0), &speed = fc.vectors.at(1), &len = fc.vectors.at(3);
+    if (dst.size() > (size_t)kMaxRoads) throw std::runtime_error("junction with more out-roads than the device model supports");
+    for (int i = 0; i < state_words(); ++i) w[i] = 0;
+    w[0] = (uint32_t)s.id(); w[1] = (uint32_t)dst.size();
+    for (size_t i = 0; i < dst.size(); ++i) {
+      w[2 + 3 * i] = (uint32_t)dst[i]; w[3 + 3 * i] = (uint32_t)speed[i]; w[4 + 3 * i] = (uint32_t)len[i];
+    }
+  }
+  static int upload_model_data(ssb_engine* e, context& cx) {
+    if (cx.route_pool.empty()) cx.route_pool.push_back(0);
+    return ssb_set_model_data(e, 0, cx.route_pool.data(), cx.route_pool.size() * sizeof(int64_t));
+  }
+};
+}  // namespace scalesim
+#endif

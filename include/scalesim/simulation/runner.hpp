@@ -1,0 +1,283 @@
+// scalesim::runner<App> — same entry points as the reference's driver (include/scalesim/simulation/runner.hpp:28-60:
+// init_main(&argc, &argv), run()), but the Time Warp core behind it is the device engine of libscalesim_b200.so:
+//
+//   run():  App::init()                                      (runner.hpp:82)
+//           App::init_partition_index(world)  -> ssb_set_partition            (runner.hpp:98)
+//           App::init_states_in_this_rank     -> ssb_load_states              (runner.hpp:108-118)
+//           App::init_events + shuffle by partition[destination] -> ssb_load_events   (runner.hpp:131-147)
+//           ssb_run                           = runner::loop                   (runner.hpp:350-396)
+//           ssb_drain_committed -> "RE,..." lines on stdout                     (queue.hpp:203-211, sim_obj.hpp:66-77)
+//           report on stderr                                                    (runner.hpp:482-507)
+//
+// The application's host event_handler is not on the hot path: its device twin runs in the kernels. It is still
+// used here as the checker of that twin: with SCALESIM_B200_VERIFY=<k> the chains of the first k initial events are
+// also advanced on the host with App::event_handler and must be among the committed records.
+//
+// One process drives one GPU (one partition). Several partitions: start `world` processes with
+// SCALESIM_B200_RANK / SCALESIM_B200_WORLD set and SCALESIM_B200_COMM_FILE pointing to a file they can all reach
+// (rank 0 writes the NCCL unique id there); CUDA device = SCALESIM_B200_DEVICE or the rank.
+// Tunables: SCALESIM_B200_BUCKET (ticks), SCALESIM_B200_WINDOW (buckets), SCALESIM_B200_MAX_EVENTS,
+// SCALESIM_B200_MAX_BATCH, SCALESIM_B200_QUIET=1 (digest instead of result lines).
+#ifndef SCALESIM_B200_SIMULATION_RUNNER_HPP_
+#define SCALESIM_B200_SIMULATION_RUNNER_HPP_
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+#include <boost/make_shared.hpp>
+#include <boost/optional.hpp>
+#include <boost/shared_ptr.hpp>
+#include <gflags/gflags.h>
+#include <glog/logging.h>
+#include "scalesim/simulation/device_model.hpp"
+#include "scalesim/util.hpp"
+#include "scalesim_b200.h"
+
+namespace scalesim {
+
+template <class App>
+class runner {
+ public:
+  runner() : engine_(NULL), rank_(0), world_(1) {}
+  virtual ~runner() { if (engine_) ssb_destroy(engine_); }
+  void init_main(int* argc, char** argv[]);
+  void run();
+
+ private:
+  runner(const runner&);
+  void operator=(const runner&);
+  typedef device_model<App> model;
+  App app_;
+  ssb_engine* engine_;
+  int rank_, world_;
+
+  static long env_long(const char* name, long dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atol(v) : dflt;
+  }
+  void fail(const std::string& what, int rc) {
+    LOG(ERROR) << what << " failed (status " << rc << "): " << ssb_last_error(engine_);
+    std::exit(1);
+  }
+  void comm_init();
+  void verify_twin(const ev_vec<App>& initial, const std::vector<ssb_record>& committed, long k);
+};
+
+template <class App>
+void runner<App>::init_main(int* argc, char** argv[]) {
+  gflags::SetUsageMessage(
+      "\n=====How to run simulation code====\n"
+      "    $ {Binary} {Application Args}\n"
+      "Example of TrafficSim:\n"
+      "    $ ./apps/TrafficSim {partition file} {road file} {trip file}\n"
+      "Example of PHOLD:\n"
+      "    $ ./apps/PHOLD {# of LPs} {# of initial messages} {remote ratio} {lambda} {# of what-ifs} {cut interval}\n"
+      "Several GPUs: one process per GPU with SCALESIM_B200_RANK / SCALESIM_B200_WORLD / SCALESIM_B200_COMM_FILE.\n"
+      "===================================");
+  gflags::ParseCommandLineFlags(argc, argv, true);
+  FLAGS_logtostderr = 1;
+  FLAGS_minloglevel = 0;
+  google::InitGoogleLogging((*argv)[0]);
+  google::InstallFailureSignalHandler();
+  rank_ = (int)env_long("SCALESIM_B200_RANK", 0);
+  world_ = (int)env_long("SCALESIM_B200_WORLD", 1);
+}
+
+template <class App>
+void runner<App>::comm_init() {
+  if (world_ <= 1) return;
+  const char* path = std::getenv("SCALESIM_B200_COMM_FILE");
+  if (!path) { LOG(ERROR) << "SCALESIM_B200_COMM_FILE must be set when SCALESIM_B200_WORLD > 1"; std::exit(1); }
+  char id[128];
+  if (rank_ == 0) {
+    int rc = ssb_comm_unique_id(id);
+    if (rc) fail("ssb_comm_unique_id", rc);
+    std::string tmp = std::string(path) + ".tmp";
+    { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(id, 128); }
+    std::rename(tmp.c_str(), path);
+  } else {
+    for (int tries = 0;; ++tries) {
+      std::ifstream f(path, std::ios::binary);
+      if (f && f.read(id, 128) && f.gcount() == 128) break;
+      if (tries > 600) { LOG(ERROR) << "timed out waiting for " << path; std::exit(1); }
+      std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+  }
+  int rc = ssb_comm_init(engine_, id);
+  if (rc) fail("ssb_comm_init", rc);
+}
+
+template <class App>
+void runner<App>::run() {
+  if (FLAGS_diff_init || FLAGS_diff_repeat) {
+    LOG(ERROR) << "--diff_init / --diff_repeat (exact-differential store) are not part of this build yet";
+    std::exit(2);
+  }
+  typedef std::chrono::steady_clock clk;
+  clk::time_point t0 = clk::now();
+  app_.init();
+  LOG_IF(INFO, rank_ == 0) << "Initiate application";
+
+  std::pair<parti_ptr, parti_indx_ptr> parti = app_.init_partition_index(world_);
+  const std::vector<long>& part = *parti.first;
+  const long n_lp = model::n_lp(parti.first);
+  typename model::context cx;
+
+  // states of this rank
+  st_vec<App> states;
+  app_.init_states_in_this_rank(states, rank_, world_, parti.first);
+  // events: every rank reads the whole scenario and keeps what it owns (the reference shuffles instead, runner.hpp:131-147)
+  ev_vec<App> mine;
+  for (int r = 0; r < world_; ++r) {
+    ev_vec<App> parsed;
+    app_.init_events(parsed, r, world_);
+    for (typename ev_vec<App>::iterator it = parsed.begin(); it != parsed.end(); ++it) {
+      long d = (*it)->destination();
+      if (d >= 0 && d < n_lp && part[d] % world_ == rank_) mine.push_back(*it);
+    }
+  }
+  std::vector<ssb_event> pod(mine.size());
+  for (size_t i = 0; i < mine.size(); ++i) model::pack_event(*mine[i], pod[i], cx);
+
+  ssb_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.abi_version = SSB_ABI_VERSION;
+  cfg.model = model::model_id();
+  cfg.device = (int)env_long("SCALESIM_B200_DEVICE", rank_);
+  cfg.rank = rank_; cfg.world = world_;
+  cfg.n_lp = n_lp;
+  cfg.finish_time = App::finish_time();
+  cfg.bucket_ticks = env_long("SCALESIM_B200_BUCKET", model::default_bucket_ticks());
+  cfg.window_buckets = (int)env_long("SCALESIM_B200_WINDOW", 1);
+  cfg.max_events = env_long("SCALESIM_B200_MAX_EVENTS", (long)(pod.size() * 1.6) + (1 << 18));
+  cfg.max_batch = env_long("SCALESIM_B200_MAX_BATCH", (long)pod.size() / 2 + (1 << 16));
+  const bool quiet = env_long("SCALESIM_B200_QUIET", 0) != 0;
+  cfg.max_committed = quiet ? 0 : (1 << 24);
+  cfg.max_snapshots = 1 << 20;
+  cfg.rounds_per_sync = 4;
+  int rc = ssb_create(&cfg, &engine_);
+  if (rc) { LOG(ERROR) << "ssb_create failed (status " << rc << "): " << ssb_last_error(NULL); std::exit(1); }
+  comm_init();
+  std::vector<int64_t> part64(part.begin(), part.end());
+  for (size_t i = 0; i < part64.size(); ++i) part64[i] %= world_;
+  if ((rc = ssb_set_partition(engine_, part64.data(), (int64_t)part64.size()))) fail("ssb_set_partition", rc);
+  if ((rc = model::upload_model_data(engine_, cx))) fail("ssb_set_model_data", rc);
+  {
+    const int sw = model::state_words();
+    std::vector<int64_t> ids(states.size());
+    std::vector<uint32_t> words(states.size() * (size_t)sw);
+    for (size_t i = 0; i < states.size(); ++i) {
+      ids[i] = states[i]->id();
+      model::pack_state(*states[i], &words[i * (size_t)sw]);
+    }
+    if ((rc = ssb_load_states(engine_, ids.data(), words.data(), (int64_t)ids.size()))) fail("ssb_load_states", rc);
+  }
+  if ((rc = ssb_load_events(engine_, pod.data(), (int64_t)pod.size()))) fail("ssb_load_events", rc);
+  double init_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  LOG_IF(INFO, rank_ == 0)
+      << "\n====================================================================\n"
+      << " Number of partitions: " << world_ << " (one B200 each)\n"
+      << "     Total events num (this partition): " << pod.size() << "\n"
+      << "     Total states num (this partition): " << states.size() << "\n"
+      << " Total init time: " << (long)init_ms << " ms\n"
+      << "====================================================================\n";
+
+  LOG_IF(INFO, rank_ == 0) << "Start Simulation";
+  // the committed log is drained while the simulation advances: a window of rounds, then the records so far
+  std::vector<ssb_record> buf(1 << 22);
+  std::vector<ssb_record> kept;
+  const long verify_k = env_long("SCALESIM_B200_VERIFY", 0);
+  clk::time_point t1 = clk::now();
+  ssb_stats st;
+  std::memset(&st, 0, sizeof(st));
+  std::vector<char> line(1 << 16);
+  std::setvbuf(stdout, NULL, _IOFBF, 1 << 22);
+  for (;;) {
+    int done = 0;
+    for (int i = 0; i < 4 && !done; ++i)
+      if ((rc = ssb_step(engine_, &done))) fail("ssb_step", rc);
+    if (!quiet) {
+      for (;;) {
+        int64_t n = 0;
+        if ((rc = ssb_drain_committed(engine_, buf.data(), (int64_t)buf.size(), &n))) fail("ssb_drain_committed", rc);
+        for (int64_t i = 0; i < n; ++i) {
+          const ssb_record& r = buf[(size_t)i];
+          std::printf("RE,%ld,%ld,%ld,%ld,%ld%s\n", (long)r.id, (long)r.src, (long)r.send_time, (long)r.dst,
+                      (long)r.recv_time, r.tag == 1 ? ",START" : (r.tag == 2 ? ",END" : ""));
+        }
+        if (verify_k > 0) kept.insert(kept.end(), buf.begin(), buf.begin() + n);
+        if (n < (int64_t)buf.size()) break;
+      }
+    }
+    if (done) break;
+  }
+  std::fflush(stdout);
+  double sim_ms = std::chrono::duration<double, std::milli>(clk::now() - t1).count();
+  if ((rc = ssb_get_stats(engine_, &st))) fail("ssb_get_stats", rc);
+  uint64_t dg[4];
+  ssb_committed_digest(engine_, dg);
+  if (verify_k > 0 && !quiet) verify_twin(mine, kept, verify_k);
+
+  LOG(INFO) << "Finish Simulation";
+  LOG(INFO)
+      << "\n====================================================================\n"
+      << " Partition " << rank_ << " of " << world_ << "\n"
+      << " Simulation elapsed time: " << (long)sim_ms << " ms (window loop + draining " << (quiet ? "nothing" : "the result lines") << ")\n"
+      << "\n"
+      << " # of global synchronizations   : " << st.rounds << "\n"
+      << " # of processing events         : " << st.processed << "\n"
+      << " # of cancels (= # of rollback) : " << st.antis_sent << "\n"
+      << " # of output events             : " << st.committed << "\n"
+      << " Rollback efficiency            : "
+      << (st.processed ? ((float)(st.processed - st.antis_sent)) / ((float)st.processed) : 1.0f) << "\n"
+      << " rollbacks " << st.rollbacks << ", undone " << st.undone << ", annihilated " << st.annihilated
+      << ", duplicates " << st.duplicates << ", sent to other partitions " << st.remote_sent << "\n"
+      << " committed digest: " << dg[0] << " " << dg[1] << " " << dg[2] << " " << dg[3] << "\n"
+      << "====================================================================\n";
+  ssb_destroy(engine_);
+  engine_ = NULL;
+}
+
+// host handler vs device twin: advance the chains of the first k initial events with App::event_handler on the host
+// and look every visited event up among the committed records
+template <class App>
+void runner<App>::verify_twin(const ev_vec<App>& initial, const std::vector<ssb_record>& committed, long k) {
+  if (world_ != 1) { LOG(INFO) << "SCALESIM_B200_VERIFY needs a single partition; skipped"; return; }
+  std::map<std::pair<long, long>, const ssb_record*> idx;     // (recv_time, id) -> record
+  for (size_t i = 0; i < committed.size(); ++i) idx[std::make_pair((long)committed[i].recv_time, (long)committed[i].id)] = &committed[i];
+  st_vec<App> states;
+  parti_ptr all(new std::vector<long>());
+  std::pair<parti_ptr, parti_indx_ptr> parti = app_.init_partition_index(1);
+  app_.init_states_in_this_rank(states, 0, 1, parti.first);
+  std::map<long, st_ptr<App> > st_of;
+  for (size_t i = 0; i < states.size(); ++i) st_of[states[i]->id()] = states[i];
+  long checked = 0, bad = 0;
+  for (long c = 0; c < k && c < (long)initial.size(); ++c) {
+    ev_ptr<App> e = initial[(size_t)c];
+    while (e && e->receive_time() < App::finish_time()) {
+      typename std::map<std::pair<long, long>, const ssb_record*>::iterator f =
+          idx.find(std::make_pair(e->receive_time(), e->id()));
+      ++checked;
+      if (f == idx.end() || f->second->dst != e->destination() || f->second->src != e->source() ||
+          f->second->send_time != e->send_time()) {
+        if (bad++ < 5) LOG(ERROR) << "device twin mismatch at event id " << e->id() << " t " << e->receive_time();
+      }
+      typename std::map<long, st_ptr<App> >::iterator s = st_of.find(e->destination());
+      if (s == st_of.end()) break;
+      boost::optional<std::pair<ev_vec<App>, st_ptr<App> > > up = app_.event_handler(e, s->second);
+      if (!up || up->first.empty()) break;
+      e = up->first[0];
+    }
+  }
+  LOG(INFO) << "host-handler check of the device twin: " << checked << " events, " << bad << " mismatches";
+  if (bad) std::exit(3);
+}
+
+}  // namespace scalesim
+#endif
