@@ -239,10 +239,7 @@ def main():
                             max_committed=per_rank_committed_cap if keep else 0,
                             max_events=int(args.init_per_gpu * 1.6) + (1 << 20), rounds_per_sync=args.rounds_per_sync,
                             load=False)
-    if world > 1:
-        obj = [ssb.Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        eng.comm_init(obj[0])
+    ssb.dist.init_engine_comm(eng, rank, world)
     rec_pin = torch.empty(per_rank_committed_cap * 32, dtype=torch.uint8).pin_memory() if keep else None
 
     def barrier():
@@ -251,18 +248,10 @@ def main():
             dist.barrier()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return ssb.dist.max_over_ranks(x, world)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.int64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return int(t.item())
+        return ssb.dist.sum_over_ranks(x, world)
 
     def one_step():
         """device-resident timing: inputs already in HBM when the timed region (the window loop) starts"""

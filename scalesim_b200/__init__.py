@@ -24,10 +24,10 @@ from .capi import (  # noqa: F401
     records_to_lines,
     digest_records,
 )
-from . import phold, traffic  # noqa: F401
+from . import dist, phold, traffic  # noqa: F401
 
 __all__ = [
     "Engine", "EngineError", "Config", "Stats", "EVENT_DTYPE", "RECORD_DTYPE", "RAW_RECORD_DTYPE", "FLAG_KERNEL_TIMING", "raw_to_records",
     "MODEL_PHOLD", "MODEL_TRAFFIC", "MODEL_PHOLD_STATEFUL", "library_path", "load_library",
-    "records_to_lines", "digest_records", "phold", "traffic",
+    "records_to_lines", "digest_records", "dist", "phold", "traffic",
 ]

@@ -1,0 +1,55 @@
+"""The drop-in binaries: the reference's UNMODIFIED application sources (phold.hpp, traffic_sim.hpp, both main_*.cc)
+compiled against include/scalesim and linked to libscalesim_b200.so. Their stdout must be the reference's."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from fixtures import golden, golden_lines, sha256_lines, write_ring_files
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(exe, args, env=None):
+    path = os.path.join(ROOT, "apps", exe)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built (needs the reference tree at build time)")
+    p = subprocess.run([path] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, **(env or {})), timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return [l for l in p.stdout.splitlines() if l.startswith("RE,")], p.stderr
+
+
+def test_phold_dropin_equals_reference():
+    lines, err = _run("PHOLD", [100, 1600, 0.1, 1.0, 1, 50], {"SCALESIM_B200_VERIFY": "400"})
+    assert sorted(lines) == golden_lines("phold_100_1600")
+    assert "# of output events             : 7517" in err
+    assert "0 mismatches" in err           # App::event_handler on the host agrees with the device twin
+
+
+def test_phold_dropin_optimistic_window():
+    lines, err = _run("PHOLD", [1000, 4000, 0.25, 2.0, 1, 50], {"SCALESIM_B200_WINDOW": "4"})
+    assert sha256_lines(lines) == golden("phold_1000_4000")["sha256"]
+
+
+def test_trafficsim_dropin_equals_reference():
+    g = golden("ring")
+    with tempfile.TemporaryDirectory() as td:
+        rd, trip, part = write_ring_files(td)
+        part1 = os.path.join(td, "part1")
+        with open(part1, "w") as f:
+            f.write("0\n" * 10)
+        lines, err = _run("TrafficSim", [part1, rd, trip], {"SCALESIM_B200_VERIFY": "3"})
+    assert sorted(lines) == g["lines"]
+    assert "0 mismatches" in err
+
+
+def test_dropin_rejects_diff_flags():
+    path = os.path.join(ROOT, "apps", "PHOLD")
+    if not os.path.exists(path):
+        pytest.skip("not built")
+    p = subprocess.run([path, "--diff_init", "--sim_id=1", "--store_dir=/tmp/x", "100", "1600", "0.1", "1.0", "1", "50"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert p.returncode == 2 and "not part of this build" in p.stderr
