@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--rounds-per-sync", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-partition event exchange")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -239,7 +240,7 @@ def main():
                             max_committed=per_rank_committed_cap if keep else 0,
                             max_events=int(args.init_per_gpu * 1.6) + (1 << 20), rounds_per_sync=args.rounds_per_sync,
                             load=False)
-    ssb.dist.init_engine_comm(eng, rank, world)
+    ssb.dist.init_engine_comm(eng, rank, world, p2p=args.exchange == "p2p")
     rec_pin = torch.empty(per_rank_committed_cap * 32, dtype=torch.uint8).pin_memory() if keep else None
 
     def barrier():
@@ -340,6 +341,8 @@ def main():
                                    f"{args.remote:g} remote, finish 500000 ticks, partition lp % {world} "
                                    f"(BASELINE.json config 2 per GPU)",
                        "bucket_ticks": args.bucket, "window_buckets": args.window,
+                       "exchange": ("peer-memory writes over NVLink + NCCL allreduce-min" if args.exchange == "p2p"
+                                    else "NCCL send/recv + allreduce-min") if world > 1 else "none (1 GPU)",
                        "committed_per_step": committed_per_step, "rounds_per_step": rounds_total // args.steps,
                        "l2": "inputs larger than L2 (event pool + tables > 600 MB per GPU); no flush between steps",
                        "rollbacks": last.rollbacks, "antis": last.antis_sent},

@@ -17,7 +17,8 @@
 // SCALESIM_B200_RANK / SCALESIM_B200_WORLD set and SCALESIM_B200_COMM_FILE pointing to a file they can all reach
 // (rank 0 writes the NCCL unique id there); CUDA device = SCALESIM_B200_DEVICE or the rank.
 // Tunables: SCALESIM_B200_BUCKET (ticks), SCALESIM_B200_WINDOW (buckets), SCALESIM_B200_MAX_EVENTS,
-// SCALESIM_B200_MAX_BATCH, SCALESIM_B200_QUIET=1 (digest instead of result lines).
+// SCALESIM_B200_MAX_BATCH, SCALESIM_B200_QUIET=1 (digest instead of result lines), SCALESIM_B200_P2P=0 (exchange by
+// ncclSend/ncclRecv instead of peer-memory writes).
 #ifndef SCALESIM_B200_SIMULATION_RUNNER_HPP_
 #define SCALESIM_B200_SIMULATION_RUNNER_HPP_
 
@@ -111,6 +112,26 @@ void runner<App>::comm_init() {
   }
   int rc = ssb_comm_init(engine_, id);
   if (rc) fail("ssb_comm_init", rc);
+  if (env_long("SCALESIM_B200_P2P", 1) == 0) return;   // 0: events travel by ncclSend/ncclRecv
+  // peer-memory exchange: swap the CUDA IPC handles of the engines' mailboxes through files next to the id file
+  char mine[64];
+  if ((rc = ssb_comm_export(engine_, mine))) fail("ssb_comm_export", rc);
+  {
+    std::string f = std::string(path) + ".h" + std::to_string(rank_), tmp = f + ".tmp";
+    { std::ofstream o(tmp.c_str(), std::ios::binary); o.write(mine, 64); }
+    std::rename(tmp.c_str(), f.c_str());
+  }
+  std::vector<char> all((size_t)world_ * 64);
+  for (int r = 0; r < world_; ++r) {
+    std::string f = std::string(path) + ".h" + std::to_string(r);
+    for (int tries = 0;; ++tries) {
+      std::ifstream in(f.c_str(), std::ios::binary);
+      if (in && in.read(&all[(size_t)r * 64], 64) && in.gcount() == 64) break;
+      if (tries > 600) { LOG(ERROR) << "timed out waiting for " << f; std::exit(1); }
+      std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+  }
+  if ((rc = ssb_comm_import(engine_, all.data(), world_))) fail("ssb_comm_import", rc);
 }
 
 template <class App>

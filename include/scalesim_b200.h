@@ -185,6 +185,13 @@ int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_
 /* 128-byte NCCL unique id; created on rank 0 and distributed by the caller (torch.distributed, MPI, files, ...) */
 int ssb_comm_unique_id(void* id128);
 int ssb_comm_init(ssb_engine* e, const void* id128);
+/* Optional, after ssb_comm_init: exchange events through peer memory over NVLink instead of ncclSend/ncclRecv.
+ * Every engine exports a 64-byte CUDA IPC handle of its mailbox; the caller gathers the handles of all ranks (rank
+ * order) and hands the world x 64 bytes to every engine. The emit kernel then appends cross-partition events straight
+ * into the destination GPU's mailbox, and the per-round GVT all-reduce doubles as the barrier — no count exchange,
+ * no host synchronisation per window. All ranks must make the same choice. */
+int ssb_comm_export(ssb_engine* e, void* handle64);
+int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world);
 
 /* ---- host helpers of the PHOLD app mirror (no device work) ---- */
 /* phold.hpp:144-164: the two 10M-entry tables, libstdc++ default_random_engine streams */

@@ -147,6 +147,8 @@ def load_library() -> C.CDLL:
     lib.ssb_kernel_times.argtypes = [vp, vp, vp, vp, i32]
     lib.ssb_comm_unique_id.argtypes = [vp]
     lib.ssb_comm_init.argtypes = [vp, vp]
+    lib.ssb_comm_export.argtypes = [vp, vp]
+    lib.ssb_comm_import.argtypes = [vp, vp, C.c_int32]
     lib.ssb_phold_build_tables.argtypes = [i64, C.c_double, C.c_double, i64, vp, vp]
     lib.ssb_phold_init_events.argtypes = [i64, i64, vp, i64, i64, i64, vp, i64]
     lib.ssb_phold_init_events.restype = i64
@@ -314,6 +316,16 @@ class Engine:
     def comm_init(self, unique_id: bytes):
         assert len(unique_id) == 128
         self._check(self._lib.ssb_comm_init(self._h, C.c_char_p(unique_id)))
+
+    def comm_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this engine's mailbox (peer-memory exchange)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.ssb_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_import(self, handles: bytes):
+        world = len(handles) // 64
+        self._check(self._lib.ssb_comm_import(self._h, C.c_char_p(handles), world))
 
 
 # ---------------------------------------------------------------------------------------

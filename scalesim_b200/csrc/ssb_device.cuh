@@ -79,6 +79,7 @@ struct Ctl {
   u32 round, load_count;
   u32 send_count[MAX_WORLD];
   u32 recv_count[MAX_WORLD];
+  u64 sent_min;       // peer-memory exchange: smallest bucket-start key of the events written to peers this round
   // statistics
   u64 n_processed, n_rollbacks, n_undone, n_antis, n_annihilated, n_dups, n_committed, n_beyond, n_remote;
   u64 log_count, log_dropped;
@@ -129,6 +130,14 @@ struct View {
   uint4* commit;       // [nb] {bucket, count, off, 0}
   Ev* sendbuf;         // [world * cap_send]
   Ev* recvbuf;         // [world * cap_send]
+  // peer-memory exchange (NVLink P2P): every partition owns a mailbox = [2 parities][world sources] x {count, records}.
+  // A sender appends straight into its region of the destination's mailbox (system-scope atomic on the count, then
+  // plain stores over NVLink); the GVT all-reduce of the next round is the barrier that makes the appends visible.
+  u32 p2p;                       // 0 = NCCL send/recv exchange, 1 = peer-memory exchange
+  Ev* mbox_data;                 // own mailbox records [2][world][cap_send]
+  u32* mbox_cnt;                 // own mailbox counts  [2][world] (one 128-byte line each)
+  Ev* peer_data[MAX_WORLD];      // peers' mailboxes (mapped with CUDA IPC)
+  u32* peer_cnt[MAX_WORLD];
   Ev* log;             // [cap_log] committed records
   u32* snap;           // [cap_snap * state_words]
   Ctl* ctl;

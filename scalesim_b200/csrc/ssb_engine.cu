@@ -88,6 +88,10 @@ struct ssb_engine {
   long long rounds = 0;
   // comm
   Nccl::Comm comm = nullptr;
+  void* mbox_block = nullptr;              // own mailbox (exported with CUDA IPC)
+  std::vector<void*> peer_blocks;          // peers' mailboxes, opened with CUDA IPC
+  size_t mbox_cnt_bytes() const { return (size_t)2 * cfg.world * 128; }
+  size_t mbox_bytes() const { return mbox_cnt_bytes() + (size_t)2 * cfg.world * v.cap_send * sizeof(Ev); }
   // initial states (for ssb_reset)
   u32* d_state0 = nullptr;
   // kernel timing
@@ -209,7 +213,7 @@ int ssb_engine::init() {
   v.cap_batch = (u32)cfg.max_batch;
   v.cap_aux = std::max<u32>(1024, v.cap_batch / 4);
   v.cap_snap = (u32)std::max<int64_t>(cfg.max_snapshots, 1024);
-  v.cap_send = cfg.world > 1 ? v.cap_batch : 1;
+  v.cap_send = cfg.world > 1 ? std::max<u32>(v.cap_batch / 4, 1u << 16) : 1;
   v.cap_log = (u64)cfg.max_committed;
   v.state_words = (u32)state_words();
 
@@ -383,7 +387,7 @@ void ssb_engine::launch_fixup(bool heavy) {
 
 // counts all-to-all, then payload all-to-all (grouped ncclSend/ncclRecv), then integrate what arrived
 int ssb_engine::exchange() {
-  if (cfg.world <= 1) return SSB_OK;
+  if (cfg.world <= 1 || v.p2p) return SSB_OK;      // peer-memory exchange: the receive side runs at the next round's start
   if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
   Nccl& n = g_nccl;
   int rc;
@@ -422,6 +426,13 @@ int ssb_engine::enqueue_round() {
     t_end();
     int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
     if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
+    if (v.p2p) {
+      // every peer's emit kernel of the previous round finished before that peer joined the all-reduce, so what they
+      // appended to this GPU's mailbox is complete: integrate it (anti-messages first) before planning the window
+      for (int pass = 1; pass <= 2; ++pass)
+        for (int r = 0; r < cfg.world; ++r)
+          if (r != cfg.rank) launch_route(2, (u32)r, (u32)pass);
+    }
   }
   t_begin(K_PLAN);
   k_plan<<<1, 1024, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
@@ -470,6 +481,8 @@ void ssb_destroy(ssb_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (void* p : e->peer_blocks) if (p) cudaIpcCloseMemHandle(p);
+  if (e->mbox_block) cudaFree(e->mbox_block);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_unpack) cudaFree(e->d_unpack);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
@@ -820,6 +833,50 @@ int ssb_comm_init(ssb_engine* e, const void* id128) {
   std::memcpy(&id, id128, 128);
   int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, id, e->cfg.rank);
   if (rc != 0) { e->set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
+  return SSB_OK;
+}
+
+int ssb_comm_export(ssb_engine* e, void* handle64) {
+  if (!e || !handle64) return SSB_ERR_INVALID;
+  if (e->cfg.world <= 1) { std::memset(handle64, 0, 64); return SSB_OK; }
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!e->mbox_block) {
+    CK(cudaMalloc(&e->mbox_block, e->mbox_bytes()));
+    CK(cudaMemsetAsync(e->mbox_block, 0, e->mbox_cnt_bytes(), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->mbox_block));
+  std::memcpy(handle64, &h, 64);
+  return SSB_OK;
+}
+
+int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
+  if (!e || !handles || world != e->cfg.world) return SSB_ERR_INVALID;
+  if (world <= 1) return SSB_OK;
+  if (!e->mbox_block) { e->set_error("ssb_comm_export must be called first"); return SSB_ERR_INVALID; }
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  e->peer_blocks.assign((size_t)world, nullptr);
+  const size_t cnt_bytes = e->mbox_cnt_bytes();
+  for (int r = 0; r < world; ++r) {
+    void* base = nullptr;
+    if (r == e->cfg.rank) {
+      base = e->mbox_block;
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+      CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      e->peer_blocks[(size_t)r] = base;
+    }
+    e->v.peer_cnt[r] = reinterpret_cast<u32*>(base);
+    e->v.peer_data[r] = reinterpret_cast<Ev*>((char*)base + cnt_bytes);
+  }
+  e->v.mbox_cnt = reinterpret_cast<u32*>(e->mbox_block);
+  e->v.mbox_data = reinterpret_cast<Ev*>((char*)e->mbox_block + cnt_bytes);
+  e->v.p2p = 1;
   return SSB_OK;
 }
 

@@ -78,7 +78,11 @@ __device__ __forceinline__ void block_local_min(const View& v, u64* sm) {
     m = warp_min_u64(m);
     if (threadIdx.x == 0) {
       u64 bm = c->n_beyond ? make_key(v.finish_time, 0) : KEY_MAX;
-      c->local_min = bm < m ? bm : m;
+      m = bm < m ? bm : m;
+      // peer-memory exchange: events this partition wrote into other partitions' mailboxes are in flight until the
+      // receivers integrate them after the all-reduce; the sender accounts for them (the reference folds the
+      // timestamp of every sent message into the sender's local minimum the same way, sender_receiver.hpp:63-67)
+      c->local_min = c->sent_min < m ? c->sent_min : m;
     }
   }
 }
@@ -159,6 +163,12 @@ __global__ void k_plan(View v, int use_global_gvt) {
   c->done = done ? 1u : 0u;
   c->round++;
   for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
+  c->sent_min = KEY_MAX;
+  if (v.p2p) {
+    // the mailbox half that was just integrated (parity of the round that ended) is free again
+    const u32 par = (c->round - 1) & 1u;
+    for (u32 r = 0; r < v.world; ++r) v.mbox_cnt[(par * v.world + r) * 32] = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -855,7 +865,16 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   u32 n0, n1 = 0;        // main count, extra count (extra region starts at cap_batch)
   if (which == 0) { src = v.anti_box; n0 = c->n_anti < v.cap_aux ? c->n_anti : v.cap_aux; }
   else if (which == 1) { src = v.outbox; n0 = c->n_arr; n1 = c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux; }
-  else if (which == 2) { src = v.recvbuf + (size_t)peer * v.cap_send; n0 = c->recv_count[peer]; }
+  else if (which == 2) {
+    if (v.p2p) {
+      const u32 par = c->round & 1u;
+      src = v.mbox_data + ((size_t)par * v.world + peer) * v.cap_send;
+      n0 = v.mbox_cnt[(par * v.world + peer) * 32];
+      if (n0 > v.cap_send) { n0 = v.cap_send; if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&c->error, E_SENDBUF); }
+    } else {
+      src = v.recvbuf + (size_t)peer * v.cap_send; n0 = c->recv_count[peer];
+    }
+  }
   else { src = v.outbox; n0 = c->load_count; }
   const u32 total = n0 + n1;
   if (total == 0) return;
@@ -870,6 +889,9 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   u32* s_ch1 = s_ch0 + nt;                              // [nt] the next chunk, if the range crosses into it
   const u32 chm = (1u << v.ch_log) - 1u;
   const u32 T_NONE = NIL, T_DIRECT = NIL - 1u;
+  __shared__ u64 s_sent_min;
+  if (threadIdx.x == 0) s_sent_min = KEY_MAX;
+  __syncthreads();
   for (u32 tile = blockIdx.x * kRouteTile; tile < total; tile += gridDim.x * kRouteTile) {
     for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) s_cnt[t] = 0;
     __syncthreads();
@@ -935,7 +957,9 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       } else if (t == rs) {
         atomicAdd(&c->n_beyond, (u64)n);
       } else {
-        s_base[t] = atomicAdd(&c->send_count[t - rs - 1], n);
+        const u32 r = t - rs - 1;
+        if (v.p2p) s_base[t] = atomicAdd_system(&v.peer_cnt[r][((c->round & 1u) * v.world + v.rank) * 32], n);
+        else s_base[t] = atomicAdd(&c->send_count[r], n);
         atomicAdd(&c->n_remote, (u64)n);
       }
     }
@@ -988,12 +1012,21 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       } else {
         const u32 r = t - rs - 1;
         const u32 p = s_base[t] + rnk[it];
-        if (p < v.cap_send) store_ev(v.sendbuf + (size_t)r * v.cap_send + p, e);
-        else atomicOr(&c->error, E_SENDBUF);
+        if (p >= v.cap_send) { atomicOr(&c->error, E_SENDBUF); continue; }
+        if (v.p2p) {
+          // straight into the destination GPU's mailbox over NVLink
+          store_ev(v.peer_data[r] + (((size_t)(c->round & 1u) * v.world + v.rank) * v.cap_send + p), e);
+          const u32 tm = key_time(e.key);
+          const u64 k = make_key(tm >= v.finish_time ? v.finish_time : tm / v.bucket_ticks * v.bucket_ticks, 0);
+          if (k < s_sent_min) atomicMin(&s_sent_min, k);
+        } else {
+          store_ev(v.sendbuf + (size_t)r * v.cap_send + p, e);
+        }
       }
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0 && s_sent_min != KEY_MAX) atomicMin(&c->sent_min, s_sent_min);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,14 +8,21 @@ import numpy as np
 from .capi import Engine
 
 
-def init_engine_comm(engine: Engine, rank: int, world: int):
-    """Rank 0 creates the NCCL unique id, everyone receives it and joins the communicator (ssb_comm_init)."""
+def init_engine_comm(engine: Engine, rank: int, world: int, p2p: bool = True):
+    """Rank 0 creates the NCCL unique id, everyone receives it and joins the communicator (ssb_comm_init). With
+    ``p2p`` the engines also swap the CUDA IPC handles of their mailboxes, so cross-partition events are written
+    straight into the destination GPU's memory over NVLink (ssb_comm_export / ssb_comm_import); otherwise they
+    travel by ncclSend/ncclRecv."""
     if world <= 1:
         return
     import torch.distributed as dist
     obj = [Engine.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)
     engine.comm_init(obj[0])
+    if p2p:
+        handles = [None] * world
+        dist.all_gather_object(handles, engine.comm_export())
+        engine.comm_import(b"".join(handles))
 
 
 def combine_digests(digests):

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, q):
+def _worker(rank, world, port, case, q, p2p=True):
     import torch.distributed as dist
     from scalesim_b200 import phold, traffic
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -35,7 +35,7 @@ def _worker(rank, world, port, case, q):
             sc = traffic.synthetic_grid(32, 32, 20000, seed=1)
             sc.partition = traffic.stripe_partition(32, 32, world)
             eng = traffic.make_engine(sc, bucket_ticks=8, window_buckets=window, rank=rank, world=world, device=rank)
-        ssb.dist.init_engine_comm(eng, rank, world)
+        ssb.dist.init_engine_comm(eng, rank, world, p2p=p2p)
         dist.barrier()
         st = eng.run()
         d = ssb.dist.all_gather_digest(eng.digest(), world)
@@ -45,14 +45,14 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
-def _run(case, world=2):
+def _run(case, world=2, p2p=True):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
@@ -62,10 +62,11 @@ def _run(case, world=2):
     return res
 
 
-@pytest.mark.parametrize("window", [1, 3])
-def test_phold_two_gpus_equals_reference(window):
+@pytest.mark.parametrize("window,p2p", [(1, True), (3, True), (1, False), (3, False)])
+def test_phold_two_gpus_equals_reference(window, p2p):
+    """p2p: events written straight into the peer GPU's mailbox over NVLink; else ncclSend/ncclRecv."""
     g = golden("phold_10000_160000")
-    res = _run(("phold", (10000, 160000, 0.1, 1.0), window))
+    res = _run(("phold", (10000, 160000, 0.1, 1.0), window), p2p=p2p)
     assert all(r[1] == g["digest"] for r in res)
     assert sum(r[2] for r in res) == g["count"]
     assert sum(r[3] for r in res) > 0          # events really crossed partitions
@@ -85,3 +86,27 @@ def test_grid_two_gpus_equals_oracle():
     s.run_closure(4, keep_records=False)
     res = _run(("traffic", None, 2))
     assert all(r[1] == s.digest() for r in res)
+
+
+def test_dropin_binaries_two_processes(tmp_path):
+    """apps/PHOLD as two processes (one per GPU), rendezvous through files: concatenated stdout == the reference's."""
+    import subprocess
+    from fixtures import golden_lines
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "apps", "PHOLD")
+    if not os.path.exists(exe):
+        pytest.skip("apps/PHOLD not built")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, SCALESIM_B200_RANK=str(r), SCALESIM_B200_WORLD="2",
+                   SCALESIM_B200_COMM_FILE=str(tmp_path / "ssb.id"))
+        procs.append(subprocess.Popen([exe, "100", "1600", "0.1", "1.0", "1", "50"], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    lines = []
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        lines += [l for l in out.splitlines() if l.startswith("RE,")]
+    assert sorted(lines) == golden_lines("phold_100_1600")
