@@ -98,15 +98,25 @@ def test_dropin_binaries_two_processes(tmp_path):
         pytest.skip("apps/PHOLD not built")
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    procs = []
+    procs, outs = [], []
     for r in range(2):
         env = dict(os.environ, SCALESIM_B200_RANK=str(r), SCALESIM_B200_WORLD="2",
                    SCALESIM_B200_COMM_FILE=str(tmp_path / "ssb.id"))
-        procs.append(subprocess.Popen([exe, "100", "1600", "0.1", "1.0", "1", "50"], env=env, stdout=subprocess.PIPE,
-                                      stderr=subprocess.PIPE, text=True))
+        # stdout goes to files: with pipes, the process nobody is reading from yet blocks in printf, stops joining
+        # the per-window all-reduce, and both processes hang
+        out = open(tmp_path / f"out.{r}", "w")
+        err = open(tmp_path / f"err.{r}", "w")
+        outs.append((out, err))
+        procs.append(subprocess.Popen([exe, "100", "1600", "0.1", "1.0", "1", "50"], env=env, stdout=out, stderr=err))
     lines = []
-    for p in procs:
-        out, err = p.communicate(timeout=300)
-        assert p.returncode == 0, err[-2000:]
-        lines += [l for l in out.splitlines() if l.startswith("RE,")]
+    for r, p in enumerate(procs):
+        try:
+            p.wait(timeout=120)
+        finally:
+            if p.poll() is None:
+                p.kill()
+        for f in outs[r]:
+            f.close()
+        assert p.returncode == 0, open(tmp_path / f"err.{r}").read()[-2000:]
+        lines += [l for l in open(tmp_path / f"out.{r}").read().splitlines() if l.startswith("RE,")]
     assert sorted(lines) == golden_lines("phold_100_1600")
