@@ -32,9 +32,9 @@ METRIC = "committed events/sec, PHOLD 1M LPs"
 UNIT = "events/s"
 B_ALG = 380.0   # algorithmic bytes per committed PHOLD event (SURVEY.md §8d / DESIGN.md §5)
 # per-kernel split of the 380 B
-B_ALG_KERNEL = {"k_exec": 164.0, "k_route": 96.0, "k_commit": 88.0, "k_hist": 12.0, "k_segs": 4.0, "k_scatter": 8.0,
-                "k_sortseg": 4.0, "k_sortheavy": 4.0}
+B_ALG_KERNEL = {"k_exec": 164.0, "k_route": 96.0, "k_commit": 88.0, "k_link": 28.0, "k_sortheavy": 4.0}
 FULL_COMMITTED_1M = 72_823_220
+LAUNCHES_PER_ROUND = 11   # plan, commit, link, segs_heavy, exec, sortheavy, exec_heavy, sortfix, fixup, route(anti), route (+ 1 memset)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -346,7 +346,7 @@ def main():
                        "committed_per_step": committed_per_step, "rounds_per_step": rounds_total // args.steps,
                        "l2": "inputs larger than L2 (event pool + tables > 600 MB per GPU); no flush between steps",
                        "rollbacks": last.rollbacks, "antis": last.antis_sent},
-            "gpu_launches": int(rounds_total * 11),
+            "gpu_launches": int(rounds_total * LAUNCHES_PER_ROUND),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -7,9 +7,10 @@
 //                    Event records are immutable once routed.
 //   * per-slot meta: Meta[max_events] (32 B: processed-chain link, sent-log entry — what set_cancel keeps in the
 //                    reference, queue.hpp:151-157 — and snapshot index) + pflag[max_events] (1 B: processed / dead).
-//   * per-LP       : cnt / lpw {segment start, length, chain head slot, its time} / lpflag / last_slot / last_time /
-//                    state words.
-//   * per-round    : arrival staging, per-LP sorted segments, outboxes.
+//   * per-LP       : lph {arrivals of this round | flags, newest arrival, chain head before the round} (zeroed every
+//                    round), last {chain head slot, its time}, segstart, state words.
+//   * per-round    : link records that chain the arrivals of one LP (16 B per arrival), sorted segments for the
+//                    long or irregular LPs only, outboxes. The event records themselves are never copied.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -70,7 +71,7 @@ struct Ctl {
   u64 beyond_min;     // min key of events dropped because receive_time >= finish_time
   u32 done, error;
   u32 cur_abs, bound_abs, commit_next;
-  u32 n_arr, seg_cursor, n_anti, n_extra, n_heavy, n_fix, n_fixheavy, commit_blocks;
+  u32 n_arr, seg_cursor, n_anti, n_extra, n_heavy, n_vheavy, n_fix, commit_blocks;
   u32 n_gather, n_commit, commit_total;
   u32 free_top, free_low;
   u32 snap_head, snap_tail;
@@ -100,6 +101,7 @@ struct View {
   u32 cap_batch, cap_aux, cap_snap, cap_send;
   u64 cap_log;
   u32 state_words;
+  u32 light_max;          // LPs with up to this many arrivals in a round are handled by list walks (<= kLightMax)
   // event pool
   Ev* ev;
   Meta* meta;
@@ -109,22 +111,18 @@ struct View {
   u32* fill;        // [nb] events appended
   u32* consumed;    // [nb] events already integrated
   // per LP
-  u32* cnt;
-  uint4* lpw;       // this round: {segment start in `sorted`, segment length, chain head slot, its receive_time}
-  u32* lpflag;      // this round: PL_* bits
-  u32* last_slot;
-  u32* last_time;
+  uint4* lph;       // this round (zeroed by a memset at its start): {arrivals (bits 0..27) | PL_* flags (28..31),
+                    //   newest arrival index + 1, chain head slot before the round, its receive_time}
+  uint2* last;      // processed-chain head {slot, receive_time}; slot NIL = nothing processed yet
+  u32* segstart;    // start of the LP's segment in `sorted` (valid for long segments of the current round)
   u32* state;       // [n_lp_local * state_words]
   // per round
-  Ev* tmp_work;        // [cap_batch] work records (event, flags = arrival index | anti << 31), arrival order
-  u32* tmp_lp;         // [cap_batch]
-  u32* tmp_rank;       // [cap_batch]
-  Ev* work;            // [cap_batch] work records grouped by LP (segments)
-  Sorted* sorted;      // [cap_batch] (key, slot, arrival) of a segment, sorted — only for long or irregular segments
-  uint4* fix;          // [cap_batch] LPs that need the sequential turn {lp, seg_start, n, 0}
-  uint4* fixheavy;     // [cap_batch / 16] same, segments that still need a warp-level sort
-  uint4* heavy;        // [cap_batch / 64] LPs with long segments {lp, seg_start, n, 0}
-  Ev* outbox;          // [cap_batch + cap_aux]: main region aligned with `sorted`, then re-execution outputs
+  uint4* link;         // [cap_batch] per arrival {key lo, key hi, previous arrival of the same LP | anti << 31, slot}
+  u32* tmp_rank;       // [cap_batch] rank of the arrival among its LP's arrivals (position in a long segment)
+  Sorted* sorted;      // [cap_batch] (key, slot, arrival) segments, sorted — only for long or irregular LPs
+  u32* fix;            // [cap_batch] LPs that need the sequential turn
+  uint4* heavy;        // [cap_batch / 16] LPs with long segments {lp, seg_start, n, 0}
+  Ev* outbox;          // [cap_batch + cap_aux]: entry i = output of arrival i, then re-execution outputs
   Ev* anti_box;        // [cap_aux] anti-messages of this round
   uint4* gather;       // [window] {bucket, start, count, out_off}
   uint4* commit;       // [nb] {bucket, count, off, 0}
@@ -154,31 +152,38 @@ __device__ __forceinline__ u32 part_local(const View& v, u32 lp) {
   return v.part_mode == 0 ? lp / v.world : v.part_local[lp];
 }
 
+// 32-byte records move as ONE 256-bit access per thread (LDG/STG.256 on sm_100a): a warp touches every DRAM sector
+// once, instead of twice with two 128-bit halves.
+__device__ __forceinline__ void ld256(const void* p, u32 (&x)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+               : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(void* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
 __device__ __forceinline__ Ev load_ev(const Ev* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1];
+  u32 x[8];
+  ld256(p, x);
   Ev e;
-  e.key = ((u64)a.y << 32) | a.x; e.dst = a.z; e.src = a.w;
-  e.send = b.x; e.p0 = b.y; e.p1 = b.z; e.flags = b.w;
+  e.key = ((u64)x[1] << 32) | x[0]; e.dst = x[2]; e.src = x[3];
+  e.send = x[4]; e.p0 = x[5]; e.p1 = x[6]; e.flags = x[7];
   return e;
 }
 __device__ __forceinline__ Meta load_meta(const Meta* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1];
+  u32 x[8];
+  ld256(p, x);
   Meta m;
-  m.link = a.x; m.prevtime = a.y; m.sent_dst = a.z; m.snap = a.w;
-  m.sent_key = ((u64)b.y << 32) | b.x; m.pad0 = 0; m.pad1 = 0;
+  m.link = x[0]; m.prevtime = x[1]; m.sent_dst = x[2]; m.snap = x[3];
+  m.sent_key = ((u64)x[5] << 32) | x[4]; m.pad0 = 0; m.pad1 = 0;
   return m;
 }
 __device__ __forceinline__ void store_meta(Meta* p, const Meta& m) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4(m.link, m.prevtime, m.sent_dst, m.snap);
-  q[1] = make_uint4((u32)m.sent_key, (u32)(m.sent_key >> 32), 0u, 0u);
+  st256(p, m.link, m.prevtime, m.sent_dst, m.snap, (u32)m.sent_key, (u32)(m.sent_key >> 32), 0u, 0u);
 }
 __device__ __forceinline__ void store_ev(Ev* p, const Ev& e) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4((u32)e.key, (u32)(e.key >> 32), e.dst, e.src);
-  q[1] = make_uint4(e.send, e.p0, e.p1, e.flags);
+  st256(p, (u32)e.key, (u32)(e.key >> 32), e.dst, e.src, e.send, e.p0, e.p1, e.flags);
 }
 
 // slot of position p in bucket b; the chunk must already exist

@@ -3,6 +3,7 @@
 // There is no CPU fallback: every entry point that does work needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -95,7 +96,7 @@ struct ssb_engine {
   // initial states (for ssb_reset)
   u32* d_state0 = nullptr;
   // kernel timing
-  enum { K_MIN, K_PLAN, K_COMMIT, K_HIST, K_SEGS, K_SCATTER, K_SORTHEAVY, K_EXEC, K_FIXUP, K_FIXUP_HEAVY, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
+  enum { K_MIN, K_PLAN, K_COMMIT, K_LINK, K_SEGS_HEAVY, K_EXEC, K_SORTHEAVY, K_EXEC_HEAVY, K_SORTFIX, K_FIXUP, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
   struct Timed { int id; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -123,8 +124,9 @@ struct ssb_engine {
     timed.clear();
   }
   int reset_sim();
-  static size_t heavy_smem() { return (size_t)kHeavyWarps * kHeavyCap * sizeof(Sorted); }
-  void launch_fixup(bool heavy);
+  static size_t heavy_smem() { return (size_t)kBlockSortCap * sizeof(Sorted); }
+  void launch_fixup();
+  void launch_exec_heavy();
 
   void set_error(const std::string& s) { error = s; }
 
@@ -216,6 +218,8 @@ int ssb_engine::init() {
   v.cap_send = cfg.world > 1 ? std::max<u32>(v.cap_batch / 4, 1u << 16) : 1;
   v.cap_log = (u64)cfg.max_committed;
   v.state_words = (u32)state_words();
+  v.light_max = 8;
+  if (const char* lm = getenv("SSB_LIGHT_MAX")) { int x = atoi(lm); if (x >= 1 && x <= (int)kLightMax) v.light_max = (u32)x; }
 
   const size_t n_slots = (size_t)n_chunks << v.ch_log;
   int rc;
@@ -226,20 +230,15 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.free_stack, n_chunks))) return rc;
   if ((rc = alloc(&v.fill, v.nb))) return rc;
   if ((rc = alloc(&v.consumed, v.nb))) return rc;
-  if ((rc = alloc(&v.cnt, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.lpw, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.lpflag, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.last_slot, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.last_time, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.lph, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.last, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.segstart, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.state, (size_t)v.n_lp_local * v.state_words))) return rc;
-  if ((rc = alloc(&v.tmp_work, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.work, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.tmp_lp, v.cap_batch))) return rc;
+  if ((rc = alloc(&v.link, v.cap_batch))) return rc;
   if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
   if ((rc = alloc(&v.sorted, v.cap_batch))) return rc;
   if ((rc = alloc(&v.fix, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.fixheavy, v.cap_batch / 16 + 64))) return rc;
-  if ((rc = alloc(&v.heavy, v.cap_batch / 64 + 64))) return rc;
+  if ((rc = alloc(&v.heavy, v.cap_batch / 16 + 64))) return rc;
   if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
   if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
   if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1)))) return rc;
@@ -259,9 +258,6 @@ int ssb_engine::init() {
   route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
   CK(cudaFuncSetAttribute(k_sortheavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
-  CK(cudaFuncSetAttribute(k_fixup_heavy<PholdModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
-  CK(cudaFuncSetAttribute(k_fixup_heavy<PholdStatefulModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
-  CK(cudaFuncSetAttribute(k_fixup_heavy<TrafficModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   return SSB_OK;
@@ -280,9 +276,7 @@ int ssb_engine::reset_sim() {
   if ((rc = fill32(v.chunk_tab, NIL, (size_t)v.nb * v.maxc))) return rc;
   CK(cudaMemsetAsync(v.fill, 0, sizeof(u32) * v.nb, stream));
   CK(cudaMemsetAsync(v.consumed, 0, sizeof(u32) * v.nb, stream));
-  CK(cudaMemsetAsync(v.cnt, 0, sizeof(u32) * v.n_lp_local, stream));
-  if ((rc = fill32(v.last_slot, NIL, v.n_lp_local))) return rc;
-  CK(cudaMemsetAsync(v.last_time, 0, sizeof(u32) * v.n_lp_local, stream));
+  k_fill_u2<<<grid(v.n_lp_local, 256), 256, 0, stream>>>(v.last, make_uint2(NIL, 0u), v.n_lp_local);
   CK(cudaMemcpyAsync(v.state, d_state0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, cudaMemcpyDeviceToDevice, stream));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
@@ -366,17 +360,16 @@ void ssb_engine::launch_exec() {
   }
 }
 
-void ssb_engine::launch_fixup(bool heavy) {
-  if (heavy) {
-    const int g = n_sm * 3, t = kHeavyWarps * 32;
-    const size_t sm = heavy_smem();
-    switch (cfg.model) {
-      case SSB_MODEL_PHOLD: k_fixup_heavy<PholdModel><<<g, t, sm, stream>>>(v, phold_data()); break;
-      case SSB_MODEL_PHOLD_STATEFUL: k_fixup_heavy<PholdStatefulModel><<<g, t, sm, stream>>>(v, phold_data()); break;
-      case SSB_MODEL_TRAFFIC: k_fixup_heavy<TrafficModel><<<g, t, sm, stream>>>(v, traffic_data()); break;
-    }
-    return;
+void ssb_engine::launch_exec_heavy() {
+  const int g = n_sm * 8;
+  switch (cfg.model) {
+    case SSB_MODEL_PHOLD: k_exec_heavy<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_PHOLD_STATEFUL: k_exec_heavy<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
+    case SSB_MODEL_TRAFFIC: k_exec_heavy<TrafficModel><<<g, 256, 0, stream>>>(v, traffic_data()); break;
   }
+}
+
+void ssb_engine::launch_fixup() {
   const int g = n_sm * 8;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_fixup<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
@@ -437,30 +430,31 @@ int ssb_engine::enqueue_round() {
   t_begin(K_PLAN);
   k_plan<<<1, 1024, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
   t_end();
+  CK(cudaMemsetAsync(v.lph, 0, sizeof(uint4) * (size_t)v.n_lp_local, stream));   // per-LP round words
   t_begin(K_COMMIT);
   launch_commit();
   t_end();
   const int g = n_sm * 8;
-  t_begin(K_HIST);
-  k_hist<<<g, 256, 0, stream>>>(v);
+  t_begin(K_LINK);
+  k_link<<<g, 256, 0, stream>>>(v);
   t_end();
-  t_begin(K_SEGS);
-  k_segs<<<g, 256, 0, stream>>>(v);
-  t_end();
-  t_begin(K_SCATTER);
-  k_scatter<<<g, 256, 0, stream>>>(v);
-  t_end();
-  t_begin(K_SORTHEAVY);
-  k_sortheavy<<<n_sm * 3, kHeavyWarps * 32, heavy_smem(), stream>>>(v);
+  t_begin(K_SEGS_HEAVY);
+  k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
   t_end();
   t_begin(K_EXEC);
   launch_exec();
   t_end();
-  t_begin(K_FIXUP);
-  launch_fixup(false);
+  t_begin(K_SORTHEAVY);
+  k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(v, 0);
   t_end();
-  t_begin(K_FIXUP_HEAVY);
-  launch_fixup(true);
+  t_begin(K_EXEC_HEAVY);
+  launch_exec_heavy();
+  t_end();
+  t_begin(K_SORTFIX);
+  k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(v, 1);
+  t_end();
+  t_begin(K_FIXUP);
+  launch_fixup();
   t_end();
   launch_route(0, 0, 0);
   launch_route(1, 0, 0);
@@ -505,7 +499,7 @@ int ssb_create(const ssb_config* cfg, ssb_engine** out) {
   if (cfg->finish_time < 1 || cfg->finish_time >= 0x7FFFFFFFll) return bad("finish_time out of range (must be < 2^31)");
   if (cfg->bucket_ticks < 1 || cfg->window_buckets < 1) return bad("bucket_ticks and window_buckets must be >= 1");
   if (cfg->max_events < 1 || cfg->max_events > 0xF0000000ll) return bad("max_events out of range");
-  if (cfg->max_batch < 1 || cfg->max_batch > 0x7FFFFFFFll) return bad("max_batch out of range");
+  if (cfg->max_batch < 1 || cfg->max_batch >= (1ll << 28)) return bad("max_batch out of range (must be < 2^28)");
   if (cfg->max_committed < 0) return bad("max_committed out of range");
   ssb_engine* e = new ssb_engine();
   e->cfg = *cfg;
@@ -545,14 +539,12 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
     // per-LP arrays were sized for the modulo partition: grow them
     auto& v = e->v;
     auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
-    if (regrow(&v.cnt, mine) || regrow((u32**)&v.lpw, (size_t)mine * 4) || regrow(&v.lpflag, mine) || regrow(&v.last_slot, mine) || regrow(&v.last_time, mine) ||
+    if (regrow((u32**)&v.lph, (size_t)mine * 4) || regrow((u32**)&v.last, (size_t)mine * 2) || regrow(&v.segstart, mine) ||
         regrow(&v.state, (size_t)mine * v.state_words) || regrow(&e->d_state0, (size_t)mine * v.state_words)) {
       e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA;
     }
     cudaMemsetAsync(e->d_state0, 0, sizeof(u32) * (size_t)mine * v.state_words, e->stream);
-    cudaMemsetAsync(v.cnt, 0, sizeof(u32) * mine, e->stream);
-    e->fill32(v.last_slot, NIL, mine);
-    cudaMemsetAsync(v.last_time, 0, sizeof(u32) * mine, e->stream);
+    k_fill_u2<<<e->grid(mine, 256), 256, 0, e->stream>>>(v.last, make_uint2(NIL, 0u), mine);
     cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)mine * v.state_words, e->stream);
   }
   e->v.n_lp_local = mine;
@@ -799,8 +791,8 @@ int ssb_set_flags(ssb_engine* e, int32_t flags) {
 
 int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap) {
   if (!e || !names || !total_ms || !launches) return 0;
-  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_hist", "k_segs", "k_scatter",
-                                                    "k_sortheavy", "k_exec", "k_fixup", "k_fixup_heavy",
+  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_link", "k_segs_heavy", "k_exec",
+                                                    "k_sortheavy", "k_exec_heavy", "k_sortfix", "k_fixup",
                                                     "k_route(anti)", "k_route", "k_route(recv)"};
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);

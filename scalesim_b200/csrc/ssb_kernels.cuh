@@ -5,13 +5,14 @@
 //               window bounds, gather list, commit list
 //   k_commit    stream-compaction of every bucket that fell below GVT into the committed log + digest; the last
 //               block to finish does the fossil collection (chunks back to the pool)
-//   k_hist      arrivals of the window: per-LP histogram (rank inside the LP's segment)
-//   k_segs      per-LP segment allocation (block-aggregated), chain-head note, long-segment list
-//   k_scatter   arrivals -> per-LP segments
-//   k_sortheavy one warp per LP with a long segment: bitonic sort in shared memory
-//   k_exec      one thread per EVENT, in per-LP segment order: place in the LP's key order, handler,
-//               processed-chain link, sent-log, outbox (speculative on the LP state)
-//   k_fixup(+_heavy) the LPs that are not plain (anti-message, duplicate, straggler, state-mutating handler):
+//   k_link      arrivals of the window, in calendar order: count per LP, chain every arrival to the previous
+//               arrival of its LP (atomic exchange on the LP's list head), note the chain head, list the long LPs
+//   k_exec      one thread per EVENT, in calendar order (coalesced): place in the LP's key order by walking the
+//               LP's short arrival list, handler, processed-chain link, sent-log, outbox (speculative on the LP
+//               state); arrivals of long LPs are only dropped into the LP's segment
+//   k_segs_heavy / k_sortheavy / k_exec_heavy   LPs with more than kLightMax arrivals: segment allocation, one warp
+//               per LP bitonic sort in shared memory, execute with the sorted predecessor
+//   k_fixup     the LPs that are not plain (anti-message, duplicate, straggler, state-mutating handler):
 //               annihilate, roll back, re-execute sequentially, emit anti-messages
 //   k_route     outbox -> calendar buckets / per-destination-partition send buffers
 //               (block-aggregated atomics; anti-messages first, then positives)
@@ -27,15 +28,16 @@ constexpr int kRouteThreads = 512;
 constexpr int kRouteItems = 8;
 constexpr int kRouteTile = kRouteThreads * kRouteItems;
 
-// flag bits of lpflag[lp]
+// flag bits of an LP in this round (lph[lp].x >> kCntBits)
 constexpr u32 PL_IRREGULAR = 1u;   // anti-message, duplicate key or possible straggler in the segment
 constexpr u32 PL_MUTATED = 2u;     // a handler invocation changed the LP state
 constexpr u32 PL_SORTED = 4u;      // the segment is sorted by (key, arrival order)
 constexpr u32 PL_FIX = PL_IRREGULAR | PL_MUTATED;
-constexpr u32 kScanMax = 96;       // longer segments are sorted by k_sortheavy instead of scanned per event
-constexpr u32 kLightMax = 16;      // k_fixup sorts segments up to this length in registers/local memory
-constexpr u32 kHeavyCap = 2048;    // entries per warp in the shared-memory bitonic sort
-constexpr int kHeavyWarps = 2;
+constexpr u32 kCntBits = 28;       // lph[lp].x = arrivals of the round (bits 0..27) | PL_* << 28
+constexpr u32 kCntMask = (1u << kCntBits) - 1u;
+constexpr u32 NIL31 = 0x7FFFFFFFu; // end of an LP's arrival list
+constexpr u32 kLightMax = 16;      // upper bound of View::light_max: LPs with more arrivals in a round get a segment
+constexpr u32 kScanCap = 256;      // segments up to this length are scanned per event; longer ones are sorted first
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
@@ -158,8 +160,8 @@ __global__ void k_plan(View v, int use_global_gvt) {
   c->n_anti = 0;
   c->n_extra = 0;
   c->n_heavy = 0;
+  c->n_vheavy = 0;
   c->n_fix = 0;
-  c->n_fixheavy = 0;
   c->done = done ? 1u : 0u;
   c->round++;
   for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
@@ -272,91 +274,8 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_hist — arrivals of this window, in calendar (slot) order. Replaces the inbox append of lp::buffer
-// (logical_process.hpp:115-127): rank = position inside the LP's inbox.
+// calendar slot of the arrival with index i (arrival order = calendar order of the gathered bucket tails)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_hist(View v) {
-  Ctl* c = v.ctl;
-  const u32 n = c->n_arr;
-  const u32 ng = c->n_gather;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    u32 g = 0, hi = ng;            // binary search: last gather entry whose offset is <= i
-    while (hi - g > 1) {
-      u32 mid = (g + hi) >> 1;
-      if (v.gather[mid].w <= i) g = mid; else hi = mid;
-    }
-    uint4 ge = v.gather[g];
-    u32 slot = slot_of(v, ge.x, ge.y + (i - ge.w));
-    Ev e = load_ev(v.ev + slot);
-    u32 lp = part_local(v, e.dst);
-    u32 rank = atomicAdd(&v.cnt[lp], 1u);
-    // work record = the event with `flags` replaced by its arrival index (bit 31 = anti-message); from here to
-    // k_exec the event pool itself is not touched again
-    e.flags = i | ((e.flags & F_CANCEL) ? 0x80000000u : 0u);
-    store_ev(v.tmp_work + i, e);
-    v.tmp_lp[i] = lp;
-    v.tmp_rank[i] = rank;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_segs — one thread per LP: allocate the LP's segment of this round; 256 LPs share one atomic on the cursor
-// (warp scan + block scan). Notes the LP's processed-chain head for this round and lists the long segments.
-// Replaces scheduler::queue/dequeue (process_scheduler.hpp:55-81): "which LPs have work in this window".
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_segs(View v) {
-  Ctl* c = v.ctl;
-  if (c->n_arr == 0) return;
-  __shared__ u32 w_seg[8], b_seg;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (u32 base = blockIdx.x * 256u; base < v.n_lp_local; base += gridDim.x * 256u) {
-    u32 lp = base + threadIdx.x;
-    u32 n = lp < v.n_lp_local ? v.cnt[lp] : 0u;
-    u32 incl = n;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((int)lane >= o) incl += t;
-    }
-    if (lane == 31) w_seg[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      u32 ts = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) { u32 a = w_seg[w]; w_seg[w] = ts; ts += a; }
-      b_seg = ts ? atomicAdd(&c->seg_cursor, ts) : 0u;
-    }
-    __syncthreads();
-    if (n) {
-      const u32 start = b_seg + w_seg[warp] + incl - n;
-      v.lpw[lp] = make_uint4(start, n, v.last_slot[lp], v.last_time[lp]);
-      v.lpflag[lp] = 0;
-      v.cnt[lp] = 0;
-      if (n > kScanMax) v.heavy[atomicAdd(&c->n_heavy, 1u)] = make_uint4(lp, start, n, 0);
-    }
-    __syncthreads();
-  }
-}
-
-// first flagger of an LP puts it on the fix list (light or heavy by segment length)
-__device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 s0, u32 n, u32 bit) {
-  u32 old = atomicOr(&v.lpflag[lp], bit);
-  if ((old & PL_FIX) == 0) {
-    if (n <= kLightMax || (old & PL_SORTED)) v.fix[atomicAdd(&v.ctl->n_fix, 1u)] = make_uint4(lp, s0, n, 0);
-    else v.fixheavy[atomicAdd(&v.ctl->n_fixheavy, 1u)] = make_uint4(lp, s0, n, 0);
-  }
-}
-
-// k_scatter — arrivals -> per-LP segments of work records (arrival order inside a segment).
-__global__ void k_scatter(View v) {
-  const u32 n = v.ctl->n_arr;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const Ev e = load_ev(v.tmp_work + i);
-    store_ev(v.work + v.lpw[v.tmp_lp[i]].x + v.tmp_rank[i], e);
-  }
-}
-
-// calendar slot of the arrival with index i (inverse of k_hist's enumeration)
 __device__ __forceinline__ u32 slot_of_arrival(const View& v, u32 i) {
   u32 g = 0, hi = v.ctl->n_gather;
   while (hi - g > 1) {
@@ -365,6 +284,52 @@ __device__ __forceinline__ u32 slot_of_arrival(const View& v, u32 i) {
   }
   const uint4 ge = v.gather[g];
   return slot_of(v, ge.x, ge.y + (i - ge.w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_link — arrivals of this window, in calendar (slot) order: one coalesced pass over the event records. Replaces
+// the inbox append of lp::buffer (logical_process.hpp:115-127) and scheduler::queue (process_scheduler.hpp:55-81,
+// "which LPs have work"): every arrival is counted on its LP and chained to the LP's previous arrival of the round
+// (atomic exchange on the LP's list head), so that afterwards any arrival can see all arrivals of its LP without
+// the events being moved or sorted. The first arrival of an LP notes the LP's processed-chain head as it was before
+// the round; the arrival that makes the LP's count exceed kLightMax puts the LP on the long-segment list.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_link(View v) {
+  Ctl* c = v.ctl;
+  const u32 n = c->n_arr;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 slot = slot_of_arrival(v, i);
+    const Ev e = load_ev(v.ev + slot);
+    const u32 lp = part_local(v, e.dst);
+    u32* h = reinterpret_cast<u32*>(v.lph + lp);
+    const u32 rank = atomicAdd(h, 1u) & kCntMask;
+    const u32 prev1 = atomicExch(h + 1, i + 1u);
+    const u32 prev = prev1 ? prev1 - 1u : NIL31;
+    v.link[i] = make_uint4((u32)e.key, (u32)(e.key >> 32), prev | ((e.flags & F_CANCEL) ? 0x80000000u : 0u), slot);
+    v.tmp_rank[i] = rank;
+    if (rank == 0) *reinterpret_cast<uint2*>(h + 2) = v.last[lp];
+    if (rank == v.light_max) v.heavy[atomicAdd(&c->n_heavy, 1u)] = make_uint4(lp, 0, 0, 0);
+  }
+}
+
+// k_segs_heavy — the LPs with more than kLightMax arrivals get a segment of `sorted` (one atomic each).
+__global__ void k_segs_heavy(View v) {
+  Ctl* c = v.ctl;
+  const u32 nh = c->n_heavy;
+  for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
+    const u32 lp = v.heavy[h].x;
+    const u32 n = v.lph[lp].x & kCntMask;
+    const u32 start = atomicAdd(&c->seg_cursor, n);
+    v.segstart[lp] = start;
+    v.heavy[h] = make_uint4(lp, start, n, 0);
+    if (n > kScanCap) atomicAdd(&c->n_vheavy, 1u);
+  }
+}
+
+// first flagger of an LP puts it on the fix list
+__device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 bit) {
+  const u32 old = atomicOr(reinterpret_cast<u32*>(v.lph + lp), bit << kCntBits);
+  if (((old >> kCntBits) & PL_FIX) == 0) v.fix[atomicAdd(&v.ctl->n_fix, 1u)] = lp;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,6 +344,15 @@ __device__ __forceinline__ u32 slot_of_arrival(const View& v, u32 i) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool sorted_less(const Sorted& a, const Sorted& b) {
   return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
+}
+__device__ __forceinline__ Sorted load_sorted(const Sorted* p) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  Sorted x;
+  x.key = ((u64)q.y << 32) | q.x; x.slot = q.z; x.seq = q.w;
+  return x;
+}
+__device__ __forceinline__ void store_sorted(Sorted* p, const Sorted& x) {
+  *reinterpret_cast<uint4*>(p) = make_uint4((u32)x.key, (u32)(x.key >> 32), x.slot, x.seq);
 }
 
 template <class M>
@@ -452,12 +426,11 @@ struct Turn {
     return v.cap_batch + pos;
   }
 
-  // old_slot/old_time = the LP's chain head before this round. The LP's arrivals own the outbox entries
-  // [s0, s0+n) — one each — so whatever k_exec may already have written there for this LP is overwritten here.
-  __device__ void run(u32 lp, u32 s0, u32 n, u32 old_slot, u32 old_time) {
+  // seg[0..n) = the LP's arrivals of this round, sorted; old_slot/old_time = the LP's chain head before the round.
+  // Arrival i owns outbox entry i, so whatever k_exec may already have written for this LP is overwritten here.
+  __device__ void run(u32 lp, const Sorted* seg, u32 n, u32 old_slot, u32 old_time) {
     err = 0; n_proc = n_undone = n_anti = n_annih = n_dup = 0;
     st_dirty = false;
-    const Sorted* seg = v.sorted + s0;
     last_slot = old_slot;
     last_time = old_time;
 #pragma unroll
@@ -507,8 +480,8 @@ struct Turn {
         U = v.meta[present].link;
       }
       while (ia < n && seg[ia].key == k) {
-        const Sorted a = seg[ia];
-        const u32 my_out = s0 + ia;
+        const Sorted a = load_sorted(seg + ia);
+        const u32 my_out = a.seq & 0x7FFFFFFFu;
         if (a.seq & 0x80000000u) {
           v.pflag[a.slot] = P_DEAD;                     // the anti-message itself is consumed
           v.outbox[my_out].key = KEY_MAX;
@@ -534,8 +507,7 @@ struct Turn {
       }
     }
 
-    v.last_slot[lp] = last_slot;
-    v.last_time[lp] = last_time;
+    v.last[lp] = make_uint2(last_slot, last_time);
     if (st_dirty) {
 #pragma unroll
       for (int w = 0; w < M::kStateWords; ++w) v.state[(size_t)lp * M::kStateWords + w] = st[w];
@@ -544,206 +516,380 @@ struct Turn {
 };
 
 // ------------------------------------------------------------------------------------------------
-// warp-cooperative sort of one segment by (key, arrival order): bitonic network in shared memory (n <= kHeavyCap),
-// else one lane sorts in place. Returns true (warp-uniform) if the segment holds an anti-message or a duplicate key.
+// exec_one — the plain case of an LP turn for ONE event: run the handler on the LP's current state, link the event
+// into the LP's processed chain behind its predecessor in key order, record the sent-log entry, write the produced
+// event to outbox entry i. This is the speculative form of runner::run_lp_aggr (runner.hpp:530-570): all events of
+// an LP are executed against the same state, which is exactly the sequential result as long as no invocation changes
+// the state (neither shipped application ever does). The moment one does, the LP is flagged and k_fixup re-executes
+// its whole turn sequentially — handlers that mutate state keep exact semantics.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Sorted sorted_from_work(const View& v, const Ev* wk) {
-  Sorted x;
-  x.key = wk->key;
-  x.seq = wk->flags;
-  x.slot = slot_of_arrival(v, x.seq & 0x7FFFFFFFu);
-  return x;
-}
-
-// builds sorted[s0 .. s0+n) = (key, slot, arrival) of work[s0 .. s0+n), sorted
-__device__ __forceinline__ bool warp_sort_segment(const View& v, u32 s0, u32 n, Sorted* buf, u32 lane) {
-  u32 flag = 0;
-  Sorted* seg = v.sorted + s0;
-  if (n <= kHeavyCap) {
-    u32 P = 1;
-    while (P < n) P <<= 1;
-    for (u32 i = lane; i < P; i += 32) {
-      Sorted x;
-      if (i < n) x = sorted_from_work(v, v.work + s0 + i); else { x.key = KEY_MAX; x.slot = NIL; x.seq = 0x7FFFFFFFu; }
-      buf[i] = x;
-    }
-    __syncwarp();
-    for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
-      for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-        for (u32 i = lane; i < P; i += 32) {
-          u32 ixj = i ^ j2;
-          if (ixj > i) {
-            Sorted x = buf[i], y = buf[ixj];
-            bool asc = (i & k2) == 0;
-            if (sorted_less(y, x) == asc) { buf[i] = y; buf[ixj] = x; }
-          }
-        }
-        __syncwarp();
-      }
-    }
-    for (u32 i = lane; i < n; i += 32) {
-      Sorted x = buf[i];
-      seg[i] = x;
-      flag |= x.seq >> 31;
-      if (i && buf[i - 1].key == x.key) flag = 1;
-    }
+template <class M>
+__device__ __forceinline__ void exec_one(const View& v, const typename M::Data& md, u32 i, u32 slot, Ev e, u32 lp,
+                                         u32 pred_slot, u32 pred_time, bool is_last, u32& err) {
+  e.flags = 0;
+  u32 st[M::kStateWords], pre[M::kStateWords];
+#pragma unroll
+  for (int q = 0; q < M::kStateWords; ++q) { st[q] = v.state[(size_t)lp * M::kStateWords + q]; pre[q] = st[q]; }
+  Ev out;
+  const bool has = M::handle(md, e, st, out, err);
+  bool changed = false;
+#pragma unroll
+  for (int q = 0; q < M::kStateWords; ++q) changed |= (pre[q] != st[q]);
+  if (has && changed) { flag_lp(v, lp, PL_MUTATED); return; }   // state-mutating handler
+  Meta m;
+  m.link = pred_slot;
+  m.prevtime = pred_time;
+  m.sent_dst = NIL;
+  m.snap = NIL;
+  m.sent_key = 0;
+  if (has) {
+    m.sent_dst = out.dst;
+    m.sent_key = out.key;
+    store_ev(v.outbox + i, out);
   } else {
-    for (u32 i = lane; i < n; i += 32) seg[i] = sorted_from_work(v, v.work + s0 + i);
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) {
-      for (u32 i = 1; i < n; ++i) {
-        Sorted x = seg[i];
-        u32 j = i;
-        while (j > 0) {
-          Sorted y = seg[j - 1];
-          if (!sorted_less(x, y)) break;
-          seg[j] = y;
-          --j;
-        }
-        if (j != i) seg[j] = x;
-      }
-    }
-    __threadfence_block();
-    __syncwarp();
-    for (u32 i = lane; i < n; i += 32) {
-      Sorted x = seg[i];
-      flag |= x.seq >> 31;
-      if (i && seg[i - 1].key == x.key) flag = 1;
-    }
+    v.outbox[i].key = KEY_MAX;
   }
-  __syncwarp();
-  return __any_sync(0xffffffffu, flag != 0);
+  store_meta(v.meta + slot, m);
+  v.pflag[slot] = P_PROCESSED;
+  if (is_last) v.last[lp] = make_uint2(slot, key_time(e.key));
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_sortheavy — one warp per LP whose segment is too long for the per-event scan of k_exec (> kScanMax, the hot
-// LPs): sort it (R1) and classify it.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kHeavyWarps * 32) k_sortheavy(View v) {
-  extern __shared__ uint4 smem_heavy[];
-  Ctl* c = v.ctl;
-  const u32 nh = c->n_heavy;
-  if (nh == 0) return;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kHeavyCap;
-  for (u32 h = blockIdx.x * kHeavyWarps + warp; h < nh; h += gridDim.x * kHeavyWarps) {
-    uint4 a = v.heavy[h];
-    const u32 lp = a.x, s0 = a.y, n = a.z;
-    const Sorted* seg = v.sorted + s0;
-    bool irregular = warp_sort_segment(v, s0, n, buf, lane);
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) {
-      const uint4 w = v.lpw[lp];
-      if (w.z != NIL && key_time(seg[0].key) <= w.w) irregular = true;     // possible straggler
-      atomicOr(&v.lpflag[lp], PL_SORTED);
-      if (irregular) flag_lp(v, lp, s0, n, PL_IRREGULAR);
-    }
-    __syncwarp();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_exec — one thread per EVENT of the window, in per-LP segment order over the work records (a coalesced stream;
-// the threads of one segment share its cache lines): find the event's place in its LP's key order (R1), run the
-// handler on the LP's current state, link the event into the LP's processed chain, record the sent-log entry, write
-// the produced event to the outbox. Skew-free: a hot LP's events are spread over many threads.
-//
-// Place in key order: segments up to kScanMax events are scanned by each of their events (all threads of a segment
-// read the same few cache lines): predecessor = largest smaller key, "last" = no larger key. The scan also finds the
-// irregular turns — an anti-message, a duplicate key, or a key not later than the LP's newest processed event
-// (straggler, R5) — which are left to the sequential lp_turn of k_fixup. Longer segments were sorted by k_sortheavy
-// and are searched.
-//
-// This is the speculative form of runner::run_lp_aggr (runner.hpp:530-570): all events of an LP are executed against
-// the same state. That is exactly the sequential result as long as no invocation changes the state (neither shipped
-// application ever does). The moment one does, the LP is flagged and k_fixup re-executes its whole segment
-// sequentially — handlers that mutate state keep exact semantics.
+// k_exec — one thread per EVENT of the window, in calendar (slot) order, so the event read and the meta / pflag /
+// outbox writes are coalesced streams; only the per-LP words are gathered. Skew-free: a hot LP's events are spread
+// over many threads.
+//   * LP with up to kLightMax arrivals: the thread walks the LP's arrival list (link records) to find its place in
+//     the LP's key order (R1): predecessor = largest smaller key, "last" = no larger key. The walk also finds the
+//     irregular turns — an anti-message, a duplicate key, or a key not later than the LP's newest processed event
+//     (straggler, R5) — which are left to the sequential lp_turn of k_fixup.
+//   * LP with more arrivals: the thread only drops (key, slot, arrival) into the LP's segment of `sorted`;
+//     k_sortheavy sorts the segment and k_exec_heavy executes it.
 // ------------------------------------------------------------------------------------------------
 template <class M>
 __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
   Ctl* c = v.ctl;
   const u32 n_arr = c->n_arr;
   u32 err = 0;
-  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n_arr; j += gridDim.x * blockDim.x) {
-    Ev e = load_ev(v.work + j);
-    const u32 seq = e.flags;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_arr; i += gridDim.x * blockDim.x) {
+    const u32 slot = slot_of_arrival(v, i);
+    const Ev e = load_ev(v.ev + slot);
     const u32 lp = part_local(v, e.dst);
-    const uint4 w = v.lpw[lp];
-    const u32 s0 = w.x, n = w.y;
-    const u32 fl = v.lpflag[lp];
-    if (fl & PL_FIX) continue;                          // handled by k_fixup
-    u32 pred_slot = w.z, pred_time = w.w;
+    const uint4 h = v.lph[lp];
+    const u32 n = h.x & kCntMask;
+    if ((h.x >> kCntBits) & PL_FIX) continue;             // handled by k_fixup
+    const u32 anti = (e.flags & F_CANCEL) ? 0x80000000u : 0u;
+    if (n > v.light_max) {
+      Sorted x;
+      x.key = e.key; x.slot = slot; x.seq = i | anti;
+      store_sorted(v.sorted + v.segstart[lp] + v.tmp_rank[i], x);
+      continue;
+    }
+    u32 pred_slot = h.z, pred_time = h.w;
     bool is_last = true;
-    bool bad = (seq >> 31) != 0;
-    if (w.z != NIL && key_time(e.key) <= w.w) bad = true;
-    if (fl & PL_SORTED) {
-      const Sorted* seg = v.sorted + s0;
-      u32 lo = 0, hi = n;                               // position of my key in the sorted segment
-      while (hi - lo > 1) {
-        u32 mid = (lo + hi) >> 1;
-        if (seg[mid].key <= e.key) lo = mid; else hi = mid;
-      }
-      if (lo > 0) { const Sorted sp = seg[lo - 1]; pred_slot = sp.slot; pred_time = key_time(sp.key); }
-      is_last = lo == n - 1;
-    } else if (n > 1) {
+    bool bad = anti != 0 || (h.z != NIL && key_time(e.key) <= h.w);
+    if (n > 1) {
       u64 pk = 0;
-      u32 pseq = 0;
       bool have = false;
-      const Ev* seg = v.work + s0;
-      for (u32 k = 0; k < n; ++k) {
-        if (s0 + k == j) continue;
-        const u64 tk = seg[k].key;
-        if (seg[k].flags >> 31) bad = true;
-        if (tk == e.key) bad = true;
-        else if (tk < e.key) {
-          if (!have || tk > pk) { pk = tk; pseq = seg[k].flags; have = true; }
-        } else {
-          is_last = false;
+      u32 k = h.y - 1u;
+      for (u32 step = 0; step < n && k != NIL31; ++step) {
+        const uint4 L = v.link[k];
+        if (k != i) {
+          const u64 tk = ((u64)L.y << 32) | L.x;
+          if (L.z >> 31) bad = true;
+          if (tk == e.key) bad = true;
+          else if (tk < e.key) {
+            if (!have || tk > pk) { pk = tk; pred_slot = L.w; have = true; }
+          } else {
+            is_last = false;
+          }
         }
+        k = L.z & 0x7FFFFFFFu;
       }
-      if (have && !bad) { pred_slot = slot_of_arrival(v, pseq & 0x7FFFFFFFu); pred_time = key_time(pk); }
+      if (have) pred_time = key_time(pk);
     }
-    if (bad) { flag_lp(v, lp, s0, n, PL_IRREGULAR); continue; }
-    const u32 slot = slot_of_arrival(v, seq);
-    e.flags = 0;
-    u32 st[M::kStateWords], pre[M::kStateWords];
-#pragma unroll
-    for (int q = 0; q < M::kStateWords; ++q) { st[q] = v.state[(size_t)lp * M::kStateWords + q]; pre[q] = st[q]; }
-    Ev out;
-    bool has = M::handle(md, e, st, out, err);
-    bool changed = false;
-#pragma unroll
-    for (int q = 0; q < M::kStateWords; ++q) changed |= (pre[q] != st[q]);
-    if (has && changed) { flag_lp(v, lp, s0, n, PL_MUTATED); continue; }   // state-mutating handler
-    Meta m;
-    m.link = pred_slot;
-    m.prevtime = pred_time;
-    m.sent_dst = NIL;
-    m.snap = NIL;
-    m.sent_key = 0;
-    if (has) {
-      m.sent_dst = out.dst;
-      m.sent_key = out.key;
-      store_ev(v.outbox + j, out);
-    } else {
-      v.outbox[j].key = KEY_MAX;
-    }
-    store_meta(v.meta + slot, m);
-    v.pflag[slot] = P_PROCESSED;
-    if (is_last) { v.last_slot[lp] = slot; v.last_time[lp] = key_time(e.key); }
+    if (bad) { flag_lp(v, lp, PL_IRREGULAR); continue; }
+    exec_one<M>(v, md, i, slot, e, lp, pred_slot, pred_time, is_last, err);
   }
   if (err) atomicOr(&c->error, err);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_fixup / k_fixup_heavy — the LPs whose turn is not plain (anti-message, duplicate, straggler, state-mutating
-// handler): sort the segment if it is not sorted yet, then the exact sequential lp_turn. k_fixup: one thread per LP
-// (short or already sorted segments); k_fixup_heavy: one warp per LP (bitonic sort, then lane 0 runs the turn).
+// k_sortheavy — the LPs with a long segment (the hot LPs): sort it by (key, arrival order) (R1) and classify it:
+// an anti-message, a duplicate key or a possible straggler makes the turn irregular (-> k_fixup).
+//   n <= 32            one warp, one entry per lane, bitonic network over register shuffles
+//   n <= kWarpSortCap  one warp, bitonic network in the warp's slice of shared memory
+//   n <= kBlockSortCap one block, bitonic network in shared memory
+//   longer             one thread sorts in place (not reached by any shipped workload)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fixup_stats(Ctl* c, u32 lane, u64 n_proc, u64 n_redo, u64 n_undone, u64 n_anti,
-                                            u64 n_annih, u64 n_dup, u32 err) {
+constexpr u32 kWarpSortCap = 128;
+constexpr u32 kBlockSortCap = 2048;
+constexpr int kSortThreads = 256;
+
+__device__ __forceinline__ Sorted shfl_xor_sorted(const Sorted& x, int m) {
+  Sorted y;
+  u32 lo = __shfl_xor_sync(0xffffffffu, (u32)x.key, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(x.key >> 32), m);
+  y.key = ((u64)hi << 32) | lo;
+  y.slot = __shfl_xor_sync(0xffffffffu, x.slot, m);
+  y.seq = __shfl_xor_sync(0xffffffffu, x.seq, m);
+  return y;
+}
+
+// after sorting: flag the LP (lane/thread 0 of the group calls this)
+__device__ __forceinline__ void classify_heavy(const View& v, u32 lp, u64 first_key, bool irregular) {
+  const uint4 w = v.lph[lp];
+  if (w.z != NIL && key_time(first_key) <= w.w) irregular = true;     // possible straggler
+  atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
+  if (irregular) flag_lp(v, lp, PL_IRREGULAR);
+}
+
+// work item idx of the sort pass. mode 0 (before k_exec_heavy): the long-segment list, segments longer than kScanCap;
+// mode 1 (before k_fixup): the fix list, long segments that are not sorted yet.
+__device__ __forceinline__ bool sort_item(const View& v, int mode, u32 idx, u32& lp, u32& start, u32& n) {
+  if (mode == 0) {
+    const uint4 a = v.heavy[idx];
+    lp = a.x; start = a.y; n = a.z;
+    return n > kScanCap;
+  }
+  lp = v.fix[idx];
+  const u32 x = v.lph[lp].x;
+  n = x & kCntMask;
+  if (n <= v.light_max || ((x >> kCntBits) & PL_SORTED)) return false;
+  start = v.segstart[lp];
+  return true;
+}
+__device__ __forceinline__ void sort_done(const View& v, int mode, u32 lp, u64 first_key, bool irregular) {
+  if (mode == 0) classify_heavy(v, lp, first_key, irregular);
+  else atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
+  extern __shared__ uint4 smem_heavy[];
+  __shared__ u32 s_flag;
+  Ctl* c = v.ctl;
+  const u32 nh = mode == 0 ? (c->n_vheavy ? c->n_heavy : 0u) : c->n_fix;
+  if (nh == 0) return;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr u32 kWarps = kSortThreads / 32;
+  Sorted* wbuf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kWarpSortCap;
+  const Sorted pad = {KEY_MAX, NIL, 0x7FFFFFFFu};
+  // warp-level
+  for (u32 h = blockIdx.x * kWarps + warp; h < nh; h += gridDim.x * kWarps) {
+    u32 lp, start, n;
+    if (!sort_item(v, mode, h, lp, start, n) || n > kWarpSortCap) continue;
+    Sorted* seg = v.sorted + start;
+    u32 flag = 0;
+    u64 first_key;
+    if (n <= 32) {
+      Sorted x = lane < n ? load_sorted(seg + lane) : pad;
+#pragma unroll
+      for (u32 k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          const Sorted y = shfl_xor_sorted(x, (int)j2);
+          const bool keep_min = ((lane & j2) == 0) == ((lane & k2) == 0);
+          if (keep_min ? sorted_less(y, x) : sorted_less(x, y)) x = y;
+        }
+      }
+      const u32 klo = __shfl_up_sync(0xffffffffu, (u32)x.key, 1), khi = __shfl_up_sync(0xffffffffu, (u32)(x.key >> 32), 1);
+      if (lane < n) {
+        store_sorted(seg + lane, x);
+        flag = x.seq >> 31;
+        if (lane && (((u64)khi << 32) | klo) == x.key) flag = 1;
+      }
+      first_key = ((u64)__shfl_sync(0xffffffffu, (u32)(x.key >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)x.key, 0);
+    } else {
+      u32 P = 64;
+      while (P < n) P <<= 1;
+      for (u32 i = lane; i < P; i += 32) wbuf[i] = i < n ? load_sorted(seg + i) : pad;
+      __syncwarp();
+      for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
+        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          for (u32 i = lane; i < P; i += 32) {
+            const u32 ixj = i ^ j2;
+            if (ixj > i) {
+              const Sorted x = wbuf[i], y = wbuf[ixj];
+              if (sorted_less(y, x) == ((i & k2) == 0)) { wbuf[i] = y; wbuf[ixj] = x; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      for (u32 i = lane; i < n; i += 32) {
+        const Sorted x = wbuf[i];
+        store_sorted(seg + i, x);
+        flag |= x.seq >> 31;
+        if (i && wbuf[i - 1].key == x.key) flag = 1;
+      }
+      first_key = wbuf[0].key;
+      __syncwarp();
+    }
+    const bool irregular = __any_sync(0xffffffffu, flag != 0);
+    if (lane == 0) sort_done(v, mode, lp, first_key, irregular);
+  }
+  // block-level (rare): segments longer than kWarpSortCap
+  __syncthreads();
+  Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy);
+  for (u32 h = blockIdx.x; h < nh; h += gridDim.x) {
+    u32 lp, start, n;
+    if (!sort_item(v, mode, h, lp, start, n) || n <= kWarpSortCap) continue;
+    Sorted* seg = v.sorted + start;
+    if (threadIdx.x == 0) s_flag = 0;
+    if (n <= kBlockSortCap) {
+      u32 P = 256;
+      while (P < n) P <<= 1;
+      for (u32 i = threadIdx.x; i < P; i += kSortThreads) buf[i] = i < n ? load_sorted(seg + i) : pad;
+      __syncthreads();
+      for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
+        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          for (u32 i = threadIdx.x; i < P; i += kSortThreads) {
+            const u32 ixj = i ^ j2;
+            if (ixj > i) {
+              const Sorted x = buf[i], y = buf[ixj];
+              if (sorted_less(y, x) == ((i & k2) == 0)) { buf[i] = y; buf[ixj] = x; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      u32 flag = 0;
+      for (u32 i = threadIdx.x; i < n; i += kSortThreads) {
+        const Sorted x = buf[i];
+        store_sorted(seg + i, x);
+        flag |= x.seq >> 31;
+        if (i && buf[i - 1].key == x.key) flag = 1;
+      }
+      if (flag) s_flag = 1;
+      __syncthreads();
+      if (threadIdx.x == 0) sort_done(v, mode, lp, buf[0].key, s_flag != 0);
+      __syncthreads();
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u32 flag = 0;
+        for (u32 i = 1; i < n; ++i) {
+          Sorted x = seg[i];
+          u32 j = i;
+          while (j > 0) {
+            Sorted y = seg[j - 1];
+            if (!sorted_less(x, y)) break;
+            seg[j] = y;
+            --j;
+          }
+          if (j != i) seg[j] = x;
+        }
+        for (u32 i = 0; i < n; ++i) {
+          flag |= seg[i].seq >> 31;
+          if (i && seg[i - 1].key == seg[i].key) flag = 1;
+        }
+        __threadfence();
+        sort_done(v, mode, lp, seg[0].key, flag != 0);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_exec_heavy — one thread per entry of the long segments (the hot LPs). The threads of a segment scan it together
+// (the same 16-byte entries, broadcast inside a warp): predecessor = largest smaller key, "last" = no larger key,
+// irregular = anti-message / duplicate key / possible straggler. Segments longer than kScanCap were sorted and
+// classified by k_sortheavy: there the predecessor is the entry before.
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(256) k_exec_heavy(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  if (c->n_heavy == 0) return;
+  const u32 total = c->seg_cursor;
+  u32 err = 0;
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+    const Sorted x = load_sorted(v.sorted + j);
+    const Ev e = load_ev(v.ev + x.slot);
+    const u32 lp = part_local(v, e.dst);
+    const uint4 h = v.lph[lp];
+    const u32 fl = h.x >> kCntBits;
+    if (fl & PL_FIX) continue;
+    const u32 start = v.segstart[lp], n = h.x & kCntMask;
+    const u32 pos = j - start;
+    u32 pred_slot = h.z, pred_time = h.w;
+    bool is_last;
+    if (fl & PL_SORTED) {
+      if (pos) { const Sorted p = load_sorted(v.sorted + j - 1); pred_slot = p.slot; pred_time = key_time(p.key); }
+      is_last = pos + 1u == n;
+    } else {
+      bool bad = (x.seq >> 31) != 0 || (h.z != NIL && key_time(x.key) <= h.w);
+      u64 pk = 0;
+      bool have = false;
+      is_last = true;
+      const uint4* seg = reinterpret_cast<const uint4*>(v.sorted + start);
+      for (u32 k = 0; k < n; ++k) {
+        const uint4 q = seg[k];
+        if (k == pos) continue;
+        const u64 tk = ((u64)q.y << 32) | q.x;
+        if (q.w >> 31) bad = true;
+        if (tk == x.key) bad = true;
+        else if (tk < x.key) {
+          if (!have || tk > pk) { pk = tk; pred_slot = q.z; have = true; }
+        } else {
+          is_last = false;
+        }
+      }
+      if (have) pred_time = key_time(pk);
+      if (bad) { flag_lp(v, lp, PL_IRREGULAR); continue; }
+    }
+    exec_one<M>(v, md, x.seq & 0x7FFFFFFFu, x.slot, e, lp, pred_slot, pred_time, is_last, err);
+  }
+  if (err) atomicOr(&c->error, err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fixup — the LPs whose turn is not plain (anti-message, duplicate, straggler, state-mutating handler): one thread
+// per LP runs the exact sequential lp_turn. Long segments were sorted by k_sortheavy; a short one is collected
+// from the LP's arrival list and sorted here.
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_fixup(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  const u32 nf = c->n_fix;
+  if (nf == 0) return;
+  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0, n_redo = 0;
+  u32 err = 0;
+  const u32 lane = threadIdx.x & 31;
+  const u32 nthreads = gridDim.x * blockDim.x;
+  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nf; base += nthreads) {
+    u32 k = base + lane;
+    if (k < nf) {
+      const u32 lp = v.fix[k];
+      const uint4 h = v.lph[lp];
+      const u32 n = h.x & kCntMask;
+      u32 s0;
+      if ((h.x >> kCntBits) & PL_SORTED) {
+        s0 = v.segstart[lp];
+      } else {
+        Sorted loc[kLightMax];
+        u32 m = 0;
+        for (u32 a = h.y - 1u; a != NIL31 && m < kLightMax; ++m) {
+          const uint4 L = v.link[a];
+          loc[m].key = ((u64)L.y << 32) | L.x; loc[m].slot = L.w; loc[m].seq = a | (L.z & 0x80000000u);
+          a = L.z & 0x7FFFFFFFu;
+        }
+        if (m != n) err |= E_INTERNAL;
+        for (u32 q = 1; q < m; ++q) {
+          Sorted x = loc[q];
+          u32 j = q;
+          while (j > 0 && sorted_less(x, loc[j - 1])) { loc[j] = loc[j - 1]; --j; }
+          loc[j] = x;
+        }
+        s0 = atomicAdd(&c->seg_cursor, m);
+        for (u32 q = 0; q < m; ++q) store_sorted(v.sorted + s0 + q, loc[q]);
+      }
+      n_redo += n;
+      Turn<M> t(v, md);
+      t.run(lp, v.sorted + s0, n, h.z, h.w);
+      n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
+      err |= t.err;
+    }
+  }
+  __syncwarp();
   n_proc = warp_sum_u64(n_proc);
   n_redo = warp_sum_u64(n_redo);
   n_undone = warp_sum_u64(n_undone);
@@ -758,74 +904,6 @@ __device__ __forceinline__ void fixup_stats(Ctl* c, u32 lane, u64 n_proc, u64 n_
     if (n_dup) atomicAdd(&c->n_dups, n_dup);
   }
   if (err) atomicOr(&c->error, err);
-}
-
-template <class M>
-__global__ void k_fixup(View v, typename M::Data md) {
-  Ctl* c = v.ctl;
-  const u32 nf = c->n_fix;
-  if (nf == 0) return;
-  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0, n_redo = 0;
-  u32 err = 0;
-  const u32 lane = threadIdx.x & 31;
-  const u32 nthreads = gridDim.x * blockDim.x;
-  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nf; base += nthreads) {
-    u32 k = base + lane;
-    if (k < nf) {
-      const uint4 f = v.fix[k];
-      const u32 lp = f.x, s0 = f.y, n = f.z;
-      const uint4 w = v.lpw[lp];
-      if (!(v.lpflag[lp] & PL_SORTED)) {
-        Sorted* seg = v.sorted + s0;
-        Sorted loc[kLightMax];
-        for (u32 q = 0; q < n; ++q) loc[q] = sorted_from_work(v, v.work + s0 + q);
-        for (u32 q = 1; q < n; ++q) {
-          Sorted x = loc[q];
-          u32 j = q;
-          while (j > 0 && sorted_less(x, loc[j - 1])) { loc[j] = loc[j - 1]; --j; }
-          loc[j] = x;
-        }
-        for (u32 q = 0; q < n; ++q) seg[q] = loc[q];
-      }
-      n_redo += n;
-      Turn<M> t(v, md);
-      t.run(lp, s0, n, w.z, w.w);
-      n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
-      err |= t.err;
-    }
-  }
-  __syncwarp();
-  fixup_stats(c, lane, n_proc, n_redo, n_undone, n_anti, n_annih, n_dup, err);
-}
-
-template <class M>
-__global__ void __launch_bounds__(kHeavyWarps * 32) k_fixup_heavy(View v, typename M::Data md) {
-  extern __shared__ uint4 smem_heavy[];
-  Ctl* c = v.ctl;
-  const u32 nf = c->n_fixheavy;
-  if (nf == 0) return;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kHeavyCap;
-  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0, n_redo = 0;
-  u32 err = 0;
-  for (u32 h = blockIdx.x * kHeavyWarps + warp; h < nf; h += gridDim.x * kHeavyWarps) {
-    const uint4 f = v.fixheavy[h];
-    const u32 lp = f.x, s0 = f.y, n = f.z;
-    warp_sort_segment(v, s0, n, buf, lane);
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) {
-      const uint4 w = v.lpw[lp];
-      n_redo += n;
-      Turn<M> t(v, md);
-      t.run(lp, s0, n, w.z, w.w);
-      n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
-      err |= t.err;
-    }
-    __syncwarp();
-  }
-  __syncwarp();
-  fixup_stats(c, lane, n_proc, n_redo, n_undone, n_anti, n_annih, n_dup, err);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1074,6 +1152,9 @@ __global__ void k_unpack_log(const Ev* log, u64 first, u32 n, long long* out) {
 }
 
 __global__ void k_fill_u32(u32* p, u32 val, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
+}
+__global__ void k_fill_u2(uint2* p, uint2 val, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
 }
 __global__ void k_iota_u32(u32* p, u32 start, size_t n) {
