@@ -8,7 +8,7 @@
 //   * per-slot meta: Meta[max_events] (32 B: processed-chain link, sent-log entry — what set_cancel keeps in the
 //                    reference, queue.hpp:151-157 — and snapshot index) + pflag[max_events] (1 B: processed / dead).
 //   * per-LP       : lph {arrivals of this round | flags, newest arrival, chain head before the round} (zeroed every
-//                    round), last {chain head slot, its time}, segstart, state words.
+//                    round), last {chain head slot, its time}, state words.
 //   * per-round    : link records that chain the arrivals of one LP (16 B per arrival), sorted segments for the
 //                    long or irregular LPs only, outboxes. The event records themselves are never copied.
 #pragma once
@@ -37,6 +37,8 @@ constexpr u32 E_SNAP = 8u;        // snapshot ring overflow
 constexpr u32 E_HORIZON = 16u;    // bucket index beyond the calendar
 constexpr u32 E_SENDBUF = 32u;    // remote send buffer overflow
 constexpr u32 E_INTERNAL = 64u;   // invariant violated
+constexpr u32 E_STALL = 128u;     // GVT did not advance for kStallRounds rounds
+constexpr u32 kStallRounds = 100000u;
 
 // Event record: timestamp order of the reference (util/timestamp.hpp:53-59) is the u64 order of `key`.
 struct __align__(32) Ev {
@@ -71,7 +73,7 @@ struct Ctl {
   u64 beyond_min;     // min key of events dropped because receive_time >= finish_time
   u32 done, error;
   u32 cur_abs, bound_abs, commit_next;
-  u32 n_arr, seg_cursor, n_anti, n_extra, n_heavy, n_vheavy, n_fix, commit_blocks;
+  u32 n_arr, seg_cursor, n_anti, n_extra, n_heavy, n_vheavy, n_fix, commit_blocks, heavy_blocks;
   u32 n_gather, n_commit, commit_total;
   u32 free_top, free_low;
   u32 snap_head, snap_tail;
@@ -80,6 +82,8 @@ struct Ctl {
   u32 round, load_count;
   u32 send_count[MAX_WORLD];
   u32 recv_count[MAX_WORLD];
+  u64 prev_gvt;       // stall detection of the graph's loop
+  u32 stall, pad_stall;
   u64 sent_min;       // peer-memory exchange: smallest bucket-start key of the events written to peers this round
   // statistics
   u64 n_processed, n_rollbacks, n_undone, n_antis, n_annihilated, n_dups, n_committed, n_beyond, n_remote;
@@ -101,6 +105,8 @@ struct View {
   u32 cap_batch, cap_aux, cap_snap, cap_send;
   u64 cap_log;
   u32 state_words;
+  u32 use_graph;          // 1 = the kernels run inside the window-loop graph and drive its conditional nodes
+  cudaGraphConditionalHandle h_loop, h_vheavy, h_fix;
   u32 light_max;          // LPs with up to this many arrivals in a round are handled by list walks (<= kLightMax)
   // event pool
   Ev* ev;
@@ -112,9 +118,8 @@ struct View {
   u32* consumed;    // [nb] events already integrated
   // per LP
   uint4* lph;       // this round (zeroed by a memset at its start): {arrivals (bits 0..27) | PL_* flags (28..31),
-                    //   newest arrival index + 1, chain head slot before the round, its receive_time}
+                    //   newest arrival index + 1 (long LP: start of its segment in `sorted`), chain head slot before the round, its time}
   uint2* last;      // processed-chain head {slot, receive_time}; slot NIL = nothing processed yet
-  u32* segstart;    // start of the LP's segment in `sorted` (valid for long segments of the current round)
   u32* state;       // [n_lp_local * state_words]
   // per round
   uint4* link;         // [cap_batch] per arrival {key lo, key hi, previous arrival of the same LP | anti << 31, slot}

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -125,8 +126,16 @@ struct ssb_engine {
   }
   int reset_sim();
   static size_t heavy_smem() { return (size_t)kBlockSortCap * sizeof(Sorted); }
-  void launch_fixup();
-  void launch_exec_heavy();
+  void launch_fixup(const View& vv);
+  void launch_exec_heavy(const View& vv);
+  // whole window loop as ONE CUDA graph: WHILE(!done) { round }, with IF nodes around the rarely needed kernels
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  View vg;                       // view baked into the graph's kernel nodes (use_graph = 1 + the conditional handles)
+  bool graph_dirty = true;
+  bool graph_enabled = true;
+  int build_graph();
+  void destroy_graph();
 
   void set_error(const std::string& s) { error = s; }
 
@@ -171,9 +180,9 @@ struct ssb_engine {
   int exchange();
   template <class M> void launch_model_kernels_commit(const typename M::Data& md);
   template <class M> void launch_model_kernels_exec(const typename M::Data& md);
-  void launch_commit();
-  void launch_exec();
-  void launch_route(int which, u32 peer, u32 filter);
+  void launch_commit(const View& vv);
+  void launch_exec(const View& vv);
+  void launch_route(const View& vv, int which, u32 peer, u32 filter);
   u32 owner_of(long long lp) const { return h_owner.empty() ? (u32)(lp % cfg.world) : h_owner[(size_t)lp]; }
   u32 local_of(long long lp) const { return h_local.empty() ? (u32)(lp / cfg.world) : h_local[(size_t)lp]; }
 };
@@ -219,6 +228,7 @@ int ssb_engine::init() {
   v.cap_log = (u64)cfg.max_committed;
   v.state_words = (u32)state_words();
   v.light_max = 8;
+  if (getenv("SSB_NO_GRAPH")) graph_enabled = false;
   if (const char* lm = getenv("SSB_LIGHT_MAX")) { int x = atoi(lm); if (x >= 1 && x <= (int)kLightMax) v.light_max = (u32)x; }
 
   const size_t n_slots = (size_t)n_chunks << v.ch_log;
@@ -232,7 +242,6 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.consumed, v.nb))) return rc;
   if ((rc = alloc(&v.lph, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.last, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.segstart, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.state, (size_t)v.n_lp_local * v.state_words))) return rc;
   if ((rc = alloc(&v.link, v.cap_batch))) return rc;
   if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
@@ -266,7 +275,7 @@ int ssb_engine::init() {
 int ssb_engine::reset_sim() {
   Ctl init;
   std::memset(&init, 0, sizeof(init));
-  init.local_min = KEY_MAX; init.gvt = 0;
+  init.local_min = KEY_MAX; init.gvt = 0; init.prev_gvt = KEY_MAX;
   init.free_top = n_chunks - 1; init.free_low = n_chunks - 1;
   CK(cudaStreamSynchronize(stream));
   CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
@@ -305,6 +314,7 @@ int ssb_engine::check_device_error() {
   if (e & E_HORIZON) s += " calendar horizon exceeded";
   if (e & E_SENDBUF) s += " send buffer overflow (raise max_batch)";
   if (e & E_INTERNAL) s += " internal invariant violated";
+  if (e & E_STALL) s += " no GVT progress in 100000 rounds";
   set_error(s);
   if (e & (E_POOL | E_BATCH | E_SNAP | E_SENDBUF)) return SSB_ERR_CAPACITY;
   if (e & E_RANGE) return SSB_ERR_RANGE;
@@ -336,13 +346,13 @@ int ssb_engine::model_ready() {
   return SSB_OK;
 }
 
-void ssb_engine::launch_route(int which, u32 peer, u32 filter) {
+void ssb_engine::launch_route(const View& vv, int which, u32 peer, u32 filter) {
   t_begin(which == 0 ? K_ROUTE_ANTI : (which == 2 ? K_ROUTE_RECV : K_ROUTE));
-  k_route<<<n_sm * 2, kRouteThreads, route_smem, stream>>>(v, which, peer, filter);
+  k_route<<<n_sm * 2, kRouteThreads, route_smem, stream>>>(vv, which, peer, filter);
   t_end();
 }
 
-void ssb_engine::launch_commit() {
+void ssb_engine::launch_commit(const View& v) {
   const int g = n_sm * 8;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_commit<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
@@ -351,7 +361,7 @@ void ssb_engine::launch_commit() {
   }
 }
 
-void ssb_engine::launch_exec() {
+void ssb_engine::launch_exec(const View& v) {
   const int g = n_sm * 8;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_exec<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
@@ -360,7 +370,7 @@ void ssb_engine::launch_exec() {
   }
 }
 
-void ssb_engine::launch_exec_heavy() {
+void ssb_engine::launch_exec_heavy(const View& v) {
   const int g = n_sm * 8;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_exec_heavy<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
@@ -369,7 +379,7 @@ void ssb_engine::launch_exec_heavy() {
   }
 }
 
-void ssb_engine::launch_fixup() {
+void ssb_engine::launch_fixup(const View& v) {
   const int g = n_sm * 8;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_fixup<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
@@ -406,7 +416,7 @@ int ssb_engine::exchange() {
 #undef NC
   for (int pass = 1; pass <= 2; ++pass)
     for (int r = 0; r < cfg.world; ++r)
-      if (r != cfg.rank && h_ctl->recv_count[r]) launch_route(2, (u32)r, (u32)pass);
+      if (r != cfg.rank && h_ctl->recv_count[r]) launch_route(v, 2, (u32)r, (u32)pass);
   CK(cudaGetLastError());
   return SSB_OK;
 }
@@ -424,7 +434,7 @@ int ssb_engine::enqueue_round() {
       // appended to this GPU's mailbox is complete: integrate it (anti-messages first) before planning the window
       for (int pass = 1; pass <= 2; ++pass)
         for (int r = 0; r < cfg.world; ++r)
-          if (r != cfg.rank) launch_route(2, (u32)r, (u32)pass);
+          if (r != cfg.rank) launch_route(v, 2, (u32)r, (u32)pass);
     }
   }
   t_begin(K_PLAN);
@@ -432,7 +442,7 @@ int ssb_engine::enqueue_round() {
   t_end();
   CK(cudaMemsetAsync(v.lph, 0, sizeof(uint4) * (size_t)v.n_lp_local, stream));   // per-LP round words
   t_begin(K_COMMIT);
-  launch_commit();
+  launch_commit(v);
   t_end();
   const int g = n_sm * 8;
   t_begin(K_LINK);
@@ -442,25 +452,110 @@ int ssb_engine::enqueue_round() {
   k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
   t_end();
   t_begin(K_EXEC);
-  launch_exec();
+  launch_exec(v);
   t_end();
   t_begin(K_SORTHEAVY);
   k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(v, 0);
   t_end();
   t_begin(K_EXEC_HEAVY);
-  launch_exec_heavy();
+  launch_exec_heavy(v);
   t_end();
   t_begin(K_SORTFIX);
   k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(v, 1);
   t_end();
   t_begin(K_FIXUP);
-  launch_fixup();
+  launch_fixup(v);
   t_end();
-  launch_route(0, 0, 0);
-  launch_route(1, 0, 0);
+  launch_route(v, 0, 0, 0);
+  launch_route(v, 1, 0, 0);
   CK(cudaGetLastError());
   ++rounds;
   return exchange();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The window loop as one CUDA graph (single partition): a WHILE node whose condition k_plan keeps at "GVT has not
+// reached finish_time and no device error", and inside it one round. The commit pass runs as a parallel branch next
+// to link/exec (they touch disjoint buckets; both join before k_route, which is the only other user of the chunk
+// free stack). The kernels that only irregular turns need sit in IF nodes: k_sortheavy (a segment longer than
+// kScanCap exists) and k_sortheavy(fix) + k_fixup + k_route(anti) (some LP needs the sequential turn); their
+// conditions are set on the device by k_exec and by the last block of k_exec_heavy. The host launches the graph once
+// per ssb_run and is not involved in the loop at all.
+// ------------------------------------------------------------------------------------------------
+void ssb_engine::destroy_graph() {
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+  graph_dirty = true;
+}
+
+int ssb_engine::build_graph() {
+  destroy_graph();
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGraphCreate(&graph, 0));
+  vg = v;
+  vg.use_graph = 1;
+  CK(cudaGraphConditionalHandleCreate(&vg.h_loop, graph, 1, cudaGraphCondAssignDefault));
+  CK(cudaGraphConditionalHandleCreate(&vg.h_vheavy, graph, 0, cudaGraphCondAssignDefault));
+  CK(cudaGraphConditionalHandleCreate(&vg.h_fix, graph, 0, cudaGraphCondAssignDefault));
+  auto add_cond = [&](cudaGraph_t parent, cudaGraphConditionalHandle h, cudaGraphConditionalNodeType type,
+                      const std::vector<cudaGraphNode_t>& deps, cudaGraphNode_t* node, cudaGraph_t* body) -> cudaError_t {
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = h;
+    p.conditional.type = type;
+    p.conditional.size = 1;
+    cudaError_t err = cudaGraphAddNode(node, parent, deps.empty() ? nullptr : deps.data(), deps.size(), &p);
+    if (err == cudaSuccess) *body = p.conditional.phGraph_out[0];
+    return err;
+  };
+  // captures what `fn` enqueues on `stream` into graph `g` behind `deps`; returns the tail nodes
+  auto capture = [&](cudaGraph_t g, const std::vector<cudaGraphNode_t>& deps, std::vector<cudaGraphNode_t>* tail,
+                     const std::function<void()>& fn) -> cudaError_t {
+    cudaError_t err = cudaStreamBeginCaptureToGraph(stream, g, deps.empty() ? nullptr : deps.data(), nullptr, deps.size(),
+                                                    cudaStreamCaptureModeThreadLocal);
+    if (err != cudaSuccess) return err;
+    fn();
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t* d = nullptr;
+    size_t nd = 0;
+    err = cudaStreamGetCaptureInfo(stream, &st, nullptr, nullptr, &d, &nd);
+    if (err == cudaSuccess && tail) tail->assign(d, d + nd);
+    cudaGraph_t out = nullptr;
+    cudaError_t err2 = cudaStreamEndCapture(stream, &out);
+    return err != cudaSuccess ? err : err2;
+  };
+  cudaGraphNode_t n_while, n_if_vheavy, n_if_fix;
+  cudaGraph_t body, b_vheavy, b_fix;
+  CK(add_cond(graph, vg.h_loop, cudaGraphCondTypeWhile, {}, &n_while, &body));
+  const int g8 = n_sm * 8;
+  std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_heavy;
+  CK(capture(body, {}, &t_plan, [&] {
+    cudaMemsetAsync(vg.lph, 0, sizeof(uint4) * (size_t)vg.n_lp_local, stream);
+    k_plan<<<1, 1024, 0, stream>>>(vg, 0);
+  }));
+  CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));
+  CK(capture(body, t_plan, &t_exec, [&] {
+    k_link<<<g8, 256, 0, stream>>>(vg);
+    k_segs_heavy<<<n_sm, 256, 0, stream>>>(vg);
+    launch_exec(vg);
+  }));
+  CK(add_cond(body, vg.h_vheavy, cudaGraphCondTypeIf, t_exec, &n_if_vheavy, &b_vheavy));
+  CK(capture(b_vheavy, {}, nullptr, [&] { k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(vg, 0); }));
+  CK(capture(body, {n_if_vheavy}, &t_heavy, [&] { launch_exec_heavy(vg); }));
+  // k_route(anti) pops chunks off the free stack that the commit pass pushes to: the IF node waits for both branches
+  std::vector<cudaGraphNode_t> join = t_heavy;
+  join.insert(join.end(), t_commit.begin(), t_commit.end());
+  CK(add_cond(body, vg.h_fix, cudaGraphCondTypeIf, join, &n_if_fix, &b_fix));
+  CK(capture(b_fix, {}, nullptr, [&] {
+    k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(vg, 1);
+    launch_fixup(vg);
+    launch_route(vg, 0, 0, 0);
+  }));
+  CK(capture(body, {n_if_fix}, nullptr, [&] { launch_route(vg, 1, 0, 0); }));
+  CK(cudaGetLastError());
+  CK(cudaGraphInstantiate(&graph_exec, graph, 0));
+  graph_dirty = false;
+  return SSB_OK;
 }
 
 // ======================================= C ABI =======================================
@@ -474,6 +569,7 @@ void ssb_destroy(ssb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  e->destroy_graph();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (void* p : e->peer_blocks) if (p) cudaIpcCloseMemHandle(p);
   if (e->mbox_block) cudaFree(e->mbox_block);
@@ -517,6 +613,7 @@ int ssb_create(const ssb_config* cfg, ssb_engine** out) {
 int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
   if (!e) return SSB_ERR_INVALID;
   if (e->partition_set) { e->set_error("partition already set"); return SSB_ERR_INVALID; }
+  e->graph_dirty = true;
   cudaSetDevice(e->cfg.device);
   if (!lp_to_part) { e->partition_set = true; return SSB_OK; }   // default: lp % world
   if (n_lp != e->cfg.n_lp) { e->set_error("partition length != n_lp"); return SSB_ERR_INVALID; }
@@ -539,7 +636,7 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
     // per-LP arrays were sized for the modulo partition: grow them
     auto& v = e->v;
     auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
-    if (regrow((u32**)&v.lph, (size_t)mine * 4) || regrow((u32**)&v.last, (size_t)mine * 2) || regrow(&v.segstart, mine) ||
+    if (regrow((u32**)&v.lph, (size_t)mine * 4) || regrow((u32**)&v.last, (size_t)mine * 2) ||
         regrow(&v.state, (size_t)mine * v.state_words) || regrow(&e->d_state0, (size_t)mine * v.state_words)) {
       e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA;
     }
@@ -562,6 +659,7 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
 
 int ssb_set_model_data(ssb_engine* e, int slot, const void* data, size_t bytes) {
   if (!e || !data) return SSB_ERR_INVALID;
+  e->graph_dirty = true;
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   if (e->cfg.model == SSB_MODEL_PHOLD || e->cfg.model == SSB_MODEL_PHOLD_STATEFUL) {
@@ -634,7 +732,7 @@ int ssb_load_events(ssb_engine* e, const ssb_event* ev, int64_t n) {
     u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
     CK(cudaMemcpyAsync(e->d_stage, ev + done, sizeof(HostEvent) * m, cudaMemcpyHostToDevice, e->stream));
     k_pack<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, e->d_stage, m);
-    e->launch_route(3, 0, 0);
+    e->launch_route(e->v, 3, 0, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));   // the host buffer may be reused by the caller; staging is single-buffered
     done += m;
@@ -661,10 +759,18 @@ int ssb_run(ssb_engine* e, ssb_stats* stats) {
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->model_ready();
   if (rc) return rc;
+  const bool use_graph = e->graph_enabled && e->cfg.world == 1 && !e->timing();
+  if (use_graph && e->graph_dirty && (rc = e->build_graph())) return rc;
   CK(cudaEventRecord(e->ev0, e->stream));
   u64 last_gvt = ~0ull;
   long long stalled = 0;
-  for (;;) {
+  if (use_graph) {
+    CK(cudaGraphLaunch(e->graph_exec, e->stream));
+    if ((rc = e->sync_ctl())) return rc;
+    e->rounds = e->h_ctl->round;
+    if ((rc = e->check_device_error())) return rc;
+    if (!e->h_ctl->done) { e->set_error("window loop ended before GVT reached finish_time"); return SSB_ERR_INVALID; }
+  } else for (;;) {
     for (int i = 0; i < e->cfg.rounds_per_sync; ++i)
       if ((rc = e->enqueue_round())) return rc;
     if ((rc = e->sync_ctl())) return rc;

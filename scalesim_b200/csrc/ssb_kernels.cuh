@@ -166,6 +166,11 @@ __global__ void k_plan(View v, int use_global_gvt) {
   c->round++;
   for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
   c->sent_min = KEY_MAX;
+  if (v.use_graph) {
+    // GVT must keep advancing (every round commits or integrates something): give up instead of spinning forever
+    if (gvt == c->prev_gvt) { if (++c->stall > kStallRounds) atomicOr(&c->error, E_STALL); } else { c->stall = 0; c->prev_gvt = gvt; }
+    cudaGraphSetConditional(v.h_loop, (done || c->error) ? 0u : 1u);
+  }
   if (v.p2p) {
     // the mailbox half that was just integrated (parity of the round that ended) is free again
     const u32 par = (c->round - 1) & 1u;
@@ -320,7 +325,7 @@ __global__ void k_segs_heavy(View v) {
     const u32 lp = v.heavy[h].x;
     const u32 n = v.lph[lp].x & kCntMask;
     const u32 start = atomicAdd(&c->seg_cursor, n);
-    v.segstart[lp] = start;
+    v.lph[lp].y = start;          // the list head is not needed for a long LP: the word now holds its segment start
     v.heavy[h] = make_uint4(lp, start, n, 0);
     if (n > kScanCap) atomicAdd(&c->n_vheavy, 1u);
   }
@@ -570,6 +575,7 @@ __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
   Ctl* c = v.ctl;
   const u32 n_arr = c->n_arr;
   u32 err = 0;
+  if (v.use_graph && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(v.h_vheavy, c->n_vheavy ? 1u : 0u);
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_arr; i += gridDim.x * blockDim.x) {
     const u32 slot = slot_of_arrival(v, i);
     const Ev e = load_ev(v.ev + slot);
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
     if (n > v.light_max) {
       Sorted x;
       x.key = e.key; x.slot = slot; x.seq = i | anti;
-      store_sorted(v.sorted + v.segstart[lp] + v.tmp_rank[i], x);
+      store_sorted(v.sorted + h.y + v.tmp_rank[i], x);
       continue;
     }
     u32 pred_slot = h.z, pred_time = h.w;
@@ -654,7 +660,7 @@ __device__ __forceinline__ bool sort_item(const View& v, int mode, u32 idx, u32&
   const u32 x = v.lph[lp].x;
   n = x & kCntMask;
   if (n <= v.light_max || ((x >> kCntBits) & PL_SORTED)) return false;
-  start = v.segstart[lp];
+  start = v.lph[lp].y;
   return true;
 }
 __device__ __forceinline__ void sort_done(const View& v, int mode, u32 lp, u64 first_key, bool irregular) {
@@ -798,8 +804,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
 template <class M>
 __global__ void __launch_bounds__(256) k_exec_heavy(View v, typename M::Data md) {
   Ctl* c = v.ctl;
-  if (c->n_heavy == 0) return;
-  const u32 total = c->seg_cursor;
+  const u32 total = c->n_heavy ? c->seg_cursor : 0u;
   u32 err = 0;
   for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
     const Sorted x = load_sorted(v.sorted + j);
@@ -808,7 +813,7 @@ __global__ void __launch_bounds__(256) k_exec_heavy(View v, typename M::Data md)
     const uint4 h = v.lph[lp];
     const u32 fl = h.x >> kCntBits;
     if (fl & PL_FIX) continue;
-    const u32 start = v.segstart[lp], n = h.x & kCntMask;
+    const u32 start = h.y, n = h.x & kCntMask;
     const u32 pos = j - start;
     u32 pred_slot = h.z, pred_time = h.w;
     bool is_last;
@@ -839,6 +844,17 @@ __global__ void __launch_bounds__(256) k_exec_heavy(View v, typename M::Data md)
     exec_one<M>(v, md, x.seq & 0x7FFFFFFFu, x.slot, e, lp, pred_slot, pred_time, is_last, err);
   }
   if (err) atomicOr(&c->error, err);
+  if (v.use_graph) {
+    // the last block to finish knows the final fix list: it opens or closes the IF node around k_fixup
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&c->heavy_blocks, 1u) == gridDim.x - 1) {
+        c->heavy_blocks = 0;
+        cudaGraphSetConditional(v.h_fix, *reinterpret_cast<volatile u32*>(&c->n_fix) ? 1u : 0u);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -863,7 +879,7 @@ __global__ void k_fixup(View v, typename M::Data md) {
       const u32 n = h.x & kCntMask;
       u32 s0;
       if ((h.x >> kCntBits) & PL_SORTED) {
-        s0 = v.segstart[lp];
+        s0 = h.y;
       } else {
         Sorted loc[kLightMax];
         u32 m = 0;
