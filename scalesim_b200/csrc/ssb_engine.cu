@@ -72,6 +72,7 @@ struct ssb_engine {
   int n_sm = 148;
   u32 n_chunks = 0;
   size_t route_smem = 0;
+  int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
   std::vector<void*> allocs;
   // partition (host copies)
   std::vector<u32> h_owner, h_local;
@@ -264,8 +265,11 @@ int ssb_engine::init() {
   CK(cudaMemsetAsync(d_state0, 0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, stream));
   if ((rc = reset_sim())) return rc;
   v.route_slots = std::min<u32>(v.nb, 2048);
-  route_smem = (size_t)(v.route_slots + 1 + v.world) * 16;
+  route_smem = (size_t)kRouteTile * sizeof(Ev) + (size_t)(v.route_slots + 1 + v.world) * 16;
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&route_bps, k_route, kRouteThreads, route_smem));
+  if (route_bps < 1) route_bps = 1;
+  if (const char* rb = getenv("SSB_ROUTE_BPS")) { int x = atoi(rb); if (x >= 1 && x <= route_bps) route_bps = x; }
   CK(cudaFuncSetAttribute(k_sortheavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
@@ -348,7 +352,7 @@ int ssb_engine::model_ready() {
 
 void ssb_engine::launch_route(const View& vv, int which, u32 peer, u32 filter) {
   t_begin(which == 0 ? K_ROUTE_ANTI : (which == 2 ? K_ROUTE_RECV : K_ROUTE));
-  k_route<<<n_sm * 2, kRouteThreads, route_smem, stream>>>(vv, which, peer, filter);
+  k_route<<<n_sm * route_bps, kRouteThreads, route_smem, stream>>>(vv, which, peer, filter);
   t_end();
 }
 

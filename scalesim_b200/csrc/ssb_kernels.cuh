@@ -24,9 +24,9 @@
 
 namespace ssb {
 
-constexpr int kRouteThreads = 512;
-constexpr int kRouteItems = 8;
-constexpr int kRouteTile = kRouteThreads * kRouteItems;
+constexpr int kRouteThreads = 256;
+constexpr int kRouteItems = 4;
+constexpr int kRouteTile = kRouteThreads * kRouteItems;   // records staged in shared memory per tile (32 KB)
 
 // flag bits of an LP in this round (lph[lp].x >> kCntBits)
 constexpr u32 PL_IRREGULAR = 1u;   // anti-message, duplicate key or possible straggler in the segment
@@ -952,8 +952,33 @@ __device__ __forceinline__ u32 wait_chunk(const View& v, const u32* entry) {
   return ch;
 }
 
+// --- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+/sm_100a) ---
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Each block stages one tile of the source (a contiguous run of 32-byte records) in shared memory with ONE TMA bulk
+// copy, builds the per-target histogram from the staged records, claims one range per target with a single global
+// atomic, and scatters the records from shared memory with 256-bit stores. Tiles are sized so that every block of
+// the persistent grid gets the same number of equally large tiles (no tail wave).
 __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 peer, u32 filter) {
-  extern __shared__ u64 smem64[];
+  extern __shared__ __align__(128) unsigned char smem_route[];
+  __shared__ u64 s_bar;
+  __shared__ u64 s_sent_min;
   Ctl* c = v.ctl;
   const Ev* src;
   u32 n0, n1 = 0;        // main count, extra count (extra region starts at cap_batch)
@@ -972,37 +997,51 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   else { src = v.outbox; n0 = c->load_count; }
   const u32 total = n0 + n1;
   if (total == 0) return;
+  // equal tiles for all blocks: `passes` tiles of `tile` records each (tile is a multiple of 32 records = 1 KB)
+  const u32 passes = (total + gridDim.x * kRouteTile - 1) / (gridDim.x * kRouteTile);
+  u32 tile = (total + gridDim.x * passes - 1) / (gridDim.x * passes);
+  tile = (tile + 31u) & ~31u;
   // shared-memory targets: [0, rs) = buckets base .. base+rs-1, rs = "beyond", rs+1+r = partition r.
   // Buckets further ahead than the table (tiny bucket_ticks) take one global atomic per event instead.
   const u32 rs = v.route_slots;
   const u32 nt = rs + 1 + v.world;
   const u32 base = c->commit_next;
-  u32* s_cnt = reinterpret_cast<u32*>(smem64);          // [nt] events of the tile per target
+  Ev* s_tile = reinterpret_cast<Ev*>(smem_route);                                  // [kRouteTile] staged records
+  u32* s_cnt = reinterpret_cast<u32*>(smem_route + (size_t)kRouteTile * sizeof(Ev)); // [nt] events of the tile per target
   u32* s_base = s_cnt + nt;                             // [nt] first position claimed in the target
   u32* s_ch0 = s_base + nt;                             // [nt] chunk of that first position
   u32* s_ch1 = s_ch0 + nt;                              // [nt] the next chunk, if the range crosses into it
   const u32 chm = (1u << v.ch_log) - 1u;
   const u32 T_NONE = NIL, T_DIRECT = NIL - 1u;
-  __shared__ u64 s_sent_min;
-  if (threadIdx.x == 0) s_sent_min = KEY_MAX;
+  if (threadIdx.x == 0) { s_sent_min = KEY_MAX; mbar_init(&s_bar, 1); }
   __syncthreads();
-  for (u32 tile = blockIdx.x * kRouteTile; tile < total; tile += gridDim.x * kRouteTile) {
+  u32 phase = 0;
+  for (u32 t0 = blockIdx.x * tile; t0 < total; t0 += gridDim.x * tile) {
+    const u32 cnt = total - t0 < tile ? total - t0 : tile;
+    if (threadIdx.x == 0) {
+      // virtual index space [main | extra]: a tile that straddles the boundary takes two copies
+      const u32 a = t0 < n0 ? (n0 - t0 < cnt ? n0 - t0 : cnt) : 0u;      // records from the main region
+      mbar_expect_tx(&s_bar, cnt * (u32)sizeof(Ev));
+      if (a) bulk_g2s(s_tile, src + t0, a * (u32)sizeof(Ev), &s_bar);
+      if (cnt > a) bulk_g2s(s_tile + a, src + v.cap_batch + (t0 + a - n0), (cnt - a) * (u32)sizeof(Ev), &s_bar);
+    }
     for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) s_cnt[t] = 0;
     __syncthreads();
+    mbar_wait(&s_bar, phase);
+    phase ^= 1u;
     u32 tgt[kRouteItems], rnk[kRouteItems];
-    // pass 1: target of every event (first half of the record is enough), rank inside the tile's share of the target
+    // pass 1: target of every event, rank inside the tile's share of the target
 #pragma unroll
     for (int it = 0; it < kRouteItems; ++it) {
-      u32 i = tile + it * kRouteThreads + threadIdx.x;
+      const u32 i = it * kRouteThreads + threadIdx.x;
       tgt[it] = T_NONE;
       rnk[it] = 0;
-      if (i < total) {
-        u32 idx = i < n0 ? i : v.cap_batch + (i - n0);
-        const uint4 h = reinterpret_cast<const uint4*>(src + idx)[0];     // key lo, key hi, dst, src
+      if (i < cnt) {
+        const uint4 h = reinterpret_cast<const uint4*>(s_tile + i)[0];     // key lo, key hi, dst, src
         const u64 key = ((u64)h.y << 32) | h.x;
         bool take = key != KEY_MAX;
         if (take && filter) {
-          const u32 fl = src[idx].flags;
+          const u32 fl = s_tile[i].flags;
           take = filter == 1u ? (fl & F_CANCEL) != 0 : (fl & F_CANCEL) == 0;
         }
         if (take) {
@@ -1061,9 +1100,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
 #pragma unroll
     for (int it = 0; it < kRouteItems; ++it) {
       if (tgt[it] == T_DIRECT && (rnk[it] & chm) == 0) {
-        u32 i = tile + it * kRouteThreads + threadIdx.x;
-        u32 idx = i < n0 ? i : v.cap_batch + (i - n0);
-        const u32 b = key_time(src[idx].key) / v.bucket_ticks;
+        const u32 i = it * kRouteThreads + threadIdx.x;
+        const u32 b = key_time(s_tile[i].key) / v.bucket_ticks;
         u32 ch = alloc_chunk(v);
         if ((rnk[it] >> v.ch_log) >= v.maxc) atomicOr(&c->error, E_POOL);
         else atomicExch(&v.chunk_tab[(size_t)b * v.maxc + (rnk[it] >> v.ch_log)], ch);
@@ -1078,15 +1116,16 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       }
     }
     __syncthreads();
-    // copy the records (re-read from the outbox: L1/L2 hits) to their slots
+    // scatter the staged records to their slots
 #pragma unroll
     for (int it = 0; it < kRouteItems; ++it) {
       const u32 t = tgt[it];
       if (t == T_NONE || t == rs) continue;
-      u32 i = tile + it * kRouteThreads + threadIdx.x;
-      u32 idx = i < n0 ? i : v.cap_batch + (i - n0);
-      Ev e = load_ev(src + idx);
-      e.flags &= F_CANCEL;
+      const u32 i = it * kRouteThreads + threadIdx.x;
+      const uint4* q = reinterpret_cast<const uint4*>(s_tile + i);
+      const uint4 qa = q[0], qb = q[1];
+      const u32 fl = qb.w & F_CANCEL;
+      const u32 tm = qa.y;                       // key hi = receive_time
       if (t < rs || t == T_DIRECT) {
         u32 p, ch;
         if (t < rs) {
@@ -1097,11 +1136,11 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         } else {
           p = rnk[it];
           if ((p >> v.ch_log) >= v.maxc) continue;
-          ch = wait_chunk(v, &v.chunk_tab[(size_t)(key_time(e.key) / v.bucket_ticks) * v.maxc + (p >> v.ch_log)]);
+          ch = wait_chunk(v, &v.chunk_tab[(size_t)(tm / v.bucket_ticks) * v.maxc + (p >> v.ch_log)]);
         }
         if (ch == NIL) continue;
         const size_t slot = ((size_t)ch << v.ch_log) | (p & chm);
-        store_ev(v.ev + slot, e);
+        st256(v.ev + slot, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
         v.pflag[slot] = 0;
       } else {
         const u32 r = t - rs - 1;
@@ -1109,16 +1148,16 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         if (p >= v.cap_send) { atomicOr(&c->error, E_SENDBUF); continue; }
         if (v.p2p) {
           // straight into the destination GPU's mailbox over NVLink
-          store_ev(v.peer_data[r] + (((size_t)(c->round & 1u) * v.world + v.rank) * v.cap_send + p), e);
-          const u32 tm = key_time(e.key);
+          st256(v.peer_data[r] + (((size_t)(c->round & 1u) * v.world + v.rank) * v.cap_send + p),
+                qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
           const u64 k = make_key(tm >= v.finish_time ? v.finish_time : tm / v.bucket_ticks * v.bucket_ticks, 0);
           if (k < s_sent_min) atomicMin(&s_sent_min, k);
         } else {
-          store_ev(v.sendbuf + (size_t)r * v.cap_send + p, e);
+          st256(v.sendbuf + (size_t)r * v.cap_send + p, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
         }
       }
     }
-    __syncthreads();
+    __syncthreads();      // everyone is done with the staged tile before the next bulk copy overwrites it
   }
   if (threadIdx.x == 0 && s_sent_min != KEY_MAX) atomicMin(&c->sent_min, s_sent_min);
 }
