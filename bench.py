@@ -278,8 +278,16 @@ def main():
         barrier()
         return st, dg, got, time.perf_counter() - t0
 
+    verbose = bool(os.environ.get("BENCH_VERBOSE"))
+
+    def log(msg):
+        if verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    log(f"engine ready: {n_ev} initial events on this rank")
     for _ in range(args.warmup):
-        one_step()
+        st = one_step()
+        log(f"warm-up step: loop {st.loop_ms:.2f} ms, rounds {st.rounds}, committed {st.committed}, remote {st.remote_sent}")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -319,13 +327,16 @@ def main():
     # end to end through the host API
     e2e = None
     if keep:
+        log("e2e warm-up")
         one_e2e_step()
+        log("e2e warm-up done")
         ts, ok = [], True
         want = None
         for _ in range(max(1, min(args.steps, 3))):
             st, dg, got, dt = one_e2e_step()
             ts.append(max_over_ranks(dt))
             ok = ok and got == st.committed
+            log(f"e2e step: {dt * 1000:.1f} ms, drained {got}")
         e2e_committed = sum_over_ranks(st.committed)
         e2e = {"value": e2e_committed / statistics.mean(ts), "unit": UNIT,
                "h2d_bytes_per_step": int(n_ev * ssb.EVENT_DTYPE.itemsize),

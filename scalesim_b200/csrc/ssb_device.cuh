@@ -63,8 +63,8 @@ static_assert(sizeof(Meta) == 32, "Meta must be one 32-byte sector");
 
 struct __align__(16) Sorted {
   u64 key;
-  u32 slot;
-  u32 seq;       // arrival order (bits 0..30), bit 31 = anti-message
+  u32 slot;      // calendar slot of the event
+  u32 seq;       // arrival index (bits 0..30; also the arrival order), bit 31 = anti-message
 };
 
 struct Ctl {
@@ -124,7 +124,7 @@ struct View {
   // per round
   uint4* link;         // [cap_batch] per arrival {key lo, key hi, previous arrival of the same LP | anti << 31, slot}
   u32* tmp_rank;       // [cap_batch] rank of the arrival among its LP's arrivals (position in a long segment)
-  Sorted* sorted;      // [cap_batch] (key, slot, arrival) segments, sorted — only for long or irregular LPs
+  Sorted* sorted;      // [cap_batch] (key, slot, arrival) segments of the long LPs, and of the irregular LPs sorted
   u32* fix;            // [cap_batch] LPs that need the sequential turn
   uint4* heavy;        // [cap_batch / 16] LPs with long segments {lp, seg_start, n, 0}
   Ev* outbox;          // [cap_batch + cap_aux]: entry i = output of arrival i, then re-execution outputs
@@ -167,6 +167,31 @@ __device__ __forceinline__ void ld256(const void* p, u32 (&x)[8]) {
 __device__ __forceinline__ void st256(void* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+// streaming variants (L2 evict-first): for data that is not touched again soon — committed buckets, the log, meta
+// records, events appended to future buckets — so that they do not push the current window out of L2
+__device__ __forceinline__ void ld256_ef(const void* p, u32 (&x)[8]) {
+  asm volatile("ld.global.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+               : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256_ef(void* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
+  asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+__device__ __forceinline__ Ev load_ev_ef(const Ev* p) {
+  u32 x[8];
+  ld256_ef(p, x);
+  Ev e;
+  e.key = ((u64)x[1] << 32) | x[0]; e.dst = x[2]; e.src = x[3];
+  e.send = x[4]; e.p0 = x[5]; e.p1 = x[6]; e.flags = x[7];
+  return e;
+}
+__device__ __forceinline__ void store_ev_ef(Ev* p, const Ev& e) {
+  st256_ef(p, (u32)e.key, (u32)(e.key >> 32), e.dst, e.src, e.send, e.p0, e.p1, e.flags);
+}
+__device__ __forceinline__ void store_meta_ef(Meta* p, const Meta& m) {
+  st256_ef(p, m.link, m.prevtime, m.sent_dst, m.snap, (u32)m.sent_key, (u32)(m.sent_key >> 32), 0u, 0u);
 }
 __device__ __forceinline__ Ev load_ev(const Ev* p) {
   u32 x[8];

@@ -37,7 +37,7 @@ constexpr u32 kCntBits = 28;       // lph[lp].x = arrivals of the round (bits 0.
 constexpr u32 kCntMask = (1u << kCntBits) - 1u;
 constexpr u32 NIL31 = 0x7FFFFFFFu; // end of an LP's arrival list
 constexpr u32 kLightMax = 16;      // upper bound of View::light_max: LPs with more arrivals in a round get a segment
-constexpr u32 kScanCap = 256;      // segments up to this length are scanned per event; longer ones are sorted first
+constexpr u32 kScanCap = 128;      // segments up to this length are sorted in registers by k_exec_heavy; longer ones by k_sortheavy
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
@@ -67,8 +67,7 @@ __device__ __forceinline__ u64 warp_xor_u64(u64 v) {
 // Replaces scheduler::min_locals (process_scheduler.hpp:83-90) + the local half of mpi_gsync::check_sync
 // (global_sync.hpp:95-150).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_local_min(const View& v, u64* sm) {
-  Ctl* c = v.ctl;
+__device__ __forceinline__ void block_local_min(const View& v, Ctl* c, u64* sm) {
   u64 m = KEY_MAX;
   for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x)
     if (v.fill[b] != v.consumed[b]) { u64 k = make_key(b * v.bucket_ticks, 0); m = k < m ? k : m; }
@@ -91,91 +90,101 @@ __device__ __forceinline__ void block_local_min(const View& v, u64* sm) {
 
 __global__ void k_min(View v) {
   __shared__ u64 sm[32];
-  block_local_min(v, sm);
+  block_local_min(v, v.ctl, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_plan — GVT := (all-reduced) local_min. Finish test of runner.hpp:392. Commit list = buckets entirely below GVT
 // (R8/R9). Gather list = unconsumed tails of the buckets inside the optimistic window
-// [bucket(GVT), bucket(GVT) + window).
+// [bucket(GVT), bucket(GVT) + window). The control block is staged in shared memory (one coalesced load, one
+// coalesced store): the serial bookkeeping of thread 0 then costs no global round trips. Nothing else touches the
+// control block while k_plan runs (it is the first kernel of a round).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_plan(View v, int use_global_gvt) {
   __shared__ u64 sm[32];
-  Ctl* c = v.ctl;
+  __shared__ __align__(16) u32 s_words[(sizeof(Ctl) + 3) / 4];
+  Ctl* c = reinterpret_cast<Ctl*>(s_words);
+  constexpr u32 kWords = (u32)(sizeof(Ctl) / 4);
+  static_assert(sizeof(Ctl) % 4 == 0, "Ctl is copied word-wise");
+  for (u32 w = threadIdx.x; w < kWords; w += blockDim.x) s_words[w] = reinterpret_cast<const u32*>(v.ctl)[w];
+  __syncthreads();
   if (!use_global_gvt) {     // single partition: the min-reduction is fused here
-    block_local_min(v, sm);
-    __syncthreads();
+    block_local_min(v, c, sm);
   }
-  if (threadIdx.x != 0) return;
-  u64 gvt = use_global_gvt ? c->gvt : c->local_min;
-  c->gvt = gvt;
-  u32 t = gvt == KEY_MAX ? 0xFFFFFFFFu : key_time(gvt);
-  bool done = t >= v.finish_time;
-  u32 fin_b = (v.finish_time + v.bucket_ticks - 1) / v.bucket_ticks;   // buckets [0, fin_b) hold times < finish
-  if (fin_b > v.nb) fin_b = v.nb;
-  u32 cur = done ? fin_b : t / v.bucket_ticks;
-  if (cur > fin_b) cur = fin_b;
-  c->cur_abs = cur;
-  // commit list
-  u32 nc = 0, tot = 0;
-  for (u32 b = c->commit_next; b < cur; ++b) {
-    u32 f = v.fill[b];
-    if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
-  }
-  c->commit_next = cur > c->commit_next ? cur : c->commit_next;
-  c->n_commit = nc;
-  c->commit_total = tot;
-  // snapshot ring: rounds whose window lies below GVT are dead (their snapshots can be reused)
-  while (c->rq_tail != c->rq_head && c->rq_bound[c->rq_tail % RQ_LEN] <= cur) c->rq_tail++;
-  c->snap_tail = c->rq_tail == c->rq_head ? c->snap_head : c->rq_snap[c->rq_tail % RQ_LEN];
-  // gather list
-  u32 ng = 0, total = 0;
-  u32 bound = cur;
-  if (!done) {
-    bound = cur + v.window < fin_b ? cur + v.window : fin_b;
-    for (u32 b = cur; b < bound; ++b) {
-      u32 avail = v.fill[b] - v.consumed[b];
-      if (!avail) continue;
-      u32 take = avail < v.cap_batch - total ? avail : v.cap_batch - total;
-      if (take) {
-        v.gather[ng++] = make_uint4(b, v.consumed[b], take, total);
-        total += take;
-        v.consumed[b] += take;
+  if (threadIdx.x == 0) {
+    u64 gvt = use_global_gvt ? c->gvt : c->local_min;
+    c->gvt = gvt;
+    u32 t = gvt == KEY_MAX ? 0xFFFFFFFFu : key_time(gvt);
+    bool done = t >= v.finish_time;
+    u32 fin_b = (v.finish_time + v.bucket_ticks - 1) / v.bucket_ticks;   // buckets [0, fin_b) hold times < finish
+    if (fin_b > v.nb) fin_b = v.nb;
+    u32 cur = done ? fin_b : t / v.bucket_ticks;
+    if (cur > fin_b) cur = fin_b;
+    c->cur_abs = cur;
+    // commit list
+    u32 nc = 0, tot = 0;
+    for (u32 b = c->commit_next; b < cur; ++b) {
+      u32 f = v.fill[b];
+      if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
+    }
+    c->commit_next = cur > c->commit_next ? cur : c->commit_next;
+    c->n_commit = nc;
+    c->commit_total = tot;
+    // snapshot ring: rounds whose window lies below GVT are dead (their snapshots can be reused)
+    while (c->rq_tail != c->rq_head && c->rq_bound[c->rq_tail % RQ_LEN] <= cur) c->rq_tail++;
+    c->snap_tail = c->rq_tail == c->rq_head ? c->snap_head : c->rq_snap[c->rq_tail % RQ_LEN];
+    // gather list
+    u32 ng = 0, total = 0;
+    u32 bound = cur;
+    if (!done) {
+      bound = cur + v.window < fin_b ? cur + v.window : fin_b;
+      for (u32 b = cur; b < bound; ++b) {
+        const u32 cons = v.consumed[b];
+        u32 avail = v.fill[b] - cons;
+        if (!avail) continue;
+        u32 take = avail < v.cap_batch - total ? avail : v.cap_batch - total;
+        if (take) {
+          v.gather[ng++] = make_uint4(b, cons, take, total);
+          total += take;
+          v.consumed[b] = cons + take;
+        }
+        if (take < avail) { bound = b + 1; break; }   // batch capacity reached: the rest of this bucket stays pending
       }
-      if (take < avail) { bound = b + 1; break; }   // batch capacity reached: the rest of this bucket stays pending
+      if (c->rq_head - c->rq_tail < RQ_LEN) {
+        c->rq_bound[c->rq_head % RQ_LEN] = bound;
+        c->rq_snap[c->rq_head % RQ_LEN] = c->snap_head;
+        c->rq_head++;
+      } else {
+        c->rq_bound[(c->rq_head - 1) % RQ_LEN] = bound;
+      }
     }
-    if (c->rq_head - c->rq_tail < RQ_LEN) {
-      c->rq_bound[c->rq_head % RQ_LEN] = bound;
-      c->rq_snap[c->rq_head % RQ_LEN] = c->snap_head;
-      c->rq_head++;
-    } else {
-      c->rq_bound[(c->rq_head - 1) % RQ_LEN] = bound;
+    c->bound_abs = bound;
+    c->n_gather = ng;
+    c->n_arr = total;
+    c->n_processed += total;   // k_fixup corrects this for the LPs it re-executes
+    c->seg_cursor = 0;
+    c->n_anti = 0;
+    c->n_extra = 0;
+    c->n_heavy = 0;
+    c->n_vheavy = 0;
+    c->n_fix = 0;
+    c->done = done ? 1u : 0u;
+    c->round++;
+    for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
+    c->sent_min = KEY_MAX;
+    if (v.use_graph) {
+      // GVT must keep advancing (every round commits or integrates something): give up instead of spinning forever
+      if (gvt == c->prev_gvt) { if (++c->stall > kStallRounds) c->error |= E_STALL; } else { c->stall = 0; c->prev_gvt = gvt; }
+      cudaGraphSetConditional(v.h_loop, (done || c->error) ? 0u : 1u);
+    }
+    if (v.p2p) {
+      // the mailbox half that was just integrated (parity of the round that ended) is free again
+      const u32 par = (c->round - 1) & 1u;
+      for (u32 r = 0; r < v.world; ++r) v.mbox_cnt[(par * v.world + r) * 32] = 0;
     }
   }
-  c->bound_abs = bound;
-  c->n_gather = ng;
-  c->n_arr = total;
-  c->n_processed += total;   // k_fixup corrects this for the LPs it re-executes
-  c->seg_cursor = 0;
-  c->n_anti = 0;
-  c->n_extra = 0;
-  c->n_heavy = 0;
-  c->n_vheavy = 0;
-  c->n_fix = 0;
-  c->done = done ? 1u : 0u;
-  c->round++;
-  for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
-  c->sent_min = KEY_MAX;
-  if (v.use_graph) {
-    // GVT must keep advancing (every round commits or integrates something): give up instead of spinning forever
-    if (gvt == c->prev_gvt) { if (++c->stall > kStallRounds) atomicOr(&c->error, E_STALL); } else { c->stall = 0; c->prev_gvt = gvt; }
-    cudaGraphSetConditional(v.h_loop, (done || c->error) ? 0u : 1u);
-  }
-  if (v.p2p) {
-    // the mailbox half that was just integrated (parity of the round that ended) is free again
-    const u32 par = (c->round - 1) & 1u;
-    for (u32 r = 0; r < v.world; ++r) v.mbox_cnt[(par * v.world + r) * 32] = 0;
-  }
+  __syncthreads();
+  for (u32 w = threadIdx.x; w < kWords; w += blockDim.x) reinterpret_cast<u32*>(v.ctl)[w] = s_words[w];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
       }
       uint4 ce = v.commit[lo];
       u32 slot = slot_of(v, ce.x, i - ce.z);
-      e = load_ev(v.ev + slot);
+      e = load_ev_ef(v.ev + slot);
       const unsigned char pf = v.pflag[slot];
       keep = !(e.flags & F_CANCEL) && !(pf & P_DEAD) && key_time(e.key) < v.finish_time;
       if (keep) {
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
       __syncthreads();
       if (keep) {
         u64 pos = s_pos + w_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
-        if (pos < v.cap_log) { e.flags = tg; store_ev(v.log + pos, e); }
+        if (pos < v.cap_log) { e.flags = tg; store_ev_ef(v.log + pos, e); }
         else atomicAdd(&c->log_dropped, 1ull);
       }
       __syncthreads();
@@ -487,8 +496,9 @@ struct Turn {
       while (ia < n && seg[ia].key == k) {
         const Sorted a = load_sorted(seg + ia);
         const u32 my_out = a.seq & 0x7FFFFFFFu;
+        const u32 a_slot = a.slot;
         if (a.seq & 0x80000000u) {
-          v.pflag[a.slot] = P_DEAD;                     // the anti-message itself is consumed
+          v.pflag[a_slot] = P_DEAD;                     // the anti-message itself is consumed
           v.outbox[my_out].key = KEY_MAX;
           if (present != NIL) {                         // erase (queue.hpp:87-90)
             v.pflag[present] = P_DEAD;
@@ -497,10 +507,10 @@ struct Turn {
             ++n_annih;
           }
         } else if (present == NIL) {
-          present = a.slot;                             // insert (queue.hpp:92)
+          present = a_slot;                             // insert (queue.hpp:92)
           out_idx = my_out;
         } else {
-          v.pflag[a.slot] = P_DEAD;                     // duplicate key: second insert ignored
+          v.pflag[a_slot] = P_DEAD;                     // duplicate key: second insert ignored
           v.outbox[my_out].key = KEY_MAX;
           ++n_dup;
         }
@@ -528,7 +538,7 @@ struct Turn {
 // the state (neither shipped application ever does). The moment one does, the LP is flagged and k_fixup re-executes
 // its whole turn sequentially — handlers that mutate state keep exact semantics.
 // ------------------------------------------------------------------------------------------------
-template <class M>
+template <class M, bool kLinkLater = false>
 __device__ __forceinline__ void exec_one(const View& v, const typename M::Data& md, u32 i, u32 slot, Ev e, u32 lp,
                                          u32 pred_slot, u32 pred_time, bool is_last, u32& err) {
   e.flags = 0;
@@ -554,7 +564,9 @@ __device__ __forceinline__ void exec_one(const View& v, const typename M::Data& 
   } else {
     v.outbox[i].key = KEY_MAX;
   }
-  store_meta(v.meta + slot, m);
+  // a meta record is not read again unless its LP rolls back: evict-first. Exception: the record of a long LP's event,
+  // whose chain link k_exec_heavy fills in right afterwards.
+  if (kLinkLater) store_meta(v.meta + slot, m); else store_meta_ef(v.meta + slot, m);
   v.pflag[slot] = P_PROCESSED;
   if (is_last) v.last[lp] = make_uint2(slot, key_time(e.key));
 }
@@ -582,14 +594,19 @@ __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
     const u32 lp = part_local(v, e.dst);
     const uint4 h = v.lph[lp];
     const u32 n = h.x & kCntMask;
-    if ((h.x >> kCntBits) & PL_FIX) continue;             // handled by k_fixup
     const u32 anti = (e.flags & F_CANCEL) ? 0x80000000u : 0u;
     if (n > v.light_max) {
+      // long LP: drop (key, slot, arrival) into the LP's segment and execute speculatively right here, where the
+      // event, meta and outbox accesses are coalesced; k_exec_heavy adds the processed-chain link afterwards
       Sorted x;
       x.key = e.key; x.slot = slot; x.seq = i | anti;
       store_sorted(v.sorted + h.y + v.tmp_rank[i], x);
+      if (anti) { flag_lp(v, lp, PL_IRREGULAR); continue; }
+      if ((h.x >> kCntBits) & PL_FIX) continue;
+      exec_one<M, true>(v, md, i, slot, e, lp, NIL, 0u, false, err);
       continue;
     }
+    if ((h.x >> kCntBits) & PL_FIX) continue;             // handled by k_fixup
     u32 pred_slot = h.z, pred_time = h.w;
     bool is_last = true;
     bool bad = anti != 0 || (h.z != NIL && key_time(e.key) <= h.w);
@@ -648,31 +665,18 @@ __device__ __forceinline__ void classify_heavy(const View& v, u32 lp, u64 first_
   if (irregular) flag_lp(v, lp, PL_IRREGULAR);
 }
 
-// work item idx of the sort pass. mode 0 (before k_exec_heavy): the long-segment list, segments longer than kScanCap;
-// mode 1 (before k_fixup): the fix list, long segments that are not sorted yet.
-__device__ __forceinline__ bool sort_item(const View& v, int mode, u32 idx, u32& lp, u32& start, u32& n) {
-  if (mode == 0) {
-    const uint4 a = v.heavy[idx];
-    lp = a.x; start = a.y; n = a.z;
-    return n > kScanCap;
-  }
-  lp = v.fix[idx];
-  const u32 x = v.lph[lp].x;
-  n = x & kCntMask;
-  if (n <= v.light_max || ((x >> kCntBits) & PL_SORTED)) return false;
-  start = v.lph[lp].y;
-  return true;
-}
-__device__ __forceinline__ void sort_done(const View& v, int mode, u32 lp, u64 first_key, bool irregular) {
-  if (mode == 0) classify_heavy(v, lp, first_key, irregular);
-  else atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
+// work item idx of the sort pass: the long-segment list, segments longer than kScanCap
+__device__ __forceinline__ bool sort_item(const View& v, u32 idx, u32& lp, u32& start, u32& n) {
+  const uint4 a = v.heavy[idx];
+  lp = a.x; start = a.y; n = a.z;
+  return n > kScanCap;
 }
 
-__global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
+__global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v) {
   extern __shared__ uint4 smem_heavy[];
   __shared__ u32 s_flag;
   Ctl* c = v.ctl;
-  const u32 nh = mode == 0 ? (c->n_vheavy ? c->n_heavy : 0u) : c->n_fix;
+  const u32 nh = c->n_vheavy ? c->n_heavy : 0u;
   if (nh == 0) return;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr u32 kWarps = kSortThreads / 32;
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
   // warp-level
   for (u32 h = blockIdx.x * kWarps + warp; h < nh; h += gridDim.x * kWarps) {
     u32 lp, start, n;
-    if (!sort_item(v, mode, h, lp, start, n) || n > kWarpSortCap) continue;
+    if (!sort_item(v, h, lp, start, n) || n > kWarpSortCap) continue;
     Sorted* seg = v.sorted + start;
     u32 flag = 0;
     u64 first_key;
@@ -730,14 +734,14 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
       __syncwarp();
     }
     const bool irregular = __any_sync(0xffffffffu, flag != 0);
-    if (lane == 0) sort_done(v, mode, lp, first_key, irregular);
+    if (lane == 0) classify_heavy(v, lp, first_key, irregular);
   }
   // block-level (rare): segments longer than kWarpSortCap
   __syncthreads();
   Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy);
   for (u32 h = blockIdx.x; h < nh; h += gridDim.x) {
     u32 lp, start, n;
-    if (!sort_item(v, mode, h, lp, start, n) || n <= kWarpSortCap) continue;
+    if (!sort_item(v, h, lp, start, n) || n <= kWarpSortCap) continue;
     Sorted* seg = v.sorted + start;
     if (threadIdx.x == 0) s_flag = 0;
     if (n <= kBlockSortCap) {
@@ -766,7 +770,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
       }
       if (flag) s_flag = 1;
       __syncthreads();
-      if (threadIdx.x == 0) sort_done(v, mode, lp, buf[0].key, s_flag != 0);
+      if (threadIdx.x == 0) classify_heavy(v, lp, buf[0].key, s_flag != 0);
       __syncthreads();
     } else {
       __syncthreads();
@@ -788,7 +792,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
           if (i && seg[i - 1].key == seg[i].key) flag = 1;
         }
         __threadfence();
-        sort_done(v, mode, lp, seg[0].key, flag != 0);
+        classify_heavy(v, lp, seg[0].key, flag != 0);
       }
       __syncthreads();
     }
@@ -796,54 +800,143 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v, int mode) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_exec_heavy — one thread per entry of the long segments (the hot LPs). The threads of a segment scan it together
-// (the same 16-byte entries, broadcast inside a warp): predecessor = largest smaller key, "last" = no larger key,
-// irregular = anti-message / duplicate key / possible straggler. Segments longer than kScanCap were sorted and
-// classified by k_sortheavy: there the predecessor is the entry before.
+// k_exec_heavy — one WARP per long LP (the hot LPs). k_exec has already run the handler for the LP's events, in the
+// coalesced pass; what is left is each event's place in the LP's key order (R1). The warp loads the segment
+// (key, slot, arrival) into registers — R entries per lane, R = 1, 2 or 4 — sorts it with a bitonic network over register
+// shuffles, and each entry reads its predecessor off its neighbour: processed-chain link -> 8-byte store into the
+// event's meta record, the last entry becomes the LP's chain head. An anti-message, a duplicate key or a possible
+// straggler makes the turn irregular: the sorted segment is written back for the sequential lp_turn of k_fixup
+// (also when k_exec flagged the LP because its handler changed the state). Segments longer than kScanCap were
+// sorted and classified by k_sortheavy: their entries read the neighbour straight from memory.
 // ------------------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(256) k_exec_heavy(View v, typename M::Data md) {
-  Ctl* c = v.ctl;
-  const u32 total = c->n_heavy ? c->seg_cursor : 0u;
-  u32 err = 0;
-  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
-    const Sorted x = load_sorted(v.sorted + j);
-    const Ev e = load_ev(v.ev + x.slot);
-    const u32 lp = part_local(v, e.dst);
-    const uint4 h = v.lph[lp];
-    const u32 fl = h.x >> kCntBits;
-    if (fl & PL_FIX) continue;
-    const u32 start = h.y, n = h.x & kCntMask;
-    const u32 pos = j - start;
-    u32 pred_slot = h.z, pred_time = h.w;
-    bool is_last;
-    if (fl & PL_SORTED) {
-      if (pos) { const Sorted p = load_sorted(v.sorted + j - 1); pred_slot = p.slot; pred_time = key_time(p.key); }
-      is_last = pos + 1u == n;
-    } else {
-      bool bad = (x.seq >> 31) != 0 || (h.z != NIL && key_time(x.key) <= h.w);
-      u64 pk = 0;
-      bool have = false;
-      is_last = true;
-      const uint4* seg = reinterpret_cast<const uint4*>(v.sorted + start);
-      for (u32 k = 0; k < n; ++k) {
-        const uint4 q = seg[k];
-        if (k == pos) continue;
-        const u64 tk = ((u64)q.y << 32) | q.x;
-        if (q.w >> 31) bad = true;
-        if (tk == x.key) bad = true;
-        else if (tk < x.key) {
-          if (!have || tk > pk) { pk = tk; pred_slot = q.z; have = true; }
-        } else {
-          is_last = false;
+struct KS { u64 key; u32 slot, seq; };      // sort element: key, calendar slot, arrival index | anti << 31
+__device__ __forceinline__ bool ks_less(const KS& a, const KS& b) {
+  return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
+}
+__device__ __forceinline__ KS ks_shfl_xor(const KS& x, int m) {
+  KS y;
+  const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)x.key, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(x.key >> 32), m);
+  y.key = ((u64)hi << 32) | lo;
+  y.slot = __shfl_xor_sync(0xffffffffu, x.slot, m);
+  y.seq = __shfl_xor_sync(0xffffffffu, x.seq, m);
+  return y;
+}
+
+// entry index = lane + 32 * r. Sorts 32 * R entries ascending.
+template <int R>
+__device__ __forceinline__ void warp_bitonic(KS (&x)[R], u32 lane) {
+#pragma unroll
+  for (u32 k2 = 2; k2 <= 32u * R; k2 <<= 1) {
+#pragma unroll
+    for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      if (j2 >= 32u) {
+        const u32 dr = j2 >> 5;                 // partner register
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & dr) == 0) {
+            const bool asc = (((u32)r << 5) & k2) == 0;       // lane bits are below bit 5, k2 >= 64 here
+            const bool sw = asc ? ks_less(x[r | dr], x[r]) : ks_less(x[r], x[r | dr]);
+            if (sw) { const KS t = x[r]; x[r] = x[r | dr]; x[r | dr] = t; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const KS y = ks_shfl_xor(x[r], (int)j2);
+          const u32 e = lane + ((u32)r << 5);
+          const bool keep_min = ((lane & j2) == 0) == ((e & k2) == 0);
+          if (keep_min ? ks_less(y, x[r]) : ks_less(x[r], y)) x[r] = y;
         }
       }
-      if (have) pred_time = key_time(pk);
-      if (bad) { flag_lp(v, lp, PL_IRREGULAR); continue; }
     }
-    exec_one<M>(v, md, x.seq & 0x7FFFFFFFu, x.slot, e, lp, pred_slot, pred_time, is_last, err);
   }
-  if (err) atomicOr(&c->error, err);
+}
+
+template <int R>
+__device__ __forceinline__ void heavy_turn(const View& v, u32 lp, u32 start, u32 n, const uint4 h, u32 lane) {
+  const bool fixed = ((h.x >> kCntBits) & PL_FIX) != 0;      // k_exec already sent the LP to k_fixup: only sort
+  KS x[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u32 i = lane + ((u32)r << 5);
+    if (i < n) { const uint4 q = *reinterpret_cast<const uint4*>(v.sorted + start + i); x[r].key = ((u64)q.y << 32) | q.x; x[r].slot = q.z; x[r].seq = q.w; }
+    else { x[r].key = KEY_MAX; x[r].slot = NIL; x[r].seq = 0x7FFFFFFFu; }
+  }
+  warp_bitonic<R>(x, lane);
+  // neighbours: the entry before (index - 1) of every entry
+  u32 flag = 0;
+  u64 pkey[R];
+  u32 pslot[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    u32 lo = __shfl_up_sync(0xffffffffu, (u32)x[r].key, 1), hi = __shfl_up_sync(0xffffffffu, (u32)(x[r].key >> 32), 1);
+    u32 sl = __shfl_up_sync(0xffffffffu, x[r].slot, 1);
+    if (r > 0) {      // lane 0 takes the last lane's entry of the previous register
+      const u32 lo2 = __shfl_sync(0xffffffffu, (u32)x[r - 1].key, 31), hi2 = __shfl_sync(0xffffffffu, (u32)(x[r - 1].key >> 32), 31);
+      const u32 sl2 = __shfl_sync(0xffffffffu, x[r - 1].slot, 31);
+      if (lane == 0) { lo = lo2; hi = hi2; sl = sl2; }
+    }
+    pkey[r] = ((u64)hi << 32) | lo;
+    pslot[r] = sl;
+    const u32 i = lane + ((u32)r << 5);
+    if (i < n) {
+      flag |= x[r].seq >> 31;
+      if (i && pkey[r] == x[r].key) flag = 1;
+    }
+  }
+  const u64 first_key = ((u64)__shfl_sync(0xffffffffu, (u32)(x[0].key >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)x[0].key, 0);
+  bool irregular = __any_sync(0xffffffffu, flag != 0);
+  if (h.z != NIL && key_time(first_key) <= h.w) irregular = true;      // possible straggler
+  if (irregular || fixed) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 i = lane + ((u32)r << 5);
+      if (i < n) *reinterpret_cast<uint4*>(v.sorted + start + i) = make_uint4((u32)x[r].key, (u32)(x[r].key >> 32), x[r].slot, x[r].seq);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
+      if (!fixed) flag_lp(v, lp, PL_IRREGULAR);
+    }
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u32 i = lane + ((u32)r << 5);
+    if (i < n) {
+      u32 ps = pslot[r], ptime = key_time(pkey[r]);
+      if (i == 0) { ps = h.z; ptime = h.w; }
+      *reinterpret_cast<uint2*>(v.meta + x[r].slot) = make_uint2(ps, ptime);
+      if (i + 1u == n) v.last[lp] = make_uint2(x[r].slot, key_time(x[r].key));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_exec_heavy(View v) {
+  Ctl* c = v.ctl;
+  const u32 nh = c->n_heavy;
+  const u32 lane = threadIdx.x & 31;
+  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 hi = wid; hi < nh; hi += nw) {
+    const uint4 a = v.heavy[hi];
+    const u32 lp = a.x, start = a.y, n = a.z;
+    const uint4 h = v.lph[lp];
+    const u32 fl = h.x >> kCntBits;
+    if (fl & PL_SORTED) {
+      // sorted and classified by k_sortheavy (n > kScanCap)
+      if (fl & PL_FIX) continue;
+      for (u32 i = lane; i < n; i += 32) {
+        const Sorted x = load_sorted(v.sorted + start + i);
+        u32 pslot = h.z, ptime = h.w;
+        if (i) { const Sorted p = load_sorted(v.sorted + start + i - 1); pslot = p.slot; ptime = key_time(p.key); }
+        *reinterpret_cast<uint2*>(v.meta + x.slot) = make_uint2(pslot, ptime);
+        if (i + 1u == n) v.last[lp] = make_uint2(x.slot, key_time(x.key));
+      }
+    } else if (n <= 32) heavy_turn<1>(v, lp, start, n, h, lane);
+    else if (n <= 64) heavy_turn<2>(v, lp, start, n, h, lane);
+    else heavy_turn<4>(v, lp, start, n, h, lane);
+  }
   if (v.use_graph) {
     // the last block to finish knows the final fix list: it opens or closes the IF node around k_fixup
     __syncthreads();
@@ -1140,7 +1233,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         }
         if (ch == NIL) continue;
         const size_t slot = ((size_t)ch << v.ch_log) | (p & chm);
-        st256(v.ev + slot, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
+        st256_ef(v.ev + slot, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
         v.pflag[slot] = 0;
       } else {
         const u32 r = t - rs - 1;
