@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-partition event exchange")
     args = ap.parse_args()
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line and nothing else
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -356,7 +357,7 @@ def main():
                                    f"{args.remote:g} remote, finish 500000 ticks, partition lp % {world} "
                                    f"(BASELINE.json config 2 per GPU)",
                        "bucket_ticks": args.bucket, "window_buckets": args.window,
-                       "exchange": ("peer-memory writes over NVLink + NCCL allreduce-min" if args.exchange == "p2p"
+                       "exchange": ("peer-memory writes over NVLink, GVT min-reduction + barrier through the same mailboxes" if args.exchange == "p2p"
                                     else "NCCL send/recv + allreduce-min") if world > 1 else "none (1 GPU)",
                        "committed_per_step": committed_per_step, "rounds_per_step": rounds_total // args.steps,
                        "l2": "inputs larger than L2 (event pool + tables > 600 MB per GPU); no flush between steps",

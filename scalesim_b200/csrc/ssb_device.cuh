@@ -37,6 +37,7 @@ constexpr u32 E_SNAP = 8u;        // snapshot ring overflow
 constexpr u32 E_HORIZON = 16u;    // bucket index beyond the calendar
 constexpr u32 E_SENDBUF = 32u;    // remote send buffer overflow
 constexpr u32 E_INTERNAL = 64u;   // invariant violated
+constexpr u32 E_COMM = 256u;      // a peer did not reach the GVT exchange in time
 constexpr u32 E_STALL = 128u;     // GVT did not advance for kStallRounds rounds
 constexpr u32 kStallRounds = 100000u;
 
@@ -83,7 +84,8 @@ struct Ctl {
   u32 send_count[MAX_WORLD];
   u32 recv_count[MAX_WORLD];
   u64 prev_gvt;       // stall detection of the graph's loop
-  u32 stall, pad_stall;
+  u32 stall;
+  u32 epoch;          // number of resets: keeps the GVT-exchange stamps of consecutive simulations apart
   u64 sent_min;       // peer-memory exchange: smallest bucket-start key of the events written to peers this round
   // statistics
   u64 n_processed, n_rollbacks, n_undone, n_antis, n_annihilated, n_dups, n_committed, n_beyond, n_remote;
@@ -133,14 +135,18 @@ struct View {
   uint4* commit;       // [nb] {bucket, count, off, 0}
   Ev* sendbuf;         // [world * cap_send]
   Ev* recvbuf;         // [world * cap_send]
-  // peer-memory exchange (NVLink P2P): every partition owns a mailbox = [2 parities][world sources] x {count, records}.
+  // peer-memory exchange (NVLink P2P): every partition owns a mailbox block, mapped into all peers with CUDA IPC:
+  //   counts   [2 parities][world sources][2 kinds]  one 128-byte line each (kind 0 = positives, 1 = anti-messages)
+  //   GVT slot [2 parities][world sources]           u64 = round << 32 | local minimum time
+  //   records  [2 parities][world sources] x { cap_send positives, cap_anti anti-messages }
   // A sender appends straight into its region of the destination's mailbox (system-scope atomic on the count, then
-  // plain stores over NVLink); the GVT all-reduce of the next round is the barrier that makes the appends visible.
+  // plain stores over NVLink). At the start of the next round every partition writes its GVT candidate into all
+  // peers' slots and waits for theirs (k_gvt): that exchange is the GVT min-reduction AND the barrier that makes the
+  // appended events visible.
   u32 p2p;                       // 0 = NCCL send/recv exchange, 1 = peer-memory exchange
-  Ev* mbox_data;                 // own mailbox records [2][world][cap_send]
-  u32* mbox_cnt;                 // own mailbox counts  [2][world] (one 128-byte line each)
-  Ev* peer_data[MAX_WORLD];      // peers' mailboxes (mapped with CUDA IPC)
-  u32* peer_cnt[MAX_WORLD];
+  u32 cap_anti;                  // anti-message records per (parity, source)
+  u32 mb_gvt_off, mb_data_off;   // byte offsets inside a mailbox block
+  char* peer_base[MAX_WORLD];    // mailbox blocks of all partitions (own block at [rank])
   Ev* log;             // [cap_log] committed records
   u32* snap;           // [cap_snap * state_words]
   Ctl* ctl;
@@ -214,6 +220,17 @@ __device__ __forceinline__ void store_meta(Meta* p, const Meta& m) {
 }
 __device__ __forceinline__ void store_ev(Ev* p, const Ev& e) {
   st256(p, (u32)e.key, (u32)(e.key >> 32), e.dst, e.src, e.send, e.p0, e.p1, e.flags);
+}
+
+__device__ __forceinline__ u32* mb_cnt(const View& v, u32 owner, u32 par, u32 src, u32 kind) {
+  return reinterpret_cast<u32*>(v.peer_base[owner]) + ((par * v.world + src) * 2u + kind) * 32u;
+}
+__device__ __forceinline__ u64* mb_gvt(const View& v, u32 owner, u32 par, u32 src) {
+  return reinterpret_cast<u64*>(v.peer_base[owner] + v.mb_gvt_off) + par * v.world + src;
+}
+__device__ __forceinline__ Ev* mb_data(const View& v, u32 owner, u32 par, u32 src, u32 kind) {
+  return reinterpret_cast<Ev*>(v.peer_base[owner] + v.mb_data_off) +
+         (size_t)(par * v.world + src) * (v.cap_send + v.cap_anti) + (kind ? v.cap_send : 0u);
 }
 
 // slot of position p in bucket b; the chunk must already exist

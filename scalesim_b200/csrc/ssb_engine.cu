@@ -93,8 +93,12 @@ struct ssb_engine {
   Nccl::Comm comm = nullptr;
   void* mbox_block = nullptr;              // own mailbox (exported with CUDA IPC)
   std::vector<void*> peer_blocks;          // peers' mailboxes, opened with CUDA IPC
-  size_t mbox_cnt_bytes() const { return (size_t)2 * cfg.world * 128; }
-  size_t mbox_bytes() const { return mbox_cnt_bytes() + (size_t)2 * cfg.world * v.cap_send * sizeof(Ev); }
+  // mailbox block layout (see View): counts | GVT slots | records
+  size_t mbox_cnt_bytes() const { return (size_t)2 * cfg.world * 2 * 128; }
+  size_t mbox_gvt_bytes() const { return ((size_t)2 * cfg.world * 8 + 255) & ~(size_t)255; }
+  size_t mbox_bytes() const {
+    return mbox_cnt_bytes() + mbox_gvt_bytes() + (size_t)2 * cfg.world * ((size_t)v.cap_send + v.cap_anti) * sizeof(Ev);
+  }
   // initial states (for ssb_reset)
   u32* d_state0 = nullptr;
   // kernel timing
@@ -180,6 +184,7 @@ struct ssb_engine {
   int model_ready_data();
   int build_hot();
   bool hot_built = false;
+  u32 epoch = 0;
   int enqueue_round();
   int exchange();
   template <class M> void launch_model_kernels_commit(const typename M::Data& md);
@@ -229,6 +234,7 @@ int ssb_engine::init() {
   v.cap_aux = std::max<u32>(1024, v.cap_batch / 4);
   v.cap_snap = (u32)std::max<int64_t>(cfg.max_snapshots, 1024);
   v.cap_send = cfg.world > 1 ? std::max<u32>(v.cap_batch / 4, 1u << 16) : 1;
+  v.cap_anti = cfg.world > 1 ? std::min<u32>(v.cap_send, v.cap_aux) : 1;
   v.cap_log = (u64)cfg.max_committed;
   v.state_words = (u32)state_words();
   v.light_max = 8;
@@ -283,6 +289,7 @@ int ssb_engine::reset_sim() {
   Ctl init;
   std::memset(&init, 0, sizeof(init));
   init.local_min = KEY_MAX; init.gvt = 0; init.prev_gvt = KEY_MAX;
+  init.epoch = ++epoch;
   init.free_top = n_chunks - 1; init.free_low = n_chunks - 1;
   CK(cudaStreamSynchronize(stream));
   CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
@@ -322,9 +329,11 @@ int ssb_engine::check_device_error() {
   if (e & E_SENDBUF) s += " send buffer overflow (raise max_batch)";
   if (e & E_INTERNAL) s += " internal invariant violated";
   if (e & E_STALL) s += " no GVT progress in 100000 rounds";
+  if (e & E_COMM) s += " a peer partition did not reach the GVT exchange";
   set_error(s);
   if (e & (E_POOL | E_BATCH | E_SNAP | E_SENDBUF)) return SSB_ERR_CAPACITY;
   if (e & E_RANGE) return SSB_ERR_RANGE;
+  if (e & E_COMM) return SSB_ERR_COMM;
   return SSB_ERR_INVALID;
 }
 
@@ -431,7 +440,7 @@ void ssb_engine::launch_exec(const View& v) {
 }
 
 void ssb_engine::launch_exec_heavy(const View& v) {
-  k_exec_heavy<<<n_sm * 8, 256, 0, stream>>>(v);
+  k_exec_heavy<false><<<n_sm * 8, 256, 0, stream>>>(v);
 }
 
 void ssb_engine::launch_fixup(const View& v) {
@@ -478,18 +487,21 @@ int ssb_engine::exchange() {
 
 int ssb_engine::enqueue_round() {
   if (cfg.world > 1) {
-    if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
-    t_begin(K_MIN);
-    k_min<<<1, 1024, 0, stream>>>(v);
-    t_end();
-    int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
-    if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
     if (v.p2p) {
-      // every peer's emit kernel of the previous round finished before that peer joined the all-reduce, so what they
-      // appended to this GPU's mailbox is complete: integrate it (anti-messages first) before planning the window
-      for (int pass = 1; pass <= 2; ++pass)
-        for (int r = 0; r < cfg.world; ++r)
-          if (r != cfg.rank) launch_route(v, 2, (u32)r, (u32)pass);
+      // GVT candidates cross through the mailboxes; when all have arrived, what the peers appended to this GPU's
+      // mailbox in the previous round is complete: integrate it (anti-messages first) before planning the window
+      t_begin(K_MIN);
+      k_gvt<<<1, 256, 0, stream>>>(v);
+      t_end();
+      launch_route(v, 2, 1, 0);
+      launch_route(v, 2, 0, 0);
+    } else {
+      if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
+      t_begin(K_MIN);
+      k_min<<<1, 1024, 0, stream>>>(v);
+      t_end();
+      int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
+      if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
     }
   }
   t_begin(K_PLAN);
@@ -511,6 +523,7 @@ int ssb_engine::enqueue_round() {
   t_end();
   t_begin(K_SORTHEAVY);
   k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(v);
+  k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(v);
   t_end();
   t_begin(K_EXEC_HEAVY);
   launch_exec_heavy(v);
@@ -583,7 +596,12 @@ int ssb_engine::build_graph() {
   std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_heavy;
   CK(capture(body, {}, &t_plan, [&] {
     cudaMemsetAsync(vg.lph, 0, sizeof(uint4) * (size_t)vg.n_lp_local, stream);
-    k_plan<<<1, 1024, 0, stream>>>(vg, 0);
+    if (cfg.world > 1) {      // peer-memory exchange: GVT + barrier, then the receive side of the previous round
+      k_gvt<<<1, 256, 0, stream>>>(vg);
+      launch_route(vg, 2, 1, 0);
+      launch_route(vg, 2, 0, 0);
+    }
+    k_plan<<<1, 1024, 0, stream>>>(vg, cfg.world > 1 ? 1 : 0);
   }));
   CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));
   CK(capture(body, t_plan, &t_exec, [&] {
@@ -592,7 +610,10 @@ int ssb_engine::build_graph() {
     launch_exec(vg);
   }));
   CK(add_cond(body, vg.h_vheavy, cudaGraphCondTypeIf, t_exec, &n_if_vheavy, &b_vheavy));
-  CK(capture(b_vheavy, {}, nullptr, [&] { k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(vg); }));
+  CK(capture(b_vheavy, {}, nullptr, [&] {
+    k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(vg);
+    k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(vg);
+  }));
   CK(capture(body, {n_if_vheavy}, &t_heavy, [&] { launch_exec_heavy(vg); }));
   // k_route(anti) pops chunks off the free stack that the commit pass pushes to: the IF node waits for both branches
   std::vector<cudaGraphNode_t> join = t_heavy;
@@ -811,7 +832,7 @@ int ssb_run(ssb_engine* e, ssb_stats* stats) {
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->model_ready();
   if (rc) return rc;
-  const bool use_graph = e->graph_enabled && e->cfg.world == 1 && !e->timing();
+  const bool use_graph = e->graph_enabled && (e->cfg.world == 1 || e->v.p2p) && !e->timing();
   if (use_graph && e->graph_dirty && (rc = e->build_graph())) return rc;
   CK(cudaEventRecord(e->ev0, e->stream));
   u64 last_gvt = ~0ull;
@@ -994,7 +1015,7 @@ int ssb_comm_export(ssb_engine* e, void* handle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   if (!e->mbox_block) {
     CK(cudaMalloc(&e->mbox_block, e->mbox_bytes()));
-    CK(cudaMemsetAsync(e->mbox_block, 0, e->mbox_cnt_bytes(), e->stream));
+    CK(cudaMemsetAsync(e->mbox_block, 0, e->mbox_cnt_bytes() + e->mbox_gvt_bytes(), e->stream));
     CK(cudaStreamSynchronize(e->stream));
   }
   cudaIpcMemHandle_t h;
@@ -1010,7 +1031,6 @@ int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   e->peer_blocks.assign((size_t)world, nullptr);
-  const size_t cnt_bytes = e->mbox_cnt_bytes();
   for (int r = 0; r < world; ++r) {
     void* base = nullptr;
     if (r == e->cfg.rank) {
@@ -1021,12 +1041,12 @@ int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
       CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
       e->peer_blocks[(size_t)r] = base;
     }
-    e->v.peer_cnt[r] = reinterpret_cast<u32*>(base);
-    e->v.peer_data[r] = reinterpret_cast<Ev*>((char*)base + cnt_bytes);
+    e->v.peer_base[r] = reinterpret_cast<char*>(base);
   }
-  e->v.mbox_cnt = reinterpret_cast<u32*>(e->mbox_block);
-  e->v.mbox_data = reinterpret_cast<Ev*>((char*)e->mbox_block + cnt_bytes);
+  e->v.mb_gvt_off = (u32)e->mbox_cnt_bytes();
+  e->v.mb_data_off = (u32)(e->mbox_cnt_bytes() + e->mbox_gvt_bytes());
   e->v.p2p = 1;
+  e->graph_dirty = true;
   return SSB_OK;
 }
 

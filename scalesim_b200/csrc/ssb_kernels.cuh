@@ -37,7 +37,8 @@ constexpr u32 kCntBits = 28;       // lph[lp].x = arrivals of the round (bits 0.
 constexpr u32 kCntMask = (1u << kCntBits) - 1u;
 constexpr u32 NIL31 = 0x7FFFFFFFu; // end of an LP's arrival list
 constexpr u32 kLightMax = 16;      // upper bound of View::light_max: LPs with more arrivals in a round get a segment
-constexpr u32 kScanCap = 128;      // segments up to this length are sorted in registers by k_exec_heavy; longer ones by k_sortheavy
+constexpr u32 kRegSortSmall = 128; // register sort with up to 4 entries per lane (the every-round kernel)
+constexpr u32 kScanCap = kRegSortSmall;      // segments up to this length are sorted in registers by k_exec_heavy; longer ones by k_sortheavy
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
@@ -91,6 +92,48 @@ __device__ __forceinline__ void block_local_min(const View& v, Ctl* c, u64* sm) 
 __global__ void k_min(View v) {
   __shared__ u64 sm[32];
   block_local_min(v, v.ctl, sm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gvt — peer-memory GVT (replaces mpi_gsync::check_sync, global_sync.hpp:95-150, and the NCCL all-reduce): the
+// block min-reduction of this partition, then thread r writes the candidate into partition r's mailbox slot
+// (one 8-byte store over NVLink: round << 32 | time) and waits until partition r's candidate for the same round has
+// arrived in the own mailbox. GVT = min over all. Every partition's appends of the previous round precede its slot
+// write (kernel boundary + system fence), so once the slots are in, the mailbox records are complete: the exchange
+// doubles as the barrier. One process per GPU: all partitions run this kernel at the same time, each on its own
+// GPU; the wait is bounded and raises E_COMM instead of hanging.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gvt(View v) {
+  __shared__ u64 sm[32];
+  __shared__ u32 s_t[MAX_WORLD];
+  Ctl* c = v.ctl;
+  block_local_min(v, c, sm);
+  __syncthreads();
+  const u32 par = (c->round + 1u) & 1u;
+  const u32 R = c->round + 1u + (c->epoch << 24);      // stamp of the round that is about to start
+  const u64 lm = c->local_min;
+  const u32 my_t = lm == KEY_MAX ? 0xFFFFFFFFu : key_time(lm);
+  if (threadIdx.x < v.world) {
+    const u32 r = threadIdx.x;
+    u32 t = my_t;
+    if (r != v.rank) {
+      __threadfence_system();
+      *reinterpret_cast<volatile u64*>(mb_gvt(v, r, par, v.rank)) = ((u64)R << 32) | my_t;
+      const volatile u64* mine = mb_gvt(v, v.rank, par, r);
+      u64 x = *mine;
+      for (u32 spin = 0; (u32)(x >> 32) != R && spin < (1u << 27); ++spin) { __nanosleep(20); x = *mine; }
+      if ((u32)(x >> 32) != R) { atomicOr(&c->error, E_COMM); t = 0xFFFFFFFFu; }
+      else t = (u32)x;
+      __threadfence_system();
+    }
+    s_t[r] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = 0xFFFFFFFFu;
+    for (u32 r = 0; r < v.world; ++r) t = s_t[r] < t ? s_t[r] : t;
+    c->gvt = t == 0xFFFFFFFFu ? KEY_MAX : make_key(t, 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,7 +223,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     if (v.p2p) {
       // the mailbox half that was just integrated (parity of the round that ended) is free again
       const u32 par = (c->round - 1) & 1u;
-      for (u32 r = 0; r < v.world; ++r) v.mbox_cnt[(par * v.world + r) * 32] = 0;
+      for (u32 r = 0; r < v.world; ++r) { *mb_cnt(v, v.rank, par, r, 0) = 0; *mb_cnt(v, v.rank, par, r, 1) = 0; }
     }
   }
   __syncthreads();
@@ -336,7 +379,7 @@ __global__ void k_segs_heavy(View v) {
     const u32 start = atomicAdd(&c->seg_cursor, n);
     v.lph[lp].y = start;          // the list head is not needed for a long LP: the word now holds its segment start
     v.heavy[h] = make_uint4(lp, start, n, 0);
-    if (n > kScanCap) atomicAdd(&c->n_vheavy, 1u);
+    if (n > kRegSortSmall) atomicAdd(&c->n_vheavy, 1u);
   }
 }
 
@@ -676,7 +719,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v) {
   extern __shared__ uint4 smem_heavy[];
   __shared__ u32 s_flag;
   Ctl* c = v.ctl;
-  const u32 nh = c->n_vheavy ? c->n_heavy : 0u;
+  const u32 nh = c->n_vheavy ? c->n_heavy : 0u;      // n_vheavy counts segments > kRegSortSmall; sort_item picks > kScanCap
   if (nh == 0) return;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr u32 kWarps = kSortThreads / 32;
@@ -913,6 +956,10 @@ __device__ __forceinline__ void heavy_turn(const View& v, u32 lp, u32 start, u32
   }
 }
 
+// kBig = false: segments of up to kRegSortSmall entries (1, 2 or 4 per lane) — every round.
+// kBig = true : the longer ones, sorted and classified by k_sortheavy (block-wide bitonic network in shared memory):
+//               the predecessor is the entry before. Only launched when such a segment exists.
+template <bool kBig>
 __global__ void __launch_bounds__(256) k_exec_heavy(View v) {
   Ctl* c = v.ctl;
   const u32 nh = c->n_heavy;
@@ -921,23 +968,30 @@ __global__ void __launch_bounds__(256) k_exec_heavy(View v) {
   for (u32 hi = wid; hi < nh; hi += nw) {
     const uint4 a = v.heavy[hi];
     const u32 lp = a.x, start = a.y, n = a.z;
+    if ((n > kRegSortSmall) != kBig) continue;
     const uint4 h = v.lph[lp];
-    const u32 fl = h.x >> kCntBits;
-    if (fl & PL_SORTED) {
-      // sorted and classified by k_sortheavy (n > kScanCap)
-      if (fl & PL_FIX) continue;
-      for (u32 i = lane; i < n; i += 32) {
-        const Sorted x = load_sorted(v.sorted + start + i);
-        u32 pslot = h.z, ptime = h.w;
-        if (i) { const Sorted p = load_sorted(v.sorted + start + i - 1); pslot = p.slot; ptime = key_time(p.key); }
-        *reinterpret_cast<uint2*>(v.meta + x.slot) = make_uint2(pslot, ptime);
-        if (i + 1u == n) v.last[lp] = make_uint2(x.slot, key_time(x.key));
+    if (!kBig) {
+      if (n <= 32) heavy_turn<1>(v, lp, start, n, h, lane);
+      else if (n <= 64) heavy_turn<2>(v, lp, start, n, h, lane);
+      else heavy_turn<4>(v, lp, start, n, h, lane);
+    } else {
+      const u32 fl = h.x >> kCntBits;
+      if (fl & PL_SORTED) {
+        // sorted and classified by k_sortheavy (n > kScanCap)
+        if (fl & PL_FIX) continue;
+        for (u32 i = lane; i < n; i += 32) {
+          const Sorted x = load_sorted(v.sorted + start + i);
+          u32 pslot = h.z, ptime = h.w;
+          if (i) { const Sorted p = load_sorted(v.sorted + start + i - 1); pslot = p.slot; ptime = key_time(p.key); }
+          *reinterpret_cast<uint2*>(v.meta + x.slot) = make_uint2(pslot, ptime);
+          if (i + 1u == n) v.last[lp] = make_uint2(x.slot, key_time(x.key));
+        }
+      } else {
+        atomicOr(&c->error, E_INTERNAL);      // every segment longer than kRegSortSmall is sorted by k_sortheavy
       }
-    } else if (n <= 32) heavy_turn<1>(v, lp, start, n, h, lane);
-    else if (n <= 64) heavy_turn<2>(v, lp, start, n, h, lane);
-    else heavy_turn<4>(v, lp, start, n, h, lane);
+    }
   }
-  if (v.use_graph) {
+  if (!kBig && v.use_graph) {
     // the last block to finish knows the final fix list: it opens or closes the IF node around k_fixup
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1072,23 +1126,37 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   extern __shared__ __align__(128) unsigned char smem_route[];
   __shared__ u64 s_bar;
   __shared__ u64 s_sent_min;
+  __shared__ const Ev* s_seg[MAX_WORLD + 2];     // the source = a concatenation of up to world + 1 record runs
+  __shared__ u32 s_off[MAX_WORLD + 3];
+  __shared__ u32 s_nseg;
   Ctl* c = v.ctl;
-  const Ev* src;
-  u32 n0, n1 = 0;        // main count, extra count (extra region starts at cap_batch)
-  if (which == 0) { src = v.anti_box; n0 = c->n_anti < v.cap_aux ? c->n_anti : v.cap_aux; }
-  else if (which == 1) { src = v.outbox; n0 = c->n_arr; n1 = c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux; }
-  else if (which == 2) {
-    if (v.p2p) {
-      const u32 par = c->round & 1u;
-      src = v.mbox_data + ((size_t)par * v.world + peer) * v.cap_send;
-      n0 = v.mbox_cnt[(par * v.world + peer) * 32];
-      if (n0 > v.cap_send) { n0 = v.cap_send; if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&c->error, E_SENDBUF); }
-    } else {
-      src = v.recvbuf + (size_t)peer * v.cap_send; n0 = c->recv_count[peer];
+  if (threadIdx.x == 0) {
+    u32 ns = 0, tot = 0;
+    auto add = [&](const Ev* p, u32 n) { if (n) { s_seg[ns] = p; s_off[ns] = tot; tot += n; ++ns; } };
+    if (which == 0) add(v.anti_box, c->n_anti < v.cap_aux ? c->n_anti : v.cap_aux);
+    else if (which == 1) { add(v.outbox, c->n_arr); add(v.outbox + v.cap_batch, c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux); }
+    else if (which == 2) {
+      if (v.p2p) {
+        // own mailbox, all sources; `peer` = kind (1 = anti-message regions, integrated first; 0 = positives)
+        const u32 par = c->round & 1u, kind = peer, cap = kind ? v.cap_anti : v.cap_send;
+        for (u32 r = 0; r < v.world; ++r) {
+          if (r == v.rank) continue;
+          u32 n = *mb_cnt(v, v.rank, par, r, kind);
+          if (n > cap) { n = cap; if (blockIdx.x == 0) atomicOr(&c->error, E_SENDBUF); }
+          add(mb_data(v, v.rank, par, r, kind), n);
+        }
+      } else {
+        add(v.recvbuf + (size_t)peer * v.cap_send, c->recv_count[peer]);
+      }
     }
+    else add(v.outbox, c->load_count);
+    s_off[ns] = tot;
+    s_nseg = ns;
+    s_sent_min = KEY_MAX;
+    mbar_init(&s_bar, 1);
   }
-  else { src = v.outbox; n0 = c->load_count; }
-  const u32 total = n0 + n1;
+  __syncthreads();
+  const u32 total = s_off[s_nseg];
   if (total == 0) return;
   // equal tiles for all blocks: `passes` tiles of `tile` records each (tile is a multiple of 32 records = 1 KB)
   const u32 passes = (total + gridDim.x * kRouteTile - 1) / (gridDim.x * kRouteTile);
@@ -1106,17 +1174,20 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   u32* s_ch1 = s_ch0 + nt;                              // [nt] the next chunk, if the range crosses into it
   const u32 chm = (1u << v.ch_log) - 1u;
   const u32 T_NONE = NIL, T_DIRECT = NIL - 1u;
-  if (threadIdx.x == 0) { s_sent_min = KEY_MAX; mbar_init(&s_bar, 1); }
-  __syncthreads();
+  const u32 send_kind = which == 0 ? 1u : 0u;      // anti-messages travel in their own mailbox region
   u32 phase = 0;
   for (u32 t0 = blockIdx.x * tile; t0 < total; t0 += gridDim.x * tile) {
     const u32 cnt = total - t0 < tile ? total - t0 : tile;
     if (threadIdx.x == 0) {
-      // virtual index space [main | extra]: a tile that straddles the boundary takes two copies
-      const u32 a = t0 < n0 ? (n0 - t0 < cnt ? n0 - t0 : cnt) : 0u;      // records from the main region
+      // one bulk copy per source run the tile overlaps
       mbar_expect_tx(&s_bar, cnt * (u32)sizeof(Ev));
-      if (a) bulk_g2s(s_tile, src + t0, a * (u32)sizeof(Ev), &s_bar);
-      if (cnt > a) bulk_g2s(s_tile + a, src + v.cap_batch + (t0 + a - n0), (cnt - a) * (u32)sizeof(Ev), &s_bar);
+      u32 sg = 0;
+      while (s_off[sg + 1] <= t0) ++sg;
+      for (u32 pos = t0, left = cnt, dst = 0; left; ++sg) {
+        const u32 avail = s_off[sg + 1] - pos, take = avail < left ? avail : left;
+        bulk_g2s(s_tile + dst, s_seg[sg] + (pos - s_off[sg]), take * (u32)sizeof(Ev), &s_bar);
+        dst += take; pos += take; left -= take;
+      }
     }
     for (u32 t = threadIdx.x; t < nt; t += kRouteThreads) s_cnt[t] = 0;
     __syncthreads();
@@ -1184,7 +1255,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         atomicAdd(&c->n_beyond, (u64)n);
       } else {
         const u32 r = t - rs - 1;
-        if (v.p2p) s_base[t] = atomicAdd_system(&v.peer_cnt[r][((c->round & 1u) * v.world + v.rank) * 32], n);
+        if (v.p2p) s_base[t] = atomicAdd_system(mb_cnt(v, r, c->round & 1u, v.rank, send_kind), n);
         else s_base[t] = atomicAdd(&c->send_count[r], n);
         atomicAdd(&c->n_remote, (u64)n);
       }
@@ -1238,11 +1309,10 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       } else {
         const u32 r = t - rs - 1;
         const u32 p = s_base[t] + rnk[it];
-        if (p >= v.cap_send) { atomicOr(&c->error, E_SENDBUF); continue; }
+        if (p >= (v.p2p && send_kind ? v.cap_anti : v.cap_send)) { atomicOr(&c->error, E_SENDBUF); continue; }
         if (v.p2p) {
           // straight into the destination GPU's mailbox over NVLink
-          st256(v.peer_data[r] + (((size_t)(c->round & 1u) * v.world + v.rank) * v.cap_send + p),
-                qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
+          st256(mb_data(v, r, c->round & 1u, v.rank, send_kind) + p, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
           const u64 k = make_key(tm >= v.finish_time ? v.finish_time : tm / v.bucket_ticks * v.bucket_ticks, 0);
           if (k < s_sent_min) atomicMin(&s_sent_min, k);
         } else {

@@ -16,13 +16,15 @@ def init_engine_comm(engine: Engine, rank: int, world: int, p2p: bool = True):
     if world <= 1:
         return
     import torch.distributed as dist
-    obj = [Engine.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(obj, src=0)
-    engine.comm_init(obj[0])
     if p2p:
+        # peer-memory exchange: events and GVT candidates cross through the mailboxes; no NCCL communicator needed
         handles = [None] * world
         dist.all_gather_object(handles, engine.comm_export())
         engine.comm_import(b"".join(handles))
+        return
+    obj = [Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    engine.comm_init(obj[0])
 
 
 def combine_digests(digests):
