@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -105,7 +105,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU side: the reference itself (oracle/_ref) or the oracle port, on a bounded sample
 # ------------------------------------------------------------------------------------------------
-SAMPLES = [(10000, 160000, 728183), (2500, 40000, None), (1000, 16000, None)]
+SAMPLES = [(30000, 480000, 2184583), (10000, 160000, 728183), (2500, 40000, None), (1000, 16000, None)]
 
 
 def cpu_threads():
@@ -187,6 +187,54 @@ def reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# Secondary workload: grid TrafficSim (BASELINE.json config 3: 1024 x 1024 torus grid, 10M trips, row-stripe partition)
+# ------------------------------------------------------------------------------------------------
+B_ALG_TRAFFIC = 392.0   # algorithmic bytes per committed TrafficSim event
+
+
+def traffic_measure(args, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks, log):
+    import numpy as np
+    import scalesim_b200 as ssb
+    from scalesim_b200 import traffic
+    t0 = time.perf_counter()
+    sc = traffic.synthetic_grid(args.traffic_grid, args.traffic_grid, args.traffic_trips, seed=1)
+    sc.partition = traffic.stripe_partition(args.traffic_grid, args.traffic_grid, world) if world > 1 else None
+    log(f"traffic scenario: {sc.trip_id.size} trips, {sc.route_nodes.size} route nodes, built in {time.perf_counter() - t0:.1f} s")
+    per = (args.traffic_trips + world - 1) // world
+    eng = traffic.make_engine(sc, bucket_ticks=args.traffic_bucket, window_buckets=args.traffic_window, rank=rank, world=world,
+                              device=local_rank, max_events=int(per * 2.0) + (1 << 20), max_batch=per + (1 << 16),
+                              rounds_per_sync=32, load=False)
+    ssb.dist.init_engine_comm(eng, rank, world, p2p=args.exchange == "p2p")
+    ev = traffic.pack_events(sc)
+    if world > 1:
+        ev = ev[sc.partition[ev["dst"]] % world == rank]
+    ev = np.ascontiguousarray(ev)
+    del sc
+    ms, committed, rounds, last = [], 0, 0, None
+    for i in range(2 + max(1, min(args.steps, 3))):
+        eng.reset()
+        eng.load_events(ev)
+        barrier()
+        st = eng.run()
+        barrier()
+        if i >= 2:
+            ms.append(max_over_ranks(st.loop_ms))
+            committed += sum_over_ranks(st.committed)
+            rounds += st.rounds
+            last = st
+    n = len(ms)
+    value = committed / (sum(ms) / 1000.0)
+    eng.close()
+    return {"metric": "committed events/sec, grid TrafficSim", "value": value, "unit": UNIT, "ms_per_step": sum(ms) / n,
+            "committed_per_step": committed // n, "rounds_per_step": rounds // n, "rollbacks": last.rollbacks,
+            "antis": last.antis_sent, "bucket_ticks": args.traffic_bucket, "window_buckets": args.traffic_window,
+            "workload": f"TrafficSim {args.traffic_grid}x{args.traffic_grid} torus grid, {args.traffic_trips} trips "
+                        f"(8..64 hops), finish 10800 s, {world} row-stripe partition(s) (BASELINE.json config 3)",
+            "whole_path_roofline": {"alg_bytes_per_event": B_ALG_TRAFFIC, "achieved_gbs": value / world * B_ALG_TRAFFIC / 1e9,
+                                    "frac": value / world * B_ALG_TRAFFIC / 1e9 / peaks()[0]}}
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,6 +250,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-partition event exchange")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the secondary grid TrafficSim measurement")
+    ap.add_argument("--traffic-only", action="store_true")
+    ap.add_argument("--traffic-grid", type=int, default=1024)
+    ap.add_argument("--traffic-trips", type=int, default=10_000_000)
+    ap.add_argument("--traffic-bucket", type=int, default=11)
+    ap.add_argument("--traffic-window", type=int, default=1)
     args = ap.parse_args()
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line and nothing else
@@ -226,6 +280,31 @@ def main():
         dist.init_process_group("gloo")      # plumbing only (unique id, barriers, max over ranks); data path = NCCL in the engine
     torch.cuda.set_device(local_rank)
 
+    verbose = bool(os.environ.get("BENCH_VERBOSE"))
+
+    def log(msg):
+        if verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        return ssb.dist.max_over_ranks(x, world)
+
+    def sum_over_ranks(x):
+        return ssb.dist.sum_over_ranks(x, world)
+
+    if args.traffic_only:
+        t = traffic_measure(args, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks, log)
+        if rank == 0:
+            print(json.dumps(t), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     n_lp = args.lps_per_gpu * world
     n_init = args.init_per_gpu * world
     tables = phold.build_tables(args.remote, 1.0)
@@ -248,17 +327,6 @@ def main():
     ssb.dist.init_engine_comm(eng, rank, world, p2p=args.exchange == "p2p")
     rec_pin = torch.empty(per_rank_committed_cap * 32, dtype=torch.uint8).pin_memory() if keep else None
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        return ssb.dist.max_over_ranks(x, world)
-
-    def sum_over_ranks(x):
-        return ssb.dist.sum_over_ranks(x, world)
-
     def one_step():
         """device-resident timing: inputs already in HBM when the timed region (the window loop) starts"""
         eng.reset()
@@ -279,19 +347,13 @@ def main():
         barrier()
         return st, dg, got, time.perf_counter() - t0
 
-    verbose = bool(os.environ.get("BENCH_VERBOSE"))
-
-    def log(msg):
-        if verbose:
-            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
-
     log(f"engine ready: {n_ev} initial events on this rank")
+    sampler = ClockSampler(local_rank)      # samples from the first warm-up step to the last timed step (same load)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         st = one_step()
         log(f"warm-up step: loop {st.loop_ms:.2f} ms, rounds {st.rounds}, committed {st.committed}, remote {st.remote_sent}")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     step_ms, committed_total, rounds_total = [], 0, 0
     last = None
     for _ in range(args.steps):
@@ -348,6 +410,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_run(25.0)
 
+    eng.close()
+    del ev_pin, rec_pin
+    traffic_res = None
+    if not args.no_traffic:
+        traffic_res = traffic_measure(args, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks, log)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -363,10 +431,9 @@ def main():
                        "l2": "inputs larger than L2 (event pool + tables > 600 MB per GPU); no flush between steps",
                        "rollbacks": last.rollbacks, "antis": last.antis_sent},
             "gpu_launches": int(rounds_total * (LAUNCHES_PER_ROUND_GRAPH if world == 1 and last.rollbacks == 0 else LAUNCHES_PER_ROUND_STREAM)),
-            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "traffic": traffic_res,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

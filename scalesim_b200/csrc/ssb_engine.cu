@@ -522,7 +522,7 @@ int ssb_engine::enqueue_round() {
   launch_exec(v);
   t_end();
   t_begin(K_SORTHEAVY);
-  k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(v);
+  k_sortheavy<<<n_sm * 6, kSortThreads, heavy_smem(), stream>>>(v);
   k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(v);
   t_end();
   t_begin(K_EXEC_HEAVY);
@@ -611,7 +611,7 @@ int ssb_engine::build_graph() {
   }));
   CK(add_cond(body, vg.h_vheavy, cudaGraphCondTypeIf, t_exec, &n_if_vheavy, &b_vheavy));
   CK(capture(b_vheavy, {}, nullptr, [&] {
-    k_sortheavy<<<n_sm * 4, kSortThreads, heavy_smem(), stream>>>(vg);
+    k_sortheavy<<<n_sm * 6, kSortThreads, heavy_smem(), stream>>>(vg);
     k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(vg);
   }));
   CK(capture(body, {n_if_vheavy}, &t_heavy, [&] { launch_exec_heavy(vg); }));

@@ -204,7 +204,7 @@ def pack_events(sc: Scenario) -> np.ndarray:
 def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1, keep_records: bool = False,
                 rank: int = 0, world: int = 1, device: int = 0, max_events: int | None = None,
                 max_batch: int | None = None, max_committed: int | None = None, finish_time: int = FINISH_TIME,
-                rounds_per_sync: int = 8) -> Engine:
+                rounds_per_sync: int = 8, load: bool = True) -> Engine:
     """Build a TrafficSim engine the way runner<traffic_sim>::init does (runner.hpp:79-176)."""
     n_trips = sc.trip_id.size
     n_nodes = sc.route_nodes.size
@@ -227,7 +227,8 @@ def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1,
     owner = (part[ids] % world) if part is not None else (ids % world)
     mine = owner == rank
     eng.load_states(ids[mine], words[mine])
-    ev = pack_events(sc)
-    ev_owner = (part[ev["dst"]] % world) if part is not None else (ev["dst"] % world)
-    eng.load_events(ev[ev_owner == rank])
+    if load:
+        ev = pack_events(sc)
+        ev_owner = (part[ev["dst"]] % world) if part is not None else (ev["dst"] % world)
+        eng.load_events(ev[ev_owner == rank])
     return eng
