@@ -88,6 +88,8 @@ typedef struct ssb_config {
 
 #define SSB_FLAG_DEBUG_CHECKS 1   /* extra device-side invariant checks */
 #define SSB_FLAG_KERNEL_TIMING 2  /* bracket every kernel launch with CUDA events (see ssb_kernel_times) */
+#define SSB_FLAG_HISTORY 4        /* --diff_init: keep the sent-log entry of every committed event for the history store
+                                     (set at ssb_create; needs max_committed > 0) */
 
 /* Host-side POD mirror of the App::Event accessors (sim_obj.hpp:50-59) + model payload. */
 typedef struct ssb_event {
@@ -113,6 +115,16 @@ typedef struct ssb_raw_record {
   uint64_t key;
   uint32_t dst, src, send_time, p0, p1, tag;
 } ssb_raw_record;
+
+/* Sent-log entry of one committed event (what eventq::set_cancel keeps, queue.hpp:151-157): the event it produced.
+ * dst 0xffffffff = the handler produced nothing. Travels next to the ssb_raw_record of the event in the
+ * exact-differential history store (the reference's event / cancel / state LevelDBs, leveldb_store.hpp). */
+typedef struct ssb_sent_record {
+  uint32_t dst;          /* destination LP of the produced event */
+  uint32_t id;           /* its id */
+  uint32_t recv_time;    /* its receive_time */
+  uint32_t reserved;
+} ssb_sent_record;
 
 typedef struct ssb_stats {
   int64_t rounds;            /* windows executed */
@@ -169,6 +181,20 @@ int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n)
 
 /* same, without widening: n raw 32-byte records straight from the device log (one D2H copy; `out` may be pinned) */
 int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int64_t* n);
+
+/* ---- exact-differential simulation (reference --diff_init / --diff_repeat; runner.hpp:178-348, queue.hpp:179-241,
+ * logical_process.hpp:132-153, leveldb_store.hpp) ----
+ * --diff_init: with SSB_FLAG_HISTORY, ssb_drain_history hands out every committed event together with its sent-log
+ * entry — the logical content of the reference's three stores (event: key (dst, recv_time, id); cancel and state:
+ * key (dst, recv_time, id) of the events that produced something, plus one (-1,-1) state per LP). `rec` / `sent` may
+ * be pinned host buffers; the copies are asynchronous device-to-host transfers.
+ * --diff_repeat: ssb_load_history puts a recorded history back as PROCESSED events (calendar, processed chains,
+ * sent-log) without executing anything; what-if events are then injected with ssb_load_events and ssb_run re-executes
+ * exactly what they invalidate: a touched LP rolls back to the query time, its recorded outputs go out as
+ * anti-messages and cascade — the reference's lazy history load (R13), with the history already resident in HBM.
+ * Only events (re-)executed by the repeat run are committed (output / digest). */
+int ssb_drain_history(ssb_engine* e, ssb_raw_record* rec, ssb_sent_record* sent, int64_t cap, int64_t* n);
+int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n);
 
 /* Back to the state right after ssb_load_states: empty calendar, zero statistics; model data, partition and the
  * loaded initial states are kept. Lets one engine run many simulations (bench steps) without re-allocating. */

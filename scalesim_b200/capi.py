@@ -27,8 +27,11 @@ RECORD_DTYPE = np.dtype([
 RAW_RECORD_DTYPE = np.dtype([
     ("key", "<u8"), ("dst", "<u4"), ("src", "<u4"), ("send_time", "<u4"), ("p0", "<u4"), ("p1", "<u4"), ("tag", "<u4"),
 ])
+#: host mirror of ``ssb_sent_record`` (16 bytes): the event a committed event produced (dst 0xffffffff = none)
+SENT_RECORD_DTYPE = np.dtype([("dst", "<u4"), ("id", "<u4"), ("recv_time", "<u4"), ("reserved", "<u4")])
 FLAG_DEBUG_CHECKS = 1
 FLAG_KERNEL_TIMING = 2
+FLAG_HISTORY = 4
 
 
 def raw_to_records(raw: np.ndarray) -> np.ndarray:
@@ -142,6 +145,8 @@ def load_library() -> C.CDLL:
     lib.ssb_committed_digest.argtypes = [vp, vp]
     lib.ssb_drain_committed.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.ssb_drain_committed_raw.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_drain_history.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_load_history.argtypes = [vp, vp, vp, i64]
     lib.ssb_reset.argtypes = [vp]
     lib.ssb_set_flags.argtypes = [vp, C.c_int32]
     lib.ssb_kernel_times.argtypes = [vp, vp, vp, vp, i32]
@@ -287,6 +292,25 @@ class Engine:
         n = C.c_int64(0)
         self._check(self._lib.ssb_drain_committed_raw(self._h, C.c_void_p(ptr), cap, C.byref(n)))
         return n.value
+
+    def drain_history(self, cap: int | None = None):
+        """--diff_init: every committed event (``ssb_raw_record``) with its sent-log entry (``ssb_sent_record``).
+        Needs ``Config.flags & FLAG_HISTORY`` and ``max_committed > 0``."""
+        if cap is None:
+            cap = max(1, self.stats().committed)
+        rec = np.empty(cap, dtype=RAW_RECORD_DTYPE)
+        sent = np.empty(cap, dtype=SENT_RECORD_DTYPE)
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_history(self._h, _ptr(rec), _ptr(sent), cap, C.byref(n)))
+        return rec[: n.value], sent[: n.value]
+
+    def load_history(self, rec: np.ndarray, sent: np.ndarray):
+        """--diff_repeat: put a recorded history back as processed events (nothing is executed)."""
+        rec = np.ascontiguousarray(rec, dtype=RAW_RECORD_DTYPE)
+        sent = np.ascontiguousarray(sent, dtype=SENT_RECORD_DTYPE)
+        if rec.size != sent.size:
+            raise ValueError("history arrays differ in length")
+        self._check(self._lib.ssb_load_history(self._h, _ptr(rec), _ptr(sent), rec.size))
 
     def reset(self):
         self._check(self._lib.ssb_reset(self._h))

@@ -25,6 +25,7 @@ constexpr u64 KEY_MAX = ~0ull;
 constexpr u32 F_CANCEL = 1u;      // anti-message (sim_event_base::is_cancel_, sim_obj.hpp:30)
 constexpr unsigned char P_PROCESSED = 1;   // pflag: handler has run and the result stands
 constexpr unsigned char P_DEAD = 2;        // pflag: annihilated, duplicate, or a consumed anti-message
+constexpr unsigned char P_HISTORY = 4;     // pflag: loaded from the exact-differential history store and not re-executed since
 constexpr u32 TAG_START = 1u, TAG_END = 2u;
 constexpr int MAX_WORLD = 16;
 constexpr int RQ_LEN = 64;
@@ -148,6 +149,9 @@ struct View {
   u32 mb_gvt_off, mb_data_off;   // byte offsets inside a mailbox block
   char* peer_base[MAX_WORLD];    // mailbox blocks of all partitions (own block at [rank])
   Ev* log;             // [cap_log] committed records
+  uint4* log_sent;     // [cap_log] history store (--diff_init): sent-log entry of each committed event {dst, key lo, key hi, 0}
+  uint4* hist_sent;    // [cap_batch] staging of the sent-log entries while history is loaded (--diff_repeat)
+  u32 replay;          // 1 = history replay: events are linked into the processed chains, handlers do not run
   u32* snap;           // [cap_snap * state_words]
   Ctl* ctl;
 };

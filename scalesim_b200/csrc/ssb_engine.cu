@@ -186,6 +186,7 @@ struct ssb_engine {
   bool hot_built = false;
   u32 epoch = 0;
   int enqueue_round();
+  int enqueue_replay_round();
   int exchange();
   template <class M> void launch_model_kernels_commit(const typename M::Data& md);
   template <class M> void launch_model_kernels_exec(const typename M::Data& md);
@@ -231,7 +232,7 @@ int ssb_engine::init() {
   }
   v.maxc = n_chunks;
   v.cap_batch = (u32)cfg.max_batch;
-  v.cap_aux = std::max<u32>(1024, v.cap_batch / 4);
+  v.cap_aux = std::max<u32>(1024, v.cap_batch);      // anti-messages, re-execution outputs and re-queued events of a round
   v.cap_snap = (u32)std::max<int64_t>(cfg.max_snapshots, 1024);
   v.cap_send = cfg.world > 1 ? std::max<u32>(v.cap_batch / 4, 1u << 16) : 1;
   v.cap_anti = cfg.world > 1 ? std::min<u32>(v.cap_send, v.cap_aux) : 1;
@@ -265,6 +266,7 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.sendbuf, (size_t)v.world * v.cap_send))) return rc;
   if ((rc = alloc(&v.recvbuf, (size_t)v.world * v.cap_send))) return rc;
   if ((rc = alloc(&v.log, (size_t)v.cap_log))) return rc;
+  if ((cfg.flags & SSB_FLAG_HISTORY) && v.cap_log && (rc = alloc(&v.log_sent, (size_t)v.cap_log))) return rc;
   if ((rc = alloc(&v.snap, (size_t)v.cap_snap * v.state_words))) return rc;
   if ((rc = alloc(&v.ctl, 1))) return rc;
   if ((rc = alloc(&d_stage, v.cap_batch))) return rc;
@@ -450,6 +452,21 @@ void ssb_engine::launch_fixup(const View& v) {
     case SSB_MODEL_PHOLD_STATEFUL: k_fixup<PholdStatefulModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
     case SSB_MODEL_TRAFFIC: k_fixup<TrafficModel><<<g, 128, 0, stream>>>(v, traffic_data()); break;
   }
+}
+
+// one round of history replay (--diff_repeat): group the window's recorded events by LP and link them into the
+// processed chains; no handler runs, nothing is committed or sent
+int ssb_engine::enqueue_replay_round() {
+  k_plan<<<1, 1024, 0, stream>>>(v, 0);
+  CK(cudaMemsetAsync(v.lph, 0, sizeof(uint4) * (size_t)v.n_lp_local, stream));
+  k_link<<<n_sm * 8, 256, 0, stream>>>(v);
+  k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
+  launch_exec(v);
+  k_sortheavy<<<n_sm * 6, kSortThreads, heavy_smem(), stream>>>(v);
+  k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(v);
+  launch_exec_heavy(v);
+  CK(cudaGetLastError());
+  return SSB_OK;
 }
 
 // counts all-to-all, then payload all-to-all (grouped ncclSend/ncclRecv), then integrate what arrived
@@ -950,6 +967,70 @@ int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int
     CK(cudaStreamSynchronize(e->stream));
     e->log_drained = 0;
   }
+  return SSB_OK;
+}
+
+int ssb_drain_history(ssb_engine* e, ssb_raw_record* rec, ssb_sent_record* sent, int64_t cap, int64_t* n) {
+  if (!e || !n || ((!rec || !sent) && cap) || cap < 0) return SSB_ERR_INVALID;
+  static_assert(sizeof(ssb_sent_record) == sizeof(uint4), "sent record layout");
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  if (!e->v.log_sent) { set_error("history was not kept: create the engine with SSB_FLAG_HISTORY and max_committed > 0"); return SSB_ERR_INVALID; }
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  if (e->h_ctl->log_dropped) { set_error("history incomplete: committed log overflowed (raise max_committed)"); return SSB_ERR_CAPACITY; }
+  u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
+  u64 m = std::min<u64>(have - e->log_drained, (u64)cap);
+  *n = (int64_t)m;
+  if (m) {
+    CK(cudaMemcpyAsync(rec, e->v.log + e->log_drained, m * sizeof(Ev), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(sent, e->v.log_sent + e->log_drained, m * sizeof(uint4), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  e->log_drained += m;
+  if (e->log_drained == have && have == e->h_ctl->log_count) {
+    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->log_drained = 0;
+  }
+  return SSB_OK;
+}
+
+int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n) {
+  if (!e || ((!rec || !sent) && n) || n < 0) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  int rc = e->model_ready();
+  if (rc) return rc;
+  if ((rc = e->sync_ctl())) return rc;
+  if (e->h_ctl->round != 0 || e->h_ctl->load_count != 0) { set_error("ssb_load_history must be the first load after create / reset"); return SSB_ERR_INVALID; }
+  if (!e->v.hist_sent && (rc = e->alloc(&e->v.hist_sent, e->v.cap_batch))) return rc;
+  e->v.replay = 1;
+  Ev* stage = reinterpret_cast<Ev*>(e->d_stage);      // the load staging buffer (64 B per entry) holds a chunk of records
+  int64_t done = 0;
+  while (done < n) {
+    u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
+    CK(cudaMemcpyAsync(stage, rec + done, sizeof(Ev) * m, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->v.hist_sent, sent + done, sizeof(uint4) * m, cudaMemcpyHostToDevice, e->stream));
+    k_hist_stage<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, stage, m);
+    e->launch_route(e->v, 3, 0, 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    done += m;
+  }
+  // replay: window after window until every loaded event sits in its LP's processed chain
+  for (long long guard = 0;; ++guard) {
+    for (int i = 0; i < 8; ++i) if ((rc = e->enqueue_replay_round())) { e->v.replay = 0; return rc; }
+    if ((rc = e->sync_ctl())) { e->v.replay = 0; return rc; }
+    if ((rc = e->check_device_error())) { e->v.replay = 0; return rc; }
+    if (e->h_ctl->done) break;
+    if (guard > 1000000) { e->v.replay = 0; set_error("history replay does not terminate"); return SSB_ERR_INVALID; }
+  }
+  e->v.replay = 0;
+  e->graph_dirty = true;
+  k_after_replay<<<1, 1, 0, e->stream>>>(e->v);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
   return SSB_OK;
 }
 

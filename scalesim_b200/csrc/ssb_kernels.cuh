@@ -164,13 +164,15 @@ __global__ void k_plan(View v, int use_global_gvt) {
     u32 cur = done ? fin_b : t / v.bucket_ticks;
     if (cur > fin_b) cur = fin_b;
     c->cur_abs = cur;
-    // commit list
+    // commit list (history replay commits nothing: the loaded events stay in the calendar as processed events)
     u32 nc = 0, tot = 0;
-    for (u32 b = c->commit_next; b < cur; ++b) {
-      u32 f = v.fill[b];
-      if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
+    if (!v.replay) {
+      for (u32 b = c->commit_next; b < cur; ++b) {
+        u32 f = v.fill[b];
+        if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
+      }
+      c->commit_next = cur > c->commit_next ? cur : c->commit_next;
     }
-    c->commit_next = cur > c->commit_next ? cur : c->commit_next;
     c->n_commit = nc;
     c->commit_total = tot;
     // snapshot ring: rounds whose window lies below GVT are dead (their snapshots can be reused)
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
     bool keep = false;
     Ev e;
     u32 tg = 0;
+    u32 my_slot = 0;
     if (i < total) {
       u32 lo = 0, hi = nc;        // locate the bucket: binary search over the commit list offsets
       while (hi - lo > 1) {
@@ -264,9 +267,11 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
       }
       uint4 ce = v.commit[lo];
       u32 slot = slot_of(v, ce.x, i - ce.z);
+      my_slot = slot;
       e = load_ev_ef(v.ev + slot);
       const unsigned char pf = v.pflag[slot];
-      keep = !(e.flags & F_CANCEL) && !(pf & P_DEAD) && key_time(e.key) < v.finish_time;
+      // an event loaded from the history store is output again only if the repeat run re-executed it (R13)
+      keep = !(e.flags & F_CANCEL) && !(pf & (P_DEAD | P_HISTORY)) && key_time(e.key) < v.finish_time;
       if (keep) {
         if (!(pf & P_PROCESSED)) atomicOr(&c->error, E_INTERNAL);
         tg = M::tag(md, e);
@@ -287,7 +292,14 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
       __syncthreads();
       if (keep) {
         u64 pos = s_pos + w_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
-        if (pos < v.cap_log) { e.flags = tg; store_ev_ef(v.log + pos, e); }
+        if (pos < v.cap_log) {
+          e.flags = tg;
+          store_ev_ef(v.log + pos, e);
+          if (v.log_sent) {      // --diff_init: the sent-log entry goes to the history store with the event (R12)
+            const Meta m = load_meta(v.meta + my_slot);
+            v.log_sent[pos] = make_uint4(m.sent_dst, (u32)m.sent_key, (u32)(m.sent_key >> 32), 0u);
+          }
+        }
         else atomicAdd(&c->log_dropped, 1ull);
       }
       __syncthreads();
@@ -385,6 +397,7 @@ __global__ void k_segs_heavy(View v) {
 
 // first flagger of an LP puts it on the fix list
 __device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 bit) {
+  if (v.replay) atomicOr(&v.ctl->error, E_INTERNAL);      // a recorded history has no irregular turns
   const u32 old = atomicOr(reinterpret_cast<u32*>(v.lph + lp), bit << kCntBits);
   if (((old >> kCntBits) & PL_FIX) == 0) v.fix[atomicAdd(&v.ctl->n_fix, 1u)] = lp;
 }
@@ -420,7 +433,8 @@ struct Turn {
   u32 st[M::kStateWords];
   bool st_dirty;
   u32 err;
-  u32 n_proc, n_undone, n_anti, n_annih, n_dup;
+  u32 n_proc, n_undone, n_anti, n_annih, n_dup, n_requeued;
+  u32 tbound;      // first time beyond the current window
 
   __device__ Turn(const View& v_, const typename M::Data& md_) : v(v_), md(md_) {}
 
@@ -477,6 +491,19 @@ struct Turn {
     ++n_proc;
   }
 
+  // An undone event beyond the current window goes back to PENDING instead of being re-executed at once: a copy is
+  // appended to its calendar bucket (through the outbox) and the recorded slot dies. What lp::flush_buf does by
+  // lowering local_time_ (logical_process.hpp:145-156): the rolled-back events wait in the queue until the
+  // simulation reaches them again. Re-executing them eagerly would let every later arrival at this LP roll the
+  // same future back again (quadratic in a --diff_repeat cascade).
+  __device__ __forceinline__ void requeue(u32 slot) {
+    Ev e = load_ev(v.ev + slot);
+    e.flags = 0;
+    store_ev(v.outbox + extra_idx(), e);
+    v.pflag[slot] = P_DEAD;
+    ++n_requeued;
+  }
+
   __device__ __forceinline__ u32 extra_idx() {
     u32 pos = atomicAdd(&v.ctl->n_extra, 1u);
     if (pos >= v.cap_aux) { err |= E_BATCH; pos = v.cap_aux - 1; }
@@ -486,7 +513,8 @@ struct Turn {
   // seg[0..n) = the LP's arrivals of this round, sorted; old_slot/old_time = the LP's chain head before the round.
   // Arrival i owns outbox entry i, so whatever k_exec may already have written for this LP is overwritten here.
   __device__ void run(u32 lp, const Sorted* seg, u32 n, u32 old_slot, u32 old_time) {
-    err = 0; n_proc = n_undone = n_anti = n_annih = n_dup = 0;
+    err = 0; n_proc = n_undone = n_anti = n_annih = n_dup = n_requeued = 0;
+    tbound = v.ctl->bound_abs * v.bucket_ticks;
     st_dirty = false;
     last_slot = old_slot;
     last_time = old_time;
@@ -561,7 +589,8 @@ struct Turn {
       }
       if (present != NIL) {
         // a re-executed (rolled back) event has no inbox position: its output goes to the extra region
-        process(present, out_idx != NIL ? out_idx : extra_idx());
+        if (key_time(k) < tbound) process(present, out_idx != NIL ? out_idx : extra_idx());
+        else requeue(present);
       }
     }
 
@@ -585,6 +614,18 @@ template <class M, bool kLinkLater = false>
 __device__ __forceinline__ void exec_one(const View& v, const typename M::Data& md, u32 i, u32 slot, Ev e, u32 lp,
                                          u32 pred_slot, u32 pred_time, bool is_last, u32& err) {
   e.flags = 0;
+  if (v.replay) {
+    // history replay (--diff_repeat, R13): the event was processed in the recorded run; its sent-log entry came with
+    // it. Only its place in the LP's processed chain is established, nothing is executed or sent.
+    Meta m = load_meta(v.meta + slot);
+    m.link = pred_slot;
+    m.prevtime = pred_time;
+    store_meta(v.meta + slot, m);
+    v.pflag[slot] = P_PROCESSED | P_HISTORY;
+    v.outbox[i].key = KEY_MAX;
+    if (is_last) v.last[lp] = make_uint2(slot, key_time(e.key));
+    return;
+  }
   u32 st[M::kStateWords], pre[M::kStateWords];
 #pragma unroll
   for (int q = 0; q < M::kStateWords; ++q) { st[q] = v.state[(size_t)lp * M::kStateWords + q]; pre[q] = st[q]; }
@@ -1306,6 +1347,10 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         const size_t slot = ((size_t)ch << v.ch_log) | (p & chm);
         st256_ef(v.ev + slot, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
         v.pflag[slot] = 0;
+        if (which == 3 && v.replay) {      // history load: the recorded sent-log entry becomes the event's meta record
+          const uint4 sr = v.hist_sent[t0 + i];
+          st256(v.meta + slot, NIL, 0u, sr.x, NIL, sr.y, sr.z, 0u, 0u);
+        }
       } else {
         const u32 r = t - rs - 1;
         const u32 p = s_base[t] + rnk[it];
@@ -1353,6 +1398,25 @@ __global__ void k_pack(View v, const HostEvent* in, u32 n) {
     store_ev(v.outbox + i, e);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = n;
+}
+
+// history records (committed-log layout: flags = tag) -> staging for k_route: the tag is not an event flag
+__global__ void k_hist_stage(View v, const Ev* in, u32 n) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ev e = load_ev(in + i);
+    if (e.dst >= v.n_lp || key_time(e.key) >= v.finish_time) { atomicOr(&v.ctl->error, E_RANGE); e.key = KEY_MAX; }
+    e.flags = 0;
+    store_ev(v.outbox + i, e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) v.ctl->load_count = n;
+}
+
+// after the history replay: back to "nothing has run yet", with the history in place as processed events
+__global__ void k_after_replay(View v) {
+  Ctl* c = v.ctl;
+  c->gvt = 0; c->local_min = KEY_MAX; c->prev_gvt = KEY_MAX; c->stall = 0;
+  c->done = 0; c->round = 0; c->n_processed = 0; c->load_count = 0;
+  c->rq_head = 0; c->rq_tail = 0;
 }
 
 // committed log record (device Ev with flags = tag) -> ssb_record (6 x int64)

@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .capi import EVENT_DTYPE, MODEL_TRAFFIC, Config, Engine
+from .capi import EVENT_DTYPE, FLAG_HISTORY, MODEL_TRAFFIC, Config, Engine
 
 FINISH_TIME = 10800      # traffic_sim.hpp:240-247
 MAX_ROADS = 4            # TrafficModel::kMaxRoads
@@ -85,6 +85,26 @@ def read_trips(path: str):
             dep.append(_atol(fld[3]))
             nodes.extend(_atol(x) for x in fld[4:])
             start.append(len(nodes))
+    return (np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
+            np.array(nodes, dtype=np.int64))
+
+
+def read_what_if(path: str):
+    """traffic_reader::what_if_read (traffic_sim.hpp:453-599), the AE (add event) queries:
+    ``AE,{event id},0,{departure},{1st node},{2nd node},...`` -> query LP = first node, time = departure
+    (:522-558). Returns (trip_id, trip_dep, route_start, route_nodes) like read_trips. SC / DE / RE queries are
+    not supported by this build and raise."""
+    tid, dep, start, nodes = [], [], [0], []
+    with open(path) as f:
+        for line in f.read().splitlines():
+            if line[:2] == "AE":
+                fld = line.split(",")
+                tid.append(_atol(fld[1]))
+                dep.append(_atol(fld[3]))
+                nodes.extend(_atol(x) for x in fld[4:])
+                start.append(len(nodes))
+            elif line[:2] in ("SC", "DE", "RE"):
+                raise NotImplementedError(f"what-if query type {line[:2]} (state change / delete event) is not supported")
     return (np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
             np.array(nodes, dtype=np.int64))
 
@@ -204,7 +224,7 @@ def pack_events(sc: Scenario) -> np.ndarray:
 def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1, keep_records: bool = False,
                 rank: int = 0, world: int = 1, device: int = 0, max_events: int | None = None,
                 max_batch: int | None = None, max_committed: int | None = None, finish_time: int = FINISH_TIME,
-                rounds_per_sync: int = 8, load: bool = True) -> Engine:
+                rounds_per_sync: int = 8, load: bool = True, history: bool = False, extra_routes=None) -> Engine:
     """Build a TrafficSim engine the way runner<traffic_sim>::init does (runner.hpp:79-176)."""
     n_trips = sc.trip_id.size
     n_nodes = sc.route_nodes.size
@@ -213,16 +233,20 @@ def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1,
     if max_batch is None:
         max_batch = max(1 << 14, n_trips // 2 + (1 << 14))
     if max_committed is None:
-        max_committed = n_nodes + 1024 if keep_records else 0
+        max_committed = n_nodes + 1024 if (keep_records or history) else 0
     cfg = Config(model=MODEL_TRAFFIC, n_lp=sc.n_lp, finish_time=finish_time, bucket_ticks=bucket_ticks,
                  window_buckets=window_buckets, max_events=max_events, max_batch=max_batch,
-                 max_committed=max_committed, rank=rank, world=world, device=device, rounds_per_sync=rounds_per_sync)
+                 max_committed=max_committed, rank=rank, world=world, device=device, rounds_per_sync=rounds_per_sync,
+                 flags=FLAG_HISTORY if history else 0)
     eng = Engine(cfg)
     part = sc.partition
     if part is not None and part.size < sc.n_lp:
         part = np.concatenate([part, np.zeros(sc.n_lp - part.size, dtype=np.int64)])
     eng.set_partition(part % world if part is not None else None)
-    eng.set_model_data(0, sc.route_nodes.astype(np.int64))
+    pool = sc.route_nodes.astype(np.int64)
+    if extra_routes is not None and len(extra_routes):
+        pool = np.concatenate([pool, np.asarray(extra_routes, dtype=np.int64)])      # what-if trips: routes appended
+    eng.set_model_data(0, pool)
     ids, words = pack_states(sc)
     owner = (part[ids] % world) if part is not None else (ids % world)
     mine = owner == rank
@@ -231,4 +255,48 @@ def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1,
         ev = pack_events(sc)
         ev_owner = (part[ev["dst"]] % world) if part is not None else (ev["dst"] % world)
         eng.load_events(ev[ev_owner == rank])
+    return eng
+
+
+# ---------------------------------------------------------------------------------------
+# exact-differential simulation (reference --diff_init / --diff_repeat)
+# ---------------------------------------------------------------------------------------
+def run_diff_init(sc: Scenario, **kw):
+    """--diff_init: a normal run that keeps the history. Returns (engine stats, committed records, HistoryStore)."""
+    from .store import HistoryStore
+    rank, world = kw.get("rank", 0), kw.get("world", 1)
+    eng = make_engine(sc, history=True, **kw)
+    st = eng.run()
+    rec, sent = eng.drain_history()
+    eng.close()
+    part = sc.partition
+    owner = (part[sc.state_ids] % world) if part is not None else (sc.state_ids % world)
+    return st, rec, HistoryStore(rec, sent, sc.state_ids[owner == rank])
+
+
+def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
+    """--diff_repeat (runner::init_repeat, runner.hpp:178-348): the recorded history goes back into the engine as
+    processed events, then the AE queries are injected. ``sc`` provides the road network and the ORIGINAL route pool
+    (history events index into it); ``what_if`` = (trip_id, trip_dep, route_start, route_nodes) from read_what_if.
+    ``engine.run()`` then re-executes exactly what the queries invalidate and commits only that."""
+    rank, world = kw.get("rank", 0), kw.get("world", 1)
+    tid, dep, rstart, rnodes = what_if
+    n_hist = store.rec.size
+    # re-executed history is re-sent: until a bucket is fossil-collected it holds the recorded copy AND the new one
+    kw.setdefault("max_events", int((n_hist + rnodes.size) * 3) + (1 << 16))
+    kw.setdefault("max_batch", max(1 << 14, (n_hist + tid.size) // 2 + (1 << 14)))
+    kw.setdefault("max_committed", n_hist + int(rnodes.size) + 1024)
+    eng = make_engine(sc, load=False, extra_routes=rnodes, **kw)
+    eng.load_history(store.rec, store.sent)
+    ev = np.zeros(tid.size, dtype=EVENT_DTYPE)
+    ev["id"] = tid
+    ev["src"] = -1
+    ev["dst"] = rnodes[rstart[:-1]]
+    ev["recv_time"] = dep
+    ev["send_time"] = dep
+    ev["p0"] = sc.route_nodes.size + rstart[:-1]
+    ev["p1"] = np.diff(rstart)
+    part = sc.partition
+    owner = (part[ev["dst"]] % world) if part is not None else (ev["dst"] % world)
+    eng.load_events(ev[owner == rank])
     return eng

@@ -232,3 +232,50 @@ class LP:
             lib().two_lp_free(self.h)
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# exact-differential repeat (R13): which recorded events a set of injected events forces to be re-executed.
+# Plain-Python restatement of the reference's cascade (logical_process.hpp:129-157, queue.hpp:82-108, 213-225):
+# an LP touched at key m reloads / rolls back everything it holds with key >= m, cancels and re-sends the outputs of
+# those events, and every such output touches its destination LP at the output's key. The fixpoint over "earliest
+# touch per LP" is the deterministic part of the reference's --diff_repeat output; on top of it the reference prints
+# history that an LP reloaded because of a transient optimistic message (timing dependent — see make_golden_diff.py).
+# ------------------------------------------------------------------------------------------------
+def parse_line(l):
+    f = l.split(",")
+    return (int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]))      # id, src, send, dst, recv
+
+
+def repeat_closure(init_lines, new_lines):
+    """Lines of the repeat run = new_lines + every init line at an LP whose key (recv, id) is >= the LP's earliest touch."""
+    import heapq
+    by_lp = {}
+    succ = {}
+    for l in init_lines:
+        i, src, send, dst, recv = parse_line(l)
+        by_lp.setdefault(dst, []).append(((recv, i), l))
+        succ[(i, src, send)] = (dst, (recv, i))          # the output of the event (id, at LP src, key (send, id))
+    for v in by_lp.values():
+        v.sort()
+    touch = {}
+    heap = []
+    for l in new_lines:
+        i, src, send, dst, recv = parse_line(l)
+        heapq.heappush(heap, ((recv, i), dst))
+    while heap:
+        key, lp = heapq.heappop(heap)
+        old = touch.get(lp)
+        if old is not None and old <= key:
+            continue
+        touch[lp] = key
+        for k, l in by_lp.get(lp, []):
+            if k >= key and (old is None or k < old):
+                i = k[1]
+                s = succ.get((i, lp, k[0]))
+                if s is not None:
+                    heapq.heappush(heap, (s[1], s[0]))
+    out = list(new_lines)
+    for lp, m in touch.items():
+        out += [l for k, l in by_lp.get(lp, []) if k >= m]
+    return sorted(out)

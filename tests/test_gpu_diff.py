@@ -1,0 +1,90 @@
+"""GPU: exact-differential simulation through the C ABI (ssb_drain_history / ssb_load_history) against the
+reference's --diff_init / --diff_repeat runs and the repeat closure."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import scalesim_b200 as ssb
+from scalesim_b200 import store, traffic
+from fixtures import golden, ring_scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _what_if(ae_lines, tmp_path):
+    p = tmp_path / "ae.csv"
+    p.write_text("".join(l + "\n" for l in ae_lines))
+    return traffic.read_what_if(str(p))
+
+
+def _grid(g):
+    return traffic.synthetic_grid(**g["params"])
+
+
+@pytest.mark.parametrize("case,bucket,window", [("ring", 8, 1), ("ring", 41, 4), ("grid", 8, 1), ("grid", 11, 1), ("grid", 16, 8)])
+def test_diff_init_store_and_diff_repeat_equal_reference(case, bucket, window, tmp_path):
+    g = golden(case + "_diff")
+    if case == "ring":
+        sc, _ = ring_scenario()
+        sc.partition = None
+    else:
+        sc = _grid(g)
+    # --diff_init: same output as a plain run, and the store holds the reference's logical records
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=bucket, window_buckets=window)
+    assert sorted(ssb.records_to_lines(ssb.raw_to_records(rec))) == g["init_lines"]
+    assert hs.event_keys().tolist() == sorted(g["store"]["event"])
+    assert hs.cancel_keys().tolist() == sorted(g["store"]["cancel"])
+    assert hs.state_keys().tolist() == sorted(g["store"]["state"])
+    # the store survives the file round trip (written by a background thread)
+    hs.save_async(str(tmp_path), 7, 0).join()
+    hs = store.HistoryStore.load(str(tmp_path), 7, 0)
+    # --diff_repeat with the AE queries
+    eng = traffic.make_repeat_engine(sc, hs, _what_if(g["ae_lines"], tmp_path), bucket_ticks=bucket,
+                                     window_buckets=window, keep_records=True)
+    st2 = eng.run()
+    lines = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    assert lines == g["repeat_union"]
+    assert lines == O.repeat_closure(g["init_lines"], g["new_lines"])
+    assert st2.rollbacks > 0 and st2.antis_sent > 0          # the history really was rolled back and cancelled
+    assert st2.committed == len(lines) < len(g["init_lines"]) + len(g["new_lines"])
+
+
+def test_repeat_is_exact_on_a_larger_grid(tmp_path):
+    """Config-5 shape at a reduced size: init + repeat(AE) must agree with one full run over trips + added trips
+    (vehicles do not interact, so full = init + new; repeat = new + re-executed history = the closure)."""
+    sc = traffic.synthetic_grid(64, 64, 40000, seed=2)
+    extra = traffic.synthetic_grid(64, 64, 500, seed=9, max_departure=6000)
+    extra_ids = 10_000_000 + np.arange(extra.trip_id.size)
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=11, window_buckets=1)
+    init_lines = sorted(ssb.records_to_lines(ssb.raw_to_records(rec)))
+    # full run: both trip sets at once
+    full = traffic.Scenario(sc.n_lp, sc.state_ids, sc.road_start, sc.road_dst, sc.road_speed, sc.road_len,
+                            np.concatenate([sc.trip_id, extra_ids]), np.concatenate([sc.trip_dep, extra.trip_dep]),
+                            np.concatenate([sc.route_start, sc.route_start[-1] + extra.route_start[1:]]),
+                            np.concatenate([sc.route_nodes, extra.route_nodes]))
+    eng = traffic.make_engine(full, bucket_ticks=11, keep_records=True)
+    eng.run()
+    full_lines = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    new_lines = sorted(set(full_lines) - set(init_lines))
+    assert sorted(set(full_lines) - set(new_lines)) == init_lines           # added trips change nothing else
+    eng = traffic.make_repeat_engine(sc, hs, (extra_ids, extra.trip_dep, extra.route_start, extra.route_nodes),
+                                     bucket_ticks=11, window_buckets=1, keep_records=True)
+    st2 = eng.run()
+    rep = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    assert sorted(set(rep) - set(init_lines)) == new_lines
+    assert set(rep) <= set(full_lines) and len(set(rep)) == len(rep)
+    assert rep == O.repeat_closure(init_lines, new_lines)
+    assert st2.committed < len(full_lines)                                   # less work than the full run
+
+
+def test_history_needs_the_flag():
+    sc, _ = ring_scenario()
+    sc.partition = None
+    eng = traffic.make_engine(sc, keep_records=True)
+    eng.run()
+    with pytest.raises(ssb.EngineError):
+        eng.drain_history()
+    eng.close()
