@@ -22,6 +22,9 @@ struct device_model<phold> {
   static void pack_state(const phold::State& s, uint32_t* w) {
     w[0] = (uint32_t)((uint64_t)s.id() & 0xFFFFFFFFull); w[1] = (uint32_t)((uint64_t)s.id() >> 32);
   }
+  // exact-differential store: PHOLD events carry no references into model data
+  static std::vector<int64_t> model_data_blob(const context&) { return std::vector<int64_t>(); }
+  static void restore_model_data(context&, const std::vector<int64_t>&) {}
   static int upload_model_data(ssb_engine* e, context&) {
     static_assert(sizeof(long) == 8 && sizeof(int) == 4, "LP64 expected");
     int rc = ssb_set_model_data(e, 0, LATENCY_TABLE, sizeof(long) * (size_t)RAND_TABLE_SIZE);

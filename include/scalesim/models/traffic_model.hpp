@@ -40,6 +40,9 @@ struct device_model<traffic_sim> {
       w[2 + 3 * i] = (uint32_t)dst[i]; w[3 + 3 * i] = (uint32_t)speed[i]; w[4 + 3 * i] = (uint32_t)len[i];
     }
   }
+  // exact-differential store: the recorded events index into the route pool, so it travels with the history
+  static std::vector<int64_t> model_data_blob(const context& cx) { return cx.route_pool; }
+  static void restore_model_data(context& cx, const std::vector<int64_t>& blob) { cx.route_pool = blob; }
   static int upload_model_data(ssb_engine* e, context& cx) {
     if (cx.route_pool.empty()) cx.route_pool.push_back(0);
     return ssb_set_model_data(e, 0, cx.route_pool.data(), cx.route_pool.size() * sizeof(int64_t));

@@ -67,6 +67,19 @@ class runner {
     std::exit(1);
   }
   void comm_init();
+  // exact-differential history store of this rank: <store_dir>/<sim_id>/history<rank>.ssb (same file format as
+  // scalesim_b200/store.py): the committed events with their sent-log entries, the LPs that had an initial state and
+  // the model data the events refer to (TrafficSim: the route pool)
+  struct history {
+    std::vector<ssb_raw_record> rec;
+    std::vector<ssb_sent_record> sent;
+    std::vector<int64_t> state_lps, pool;
+  };
+  std::string history_path() const {
+    return (FLAGS_store_dir.empty() ? std::string(".") : FLAGS_store_dir) + "/" + FLAGS_sim_id + "/history" + std::to_string(rank_) + ".ssb";
+  }
+  void write_history(const history& h);
+  void read_history(history& h);
   void verify_twin(const ev_vec<App>& initial, const std::vector<ssb_record>& committed, long k);
 };
 
@@ -135,11 +148,45 @@ void runner<App>::comm_init() {
 }
 
 template <class App>
-void runner<App>::run() {
-  if (FLAGS_diff_init || FLAGS_diff_repeat) {
-    LOG(ERROR) << "--diff_init / --diff_repeat (exact-differential store) are not part of this build yet";
-    std::exit(2);
+void runner<App>::write_history(const history& h) {
+  const std::string p = history_path(), dir = p.substr(0, p.find_last_of('/'));
+  std::string mk = "mkdir -p '" + dir + "'";
+  if (std::system(mk.c_str()) != 0) { LOG(ERROR) << "cannot create " << dir; std::exit(1); }
+  std::ofstream f((p + ".tmp").c_str(), std::ios::binary);
+  const int64_t hdr[3] = {(int64_t)h.rec.size(), (int64_t)h.state_lps.size(), (int64_t)h.pool.size()};
+  f.write("SSBHIST2", 8);
+  f.write((const char*)hdr, sizeof(hdr));
+  f.write((const char*)h.rec.data(), (std::streamsize)(h.rec.size() * sizeof(ssb_raw_record)));
+  f.write((const char*)h.sent.data(), (std::streamsize)(h.sent.size() * sizeof(ssb_sent_record)));
+  f.write((const char*)h.state_lps.data(), (std::streamsize)(h.state_lps.size() * 8));
+  f.write((const char*)h.pool.data(), (std::streamsize)(h.pool.size() * 8));
+  f.close();
+  if (!f || std::rename((p + ".tmp").c_str(), p.c_str()) != 0) { LOG(ERROR) << "cannot write " << p; std::exit(1); }
+  LOG(INFO) << " Stored objects size : " << (h.rec.size() * (sizeof(ssb_raw_record) + sizeof(ssb_sent_record)) + h.state_lps.size() * 8)
+            << " byte (" << h.rec.size() << " events with their sent-log entries, " << h.state_lps.size() << " initial states) -> " << p;
+}
+
+template <class App>
+void runner<App>::read_history(history& h) {
+  const std::string p = history_path();
+  std::ifstream f(p.c_str(), std::ios::binary);
+  char magic[8];
+  int64_t hdr[3];
+  if (!f || !f.read(magic, 8) || std::memcmp(magic, "SSBHIST2", 8) != 0 || !f.read((char*)hdr, sizeof(hdr))) {
+    LOG(ERROR) << "no history store at " << p << " (run with --diff_init first)";
+    std::exit(1);
   }
+  h.rec.resize((size_t)hdr[0]); h.sent.resize((size_t)hdr[0]); h.state_lps.resize((size_t)hdr[1]); h.pool.resize((size_t)hdr[2]);
+  f.read((char*)h.rec.data(), (std::streamsize)(h.rec.size() * sizeof(ssb_raw_record)));
+  f.read((char*)h.sent.data(), (std::streamsize)(h.sent.size() * sizeof(ssb_sent_record)));
+  f.read((char*)h.state_lps.data(), (std::streamsize)(h.state_lps.size() * 8));
+  f.read((char*)h.pool.data(), (std::streamsize)(h.pool.size() * 8));
+  if (!f) { LOG(ERROR) << p << " is truncated"; std::exit(1); }
+}
+
+template <class App>
+void runner<App>::run() {
+  if (FLAGS_diff_init && FLAGS_diff_repeat) { LOG(ERROR) << "--diff_init and --diff_repeat exclude each other"; std::exit(2); }
   typedef std::chrono::steady_clock clk;
   clk::time_point t0 = clk::now();
   app_.init();
@@ -155,16 +202,39 @@ void runner<App>::run() {
   app_.init_states_in_this_rank(states, rank_, world_, parti.first);
   // events: every rank reads the whole scenario and keeps what it owns (the reference shuffles instead, runner.hpp:131-147)
   ev_vec<App> mine;
-  for (int r = 0; r < world_; ++r) {
-    ev_vec<App> parsed;
-    app_.init_events(parsed, r, world_);
-    for (typename ev_vec<App>::iterator it = parsed.begin(); it != parsed.end(); ++it) {
-      long d = (*it)->destination();
-      if (d >= 0 && d < n_lp && part[d] % world_ == rank_) mine.push_back(*it);
+  history hist;
+  if (!FLAGS_diff_repeat) {
+    for (int r = 0; r < world_; ++r) {
+      ev_vec<App> parsed;
+      app_.init_events(parsed, r, world_);
+      for (typename ev_vec<App>::iterator it = parsed.begin(); it != parsed.end(); ++it) {
+        long d = (*it)->destination();
+        if (d >= 0 && d < n_lp && part[d] % world_ == rank_) mine.push_back(*it);
+      }
+    }
+  } else {
+    // --diff_repeat (runner::init_repeat, runner.hpp:178-348): no events are read from the scenario. The recorded
+    // history of this rank comes back from the store, the what-if queries (App::init_what_if) are injected on top.
+    read_history(hist);
+    model::restore_model_data(cx, hist.pool);
+    for (int r = 0; r < world_; ++r) {
+      std::vector<boost::shared_ptr<const what_if<App> > > wi;
+      app_.init_what_if(wi, r, world_);
+      for (size_t i = 0; i < wi.size(); ++i) {
+        if (wi[i]->update_state_.id() != -1 || wi[i]->delete_event_id_ != -1) {
+          LOG(ERROR) << "what-if queries of type SC (state change) and DE/RE (delete event) are not part of this build yet";
+          std::exit(2);
+        }
+        if (wi[i]->add_event_.id() == -1) continue;
+        long d = wi[i]->lp_id_;
+        if (d >= 0 && d < n_lp && part[d] % world_ == rank_)
+          mine.push_back(boost::make_shared<event<App> >(wi[i]->add_event_));
+      }
     }
   }
   std::vector<ssb_event> pod(mine.size());
   for (size_t i = 0; i < mine.size(); ++i) model::pack_event(*mine[i], pod[i], cx);
+  const size_t n_resident = pod.size() + hist.rec.size();
 
   ssb_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
@@ -176,10 +246,12 @@ void runner<App>::run() {
   cfg.finish_time = App::finish_time();
   cfg.bucket_ticks = env_long("SCALESIM_B200_BUCKET", model::default_bucket_ticks());
   cfg.window_buckets = (int)env_long("SCALESIM_B200_WINDOW", 1);
-  cfg.max_events = env_long("SCALESIM_B200_MAX_EVENTS", (long)(pod.size() * 1.6) + (1 << 18));
-  cfg.max_batch = env_long("SCALESIM_B200_MAX_BATCH", (long)pod.size() / 2 + (1 << 16));
-  const bool quiet = env_long("SCALESIM_B200_QUIET", 0) != 0;
+  // a repeat run holds the recorded copy AND the re-sent copy of what it re-executes until the bucket is fossil-collected
+  cfg.max_events = env_long("SCALESIM_B200_MAX_EVENTS", (long)(n_resident * (FLAGS_diff_repeat ? 3.0 : 1.6)) + (1 << 18));
+  cfg.max_batch = env_long("SCALESIM_B200_MAX_BATCH", (long)n_resident / 2 + (1 << 16));
+  const bool quiet = env_long("SCALESIM_B200_QUIET", 0) != 0 && !FLAGS_diff_init;
   cfg.max_committed = quiet ? 0 : (1 << 24);
+  if (FLAGS_diff_init) cfg.flags |= SSB_FLAG_HISTORY;
   cfg.max_snapshots = 1 << 20;
   cfg.rounds_per_sync = 4;
   int rc = ssb_create(&cfg, &engine_);
@@ -199,7 +271,12 @@ void runner<App>::run() {
     }
     if ((rc = ssb_load_states(engine_, ids.data(), words.data(), (int64_t)ids.size()))) fail("ssb_load_states", rc);
   }
+  if (FLAGS_diff_repeat &&
+      (rc = ssb_load_history(engine_, hist.rec.data(), hist.sent.data(), (int64_t)hist.rec.size()))) fail("ssb_load_history", rc);
   if ((rc = ssb_load_events(engine_, pod.data(), (int64_t)pod.size()))) fail("ssb_load_events", rc);
+  if (FLAGS_diff_init) {
+    for (size_t i = 0; i < states.size(); ++i) hist.state_lps.push_back(states[i]->id());
+  }
   double init_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   LOG_IF(INFO, rank_ == 0)
       << "\n====================================================================\n"
@@ -223,7 +300,23 @@ void runner<App>::run() {
     int done = 0;
     for (int i = 0; i < 4 && !done; ++i)
       if ((rc = ssb_step(engine_, &done))) fail("ssb_step", rc);
-    if (!quiet) {
+    if (FLAGS_diff_init) {
+      // --diff_init: the committed events leave the device together with their sent-log entries; the lines are printed
+      // from the same records and the history accumulates on the host (written to the store after the loop)
+      for (;;) {
+        const size_t at = hist.rec.size(), cap = 1 << 20;
+        hist.rec.resize(at + cap); hist.sent.resize(at + cap);
+        int64_t n = 0;
+        if ((rc = ssb_drain_history(engine_, &hist.rec[at], &hist.sent[at], (int64_t)cap, &n))) fail("ssb_drain_history", rc);
+        hist.rec.resize(at + (size_t)n); hist.sent.resize(at + (size_t)n);
+        for (size_t i = at; i < hist.rec.size(); ++i) {
+          const ssb_raw_record& r = hist.rec[i];
+          std::printf("RE,%ld,%ld,%ld,%ld,%ld%s\n", (long)(r.key & 0xffffffffu), r.src == 0xffffffffu ? -1L : (long)r.src,
+                      (long)r.send_time, (long)r.dst, (long)(r.key >> 32), r.tag == 1 ? ",START" : (r.tag == 2 ? ",END" : ""));
+        }
+        if (n < (int64_t)cap) break;
+      }
+    } else if (!quiet) {
       for (;;) {
         int64_t n = 0;
         if ((rc = ssb_drain_committed(engine_, buf.data(), (int64_t)buf.size(), &n))) fail("ssb_drain_committed", rc);
@@ -243,7 +336,11 @@ void runner<App>::run() {
   if ((rc = ssb_get_stats(engine_, &st))) fail("ssb_get_stats", rc);
   uint64_t dg[4];
   ssb_committed_digest(engine_, dg);
-  if (verify_k > 0 && !quiet) verify_twin(mine, kept, verify_k);
+  if (verify_k > 0 && !quiet && !FLAGS_diff_init && !FLAGS_diff_repeat) verify_twin(mine, kept, verify_k);
+  if (FLAGS_diff_init) {
+    hist.pool = model::model_data_blob(cx);
+    write_history(hist);
+  }
 
   LOG(INFO) << "Finish Simulation";
   LOG(INFO)

@@ -29,7 +29,7 @@ import numpy as np
 
 from .capi import RAW_RECORD_DTYPE, SENT_RECORD_DTYPE
 
-MAGIC = b"SSBHIST1"
+MAGIC = b"SSBHIST2"
 NONE = 0xFFFFFFFF
 
 
@@ -40,13 +40,17 @@ def key60(lp: int, time: int, ident: int) -> bytes:
 
 
 class HistoryStore:
-    def __init__(self, rec: np.ndarray, sent: np.ndarray, state_lps: np.ndarray | None = None):
+    def __init__(self, rec: np.ndarray, sent: np.ndarray, state_lps: np.ndarray | None = None,
+                 pool: np.ndarray | None = None):
         self.rec = np.ascontiguousarray(rec, dtype=RAW_RECORD_DTYPE)
         self.sent = np.ascontiguousarray(sent, dtype=SENT_RECORD_DTYPE)
         if self.rec.size != self.sent.size:
             raise ValueError("history arrays differ in length")
         #: LPs that had an initial state on this rank (each contributes the (-1,-1) state record)
         self.state_lps = np.ascontiguousarray(state_lps if state_lps is not None else np.zeros(0), dtype=np.int64)
+        #: model data the recorded events refer to (TrafficSim: the route pool); travels with the history because a
+        #: --diff_repeat run is not given the trip file
+        self.pool = np.ascontiguousarray(pool if pool is not None else np.zeros(0), dtype=np.int64)
 
     # ---- logical records of the three reference stores, as sorted (lp, time, id) rows ----
     def _keys(self, mask=None) -> np.ndarray:
@@ -77,10 +81,11 @@ class HistoryStore:
         os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p + ".tmp", "wb") as f:
             f.write(MAGIC)
-            np.array([self.rec.size, self.state_lps.size], dtype="<i8").tofile(f)
+            np.array([self.rec.size, self.state_lps.size, self.pool.size], dtype="<i8").tofile(f)
             self.rec.tofile(f)
             self.sent.tofile(f)
             self.state_lps.astype("<i8").tofile(f)
+            self.pool.astype("<i8").tofile(f)
         os.replace(p + ".tmp", p)
         return p
 
@@ -96,10 +101,11 @@ class HistoryStore:
         with open(p, "rb") as f:
             if f.read(8) != MAGIC:
                 raise ValueError(f"{p}: not a scalesim_b200 history store")
-            n, ns = (int(x) for x in np.fromfile(f, dtype="<i8", count=2))
+            n, ns, npool = (int(x) for x in np.fromfile(f, dtype="<i8", count=3))
             rec = np.fromfile(f, dtype=RAW_RECORD_DTYPE, count=n)
             sent = np.fromfile(f, dtype=SENT_RECORD_DTYPE, count=n)
             lps = np.fromfile(f, dtype="<i8", count=ns)
-        if rec.size != n or sent.size != n or lps.size != ns:
+            pool = np.fromfile(f, dtype="<i8", count=npool)
+        if rec.size != n or sent.size != n or lps.size != ns or pool.size != npool:
             raise ValueError(f"{p}: truncated")
-        return cls(rec, sent, lps)
+        return cls(rec, sent, lps, pool)

@@ -271,7 +271,7 @@ def run_diff_init(sc: Scenario, **kw):
     eng.close()
     part = sc.partition
     owner = (part[sc.state_ids] % world) if part is not None else (sc.state_ids % world)
-    return st, rec, HistoryStore(rec, sent, sc.state_ids[owner == rank])
+    return st, rec, HistoryStore(rec, sent, sc.state_ids[owner == rank], sc.route_nodes)
 
 
 def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:

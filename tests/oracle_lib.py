@@ -255,7 +255,8 @@ def repeat_closure(init_lines, new_lines):
     for l in init_lines:
         i, src, send, dst, recv = parse_line(l)
         by_lp.setdefault(dst, []).append(((recv, i), l))
-        succ[(i, src, send)] = (dst, (recv, i))          # the output of the event (id, at LP src, key (send, id))
+        if (src, send) != (dst, recv):                   # PHOLD's initial events name themselves as their source
+            succ[(i, src, send)] = (dst, (recv, i))      # the output of the event (id, at LP src, key (send, id))
     for v in by_lp.values():
         v.sort()
     touch = {}

@@ -80,6 +80,34 @@ def test_repeat_is_exact_on_a_larger_grid(tmp_path):
     assert st2.committed < len(full_lines)                                   # less work than the full run
 
 
+@pytest.mark.parametrize("window", [1, 3])
+def test_phold_diff_repeat_equals_reference(window):
+    """PHOLD 100/1600 --diff_init, then --diff_repeat with 3 what-if events (phold.hpp:232-246: id NUM_INIT_MSG + i
+    at LP i, time 1)."""
+    from scalesim_b200 import phold
+    g = golden("phold_diff")
+    n_lp, n_init, ratio, lam = g["args"]
+    tables = phold.build_tables(ratio, lam)
+    cfg = dict(tables=tables, window_buckets=window, max_committed=20000)
+    eng = phold.make_engine(n_lp, n_init, ratio, lam, flags=ssb.FLAG_HISTORY, **cfg)
+    eng.run()
+    rec, sent = eng.drain_history()
+    eng.close()
+    assert sorted(ssb.records_to_lines(ssb.raw_to_records(rec))) == g["init_lines"]
+    eng = phold.make_engine(n_lp, n_init, ratio, lam, load=False, max_events=60000, **cfg)
+    eng.load_history(rec, sent)
+    ev = np.zeros(g["what_ifs"], dtype=ssb.EVENT_DTYPE)
+    ev["id"] = n_init + np.arange(g["what_ifs"])
+    ev["src"] = ev["dst"] = np.arange(g["what_ifs"])
+    ev["recv_time"] = ev["send_time"] = 1
+    eng.load_events(ev)
+    st = eng.run()
+    lines = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    assert lines == g["repeat_union"] == g["repeat_core"]
+    assert st.rollbacks > 0
+
+
 def test_history_needs_the_flag():
     sc, _ = ring_scenario()
     sc.partition = None

@@ -46,10 +46,44 @@ def test_trafficsim_dropin_equals_reference():
     assert "0 mismatches" in err
 
 
-def test_dropin_rejects_diff_flags():
+def test_trafficsim_dropin_diff_init_and_repeat_equal_reference(tmp_path):
+    """TrafficSim --diff_init on the ring, then --diff_repeat with traffic/ring/add_ev.csv:
+    38 lines and the reference's store records, then the reference's 19 lines."""
+    from scalesim_b200 import store
+    g = golden("ring_diff")
+    rd, trip, part = write_ring_files(str(tmp_path))
+    part1 = str(tmp_path / "part1")
+    with open(part1, "w") as f:
+        f.write("0\n" * 10)
+    ae = str(tmp_path / "add_ev.csv")
+    with open(ae, "w") as f:
+        f.write("".join(l + "\n" for l in g["ae_lines"]))
+    flags = ["--sim_id=999", f"--store_dir={tmp_path}/st"]
+    lines, err = _run("TrafficSim", flags + ["--diff_init", part1, rd, trip])
+    assert sorted(lines) == g["init_lines"]
+    hs = store.HistoryStore.load(f"{tmp_path}/st", 999, 0)
+    assert hs.event_keys().tolist() == sorted(g["store"]["event"])
+    assert hs.cancel_keys().tolist() == sorted(g["store"]["cancel"])
+    assert hs.state_keys().tolist() == sorted(g["store"]["state"])
+    lines, err = _run("TrafficSim", flags + ["--diff_repeat", part1, rd, ae])
+    assert sorted(lines) == g["repeat_union"]
+    assert "# of output events             : 19" in err
+
+
+def test_phold_dropin_diff_init_and_repeat_equal_reference(tmp_path):
+    g = golden("phold_diff")
+    args = [str(x) for x in g["args"]] + [str(g["what_ifs"]), "50"]
+    flags = ["--sim_id=3", f"--store_dir={tmp_path}/st"]
+    lines, err = _run("PHOLD", flags + ["--diff_init"] + args)
+    assert sorted(lines) == g["init_lines"]
+    lines, err = _run("PHOLD", flags + ["--diff_repeat"] + args)
+    assert sorted(lines) == g["repeat_union"]
+
+
+def test_dropin_repeat_without_store_fails_loudly(tmp_path):
     path = os.path.join(ROOT, "apps", "PHOLD")
     if not os.path.exists(path):
         pytest.skip("not built")
-    p = subprocess.run([path, "--diff_init", "--sim_id=1", "--store_dir=/tmp/x", "100", "1600", "0.1", "1.0", "1", "50"],
+    p = subprocess.run([path, "--diff_repeat", "--sim_id=1", f"--store_dir={tmp_path}/none", "100", "1600", "0.1", "1.0", "1", "50"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
-    assert p.returncode == 2 and "not part of this build" in p.stderr
+    assert p.returncode == 1 and "no history store" in p.stderr

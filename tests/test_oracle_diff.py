@@ -8,7 +8,7 @@ from fixtures import golden
 from scalesim_b200 import store
 
 
-@pytest.mark.parametrize("name", ["ring_diff", "grid_diff"])
+@pytest.mark.parametrize("name", ["ring_diff", "grid_diff", "phold_diff"])
 def test_repeat_closure_equals_reference_repeat_output(name):
     g = golden(name)
     got = O.repeat_closure(g["init_lines"], g["new_lines"])
