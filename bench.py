@@ -378,8 +378,16 @@ def main():
     dom_ms, dom_launches = kt[dom]
     ev_rank = stp.committed
     achieved = B_ALG_KERNEL.get(dom, 0.0) * ev_rank / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    traffic_bytes, traffic_src = None, None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
+        nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic_bytes, traffic_src = nt[dom]["dram_bytes_per_launch"], nt["_source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic_bytes, "traffic_source": traffic_src,
+                "alg_bytes_per_launch": B_ALG_KERNEL.get(dom, 0.0) * ev_rank / max(dom_launches, 1),
+                "peak_source": peak_src,
                 "alg_bytes_per_event": B_ALG_KERNEL.get(dom), "launches": dom_launches,
                 "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "kernel_ms": {k: round(v[0], 4) for k, v in kt.items()},
