@@ -108,9 +108,12 @@ void runner<App>::comm_init() {
   if (world_ <= 1) return;
   const char* path = std::getenv("SCALESIM_B200_COMM_FILE");
   if (!path) { LOG(ERROR) << "SCALESIM_B200_COMM_FILE must be set when SCALESIM_B200_WORLD > 1"; std::exit(1); }
+  const bool p2p = env_long("SCALESIM_B200_P2P", 1) != 0;
+  int rc = 0;
+  if (!p2p) {      // events travel by ncclSend/ncclRecv, GVT by ncclAllReduce: the ranks join one NCCL communicator
   char id[128];
   if (rank_ == 0) {
-    int rc = ssb_comm_unique_id(id);
+    rc = ssb_comm_unique_id(id);
     if (rc) fail("ssb_comm_unique_id", rc);
     std::string tmp = std::string(path) + ".tmp";
     { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(id, 128); }
@@ -123,10 +126,11 @@ void runner<App>::comm_init() {
       std::this_thread::sleep_for(std::chrono::milliseconds(100));
     }
   }
-  int rc = ssb_comm_init(engine_, id);
+  rc = ssb_comm_init(engine_, id);
   if (rc) fail("ssb_comm_init", rc);
-  if (env_long("SCALESIM_B200_P2P", 1) == 0) return;   // 0: events travel by ncclSend/ncclRecv
-  // peer-memory exchange: swap the CUDA IPC handles of the engines' mailboxes through files next to the id file
+  return;
+  }
+  // peer-memory exchange (default; events AND the GVT reduction cross through the mailboxes, no NCCL): swap the CUDA IPC handles of the engines' mailboxes through files next to the id file
   char mine[64];
   if ((rc = ssb_comm_export(engine_, mine))) fail("ssb_comm_export", rc);
   {
