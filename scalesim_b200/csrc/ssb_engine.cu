@@ -130,7 +130,7 @@ struct ssb_engine {
     timed.clear();
   }
   int reset_sim();
-  static size_t heavy_smem() { return (size_t)kBlockSortCap * sizeof(Sorted); }
+  void launch_sortheavy(const View& vv) { k_sortheavy<<<n_sm * 4, kSortThreads, 0, stream>>>(vv); }
   void launch_fixup(const View& vv);
   void launch_exec_heavy(const View& vv);
   // whole window loop as ONE CUDA graph: WHILE(!done) { round }, with IF nodes around the rarely needed kernels
@@ -281,7 +281,6 @@ int ssb_engine::init() {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&route_bps, k_route, kRouteThreads, route_smem));
   if (route_bps < 1) route_bps = 1;
   if (const char* rb = getenv("SSB_ROUTE_BPS")) { int x = atoi(rb); if (x >= 1 && x <= route_bps) route_bps = x; }
-  CK(cudaFuncSetAttribute(k_sortheavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem()));
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   return SSB_OK;
@@ -442,7 +441,7 @@ void ssb_engine::launch_exec(const View& v) {
 }
 
 void ssb_engine::launch_exec_heavy(const View& v) {
-  k_exec_heavy<false><<<n_sm * 8, 256, 0, stream>>>(v);
+  k_exec_heavy<<<n_sm * 8, 256, 0, stream>>>(v);
 }
 
 void ssb_engine::launch_fixup(const View& v) {
@@ -462,8 +461,7 @@ int ssb_engine::enqueue_replay_round() {
   k_link<<<n_sm * 8, 256, 0, stream>>>(v);
   k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
   launch_exec(v);
-  k_sortheavy<<<n_sm * 6, kSortThreads, heavy_smem(), stream>>>(v);
-  k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(v);
+  launch_sortheavy(v);
   launch_exec_heavy(v);
   CK(cudaGetLastError());
   return SSB_OK;
@@ -539,8 +537,7 @@ int ssb_engine::enqueue_round() {
   launch_exec(v);
   t_end();
   t_begin(K_SORTHEAVY);
-  k_sortheavy<<<n_sm * 6, kSortThreads, heavy_smem(), stream>>>(v);
-  k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(v);
+  launch_sortheavy(v);
   t_end();
   t_begin(K_EXEC_HEAVY);
   launch_exec_heavy(v);
@@ -560,7 +557,7 @@ int ssb_engine::enqueue_round() {
 // reached finish_time and no device error", and inside it one round. The commit pass runs as a parallel branch next
 // to link/exec (they touch disjoint buckets; both join before k_route, which is the only other user of the chunk
 // free stack). The kernels that only irregular turns need sit in IF nodes: k_sortheavy (a segment longer than
-// kScanCap exists) and k_sortheavy(fix) + k_fixup + k_route(anti) (some LP needs the sequential turn); their
+// kRegSortSmall exists) and k_fixup + k_route(anti) (some LP needs the sequential turn); their
 // conditions are set on the device by k_exec and by the last block of k_exec_heavy. The host launches the graph once
 // per ssb_run and is not involved in the loop at all.
 // ------------------------------------------------------------------------------------------------
@@ -628,8 +625,7 @@ int ssb_engine::build_graph() {
   }));
   CK(add_cond(body, vg.h_vheavy, cudaGraphCondTypeIf, t_exec, &n_if_vheavy, &b_vheavy));
   CK(capture(b_vheavy, {}, nullptr, [&] {
-    k_sortheavy<<<n_sm * 6, kSortThreads, heavy_smem(), stream>>>(vg);
-    k_exec_heavy<true><<<n_sm * 4, 256, 0, stream>>>(vg);
+    launch_sortheavy(vg);
   }));
   CK(capture(body, {n_if_vheavy}, &t_heavy, [&] { launch_exec_heavy(vg); }));
   // k_route(anti) pops chunks off the free stack that the commit pass pushes to: the IF node waits for both branches

@@ -38,7 +38,6 @@ constexpr u32 kCntMask = (1u << kCntBits) - 1u;
 constexpr u32 NIL31 = 0x7FFFFFFFu; // end of an LP's arrival list
 constexpr u32 kLightMax = 16;      // upper bound of View::light_max: LPs with more arrivals in a round get a segment
 constexpr u32 kRegSortSmall = 128; // register sort with up to 4 entries per lane (the every-round kernel)
-constexpr u32 kScanCap = kRegSortSmall;      // segments up to this length are sorted in registers by k_exec_heavy; longer ones by k_sortheavy
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
@@ -721,143 +720,161 @@ __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_sortheavy — the LPs with a long segment (the hot LPs): sort it by (key, arrival order) (R1) and classify it:
-// an anti-message, a duplicate key or a possible straggler makes the turn irregular (-> k_fixup).
-//   n <= 32            one warp, one entry per lane, bitonic network over register shuffles
-//   n <= kWarpSortCap  one warp, bitonic network in the warp's slice of shared memory
-//   n <= kBlockSortCap one block, bitonic network in shared memory
-//   longer             one thread sorts in place (not reached by any shipped workload)
+// k_sortheavy — segments longer than kRegSortSmall (the very hot LPs: at N GPUs PHOLD's hot LPs hold N times as
+// many events): one BLOCK of 256 threads per LP sorts the segment by (key, arrival order) (R1) and classifies it: an
+// anti-message, a duplicate key or a possible straggler makes the turn irregular (-> k_fixup); a plain turn gets its
+// processed-chain links right here, as in k_exec_heavy.
+// Hybrid bitonic network, R = 1, 2, 4 or 8 entries per thread in registers (entry index = tid + 256 r):
+//   partner distance < 32        register shuffle inside the warp
+//   32 <= distance < 256         exchange through a 4 KB shared-memory tile (the only shared-memory traffic:
+//                                3 of the log2(P) steps of a merge level — a pure shared-memory network is bound by
+//                                shared-memory bandwidth, measured 257 us per window for 10 500 segments of ~200)
+//   distance >= 256              the other register of the same thread
+// Longer than kBlockSortCap: one thread sorts in place (not reached by any shipped workload).
 // ------------------------------------------------------------------------------------------------
-constexpr u32 kWarpSortCap = 128;
 constexpr u32 kBlockSortCap = 2048;
 constexpr int kSortThreads = 256;
 
-__device__ __forceinline__ Sorted shfl_xor_sorted(const Sorted& x, int m) {
-  Sorted y;
-  u32 lo = __shfl_xor_sync(0xffffffffu, (u32)x.key, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(x.key >> 32), m);
+struct KS { u64 key; u32 slot, seq; };      // sort element: key, calendar slot, arrival index | anti << 31
+__device__ __forceinline__ bool ks_less(const KS& a, const KS& b) {
+  return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
+}
+__device__ __forceinline__ KS ks_shfl_xor(const KS& x, int m) {
+  KS y;
+  const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)x.key, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(x.key >> 32), m);
   y.key = ((u64)hi << 32) | lo;
   y.slot = __shfl_xor_sync(0xffffffffu, x.slot, m);
   y.seq = __shfl_xor_sync(0xffffffffu, x.seq, m);
   return y;
 }
 
-// after sorting: flag the LP (lane/thread 0 of the group calls this)
-__device__ __forceinline__ void classify_heavy(const View& v, u32 lp, u64 first_key, bool irregular) {
-  const uint4 w = v.lph[lp];
-  if (w.z != NIL && key_time(first_key) <= w.w) irregular = true;     // possible straggler
-  atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
-  if (irregular) flag_lp(v, lp, PL_IRREGULAR);
-}
-
-// work item idx of the sort pass: the long-segment list, segments longer than kScanCap
-__device__ __forceinline__ bool sort_item(const View& v, u32 idx, u32& lp, u32& start, u32& n) {
-  const uint4 a = v.heavy[idx];
-  lp = a.x; start = a.y; n = a.z;
-  return n > kScanCap;
+template <int R>
+__device__ __forceinline__ void block_sort_segment(const View& v, u32 lp, Sorted* seg, u32 n, uint4* tile, u64* s_last,
+                                                   u32* s_lslot, u32* s_flag, u64& s_first) {
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  KS x[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u32 e = tid + ((u32)r << 8);
+    if (e < n) { const uint4 q = *reinterpret_cast<const uint4*>(seg + e); x[r].key = ((u64)q.y << 32) | q.x; x[r].slot = q.z; x[r].seq = q.w; }
+    else { x[r].key = KEY_MAX; x[r].slot = NIL; x[r].seq = 0x7FFFFFFFu; }
+  }
+  if (tid == 0) *s_flag = 0;
+#pragma unroll
+  for (u32 k2 = 2; k2 <= 256u * R; k2 <<= 1) {
+#pragma unroll
+    for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      if (j2 >= 256u) {
+        const u32 dr = j2 >> 8;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & dr) == 0) {
+            const bool asc = (((u32)r << 8) & k2) == 0;
+            const bool sw = asc ? ks_less(x[r | dr], x[r]) : ks_less(x[r], x[r | dr]);
+            if (sw) { const KS t = x[r]; x[r] = x[r | dr]; x[r | dr] = t; }
+          }
+        }
+      } else if (j2 >= 32u) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          tile[tid] = make_uint4((u32)x[r].key, (u32)(x[r].key >> 32), x[r].slot, x[r].seq);
+          __syncthreads();
+          const uint4 q = tile[tid ^ j2];
+          __syncthreads();
+          KS y;
+          y.key = ((u64)q.y << 32) | q.x; y.slot = q.z; y.seq = q.w;
+          const u32 e = tid + ((u32)r << 8);
+          const bool keep_min = ((tid & j2) == 0) == ((e & k2) == 0);
+          if (keep_min ? ks_less(y, x[r]) : ks_less(x[r], y)) x[r] = y;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const KS y = ks_shfl_xor(x[r], (int)j2);
+          const u32 e = tid + ((u32)r << 8);
+          const bool keep_min = ((lane & j2) == 0) == ((e & k2) == 0);
+          if (keep_min ? ks_less(y, x[r]) : ks_less(x[r], y)) x[r] = y;
+        }
+      }
+    }
+  }
+  // every entry looks at the entry before it: duplicate key, and its predecessor in the LP's processed chain
+#pragma unroll
+  for (int r = 0; r < R; ++r) if (lane == 31) { s_last[r * 8 + warp] = x[r].key; s_lslot[r * 8 + warp] = x[r].slot; }
+  __syncthreads();
+  const uint4 h = v.lph[lp];
+  const bool fixed = ((h.x >> kCntBits) & PL_FIX) != 0;      // k_exec already sent the LP to k_fixup: only sort
+  u32 flag = 0;
+  u64 pkey[R];
+  u32 pslot[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u32 e = tid + ((u32)r << 8);
+    const u32 lo = __shfl_up_sync(0xffffffffu, (u32)x[r].key, 1), hi = __shfl_up_sync(0xffffffffu, (u32)(x[r].key >> 32), 1);
+    pkey[r] = ((u64)hi << 32) | lo;
+    pslot[r] = __shfl_up_sync(0xffffffffu, x[r].slot, 1);
+    if (lane == 0 && e) {
+      const u32 w = warp ? r * 8 + warp - 1 : (r - 1) * 8 + 7;
+      pkey[r] = s_last[w]; pslot[r] = s_lslot[w];
+    }
+    if (e < n) {
+      flag |= x[r].seq >> 31;
+      if (e && pkey[r] == x[r].key) flag = 1;
+    }
+  }
+  if (tid == 0) s_first = x[0].key;
+  if (flag) *s_flag = 1;
+  __syncthreads();
+  bool irregular = *s_flag != 0;
+  if (h.z != NIL && key_time(s_first) <= h.w) irregular = true;      // possible straggler
+  if (irregular || fixed) {
+    // leave the sorted segment for the sequential lp_turn of k_fixup
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 e = tid + ((u32)r << 8);
+      if (e < n) *reinterpret_cast<uint4*>(seg + e) = make_uint4((u32)x[r].key, (u32)(x[r].key >> 32), x[r].slot, x[r].seq);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
+      if (!fixed) flag_lp(v, lp, PL_IRREGULAR);
+    }
+  } else {
+    // plain turn: k_exec has run the handlers; add every event's place in the processed chain
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 e = tid + ((u32)r << 8);
+      if (e < n) {
+        u32 ps = pslot[r], ptime = key_time(pkey[r]);
+        if (e == 0) { ps = h.z; ptime = h.w; }
+        *reinterpret_cast<uint2*>(v.meta + x[r].slot) = make_uint2(ps, ptime);
+        if (e + 1u == n) v.last[lp] = make_uint2(x[r].slot, key_time(x[r].key));
+      }
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v) {
-  extern __shared__ uint4 smem_heavy[];
+  __shared__ uint4 tile[kSortThreads];
+  __shared__ u64 s_last[8 * 8];
+  __shared__ u32 s_lslot[8 * 8];
   __shared__ u32 s_flag;
+  __shared__ u64 s_first;
   Ctl* c = v.ctl;
-  const u32 nh = c->n_vheavy ? c->n_heavy : 0u;      // n_vheavy counts segments > kRegSortSmall; sort_item picks > kScanCap
+  const u32 nh = c->n_vheavy ? c->n_heavy : 0u;      // n_vheavy counts the segments longer than kRegSortSmall
   if (nh == 0) return;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr u32 kWarps = kSortThreads / 32;
-  Sorted* wbuf = reinterpret_cast<Sorted*>(smem_heavy) + (size_t)warp * kWarpSortCap;
-  const Sorted pad = {KEY_MAX, NIL, 0x7FFFFFFFu};
-  // warp-level
-  for (u32 h = blockIdx.x * kWarps + warp; h < nh; h += gridDim.x * kWarps) {
-    u32 lp, start, n;
-    if (!sort_item(v, h, lp, start, n) || n > kWarpSortCap) continue;
-    Sorted* seg = v.sorted + start;
-    u32 flag = 0;
-    u64 first_key;
-    if (n <= 32) {
-      Sorted x = lane < n ? load_sorted(seg + lane) : pad;
-#pragma unroll
-      for (u32 k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-          const Sorted y = shfl_xor_sorted(x, (int)j2);
-          const bool keep_min = ((lane & j2) == 0) == ((lane & k2) == 0);
-          if (keep_min ? sorted_less(y, x) : sorted_less(x, y)) x = y;
-        }
-      }
-      const u32 klo = __shfl_up_sync(0xffffffffu, (u32)x.key, 1), khi = __shfl_up_sync(0xffffffffu, (u32)(x.key >> 32), 1);
-      if (lane < n) {
-        store_sorted(seg + lane, x);
-        flag = x.seq >> 31;
-        if (lane && (((u64)khi << 32) | klo) == x.key) flag = 1;
-      }
-      first_key = ((u64)__shfl_sync(0xffffffffu, (u32)(x.key >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)x.key, 0);
-    } else {
-      u32 P = 64;
-      while (P < n) P <<= 1;
-      for (u32 i = lane; i < P; i += 32) wbuf[i] = i < n ? load_sorted(seg + i) : pad;
-      __syncwarp();
-      for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
-        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-          for (u32 i = lane; i < P; i += 32) {
-            const u32 ixj = i ^ j2;
-            if (ixj > i) {
-              const Sorted x = wbuf[i], y = wbuf[ixj];
-              if (sorted_less(y, x) == ((i & k2) == 0)) { wbuf[i] = y; wbuf[ixj] = x; }
-            }
-          }
-          __syncwarp();
-        }
-      }
-      for (u32 i = lane; i < n; i += 32) {
-        const Sorted x = wbuf[i];
-        store_sorted(seg + i, x);
-        flag |= x.seq >> 31;
-        if (i && wbuf[i - 1].key == x.key) flag = 1;
-      }
-      first_key = wbuf[0].key;
-      __syncwarp();
-    }
-    const bool irregular = __any_sync(0xffffffffu, flag != 0);
-    if (lane == 0) classify_heavy(v, lp, first_key, irregular);
-  }
-  // block-level (rare): segments longer than kWarpSortCap
-  __syncthreads();
-  Sorted* buf = reinterpret_cast<Sorted*>(smem_heavy);
   for (u32 h = blockIdx.x; h < nh; h += gridDim.x) {
-    u32 lp, start, n;
-    if (!sort_item(v, h, lp, start, n) || n <= kWarpSortCap) continue;
-    Sorted* seg = v.sorted + start;
-    if (threadIdx.x == 0) s_flag = 0;
-    if (n <= kBlockSortCap) {
-      u32 P = 256;
-      while (P < n) P <<= 1;
-      for (u32 i = threadIdx.x; i < P; i += kSortThreads) buf[i] = i < n ? load_sorted(seg + i) : pad;
-      __syncthreads();
-      for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
-        for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-          for (u32 i = threadIdx.x; i < P; i += kSortThreads) {
-            const u32 ixj = i ^ j2;
-            if (ixj > i) {
-              const Sorted x = buf[i], y = buf[ixj];
-              if (sorted_less(y, x) == ((i & k2) == 0)) { buf[i] = y; buf[ixj] = x; }
-            }
-          }
-          __syncthreads();
-        }
-      }
-      u32 flag = 0;
-      for (u32 i = threadIdx.x; i < n; i += kSortThreads) {
-        const Sorted x = buf[i];
-        store_sorted(seg + i, x);
-        flag |= x.seq >> 31;
-        if (i && buf[i - 1].key == x.key) flag = 1;
-      }
-      if (flag) s_flag = 1;
-      __syncthreads();
-      if (threadIdx.x == 0) classify_heavy(v, lp, buf[0].key, s_flag != 0);
-      __syncthreads();
-    } else {
-      __syncthreads();
+    const uint4 a = v.heavy[h];
+    const u32 lp = a.x, n = a.z;
+    if (n <= kRegSortSmall) continue;
+    Sorted* seg = v.sorted + a.y;
+    if (n <= 256) block_sort_segment<1>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
+    else if (n <= 512) block_sort_segment<2>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
+    else if (n <= 1024) block_sort_segment<4>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
+    else if (n <= kBlockSortCap) block_sort_segment<8>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
+    else {
       if (threadIdx.x == 0) {
         u32 flag = 0;
         for (u32 i = 1; i < n; ++i) {
@@ -875,8 +892,20 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v) {
           flag |= seg[i].seq >> 31;
           if (i && seg[i - 1].key == seg[i].key) flag = 1;
         }
+        const uint4 hh = v.lph[lp];
+        bool irregular = flag != 0 || (hh.z != NIL && key_time(seg[0].key) <= hh.w);
         __threadfence();
-        classify_heavy(v, lp, seg[0].key, flag != 0);
+        atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
+        if ((hh.x >> kCntBits) & PL_FIX) irregular = false;      // already on the fix list
+        else if (irregular) flag_lp(v, lp, PL_IRREGULAR);
+        if (!irregular && !((hh.x >> kCntBits) & PL_FIX)) {
+          u32 ps = hh.z, pt = hh.w;
+          for (u32 i = 0; i < n; ++i) {
+            *reinterpret_cast<uint2*>(v.meta + seg[i].slot) = make_uint2(ps, pt);
+            ps = seg[i].slot; pt = key_time(seg[i].key);
+          }
+          v.last[lp] = make_uint2(ps, pt);
+        }
       }
       __syncthreads();
     }
@@ -890,22 +919,9 @@ __global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v) {
 // shuffles, and each entry reads its predecessor off its neighbour: processed-chain link -> 8-byte store into the
 // event's meta record, the last entry becomes the LP's chain head. An anti-message, a duplicate key or a possible
 // straggler makes the turn irregular: the sorted segment is written back for the sequential lp_turn of k_fixup
-// (also when k_exec flagged the LP because its handler changed the state). Segments longer than kScanCap were
-// sorted and classified by k_sortheavy: their entries read the neighbour straight from memory.
+// (also when k_exec flagged the LP because its handler changed the state). Segments longer than kRegSortSmall are
+// k_sortheavy's (one block per LP).
 // ------------------------------------------------------------------------------------------------
-struct KS { u64 key; u32 slot, seq; };      // sort element: key, calendar slot, arrival index | anti << 31
-__device__ __forceinline__ bool ks_less(const KS& a, const KS& b) {
-  return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
-}
-__device__ __forceinline__ KS ks_shfl_xor(const KS& x, int m) {
-  KS y;
-  const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)x.key, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(x.key >> 32), m);
-  y.key = ((u64)hi << 32) | lo;
-  y.slot = __shfl_xor_sync(0xffffffffu, x.slot, m);
-  y.seq = __shfl_xor_sync(0xffffffffu, x.seq, m);
-  return y;
-}
-
 // entry index = lane + 32 * r. Sorts 32 * R entries ascending.
 template <int R>
 __device__ __forceinline__ void warp_bitonic(KS (&x)[R], u32 lane) {
@@ -997,10 +1013,6 @@ __device__ __forceinline__ void heavy_turn(const View& v, u32 lp, u32 start, u32
   }
 }
 
-// kBig = false: segments of up to kRegSortSmall entries (1, 2 or 4 per lane) — every round.
-// kBig = true : the longer ones, sorted and classified by k_sortheavy (block-wide bitonic network in shared memory):
-//               the predecessor is the entry before. Only launched when such a segment exists.
-template <bool kBig>
 __global__ void __launch_bounds__(256) k_exec_heavy(View v) {
   Ctl* c = v.ctl;
   const u32 nh = c->n_heavy;
@@ -1009,30 +1021,13 @@ __global__ void __launch_bounds__(256) k_exec_heavy(View v) {
   for (u32 hi = wid; hi < nh; hi += nw) {
     const uint4 a = v.heavy[hi];
     const u32 lp = a.x, start = a.y, n = a.z;
-    if ((n > kRegSortSmall) != kBig) continue;
+    if (n > kRegSortSmall) continue;                  // k_sortheavy's
     const uint4 h = v.lph[lp];
-    if (!kBig) {
-      if (n <= 32) heavy_turn<1>(v, lp, start, n, h, lane);
-      else if (n <= 64) heavy_turn<2>(v, lp, start, n, h, lane);
-      else heavy_turn<4>(v, lp, start, n, h, lane);
-    } else {
-      const u32 fl = h.x >> kCntBits;
-      if (fl & PL_SORTED) {
-        // sorted and classified by k_sortheavy (n > kScanCap)
-        if (fl & PL_FIX) continue;
-        for (u32 i = lane; i < n; i += 32) {
-          const Sorted x = load_sorted(v.sorted + start + i);
-          u32 pslot = h.z, ptime = h.w;
-          if (i) { const Sorted p = load_sorted(v.sorted + start + i - 1); pslot = p.slot; ptime = key_time(p.key); }
-          *reinterpret_cast<uint2*>(v.meta + x.slot) = make_uint2(pslot, ptime);
-          if (i + 1u == n) v.last[lp] = make_uint2(x.slot, key_time(x.key));
-        }
-      } else {
-        atomicOr(&c->error, E_INTERNAL);      // every segment longer than kRegSortSmall is sorted by k_sortheavy
-      }
-    }
+    if (n <= 32) heavy_turn<1>(v, lp, start, n, h, lane);
+    else if (n <= 64) heavy_turn<2>(v, lp, start, n, h, lane);
+    else heavy_turn<4>(v, lp, start, n, h, lane);
   }
-  if (!kBig && v.use_graph) {
+  if (v.use_graph) {
     // the last block to finish knows the final fix list: it opens or closes the IF node around k_fixup
     __syncthreads();
     if (threadIdx.x == 0) {
