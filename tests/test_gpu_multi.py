@@ -78,6 +78,17 @@ def test_phold_half_remote_two_gpus_equals_reference():
     assert all(r[1] == g["digest"] for r in res)
 
 
+def test_config4_shape_two_gpus_equals_oracle():
+    """BASELINE.json config 4 at a reduced size: 50 % remote PHOLD (every other send crosses partitions, the hot LPs
+    hold hundreds of events per window: block-level sort path) on two GPUs; digest of the union = the oracle's closure."""
+    import oracle_lib as O
+    args = (20000, 640000, 0.5, 1.0)
+    want = O.phold_closure_digest(*args)
+    res = _run(("phold", args, 1))
+    assert all(r[1] == want for r in res)
+    assert sum(r[3] for r in res) > 0.15 * want[0]         # half of the remote sends (50 %) cross between the two partitions
+
+
 def test_grid_two_gpus_equals_oracle():
     import oracle_lib as O
     from scalesim_b200 import traffic

@@ -207,3 +207,22 @@ def test_phold_1m_full_size_count_and_digest(phold_tables_01):
     s.run_closure(8, keep_records=False)
     assert eng.digest() == s.digest()
     eng.close()
+
+
+@pytest.mark.parametrize("window", [1, 3])
+def test_graph_loop_equals_stepwise_loop(phold_tables_01, window):
+    """ssb_run (the whole window loop as one CUDA graph with WHILE / IF nodes) and ssb_step (the same kernels launched
+    round by round on the stream) must commit the same records with the same statistics."""
+    from scalesim_b200 import phold
+    eng = phold.make_engine(10000, 160000, 0.1, 1.0, tables=phold_tables_01, window_buckets=window)
+    st_graph = eng.run()
+    d_graph = eng.digest()
+    eng.close()
+    eng = phold.make_engine(10000, 160000, 0.1, 1.0, tables=phold_tables_01, window_buckets=window)
+    while not eng.step():
+        pass
+    st_step = eng.stats()
+    assert eng.digest() == d_graph == golden("phold_10000_160000")["digest"]
+    assert (st_step.committed, st_step.processed, st_step.rollbacks, st_step.antis_sent) == \
+           (st_graph.committed, st_graph.processed, st_graph.rollbacks, st_graph.antis_sent)
+    eng.close()
