@@ -9,7 +9,8 @@ One "step" = one complete PHOLD simulation (BASELINE.json config 2 per GPU: 1M L
   value : committed events / s of the window loop with the initial events already in HBM (device time, CUDA events,
           max over ranks) — the reference's "Simulation elapsed time" excludes init the same way (runner.hpp:71-73)
   e2e   : the same metric through the public host API with HOST buffers: reset + H2D of the initial events from
-          pinned memory + window loop + digest + D2H of every committed record into pinned memory, wall clock
+          pinned memory (ssb_load_events_raw, 32 B per event) + window loop + digest + D2H of every committed record
+          into pinned memory (ssb_run_drain_packed: 24 B per record, overlapped with the loop), wall clock
   --impl reference : the reference's own CPU implementation (oracle/_ref, unmodified sources; else the oracle port)
           on a bounded PHOLD sample, same metric/unit.
 """
@@ -325,9 +326,11 @@ def main():
     # initial events of this rank in pinned host memory (torch = plumbing for the pinned allocation)
     ev_np = phold.init_events(n_lp, n_init, lat, rank, world)
     n_ev = ev_np.size
-    ev_pin = torch.empty(n_ev * ssb.EVENT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    ev_view = ev_pin.numpy().view(ssb.EVENT_DTYPE)
-    ev_view[:] = ev_np
+    # ... in the compact 32-byte layout of the C ABI (ssb_load_events_raw); the widening to ssb_event would double the
+    # host-to-device bytes without adding information
+    ev_pin = torch.empty(n_ev * ssb.RAW_RECORD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    ev_view = ev_pin.numpy().view(ssb.RAW_RECORD_DTYPE)
+    ev_view[:] = ssb.events_to_raw(ev_np)
     del ev_np
     per_rank_committed_cap = int(FULL_COMMITTED_1M * args.lps_per_gpu / 1_000_000 * 1.15) + (1 << 20)
     keep = not args.no_e2e
@@ -337,12 +340,12 @@ def main():
                             max_events=int(args.init_per_gpu * 1.6) + (1 << 20), rounds_per_sync=args.rounds_per_sync,
                             load=False)
     ssb.dist.init_engine_comm(eng, rank, world, p2p=args.exchange == "p2p")
-    rec_pin = torch.empty(per_rank_committed_cap * 32, dtype=torch.uint8).pin_memory() if keep else None
+    rec_pin = torch.empty(per_rank_committed_cap * 24, dtype=torch.uint8).pin_memory() if keep else None
 
     def one_step():
         """device-resident timing: inputs already in HBM when the timed region (the window loop) starts"""
         eng.reset()
-        eng.load_events_ptr(ev_pin.data_ptr(), n_ev)
+        eng.load_events_raw_ptr(ev_pin.data_ptr(), n_ev)
         barrier()
         st = eng.run()                  # loop_ms: CUDA events on the engine's stream around the whole window loop
         barrier()
@@ -352,10 +355,10 @@ def main():
         barrier()
         t0 = time.perf_counter()
         eng.reset()
-        eng.load_events_ptr(ev_pin.data_ptr(), n_ev)                       # H2D from pinned host memory
-        st = eng.run()
+        eng.load_events_raw_ptr(ev_pin.data_ptr(), n_ev)                   # H2D from pinned host memory
+        # window loop on the device; the committed records of finished rounds stream to pinned host memory meanwhile
+        st, got = eng.run_drain_packed_ptr(rec_pin.data_ptr(), per_rank_committed_cap)
         dg = eng.digest()
-        got = eng.drain_committed_raw_ptr(rec_pin.data_ptr(), per_rank_committed_cap)   # D2H of every committed record
         barrier()
         return st, dg, got, time.perf_counter() - t0
 
@@ -422,8 +425,8 @@ def main():
             log(f"e2e step: {dt * 1000:.1f} ms, drained {got}")
         e2e_committed = sum_over_ranks(st.committed)
         e2e = {"value": e2e_committed / statistics.mean(ts), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_ev * ssb.EVENT_DTYPE.itemsize),
-               "d2h_bytes_per_step": int(st.committed * 32 + 32 + 1296),
+               "h2d_bytes_per_step": int(n_ev * ssb.RAW_RECORD_DTYPE.itemsize),
+               "d2h_bytes_per_step": int(st.committed * 24 + 32 + 1296),
                "ms_per_step": 1000.0 * statistics.mean(ts), "all_records_drained": bool(ok)}
 
     cpu = None

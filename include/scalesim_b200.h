@@ -126,6 +126,12 @@ typedef struct ssb_sent_record {
   uint32_t reserved;
 } ssb_sent_record;
 
+/* Packed committed record (24 bytes; what ssb_drain_committed_packed copies): the six fields of one "RE," line in
+ * 32 bits each. src 0xffffffff = -1. */
+typedef struct ssb_packed_record {
+  uint32_t id, src, send_time, dst, recv_time, tag;
+} ssb_packed_record;
+
 typedef struct ssb_stats {
   int64_t rounds;            /* windows executed */
   int64_t processed;         /* handler invocations ("# of processing events", runner.hpp:495) */
@@ -168,6 +174,10 @@ int ssb_read_states(ssb_engine* e, const int64_t* lp_ids, uint32_t* words, int64
 /* initial (or injected) events; events whose destination is owned by another rank are forwarded at the next step. */
 int ssb_load_events(ssb_engine* e, const ssb_event* ev, int64_t n);
 
+/* Same as ssb_load_events for events already in the compact 32-byte layout (half the host-to-device bytes):
+ * key = receive_time << 32 | id, src 0xffffffff = -1, tag bit 0 = is_cancel(). `ev` may be pinned. */
+int ssb_load_events_raw(ssb_engine* e, const ssb_raw_record* ev, int64_t n);
+
 /* Run windows until GVT.time >= finish_time (runner.hpp:392). */
 int ssb_run(ssb_engine* e, ssb_stats* stats);
 /* Run exactly one window (one round). *done = 1 when GVT.time >= finish_time. */
@@ -181,6 +191,15 @@ int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n)
 
 /* same, without widening: n raw 32-byte records straight from the device log (one D2H copy; `out` may be pinned) */
 int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int64_t* n);
+
+/* same, 24-byte records (packed on the device first: three quarters of the device-to-host bytes of the raw form) */
+int ssb_drain_committed_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int64_t* n);
+
+/* ssb_run + ssb_drain_committed_packed in one call, overlapped: while the window loop runs on the device, the
+ * committed records of the rounds that are already complete are packed and copied to `out` on a second stream
+ * (the reference prints its result lines while it simulates, runner.hpp:369-380). Returns when the simulation has
+ * finished and every record is in `out` (*n of them; cap must hold them all). */
+int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int64_t* n, ssb_stats* stats);
 
 /* ---- exact-differential simulation (reference --diff_init / --diff_repeat; runner.hpp:178-348, queue.hpp:179-241,
  * logical_process.hpp:132-153, leveldb_store.hpp) ----

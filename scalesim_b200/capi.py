@@ -27,11 +27,38 @@ RECORD_DTYPE = np.dtype([
 RAW_RECORD_DTYPE = np.dtype([
     ("key", "<u8"), ("dst", "<u4"), ("src", "<u4"), ("send_time", "<u4"), ("p0", "<u4"), ("p1", "<u4"), ("tag", "<u4"),
 ])
+#: host mirror of ``ssb_packed_record`` (24 bytes): the six fields of one committed line, 32 bits each
+PACKED_RECORD_DTYPE = np.dtype([("id", "<u4"), ("src", "<u4"), ("send_time", "<u4"), ("dst", "<u4"), ("recv_time", "<u4"),
+                                ("tag", "<u4")])
 #: host mirror of ``ssb_sent_record`` (16 bytes): the event a committed event produced (dst 0xffffffff = none)
 SENT_RECORD_DTYPE = np.dtype([("dst", "<u4"), ("id", "<u4"), ("recv_time", "<u4"), ("reserved", "<u4")])
 FLAG_DEBUG_CHECKS = 1
 FLAG_KERNEL_TIMING = 2
 FLAG_HISTORY = 4
+
+
+def events_to_raw(ev: np.ndarray) -> np.ndarray:
+    """ssb_event (64 bytes) -> the compact 32-byte layout that ssb_load_events_raw takes."""
+    raw = np.zeros(ev.shape, dtype=RAW_RECORD_DTYPE)
+    raw["key"] = (ev["recv_time"].astype(np.uint64) << np.uint64(32)) | ev["id"].astype(np.uint64)
+    raw["dst"] = ev["dst"]
+    raw["src"] = np.where(ev["src"] < 0, 0xFFFFFFFF, ev["src"]).astype(np.uint32)
+    raw["send_time"] = ev["send_time"]
+    raw["p0"] = ev["p0"]
+    raw["p1"] = ev["p1"]
+    raw["tag"] = ev["flags"] & 1
+    return raw
+
+
+def packed_to_records(p: np.ndarray) -> np.ndarray:
+    """ssb_packed_record -> ssb_record (widening; src 0xffffffff -> -1)."""
+    rec = np.empty(p.shape, dtype=RECORD_DTYPE)
+    for f in ("id", "send_time", "dst", "recv_time", "tag"):
+        rec[f] = p[f]
+    src = p["src"].astype(np.int64)
+    src[p["src"] == 0xFFFFFFFF] = -1
+    rec["src"] = src
+    return rec
 
 
 def raw_to_records(raw: np.ndarray) -> np.ndarray:
@@ -145,6 +172,9 @@ def load_library() -> C.CDLL:
     lib.ssb_committed_digest.argtypes = [vp, vp]
     lib.ssb_drain_committed.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.ssb_drain_committed_raw.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_load_events_raw.argtypes = [vp, vp, i64]
+    lib.ssb_drain_committed_packed.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_run_drain_packed.argtypes = [vp, vp, i64, C.POINTER(i64), C.POINTER(_Stats)]
     lib.ssb_drain_history.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     lib.ssb_load_history.argtypes = [vp, vp, vp, i64]
     lib.ssb_reset.argtypes = [vp]
@@ -292,6 +322,40 @@ class Engine:
         n = C.c_int64(0)
         self._check(self._lib.ssb_drain_committed_raw(self._h, C.c_void_p(ptr), cap, C.byref(n)))
         return n.value
+
+    def load_events_raw(self, raw: np.ndarray):
+        raw = np.ascontiguousarray(raw, dtype=RAW_RECORD_DTYPE)
+        self._check(self._lib.ssb_load_events_raw(self._h, _ptr(raw), raw.size))
+
+    def load_events_raw_ptr(self, ptr: int, n: int):
+        self._check(self._lib.ssb_load_events_raw(self._h, C.c_void_p(ptr), n))
+
+    def drain_committed_packed(self, cap: int | None = None) -> np.ndarray:
+        """Committed records in the 24-byte packed layout (``ssb_packed_record``)."""
+        if cap is None:
+            cap = max(1, self.stats().committed)
+        out = np.empty(cap, dtype=PACKED_RECORD_DTYPE)
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_committed_packed(self._h, _ptr(out), cap, C.byref(n)))
+        return out[: n.value]
+
+    def drain_committed_packed_ptr(self, ptr: int, cap: int) -> int:
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_drain_committed_packed(self._h, C.c_void_p(ptr), cap, C.byref(n)))
+        return n.value
+
+    def run_drain_packed_ptr(self, ptr: int, cap: int):
+        """Run the simulation while the committed records stream to host memory (ssb_run_drain_packed).
+        Returns (stats, number of records)."""
+        s = _Stats()
+        n = C.c_int64(0)
+        self._check(self._lib.ssb_run_drain_packed(self._h, C.c_void_p(ptr), cap, C.byref(n), C.byref(s)))
+        return self._stats(s), n.value
+
+    def run_drain_packed(self, cap: int):
+        out = np.empty(cap, dtype=PACKED_RECORD_DTYPE)
+        st, n = self.run_drain_packed_ptr(out.ctypes.data, cap)
+        return st, out[:n]
 
     def drain_history(self, cap: int | None = None):
         """--diff_init: every committed event (``ssb_raw_record``) with its sent-log entry (``ssb_sent_record``).

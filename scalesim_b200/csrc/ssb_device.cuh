@@ -91,6 +91,7 @@ struct Ctl {
   // statistics
   u64 n_processed, n_rollbacks, n_undone, n_antis, n_annihilated, n_dups, n_committed, n_beyond, n_remote;
   u64 log_count, log_dropped;
+  u64 log_stable;     // log_count at the start of the current round: everything below is completely written
   u64 digest[4];
 };
 

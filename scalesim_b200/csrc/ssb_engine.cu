@@ -86,6 +86,10 @@ struct ssb_engine {
   // staging
   HostEvent* d_stage = nullptr;
   long long* d_unpack = nullptr; size_t unpack_cap = 0;
+  void* d_pack[2] = {nullptr, nullptr};      // staging halves of ssb_drain_committed_packed
+  cudaStream_t copy_stream = nullptr;
+  u64* h_poll = nullptr;                     // pinned: progress of the committed log while the loop graph runs
+  cudaEvent_t pack_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   u64 log_drained = 0;
   double loop_ms = 0.0;
   long long rounds = 0;
@@ -661,6 +665,13 @@ void ssb_destroy(ssb_engine* e) {
   if (e->mbox_block) cudaFree(e->mbox_block);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_unpack) cudaFree(e->d_unpack);
+  for (int i = 0; i < 2; ++i) {
+    if (e->d_pack[i]) cudaFree(e->d_pack[i]);
+    if (e->pack_done[i]) cudaEventDestroy(e->pack_done[i]);
+    if (e->copy_done[i]) cudaEventDestroy(e->copy_done[i]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->h_poll) cudaFreeHost(e->h_poll);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
   e->t_collect();
   for (cudaEvent_t x : e->event_pool) cudaEventDestroy(x);
@@ -828,6 +839,27 @@ int ssb_load_events(ssb_engine* e, const ssb_event* ev, int64_t n) {
   return e->check_device_error();
 }
 
+int ssb_load_events_raw(ssb_engine* e, const ssb_raw_record* ev, int64_t n) {
+  if (!e || (!ev && n) || n < 0) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  static_assert(sizeof(ssb_raw_record) == sizeof(Ev), "raw record layout");
+  int64_t done = 0;
+  while (done < n) {
+    u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
+    // straight into the routing staging area: no unpack pass
+    CK(cudaMemcpyAsync(e->v.outbox, ev + done, sizeof(Ev) * m, cudaMemcpyHostToDevice, e->stream));
+    k_check_raw<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, m);
+    e->launch_route(e->v, 3, 0, 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    done += m;
+  }
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  return e->check_device_error();
+}
+
 int ssb_step(ssb_engine* e, int* done) {
   if (!e) return SSB_ERR_INVALID;
   cudaSetDevice(e->cfg.device);
@@ -963,6 +995,115 @@ int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int
     CK(cudaStreamSynchronize(e->stream));
     e->log_drained = 0;
   }
+  return SSB_OK;
+}
+
+int ssb_drain_committed_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int64_t* n) {
+  if (!e || !n || (!out && cap) || cap < 0) return SSB_ERR_INVALID;
+  static_assert(sizeof(ssb_packed_record) == 24, "packed record layout");
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  int rc = e->sync_ctl();
+  if (rc) return rc;
+  u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
+  u64 m = std::min<u64>(have - e->log_drained, (u64)cap);
+  *n = (int64_t)m;
+  // two staging halves: the pack kernel of chunk k+1 runs while chunk k crosses PCIe
+  const u64 kChunk = 1u << 22;
+  if (m && !e->d_pack[0]) {
+    CK(cudaMalloc(&e->d_pack[0], kChunk * 24));
+    CK(cudaMalloc(&e->d_pack[1], kChunk * 24));
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->pack_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->pack_done[1], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->copy_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->copy_done[1], cudaEventDisableTiming));
+  }
+  u64 done = 0;
+  for (int k = 0; done < m; ++k) {
+    const int b = k & 1;
+    const u32 cnt = (u32)std::min<u64>(m - done, kChunk);
+    if (k >= 2) CK(cudaStreamWaitEvent(e->stream, e->copy_done[b], 0));      // the half is free again
+    k_pack_log<<<e->grid(cnt, 256), 256, 0, e->stream>>>(e->v.log, e->log_drained + done, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
+    CK(cudaEventRecord(e->pack_done[b], e->stream));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->pack_done[b], 0));
+    CK(cudaMemcpyAsync(out + done, e->d_pack[b], (size_t)cnt * 24, cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaEventRecord(e->copy_done[b], e->copy_stream));
+    done += cnt;
+  }
+  if (m) { CK(cudaStreamSynchronize(e->copy_stream)); CK(cudaStreamSynchronize(e->stream)); }
+  e->log_drained += m;
+  if (e->log_drained == have && have == e->h_ctl->log_count) {
+    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->log_drained = 0;
+  }
+  return SSB_OK;
+}
+
+int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int64_t* n, ssb_stats* stats) {
+  if (!e || !n || (!out && cap) || cap < 0) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  int rc = e->model_ready();
+  if (rc) return rc;
+  const bool use_graph = e->graph_enabled && (e->cfg.world == 1 || e->v.p2p) && !e->timing();
+  if (!use_graph || e->log_drained != 0) {      // no device-side loop to overlap with: one after the other
+    if ((rc = ssb_run(e, stats))) return rc;
+    return ssb_drain_committed_packed(e, out, cap, n);
+  }
+  if (e->graph_dirty && (rc = e->build_graph())) return rc;
+  const u64 kChunk = 1u << 22;
+  if (!e->d_pack[0]) {
+    CK(cudaMalloc(&e->d_pack[0], kChunk * 24));
+    CK(cudaMalloc(&e->d_pack[1], kChunk * 24));
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&e->pack_done[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->copy_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (!e->h_poll) CK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_poll), sizeof(u64), cudaHostAllocDefault));
+  CK(cudaEventRecord(e->ev0, e->stream));
+  CK(cudaGraphLaunch(e->graph_exec, e->stream));
+  CK(cudaEventRecord(e->ev1, e->stream));
+  u64 drained = 0;
+  bool finished = false;
+  int k = 0;
+  // pack + copy [drained, upto) on the copy stream, alternating between the two staging halves
+  auto drain_to = [&](u64 upto, bool all) -> int {
+    while (drained < upto && (all || upto - drained >= (kChunk >> 2))) {
+      const u32 cnt = (u32)std::min<u64>(upto - drained, kChunk);
+      if ((u64)cap < drained + cnt) { set_error("ssb_run_drain_packed: output buffer too small"); return SSB_ERR_CAPACITY; }
+      const int b = k++ & 1;
+      k_pack_log<<<e->grid(cnt, 256), 256, 0, e->copy_stream>>>(e->v.log, drained, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
+      CK(cudaMemcpyAsync(out + drained, e->d_pack[b], (size_t)cnt * 24, cudaMemcpyDeviceToHost, e->copy_stream));
+      drained += cnt;
+    }
+    return SSB_OK;
+  };
+  while (!finished) {
+    finished = cudaEventQuery(e->ev1) == cudaSuccess;
+    CK(cudaMemcpyAsync(e->h_poll, finished ? &e->v.ctl->log_count : &e->v.ctl->log_stable, sizeof(u64), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaStreamSynchronize(e->copy_stream));      // also waits for the chunks issued so far: the halves are free
+    const u64 upto = std::min<u64>(*e->h_poll, e->v.cap_log);
+    if ((rc = drain_to(upto, finished))) { cudaStreamSynchronize(e->stream); return rc; }
+  }
+  CK(cudaStreamSynchronize(e->copy_stream));
+  CK(cudaEventSynchronize(e->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->loop_ms += ms;
+  if ((rc = e->sync_ctl())) return rc;
+  e->rounds = e->h_ctl->round;
+  if ((rc = e->check_device_error())) return rc;
+  if (!e->h_ctl->done) { set_error("window loop ended before GVT reached finish_time"); return SSB_ERR_INVALID; }
+  if (e->h_ctl->log_dropped) { set_error("committed log overflowed (raise max_committed)"); return SSB_ERR_CAPACITY; }
+  *n = (int64_t)drained;
+  CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));      // fully drained: rewind the log
+  CK(cudaStreamSynchronize(e->stream));
+  e->log_drained = 0;
+  if (stats) return ssb_get_stats(e, stats);
   return SSB_OK;
 }
 

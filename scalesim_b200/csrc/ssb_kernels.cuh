@@ -213,6 +213,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->n_vheavy = 0;
     c->n_fix = 0;
     c->done = done ? 1u : 0u;
+    c->log_stable = c->log_count;      // the commit passes of all earlier rounds are complete
     c->round++;
     for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
     c->sent_min = KEY_MAX;
@@ -1393,6 +1394,32 @@ __global__ void k_pack(View v, const HostEvent* in, u32 n) {
     store_ev(v.outbox + i, e);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = n;
+}
+
+// events loaded in the compact layout (ssb_load_events_raw): validated in place in the outbox staging area
+__global__ void k_check_raw(View v, u32 n) {
+  Ctl* c = v.ctl;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ev e = load_ev(v.outbox + i);
+    if (e.dst >= v.n_lp || key_time(e.key) >= 0x80000000u || key_id(e.key) == NIL) {
+      atomicOr(&c->error, E_RANGE);
+      v.outbox[i].key = KEY_MAX;
+    } else if (e.flags & ~F_CANCEL) {
+      v.outbox[i].flags = e.flags & F_CANCEL;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = n;
+}
+
+// committed log record -> ssb_packed_record (6 x u32)
+__global__ void k_pack_log(const Ev* log, u64 first, u32 n, u32* out) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const Ev e = load_ev(log + first + i);
+    uint2* o = reinterpret_cast<uint2*>(out + (size_t)i * 6);
+    o[0] = make_uint2(key_id(e.key), e.src);
+    o[1] = make_uint2(e.send, e.dst);
+    o[2] = make_uint2(key_time(e.key), e.flags);
+  }
 }
 
 // history records (committed-log layout: flags = tag) -> staging for k_route: the tag is not an event flag

@@ -226,3 +226,33 @@ def test_graph_loop_equals_stepwise_loop(phold_tables_01, window):
     assert (st_step.committed, st_step.processed, st_step.rollbacks, st_step.antis_sent) == \
            (st_graph.committed, st_graph.processed, st_graph.rollbacks, st_graph.antis_sent)
     eng.close()
+
+
+def test_compact_load_and_packed_drain_equal_the_wide_forms(phold_tables_01):
+    """ssb_load_events_raw (32 B per event) and ssb_drain_committed_packed (24 B per record) carry the same information
+    as ssb_load_events / ssb_drain_committed."""
+    from scalesim_b200 import phold
+    lat = phold_tables_01[0]
+    ev = phold.init_events(1000, 16000, lat)
+    eng = phold.make_engine(1000, 16000, 0.1, 1.0, tables=phold_tables_01, keep_records=True, load=False)
+    eng.load_events(ev)
+    eng.run()
+    want_digest = eng.digest()
+    want = ssb.records_to_lines(eng.drain_committed())
+    eng.reset()
+    eng.load_events_raw(ssb.events_to_raw(ev))
+    eng.run()
+    assert eng.digest() == want_digest
+    got = ssb.records_to_lines(ssb.packed_to_records(eng.drain_committed_packed()))
+    assert sorted(got) == sorted(want)
+    # ... and streamed out while the loop runs
+    eng.reset()
+    eng.load_events_raw(ssb.events_to_raw(ev))
+    st, rec = eng.run_drain_packed(100000)
+    assert st.committed == rec.size == len(want) and eng.digest() == want_digest
+    assert sorted(ssb.records_to_lines(ssb.packed_to_records(rec))) == sorted(want)
+    with pytest.raises(ssb.EngineError):
+        eng.reset()
+        eng.load_events_raw(ssb.events_to_raw(ev))
+        eng.run_drain_packed(10)          # output buffer too small: fails loudly
+    eng.close()
