@@ -207,6 +207,7 @@ void runner<App>::run() {
   // events: every rank reads the whole scenario and keeps what it owns (the reference shuffles instead, runner.hpp:131-147)
   ev_vec<App> mine;
   history hist;
+  std::vector<ssb_event> deletes;      // anti-messages of the DE / RE what-if queries
   if (!FLAGS_diff_repeat) {
     for (int r = 0; r < world_; ++r) {
       ev_vec<App> parsed;
@@ -225,19 +226,31 @@ void runner<App>::run() {
       std::vector<boost::shared_ptr<const what_if<App> > > wi;
       app_.init_what_if(wi, r, world_);
       for (size_t i = 0; i < wi.size(); ++i) {
-        if (wi[i]->update_state_.id() != -1 || wi[i]->delete_event_id_ != -1) {
-          LOG(ERROR) << "what-if queries of type SC (state change) and DE/RE (delete event) are not part of this build yet";
+        if (wi[i]->update_state_.id() != -1) {
+          LOG(ERROR) << "what-if queries of type SC (state change) are not part of this build yet";
           std::exit(2);
         }
-        if (wi[i]->add_event_.id() == -1) continue;
         long d = wi[i]->lp_id_;
-        if (d >= 0 && d < n_lp && part[d] % world_ == rank_)
-          mine.push_back(boost::make_shared<event<App> >(wi[i]->add_event_));
+        if (!(d >= 0 && d < n_lp && part[d] % world_ == rank_)) continue;
+        if (wi[i]->delete_event_id_ != -1) {
+          // delete event (runner.hpp:246-276): the recorded event loses its sent-log entry — eventq::delete_can: its
+          // output is NOT cancelled — and an anti-message goes into the LP's inbox (eventq::delete_ev,
+          // queue.hpp:227-241), which erases the event and rolls the LP back to its key
+          const uint64_t key = ((uint64_t)wi[i]->time_ << 32) | (uint64_t)(uint32_t)wi[i]->delete_event_id_;
+          for (size_t k = 0; k < hist.rec.size(); ++k)
+            if (hist.rec[k].key == key && (long)hist.rec[k].dst == d) hist.sent[k].dst = 0xffffffffu;
+          ssb_event a;
+          std::memset(&a, 0, sizeof(a));
+          a.id = wi[i]->delete_event_id_; a.src = -1; a.dst = d; a.recv_time = a.send_time = wi[i]->time_; a.flags = 1;
+          deletes.push_back(a);
+        }
+        if (wi[i]->add_event_.id() != -1) mine.push_back(boost::make_shared<event<App> >(wi[i]->add_event_));
       }
     }
   }
   std::vector<ssb_event> pod(mine.size());
   for (size_t i = 0; i < mine.size(); ++i) model::pack_event(*mine[i], pod[i], cx);
+  pod.insert(pod.end(), deletes.begin(), deletes.end());
   const size_t n_resident = pod.size() + hist.rec.size();
 
   ssb_config cfg;

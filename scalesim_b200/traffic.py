@@ -89,24 +89,42 @@ def read_trips(path: str):
             np.array(nodes, dtype=np.int64))
 
 
-def read_what_if(path: str):
-    """traffic_reader::what_if_read (traffic_sim.hpp:453-599), the AE (add event) queries:
-    ``AE,{event id},0,{departure},{1st node},{2nd node},...`` -> query LP = first node, time = departure
-    (:522-558). Returns (trip_id, trip_dep, route_start, route_nodes) like read_trips. SC / DE / RE queries are
-    not supported by this build and raise."""
-    tid, dep, start, nodes = [], [], [0], []
+@dataclass
+class WhatIf:
+    """What-if queries of a --diff_repeat run: added trips (AE) and deleted events (DE / RE)."""
+    trip_id: np.ndarray
+    trip_dep: np.ndarray
+    route_start: np.ndarray
+    route_nodes: np.ndarray
+    deletes: np.ndarray          # rows (lp, time, event id)
+
+    def __iter__(self):          # unpacks like the (trip_id, trip_dep, route_start, route_nodes) tuple of the AE part
+        return iter((self.trip_id, self.trip_dep, self.route_start, self.route_nodes))
+
+
+def read_what_if(path: str) -> WhatIf:
+    """traffic_reader::what_if_read (traffic_sim.hpp:453-599).
+    ``AE,{event id},0,{departure},{1st node},{2nd node},...`` add event: query LP = first node, time = departure (:522-558)
+    ``DE,{lp id},{time},{event id}``                           delete event (:559-580)
+    ``RE,{event id},{source},{send time},{destination},{receive time}``   delete the event of that result line (:581-596)
+    SC (state change) queries are not supported by this build and raise."""
+    tid, dep, start, nodes, dels = [], [], [0], [], []
     with open(path) as f:
         for line in f.read().splitlines():
+            fld = line.split(",")
             if line[:2] == "AE":
-                fld = line.split(",")
                 tid.append(_atol(fld[1]))
                 dep.append(_atol(fld[3]))
                 nodes.extend(_atol(x) for x in fld[4:])
                 start.append(len(nodes))
-            elif line[:2] in ("SC", "DE", "RE"):
-                raise NotImplementedError(f"what-if query type {line[:2]} (state change / delete event) is not supported")
-    return (np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
-            np.array(nodes, dtype=np.int64))
+            elif line[:2] == "DE":
+                dels.append((_atol(fld[1]), _atol(fld[2]), _atol(fld[3])))
+            elif line[:2] == "RE":
+                dels.append((_atol(fld[4]), _atol(fld[5]), _atol(fld[1])))
+            elif line[:2] == "SC":
+                raise NotImplementedError("what-if query type SC (state change) is not supported")
+    return WhatIf(np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
+                  np.array(nodes, dtype=np.int64), np.array(dels, dtype=np.int64).reshape(-1, 3))
 
 
 def read_scenario(road_csv: str, trip_csv: str, partition_file: str | None = None) -> Scenario:
@@ -281,13 +299,24 @@ def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
     ``engine.run()`` then re-executes exactly what the queries invalidate and commits only that."""
     rank, world = kw.get("rank", 0), kw.get("world", 1)
     tid, dep, rstart, rnodes = what_if
+    deletes = getattr(what_if, "deletes", np.zeros((0, 3), dtype=np.int64))
     n_hist = store.rec.size
     # re-executed history is re-sent: until a bucket is fossil-collected it holds the recorded copy AND the new one
     kw.setdefault("max_events", int((n_hist + rnodes.size) * 3) + (1 << 16))
     kw.setdefault("max_batch", max(1 << 14, (n_hist + tid.size) // 2 + (1 << 14)))
     kw.setdefault("max_committed", n_hist + int(rnodes.size) + 1024)
     eng = make_engine(sc, load=False, extra_routes=rnodes, **kw)
-    eng.load_history(store.rec, store.sent)
+    sent = store.sent
+    if deletes.size:
+        # delete event (runner.hpp:246-276): the recorded event loses its sent-log entry — eventq::delete_can,
+        # queue.hpp:238-241: its output is NOT cancelled — and an anti-message for it goes into the LP's inbox
+        # (eventq::delete_ev, :227-236), which erases it and rolls the LP back to its key
+        sent = sent.copy()
+        keys = (deletes[:, 1].astype(np.uint64) << np.uint64(32)) | deletes[:, 2].astype(np.uint64)
+        for lp, key in zip(deletes[:, 0], keys):
+            hit = np.nonzero((store.rec["key"] == key) & (store.rec["dst"] == lp))[0]
+            sent["dst"][hit] = 0xFFFFFFFF
+    eng.load_history(store.rec, sent)
     ev = np.zeros(tid.size, dtype=EVENT_DTYPE)
     ev["id"] = tid
     ev["src"] = -1
@@ -297,6 +326,14 @@ def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
     ev["p0"] = sc.route_nodes.size + rstart[:-1]
     ev["p1"] = np.diff(rstart)
     part = sc.partition
+    if deletes.size:
+        anti = np.zeros(deletes.shape[0], dtype=EVENT_DTYPE)
+        anti["id"] = deletes[:, 2]
+        anti["src"] = -1
+        anti["dst"] = deletes[:, 0]
+        anti["recv_time"] = anti["send_time"] = deletes[:, 1]
+        anti["flags"] = 1
+        ev = np.concatenate([ev, anti])
     owner = (part[ev["dst"]] % world) if part is not None else (ev["dst"] % world)
     eng.load_events(ev[owner == rank])
     return eng

@@ -247,16 +247,24 @@ def parse_line(l):
     return (int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]))      # id, src, send, dst, recv
 
 
-def repeat_closure(init_lines, new_lines):
-    """Lines of the repeat run = new_lines + every init line at an LP whose key (recv, id) is >= the LP's earliest touch."""
+def repeat_closure(init_lines, new_lines, deletes=()):
+    """Lines of the repeat run = new_lines + every init line at an LP whose key (recv, id) is >= the LP's earliest touch.
+    deletes = (lp, time, id) of deleted events (DE / RE queries, runner.hpp:246-276): the LP is touched at that key,
+    the event itself disappears, and — eventq::delete_can, queue.hpp:238-241 — its output is neither cancelled nor
+    redone, so the delete does not propagate through it. A deleted event comes BACK when the cascade of another query
+    makes its sender re-execute the event that produced it: the sender's anti-message finds nothing, the re-sent
+    positive is inserted as a new event (seen in the reference on the 12x12 grid)."""
     import heapq
+    deleted = {(int(lp), (int(t), int(i))) for lp, t, i in deletes}
     by_lp = {}
     succ = {}
+    pred = {}
     for l in init_lines:
         i, src, send, dst, recv = parse_line(l)
         by_lp.setdefault(dst, []).append(((recv, i), l))
         if (src, send) != (dst, recv):                   # PHOLD's initial events name themselves as their source
             succ[(i, src, send)] = (dst, (recv, i))      # the output of the event (id, at LP src, key (send, id))
+            pred[(dst, (recv, i))] = (src, (send, i))
     for v in by_lp.values():
         v.sort()
     touch = {}
@@ -264,19 +272,34 @@ def repeat_closure(init_lines, new_lines):
     for l in new_lines:
         i, src, send, dst, recv = parse_line(l)
         heapq.heappush(heap, ((recv, i), dst))
-    while heap:
-        key, lp = heapq.heappop(heap)
-        old = touch.get(lp)
-        if old is not None and old <= key:
-            continue
-        touch[lp] = key
-        for k, l in by_lp.get(lp, []):
-            if k >= key and (old is None or k < old):
-                i = k[1]
-                s = succ.get((i, lp, k[0]))
+    for lp, key in deleted:
+        heapq.heappush(heap, (key, lp))
+    revived = set()
+    while True:
+        while heap:
+            key, lp = heapq.heappop(heap)
+            old = touch.get(lp)
+            if old is not None and old <= key:
+                continue
+            touch[lp] = key
+            for k, l in by_lp.get(lp, []):
+                if k >= key and (old is None or k < old) and ((lp, k) not in deleted or (lp, k) in revived):
+                    s = succ.get((k[1], lp, k[0]))
+                    if s is not None:
+                        heapq.heappush(heap, (s[1], s[0]))
+        again = False
+        for d in deleted - revived:
+            p = pred.get(d)
+            if p is not None and p[0] in touch and touch[p[0]] <= p[1] and p not in (deleted - revived):
+                revived.add(d)                            # its sender re-executed the producing event: re-sent
+                s = succ.get((d[1][1], d[0], d[1][0]))
                 if s is not None:
                     heapq.heappush(heap, (s[1], s[0]))
+                again = True
+        if not again:
+            break
+    gone = deleted - revived
     out = list(new_lines)
     for lp, m in touch.items():
-        out += [l for k, l in by_lp.get(lp, []) if k >= m]
+        out += [l for k, l in by_lp.get(lp, []) if k >= m and (lp, k) not in gone]
     return sorted(out)

@@ -50,6 +50,26 @@ def test_diff_init_store_and_diff_repeat_equal_reference(case, bucket, window, t
     assert st2.committed == len(lines) < len(g["init_lines"]) + len(g["new_lines"])
 
 
+@pytest.mark.parametrize("case,bucket,window", [("ring", 8, 1), ("grid", 11, 1), ("grid", 16, 4)])
+def test_delete_event_queries_equal_reference(case, bucket, window, tmp_path):
+    """--diff_repeat with DE / RE (delete event) queries: traffic/ring/delete_ev.csv and three deletes on the grid."""
+    g = golden(case + "_diff")
+    if case == "ring":
+        sc, _ = ring_scenario()
+        sc.partition = None
+    else:
+        sc = _grid(g)
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=bucket, window_buckets=window)
+    wi = _what_if(g["de_lines"], tmp_path)
+    assert wi.deletes.shape == (len(g["de_lines"]), 3) and wi.trip_id.size == 0
+    eng = traffic.make_repeat_engine(sc, hs, wi, bucket_ticks=bucket, window_buckets=window, keep_records=True)
+    st2 = eng.run()
+    lines = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    assert lines == g["delete_union"]
+    assert st2.annihilated >= len(g["de_lines"])
+
+
 def test_repeat_is_exact_on_a_larger_grid(tmp_path):
     """Config-5 shape at a reduced size: init + repeat(AE) must agree with one full run over trips + added trips
     (vehicles do not interact, so full = init + new; repeat = new + re-executed history = the closure)."""

@@ -68,6 +68,11 @@ def test_trafficsim_dropin_diff_init_and_repeat_equal_reference(tmp_path):
     lines, err = _run("TrafficSim", flags + ["--diff_repeat", part1, rd, ae])
     assert sorted(lines) == g["repeat_union"]
     assert "# of output events             : 19" in err
+    de = str(tmp_path / "delete_ev.csv")           # traffic/ring/delete_ev.csv: one RE line
+    with open(de, "w") as f:
+        f.write("".join(l + "\n" for l in g["de_lines"]))
+    lines, err = _run("TrafficSim", flags + ["--diff_repeat", part1, rd, de])
+    assert sorted(lines) == g["delete_union"]
 
 
 def test_phold_dropin_diff_init_and_repeat_equal_reference(tmp_path):

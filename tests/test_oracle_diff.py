@@ -19,6 +19,23 @@ def test_repeat_closure_equals_reference_repeat_output(name):
     assert set(g["new_lines"]) <= set(got)
 
 
+def _deletes(g):
+    out = []
+    for l in g["de_lines"]:
+        f = l.split(",")
+        out.append((int(f[1]), int(f[2]), int(f[3])) if f[0] == "DE" else (int(f[4]), int(f[5]), int(f[1])))
+    return out
+
+
+@pytest.mark.parametrize("name", ["ring_diff", "grid_diff"])
+def test_delete_closure_equals_reference_repeat_output(name):
+    """DE / RE queries: the event is erased, its output is not cancelled (queue.hpp:227-241); on the grid one of the three
+    deleted events comes back because another query's cascade re-sends it."""
+    g = golden(name)
+    got = O.repeat_closure(g["init_lines"], [], _deletes(g))
+    assert got == g["delete_union"] == g["delete_core"]
+
+
 def test_ring_repeat_is_the_19_lines_of_the_survey():
     g = golden("ring_diff")
     assert len(g["repeat_union"]) == 19 and g["repeat_core"] == g["repeat_union"]
