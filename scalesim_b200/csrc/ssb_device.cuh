@@ -86,6 +86,9 @@ struct Ctl {
   u32 recv_count[MAX_WORLD];
   u64 prev_gvt;       // stall detection of the graph's loop
   u32 stall;
+  u32 where;          // first internal invariant that failed (1 commit of an unprocessed event, 2 irregular turn in a
+                      // history replay, 3 arrival list shorter than its count, 4 chunk never published, 5 arrival below GVT)
+  u32 where_arg;      // its argument (time / LP / bucket)
   u32 epoch;          // number of resets: keeps the GVT-exchange stamps of consecutive simulations apart
   u64 sent_min;       // peer-memory exchange: smallest bucket-start key of the events written to peers this round
   // statistics
@@ -138,6 +141,8 @@ struct View {
   Ev* sendbuf;         // [world * cap_send]
   Ev* recvbuf;         // [world * cap_send]
   // peer-memory exchange (NVLink P2P): every partition owns a mailbox block, mapped into all peers with CUDA IPC:
+  //   header   256 bytes: {cap_send, cap_anti, GVT slot offset, record offset} of THIS mailbox — partitions may be
+  //            configured with different capacities (e.g. a --diff_repeat run sizes them by the rank's history)
   //   counts   [2 parities][world sources][2 kinds]  one 128-byte line each (kind 0 = positives, 1 = anti-messages)
   //   GVT slot [2 parities][world sources]           u64 = round << 32 | local minimum time
   //   records  [2 parities][world sources] x { cap_send positives, cap_anti anti-messages }
@@ -146,8 +151,9 @@ struct View {
   // peers' slots and waits for theirs (k_gvt): that exchange is the GVT min-reduction AND the barrier that makes the
   // appended events visible.
   u32 p2p;                       // 0 = NCCL send/recv exchange, 1 = peer-memory exchange
-  u32 cap_anti;                  // anti-message records per (parity, source)
-  u32 mb_gvt_off, mb_data_off;   // byte offsets inside a mailbox block
+  u32 cap_anti;                  // anti-message records per (parity, source) of the own mailbox
+  u32 mb_cap_send[MAX_WORLD], mb_cap_anti[MAX_WORLD];     // geometry of every partition's mailbox (from its header)
+  u32 mb_gvt_off[MAX_WORLD], mb_data_off[MAX_WORLD];      // byte offsets inside the block
   char* peer_base[MAX_WORLD];    // mailbox blocks of all partitions (own block at [rank])
   Ev* log;             // [cap_log] committed records
   uint4* log_sent;     // [cap_log] history store (--diff_init): sent-log entry of each committed event {dst, key lo, key hi, 0}
@@ -157,6 +163,10 @@ struct View {
   Ctl* ctl;
 };
 
+__device__ __forceinline__ void internal_error(const View& v, u32 where, u32 arg) {
+  if (atomicCAS(&v.ctl->where, 0u, where) == 0u) v.ctl->where_arg = arg;
+  atomicOr(&v.ctl->error, E_INTERNAL);
+}
 __device__ __forceinline__ u32 key_time(u64 k) { return (u32)(k >> 32); }
 __device__ __forceinline__ u32 key_id(u64 k) { return (u32)k; }
 __device__ __forceinline__ u64 make_key(u32 t, u32 id) { return ((u64)t << 32) | id; }
@@ -228,14 +238,14 @@ __device__ __forceinline__ void store_ev(Ev* p, const Ev& e) {
 }
 
 __device__ __forceinline__ u32* mb_cnt(const View& v, u32 owner, u32 par, u32 src, u32 kind) {
-  return reinterpret_cast<u32*>(v.peer_base[owner]) + ((par * v.world + src) * 2u + kind) * 32u;
+  return reinterpret_cast<u32*>(v.peer_base[owner] + 256) + ((par * v.world + src) * 2u + kind) * 32u;
 }
 __device__ __forceinline__ u64* mb_gvt(const View& v, u32 owner, u32 par, u32 src) {
-  return reinterpret_cast<u64*>(v.peer_base[owner] + v.mb_gvt_off) + par * v.world + src;
+  return reinterpret_cast<u64*>(v.peer_base[owner] + v.mb_gvt_off[owner]) + par * v.world + src;
 }
 __device__ __forceinline__ Ev* mb_data(const View& v, u32 owner, u32 par, u32 src, u32 kind) {
-  return reinterpret_cast<Ev*>(v.peer_base[owner] + v.mb_data_off) +
-         (size_t)(par * v.world + src) * (v.cap_send + v.cap_anti) + (kind ? v.cap_send : 0u);
+  return reinterpret_cast<Ev*>(v.peer_base[owner] + v.mb_data_off[owner]) +
+         (size_t)(par * v.world + src) * (v.mb_cap_send[owner] + v.mb_cap_anti[owner]) + (kind ? v.mb_cap_send[owner] : 0u);
 }
 
 // slot of position p in bucket b; the chunk must already exist

@@ -97,8 +97,8 @@ struct ssb_engine {
   Nccl::Comm comm = nullptr;
   void* mbox_block = nullptr;              // own mailbox (exported with CUDA IPC)
   std::vector<void*> peer_blocks;          // peers' mailboxes, opened with CUDA IPC
-  // mailbox block layout (see View): counts | GVT slots | records
-  size_t mbox_cnt_bytes() const { return (size_t)2 * cfg.world * 2 * 128; }
+  // mailbox block layout (see View): header | counts | GVT slots | records
+  size_t mbox_cnt_bytes() const { return 256 + (size_t)2 * cfg.world * 2 * 128; }
   size_t mbox_gvt_bytes() const { return ((size_t)2 * cfg.world * 8 + 255) & ~(size_t)255; }
   size_t mbox_bytes() const {
     return mbox_cnt_bytes() + mbox_gvt_bytes() + (size_t)2 * cfg.world * ((size_t)v.cap_send + v.cap_anti) * sizeof(Ev);
@@ -332,7 +332,7 @@ int ssb_engine::check_device_error() {
   if (e & E_SNAP) s += " snapshot ring overflow (raise max_snapshots)";
   if (e & E_HORIZON) s += " calendar horizon exceeded";
   if (e & E_SENDBUF) s += " send buffer overflow (raise max_batch)";
-  if (e & E_INTERNAL) s += " internal invariant violated";
+  if (e & E_INTERNAL) s += " internal invariant violated (#" + std::to_string(h_ctl->where) + ", " + std::to_string(h_ctl->where_arg) + ")";
   if (e & E_STALL) s += " no GVT progress in 100000 rounds";
   if (e & E_COMM) s += " a peer partition did not reach the GVT exchange";
   set_error(s);
@@ -1234,6 +1234,8 @@ int ssb_comm_export(ssb_engine* e, void* handle64) {
   if (!e->mbox_block) {
     CK(cudaMalloc(&e->mbox_block, e->mbox_bytes()));
     CK(cudaMemsetAsync(e->mbox_block, 0, e->mbox_cnt_bytes() + e->mbox_gvt_bytes(), e->stream));
+    const u32 hdr[4] = {e->v.cap_send, e->v.cap_anti, (u32)e->mbox_cnt_bytes(), (u32)(e->mbox_cnt_bytes() + e->mbox_gvt_bytes())};
+    CK(cudaMemcpyAsync(e->mbox_block, hdr, sizeof(hdr), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
   }
   cudaIpcMemHandle_t h;
@@ -1260,9 +1262,10 @@ int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
       e->peer_blocks[(size_t)r] = base;
     }
     e->v.peer_base[r] = reinterpret_cast<char*>(base);
+    u32 hdr[4];      // the geometry of that partition's mailbox
+    CK(cudaMemcpy(hdr, base, sizeof(hdr), cudaMemcpyDeviceToHost));
+    e->v.mb_cap_send[r] = hdr[0]; e->v.mb_cap_anti[r] = hdr[1]; e->v.mb_gvt_off[r] = hdr[2]; e->v.mb_data_off[r] = hdr[3];
   }
-  e->v.mb_gvt_off = (u32)e->mbox_cnt_bytes();
-  e->v.mb_data_off = (u32)(e->mbox_cnt_bytes() + e->mbox_gvt_bytes());
   e->v.p2p = 1;
   e->graph_dirty = true;
   return SSB_OK;

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
       // an event loaded from the history store is output again only if the repeat run re-executed it (R13)
       keep = !(e.flags & F_CANCEL) && !(pf & (P_DEAD | P_HISTORY)) && key_time(e.key) < v.finish_time;
       if (keep) {
-        if (!(pf & P_PROCESSED)) atomicOr(&c->error, E_INTERNAL);
+        if (!(pf & P_PROCESSED)) internal_error(v, 1, key_time(e.key));
         tg = M::tag(md, e);
         u64 h = record_hash(e, tg);
         cnt += 1; hsum += h; hxor ^= h; hsum2 += mix64(h + 0xD1B54A32D192ED03ULL);
@@ -397,7 +397,7 @@ __global__ void k_segs_heavy(View v) {
 
 // first flagger of an LP puts it on the fix list
 __device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 bit) {
-  if (v.replay) atomicOr(&v.ctl->error, E_INTERNAL);      // a recorded history has no irregular turns
+  if (v.replay) internal_error(v, 2, lp);      // a recorded history has no irregular turns
   const u32 old = atomicOr(reinterpret_cast<u32*>(v.lph + lp), bit << kCntBits);
   if (((old >> kCntBits) & PL_FIX) == 0) v.fix[atomicAdd(&v.ctl->n_fix, 1u)] = lp;
 }
@@ -1072,7 +1072,7 @@ __global__ void k_fixup(View v, typename M::Data md) {
           loc[m].key = ((u64)L.y << 32) | L.x; loc[m].slot = L.w; loc[m].seq = a | (L.z & 0x80000000u);
           a = L.z & 0x7FFFFFFFu;
         }
-        if (m != n) err |= E_INTERNAL;
+        if (m != n) internal_error(v, 3, lp);
         for (u32 q = 1; q < m; ++q) {
           Sorted x = loc[q];
           u32 j = q;
@@ -1132,7 +1132,7 @@ __device__ __forceinline__ u32 alloc_chunk(const View& v) {
 __device__ __forceinline__ u32 wait_chunk(const View& v, const u32* entry) {
   u32 ch = __ldcg(entry);
   for (u32 spin = 0; ch == NIL && spin < (1u << 22); ++spin) ch = *reinterpret_cast<const volatile u32*>(entry);
-  if (ch == NIL) atomicOr(&v.ctl->error, E_INTERNAL);
+  if (ch == NIL) internal_error(v, 4, 0);
   return ch;
 }
 
@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
     else if (which == 2) {
       if (v.p2p) {
         // own mailbox, all sources; `peer` = kind (1 = anti-message regions, integrated first; 0 = positives)
-        const u32 par = c->round & 1u, kind = peer, cap = kind ? v.cap_anti : v.cap_send;
+        const u32 par = c->round & 1u, kind = peer, cap = kind ? v.mb_cap_anti[v.rank] : v.mb_cap_send[v.rank];
         for (u32 r = 0; r < v.world; ++r) {
           if (r == v.rank) continue;
           u32 n = *mb_cnt(v, v.rank, par, r, kind);
@@ -1258,7 +1258,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
             t = rs;
           } else {
             const u32 b = tm / v.bucket_ticks;
-            if (b < base) { atomicOr(&c->error, E_INTERNAL); continue; }   // causality: nothing may arrive below GVT
+            if (b < base) { internal_error(v, 5, (u32)which << 28 | b); continue; }   // causality: nothing may arrive below GVT
             t = b - base < rs ? b - base : T_DIRECT;
             if (t == T_DIRECT) rnk[it] = atomicAdd(&v.fill[b], 1u);        // final position
           }
@@ -1350,7 +1350,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       } else {
         const u32 r = t - rs - 1;
         const u32 p = s_base[t] + rnk[it];
-        if (p >= (v.p2p && send_kind ? v.cap_anti : v.cap_send)) { atomicOr(&c->error, E_SENDBUF); continue; }
+        if (p >= (v.p2p ? (send_kind ? v.mb_cap_anti[r] : v.mb_cap_send[r]) : v.cap_send)) { atomicOr(&c->error, E_SENDBUF); continue; }
         if (v.p2p) {
           // straight into the destination GPU's mailbox over NVLink
           st256(mb_data(v, r, c->round & 1u, v.rank, send_kind) + p, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);

@@ -45,6 +45,86 @@ def _worker(rank, world, port, case, q, p2p=True):
         dist.destroy_process_group()
 
 
+def _diff_worker(rank, world, port, q):
+    """--diff_init then --diff_repeat on the 12x12 grid with one history store per rank."""
+    import json
+    import torch.distributed as dist
+    import scalesim_b200 as ssb
+    from scalesim_b200 import traffic
+    from fixtures import golden as gold
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _diff_body(rank, world, q, dist, ssb, traffic, gold)
+    except BaseException as exc:      # the parent must not wait for a result that never comes
+        import traceback
+        q.put((rank, "error", traceback.format_exc(), 0))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def _diff_body(rank, world, q, dist, ssb, traffic, gold):
+    if True:
+        torch.cuda.set_device(rank)
+        g = gold("grid_diff")
+        sc = traffic.synthetic_grid(**g["params"])
+        sc.partition = traffic.stripe_partition(g["params"]["width"], g["params"]["height"], world)
+        eng = traffic.make_engine(sc, bucket_ticks=11, rank=rank, world=world, device=rank, history=True)
+        ssb.dist.init_engine_comm(eng, rank, world)
+        dist.barrier()
+        eng.run()
+        rec, sent = eng.drain_history()
+        eng.close()
+        init_lines = ssb.records_to_lines(ssb.raw_to_records(rec))
+        from scalesim_b200.store import HistoryStore
+        hs = HistoryStore(rec, sent, None, sc.route_nodes)
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            p = os.path.join(td, "ae.csv")
+            with open(p, "w") as f:
+                f.write("".join(l + "\n" for l in g["ae_lines"]))
+            wi = traffic.read_what_if(p)
+        eng = traffic.make_repeat_engine(sc, hs, wi, bucket_ticks=11, rank=rank, world=world, device=rank,
+                                         keep_records=True)
+        ssb.dist.init_engine_comm(eng, rank, world)
+        dist.barrier()
+        st = eng.run()
+        rep_lines = ssb.records_to_lines(eng.drain_committed())
+        eng.close()
+        q.put((rank, init_lines, rep_lines, st.remote_sent))
+
+
+def test_diff_init_and_repeat_on_two_gpus_equal_reference():
+    """Exact-differential simulation with the LPs split over two GPUs: per-rank history stores, the repeat cascade's
+    anti-messages and re-sent events cross partitions through the peer mailboxes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    g = golden("grid_diff")
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_diff_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = []
+    try:
+        for _ in range(2):
+            r = q.get(timeout=150)
+            assert r[1] != "error", r[2]
+            res.append(r)
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert sorted(res[0][1] + res[1][1]) == g["init_lines"]
+    assert sorted(res[0][2] + res[1][2]) == g["repeat_union"]
+    assert res[0][3] + res[1][3] > 0
+
+
 def _run(case, world=2, p2p=True):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
