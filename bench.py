@@ -35,11 +35,11 @@ B_ALG = 380.0   # algorithmic bytes per committed PHOLD event (SURVEY.md §8d / 
 # per-kernel split of the 380 B
 B_ALG_KERNEL = {"k_exec": 164.0, "k_route": 96.0, "k_commit": 88.0, "k_link": 28.0, "k_sortheavy": 4.0}
 FULL_COMMITTED_1M = 72_823_220
-# kernels per round. Stream path (N > 1): plan, commit, link, segs_heavy, exec, sortheavy, exec_heavy, sortfix, fixup,
-# route(anti), route (+ k_min and the receive-side routes). Graph path (N = 1): the four kernels that only irregular
-# turns need sit in IF nodes and are not launched in a rollback-free run.
-LAUNCHES_PER_ROUND_STREAM = 11
-LAUNCHES_PER_ROUND_GRAPH = 7
+# kernels per round inside the window-loop graph: plan, commit, link, segs_heavy, exec, exec_heavy, route = 7;
+# N > 1 adds k_gvt and the two receive-side routes; the IF nodes add k_sortheavy when a segment longer than 128 exists
+# (PHOLD at N >= 2) and k_fixup + route(anti) when some LP needs the sequential turn (any rollback).
+def launches_per_round(world, rollbacks):
+    return 7 + (4 if world > 1 else 0) + (2 if rollbacks else 0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -453,7 +453,7 @@ def main():
                        "committed_per_step": committed_per_step, "rounds_per_step": rounds_total // args.steps,
                        "l2": "inputs larger than L2 (event pool + tables > 600 MB per GPU); no flush between steps",
                        "rollbacks": last.rollbacks, "antis": last.antis_sent},
-            "gpu_launches": int(rounds_total * (LAUNCHES_PER_ROUND_GRAPH if world == 1 and last.rollbacks == 0 else LAUNCHES_PER_ROUND_STREAM)),
+            "gpu_launches": int(rounds_total * launches_per_round(world, last.rollbacks)),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "traffic": traffic_res,
         }
         print(json.dumps(line), flush=True)
