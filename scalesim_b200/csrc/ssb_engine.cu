@@ -72,6 +72,7 @@ struct ssb_engine {
   int n_sm = 148;
   u32 n_chunks = 0;
   size_t route_smem = 0;
+  int g_link = 8, g_exec = 8, g_commit = 4, g_heavy = 8;      // blocks per SM of the per-arrival kernels (SSB_GRID=link,exec,commit,heavy)
   int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
   std::vector<void*> allocs;
   // partition (host copies)
@@ -244,6 +245,10 @@ int ssb_engine::init() {
   v.state_words = (u32)state_words();
   v.light_max = 8;
   if (getenv("SSB_NO_GRAPH")) graph_enabled = false;
+  if (const char* gs = getenv("SSB_GRID")) {
+    int a = 0, b = 0, c2 = 0, d = 0;
+    if (sscanf(gs, "%d,%d,%d,%d", &a, &b, &c2, &d) == 4 && a > 0 && b > 0 && c2 > 0 && d > 0) { g_link = a; g_exec = b; g_commit = c2; g_heavy = d; }
+  }
   if (const char* lm = getenv("SSB_LIGHT_MAX")) { int x = atoi(lm); if (x >= 1 && x <= (int)kLightMax) v.light_max = (u32)x; }
 
   const size_t n_slots = (size_t)n_chunks << v.ch_log;
@@ -427,7 +432,7 @@ void ssb_engine::launch_route(const View& vv, int which, u32 peer, u32 filter) {
 }
 
 void ssb_engine::launch_commit(const View& v) {
-  const int g = n_sm * 8;
+  const int g = n_sm * g_commit;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_commit<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
     case SSB_MODEL_PHOLD_STATEFUL: k_commit<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
@@ -436,7 +441,7 @@ void ssb_engine::launch_commit(const View& v) {
 }
 
 void ssb_engine::launch_exec(const View& v) {
-  const int g = n_sm * 8;
+  const int g = n_sm * g_exec;
   switch (cfg.model) {
     case SSB_MODEL_PHOLD: k_exec<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
     case SSB_MODEL_PHOLD_STATEFUL: k_exec<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
@@ -445,7 +450,7 @@ void ssb_engine::launch_exec(const View& v) {
 }
 
 void ssb_engine::launch_exec_heavy(const View& v) {
-  k_exec_heavy<<<n_sm * 8, 256, 0, stream>>>(v);
+  k_exec_heavy<<<n_sm * g_heavy, 256, 0, stream>>>(v);
 }
 
 void ssb_engine::launch_fixup(const View& v) {
@@ -462,7 +467,7 @@ void ssb_engine::launch_fixup(const View& v) {
 int ssb_engine::enqueue_replay_round() {
   k_plan<<<1, 1024, 0, stream>>>(v, 0);
   CK(cudaMemsetAsync(v.lph, 0, sizeof(uint4) * (size_t)v.n_lp_local, stream));
-  k_link<<<n_sm * 8, 256, 0, stream>>>(v);
+  k_link<<<n_sm * g_link, 256, 0, stream>>>(v);
   k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
   launch_exec(v);
   launch_sortheavy(v);
@@ -530,9 +535,8 @@ int ssb_engine::enqueue_round() {
   t_begin(K_COMMIT);
   launch_commit(v);
   t_end();
-  const int g = n_sm * 8;
   t_begin(K_LINK);
-  k_link<<<g, 256, 0, stream>>>(v);
+  k_link<<<n_sm * g_link, 256, 0, stream>>>(v);
   t_end();
   t_begin(K_SEGS_HEAVY);
   k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
@@ -610,7 +614,6 @@ int ssb_engine::build_graph() {
   cudaGraphNode_t n_while, n_if_vheavy, n_if_fix;
   cudaGraph_t body, b_vheavy, b_fix;
   CK(add_cond(graph, vg.h_loop, cudaGraphCondTypeWhile, {}, &n_while, &body));
-  const int g8 = n_sm * 8;
   std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_heavy;
   CK(capture(body, {}, &t_plan, [&] {
     cudaMemsetAsync(vg.lph, 0, sizeof(uint4) * (size_t)vg.n_lp_local, stream);
@@ -623,7 +626,7 @@ int ssb_engine::build_graph() {
   }));
   CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));
   CK(capture(body, t_plan, &t_exec, [&] {
-    k_link<<<g8, 256, 0, stream>>>(vg);
+    k_link<<<n_sm * g_link, 256, 0, stream>>>(vg);
     k_segs_heavy<<<n_sm, 256, 0, stream>>>(vg);
     launch_exec(vg);
   }));
