@@ -161,3 +161,52 @@ def test_digest_functions_agree():
     # START / no-tag records (negative source) hash identically in both
     sc, g = ring_scenario()
     assert g["digest"][0] == 38
+
+
+def test_what_if_reader_parses_the_reference_query_types(tmp_path):
+    """traffic_reader::what_if_read (traffic_sim.hpp:453-599): AE / DE / RE lines; SC is refused."""
+    from scalesim_b200 import traffic
+    p = tmp_path / "wi.csv"
+    p.write_text("AE,9990,0,20,0,1,2,3\nDE,4,165,0\nRE,2,2,94,3,135\n\nAE,7,0,5,8,9\n")
+    wi = traffic.read_what_if(str(p))
+    assert wi.trip_id.tolist() == [9990, 7] and wi.trip_dep.tolist() == [20, 5]
+    assert wi.route_start.tolist() == [0, 4, 6] and wi.route_nodes.tolist() == [0, 1, 2, 3, 8, 9]
+    assert wi.deletes.tolist() == [[4, 165, 0], [3, 135, 2]]          # (lp, time, event id)
+    tid, dep, start, nodes = wi                                       # unpacks like the AE tuple
+    assert nodes.size == 6
+    p.write_text("SC,1,5;R,1,1,2,10,200,1\n")
+    with pytest.raises(NotImplementedError):
+        traffic.read_what_if(str(p))
+
+
+def test_history_store_keeps_the_model_data(tmp_path):
+    from scalesim_b200 import store
+    rec = np.zeros(3, dtype=store.RAW_RECORD_DTYPE)
+    rec["key"] = [(5 << 32) | 1, (7 << 32) | 2, (9 << 32) | 1]
+    rec["dst"] = [0, 1, 1]
+    sent = np.zeros(3, dtype=store.SENT_RECORD_DTYPE)
+    sent["dst"] = [1, store.NONE, 0]
+    hs = store.HistoryStore(rec, sent, np.array([0, 1]), np.arange(10))
+    hs.save(str(tmp_path), "sim", 3)
+    back = store.HistoryStore.load(str(tmp_path), "sim", 3)
+    assert back.pool.tolist() == list(range(10)) and back.state_lps.tolist() == [0, 1]
+    assert back.event_keys().tolist() == [[0, 5, 1], [1, 7, 2], [1, 9, 1]]
+    assert back.cancel_keys().tolist() == [[0, 5, 1], [1, 9, 1]]
+    assert back.state_keys().tolist() == [[0, -1, -1], [0, 5, 1], [1, -1, -1], [1, 9, 1]]
+    with pytest.raises(ValueError):
+        (tmp_path / "sim" / "history3.ssb").write_bytes(b"garbage!" + bytes(64))
+        store.HistoryStore.load(str(tmp_path), "sim", 3)
+
+
+def test_compact_event_layout_roundtrip():
+    ev = np.zeros(3, dtype=ssb.EVENT_DTYPE)
+    ev["id"] = [1, 2, 3]; ev["src"] = [-1, 5, 6]; ev["dst"] = [4, 5, 6]
+    ev["recv_time"] = [10, 20, 30]; ev["send_time"] = [10, 15, 25]; ev["p0"] = [0, 1, 2]; ev["flags"] = [0, 0, 1]
+    raw = ssb.events_to_raw(ev)
+    assert raw.dtype.itemsize == 32
+    assert raw["key"].tolist() == [(10 << 32) | 1, (20 << 32) | 2, (30 << 32) | 3]
+    assert raw["src"].tolist() == [0xFFFFFFFF, 5, 6] and raw["tag"].tolist() == [0, 0, 1]
+    packed = np.zeros(2, dtype=ssb.PACKED_RECORD_DTYPE)
+    packed["id"] = [1, 2]; packed["src"] = [0xFFFFFFFF, 3]; packed["recv_time"] = [7, 8]; packed["tag"] = [1, 2]
+    rec = ssb.packed_to_records(packed)
+    assert ssb.records_to_lines(rec) == ["RE,1,-1,0,0,7,START", "RE,2,3,0,0,8,END"]
