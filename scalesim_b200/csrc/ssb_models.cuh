@@ -106,15 +106,27 @@ struct TrafficModel {
     if (e.p1 <= 1u) return false;
     if (e.p0 + 1u >= d.route_len) { err |= E_INTERNAL; return false; }
     u32 next = __ldg(d.route + e.p0 + 1u);
-    u32 n = state[1];
-    int i = -1;
+    const u32 n = state[1];
+    // first road that leads to `next`, as std::find (traffic_sim.hpp:299-306); static indices only, so the state
+    // words stay in registers
+    bool found = false;
+    u64 speed = 0, len = 0;
 #pragma unroll
-    for (int r = kMaxRoads - 1; r >= 0; --r)
-      if ((u32)r < n && state[2 + 3 * r] == next) i = r;   // first match, as std::find
-    if (i < 0) return false;
-    u64 speed = state[2 + 3 * i + 1], len = state[2 + 3 * i + 2];
+    for (int r = 0; r < kMaxRoads; ++r) {
+      if (!found && (u32)r < n && state[2 + 3 * r] == next) {
+        found = true;
+        speed = state[2 + 3 * r + 1];
+        len = state[2 + 3 * r + 2];
+      }
+    }
+    if (!found) return false;
     u64 arrival = key_time(e.key);
-    u64 recv = speed != 0 ? len * 60ull * 60ull / speed / 1000ull + arrival + 5ull : len * 60ull * 60ull + arrival;
+    // len * 60 * 60 / speed / 1000, left to right, truncating (traffic_sim.hpp:314-316); 32-bit arithmetic when the
+    // product fits (roads shorter than 1 193 km), identical result
+    u64 recv;
+    if (speed == 0) recv = len * 60ull * 60ull + arrival;
+    else if (len < 1193046ull) recv = (u64)((u32)len * 3600u / (u32)speed / 1000u) + arrival + 5ull;
+    else recv = len * 60ull * 60ull / speed / 1000ull + arrival + 5ull;
     if (recv >= 0x80000000ull) { err |= E_RANGE; recv = 0x7FFFFFFFull; }
     out.key = make_key((u32)recv, key_id(e.key));
     out.dst = next;
