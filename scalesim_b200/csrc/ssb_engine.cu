@@ -193,8 +193,6 @@ struct ssb_engine {
   int enqueue_round();
   int enqueue_replay_round();
   int exchange();
-  template <class M> void launch_model_kernels_commit(const typename M::Data& md);
-  template <class M> void launch_model_kernels_exec(const typename M::Data& md);
   void launch_commit(const View& vv);
   void launch_exec(const View& vv);
   void launch_route(const View& vv, int which, u32 peer, u32 filter);

@@ -1,23 +1,25 @@
 // ssb_kernels.cuh — the Time Warp core as CUDA kernels (sm_100a).
 //
-// One round (= one optimistic window step) is, in stream order:
-//   k_plan      GVT (block min-reduction over the calendar; k_min + ncclAllReduce(min) first when world > 1),
-//               window bounds, gather list, commit list
-//   k_commit    stream-compaction of every bucket that fell below GVT into the committed log + digest; the last
-//               block to finish does the fossil collection (chunks back to the pool)
+// One round (= one optimistic window step), as the body of the window-loop graph (ssb_engine.cu: build_graph):
+//   [k_gvt      N > 1: GVT min-reduction + barrier through the peers' mailboxes; then k_route of the received
+//               anti-messages and of the received positives]
+//   k_plan      GVT (block min-reduction over the calendar when N = 1), window bounds, gather list, commit list,
+//               loop condition of the graph
+//   k_commit    (parallel branch) stream-compaction of every bucket that fell below GVT into the committed log +
+//               digest (+ sent-log entries for the history store); the last block does the fossil collection
 //   k_link      arrivals of the window, in calendar order: count per LP, chain every arrival to the previous
 //               arrival of its LP (atomic exchange on the LP's list head), note the chain head, list the long LPs
-//   k_exec      one thread per EVENT, in calendar order (coalesced): place in the LP's key order by walking the
-//               LP's short arrival list, handler, processed-chain link, sent-log, outbox (speculative on the LP
-//               state); arrivals of long LPs are only dropped into the LP's segment
-//   k_segs_heavy / k_sortheavy / k_exec_heavy   LPs with more than kLightMax arrivals: segment allocation, one warp
-//               per LP bitonic sort in shared memory, execute with the sorted predecessor
-//   k_fixup     the LPs that are not plain (anti-message, duplicate, straggler, state-mutating handler):
-//               annihilate, roll back, re-execute sequentially, emit anti-messages
-//   k_route     outbox -> calendar buckets / per-destination-partition send buffers
-//               (block-aggregated atomics; anti-messages first, then positives)
-//   [exchange + k_route of the receive buffer when world > 1]
-// Reference semantics restated per kernel; rule numbers R1..R10 refer to SURVEY.md Appendix A.
+//   k_segs_heavy  segment allocation for the LPs with more than light_max arrivals
+//   k_exec      one thread per EVENT, in calendar order (coalesced): handler, sent-log, outbox (speculative on the LP
+//               state); an event of a short LP finds its place in the LP's key order by walking the arrival list, an
+//               event of a long LP drops (key, slot, arrival) into the LP's segment
+//   [k_sortheavy  IF a segment longer than kRegSortSmall exists: one block per such LP, hybrid bitonic sort + links]
+//   k_exec_heavy  one warp per long LP: bitonic sort in registers, processed-chain links from the sorted neighbours
+//   [k_fixup + k_route(anti)  IF some LP is not plain (anti-message, duplicate, straggler, state-mutating handler):
+//               annihilate, roll back, re-execute sequentially, re-queue, emit anti-messages]
+//   k_route     outbox -> calendar buckets / the destination GPU's mailbox (TMA-staged tiles, block-aggregated atomics)
+// The same kernels in replay mode (View::replay) rebuild the processed chains of a recorded history (--diff_repeat).
+// Reference semantics restated per kernel; rule numbers R1..R13 refer to SURVEY.md Appendix A.
 #pragma once
 #include "ssb_device.cuh"
 #include "ssb_models.cuh"
