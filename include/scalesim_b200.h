@@ -28,8 +28,9 @@
  *   ssb_reset                     (no reference equivalent: the reference is one simulation per process)
  *   ssb_read_states               (no reference equivalent: sim_state::result_out is empty,
  *                                 sim_obj.hpp:97; used by the parity tests for final LP states)
- *   ssb_comm_*                    event_com / mpi_thr / mpi_gsync (com/*.hpp) — replaced by NCCL
- *                                 all-to-all + allreduce-min between one-engine-per-GPU processes
+ *   ssb_comm_*                    event_com / mpi_thr / mpi_gsync (com/*.hpp) — replaced by peer-memory mailboxes over
+ *                                 NVLink (events + GVT min-reduction), or NCCL send/recv + allreduce-min, between
+ *                                 one-engine-per-GPU processes
  */
 #ifndef SCALESIM_B200_H_
 #define SCALESIM_B200_H_
@@ -60,7 +61,7 @@ enum ssb_status {
   SSB_ERR_RANGE = 3,        /* a value does not fit the device record (see limits below) */
   SSB_ERR_CAPACITY = 4,     /* a device pool overflowed (max_events / max_batch / ...) */
   SSB_ERR_MODEL = 5,        /* model data missing or inconsistent */
-  SSB_ERR_COMM = 6          /* NCCL failure */
+  SSB_ERR_COMM = 6          /* NCCL failure, or a peer partition did not reach the GVT exchange */
 };
 
 /*
@@ -226,15 +227,17 @@ int ssb_set_flags(ssb_engine* e, int32_t flags);
  * Returns the number of kernels written (<= cap). */
 int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap);
 
-/* ---- multi-GPU: one engine per process/GPU, NCCL between them ---- */
-/* 128-byte NCCL unique id; created on rank 0 and distributed by the caller (torch.distributed, MPI, files, ...) */
+/* ---- multi-GPU: one engine per process/GPU ---- */
+/* NCCL exchange mode: 128-byte NCCL unique id; created on rank 0 and distributed by the caller (torch.distributed, MPI, files, ...) */
 int ssb_comm_unique_id(void* id128);
 int ssb_comm_init(ssb_engine* e, const void* id128);
-/* Optional, after ssb_comm_init: exchange events through peer memory over NVLink instead of ncclSend/ncclRecv.
- * Every engine exports a 64-byte CUDA IPC handle of its mailbox; the caller gathers the handles of all ranks (rank
- * order) and hands the world x 64 bytes to every engine. The emit kernel then appends cross-partition events straight
- * into the destination GPU's mailbox, and the per-round GVT all-reduce doubles as the barrier — no count exchange,
- * no host synchronisation per window. All ranks must make the same choice. */
+/* Peer-memory exchange mode (instead of ssb_comm_unique_id / ssb_comm_init; no NCCL involved): every engine
+ * exports a 64-byte CUDA IPC handle of its mailbox; the caller gathers the handles of all ranks (rank order) and hands
+ * the world x 64 bytes to every engine. The emit kernel then appends cross-partition events straight into the
+ * destination GPU's mailbox over NVLink; at the start of every round the partitions write their GVT candidates into
+ * each other's mailboxes and wait for the peers' (k_gvt) — the GVT min-reduction and the barrier in one step, without
+ * a host-launched collective, so the whole window loop runs as one CUDA graph per GPU. All ranks must make the same
+ * choice. One process per GPU (the exchange waits on the peers; ranks sharing a GPU could deadlock). */
 int ssb_comm_export(ssb_engine* e, void* handle64);
 int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world);
 

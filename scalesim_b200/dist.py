@@ -1,6 +1,6 @@
-"""Multi-GPU plumbing: one process per GPU. torch.distributed is used only for the rendezvous (NCCL unique id
-broadcast), barriers and the reductions of results across ranks — the data path (per-window all-to-all of events and
-the GVT allreduce-min) is NCCL inside libscalesim_b200.so."""
+"""Multi-GPU plumbing: one process per GPU. torch.distributed is used only for the rendezvous (mailbox IPC handles or
+the NCCL unique id) and for combining per-rank results; the data path (cross-partition events, the GVT min-reduction)
+is inside libscalesim_b200.so: peer-memory mailboxes over NVLink by default, NCCL send/recv + all-reduce on request."""
 from __future__ import annotations
 
 import numpy as np
