@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <map>
 #include <string>
@@ -154,8 +155,9 @@ void runner<App>::comm_init() {
 template <class App>
 void runner<App>::write_history(const history& h) {
   const std::string p = history_path(), dir = p.substr(0, p.find_last_of('/'));
-  std::string mk = "mkdir -p '" + dir + "'";
-  if (std::system(mk.c_str()) != 0) { LOG(ERROR) << "cannot create " << dir; std::exit(1); }
+  std::error_code ec;
+  std::filesystem::create_directories(dir, ec);
+  if (ec) { LOG(ERROR) << "cannot create " << dir << ": " << ec.message(); std::exit(1); }
   std::ofstream f((p + ".tmp").c_str(), std::ios::binary);
   const int64_t hdr[3] = {(int64_t)h.rec.size(), (int64_t)h.state_lps.size(), (int64_t)h.pool.size()};
   f.write("SSBHIST2", 8);

@@ -6,7 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <chrono>
 #include <functional>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1088,7 +1090,9 @@ int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int
     CK(cudaMemcpyAsync(e->h_poll, finished ? &e->v.ctl->log_count : &e->v.ctl->log_stable, sizeof(u64), cudaMemcpyDeviceToHost, e->copy_stream));
     CK(cudaStreamSynchronize(e->copy_stream));      // also waits for the chunks issued so far: the halves are free
     const u64 upto = std::min<u64>(*e->h_poll, e->v.cap_log);
+    const u64 before = drained;
     if ((rc = drain_to(upto, finished))) { cudaStreamSynchronize(e->stream); return rc; }
+    if (!finished && drained == before) std::this_thread::sleep_for(std::chrono::microseconds(50));   // nothing new yet
   }
   CK(cudaStreamSynchronize(e->copy_stream));
   CK(cudaEventSynchronize(e->ev1));
