@@ -425,8 +425,9 @@ def main():
             log(f"e2e step: {dt * 1000:.1f} ms, drained {got}")
         e2e_committed = sum_over_ranks(st.committed)
         e2e = {"value": e2e_committed / statistics.mean(ts), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_ev * ssb.RAW_RECORD_DTYPE.itemsize),
-               "d2h_bytes_per_step": int(st.committed * 24 + 32 + 1296),
+               # whole-job bytes per step (all ranks): initial events in, committed records + digest + statistics out
+               "h2d_bytes_per_step": int(sum_over_ranks(n_ev * ssb.RAW_RECORD_DTYPE.itemsize)),
+               "d2h_bytes_per_step": int(sum_over_ranks(st.committed * 24 + 32 + 1296)),
                "ms_per_step": 1000.0 * statistics.mean(ts), "all_records_drained": bool(ok)}
 
     cpu = None
