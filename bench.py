@@ -32,14 +32,16 @@ sys.path.insert(0, ROOT)
 METRIC = "committed events/sec, PHOLD 1M LPs"
 UNIT = "events/s"
 B_ALG = 380.0   # algorithmic bytes per committed PHOLD event (SURVEY.md §8d / DESIGN.md §5)
-# per-kernel split of the 380 B
-B_ALG_KERNEL = {"k_exec": 164.0, "k_route": 96.0, "k_commit": 88.0, "k_link": 28.0, "k_sortheavy": 4.0}
+# per-kernel split of the 380 B: execute (pop read 48 + table gathers 12 + state read 8 + snapshot write 24 +
+# sent-log write 24 + emit write 48), route (bucket read 48 + pending write 48), commit + fossil (read 48 + 40-byte
+# result record + fossil key reads 32)
+B_ALG_KERNEL = {"k_exec": 164.0, "k_route": 96.0, "k_commit": 120.0}
 FULL_COMMITTED_1M = 72_823_220
-# kernels per round inside the window-loop graph: plan, commit, link, segs_heavy, exec, exec_heavy, route = 7;
-# N > 1 adds k_gvt and the two receive-side routes; the IF nodes add k_sortheavy when a segment longer than 128 exists
-# (PHOLD at N >= 2) and k_fixup + route(anti) when some LP needs the sequential turn (any rollback).
-def launches_per_round(world, rollbacks):
-    return 7 + (4 if world > 1 else 0) + (2 if rollbacks else 0)
+# kernels per round inside the window-loop graph: plan, commit, exec, route = 4; N > 1 adds k_gvt and the two
+# receive-side routes; a round with an irregular LP turn (ssb_stats.fix_rounds) adds the IF node's six kernels:
+# k_fix_count, k_fix_segs, k_fix_scatter, k_fix_sort, k_fix_turn, k_route(anti).
+def launches(st, world):
+    return int(st.rounds * (4 + (3 if world > 1 else 0)) + st.fix_rounds * 6)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -262,6 +264,7 @@ def main():
     ap.add_argument("--rounds-per-sync", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) digest check against the CPU oracle")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-partition event exchange")
     ap.add_argument("--no-traffic", action="store_true", help="skip the secondary grid TrafficSim measurement")
     ap.add_argument("--traffic-only", action="store_true")
@@ -369,14 +372,31 @@ def main():
     for _ in range(args.warmup):
         st = one_step()
         log(f"warm-up step: loop {st.loop_ms:.2f} ms, rounds {st.rounds}, committed {st.committed}, remote {st.remote_sent}")
-    step_ms, committed_total, rounds_total = [], 0, 0
+    step_ms, committed_total, rounds_total, launches_total = [], 0, 0, 0
     last = None
     for _ in range(args.steps):
         st = one_step()
         step_ms.append(max_over_ranks(st.loop_ms))
         committed_total += sum_over_ranks(st.committed)
         rounds_total += st.rounds
+        launches_total += launches(st, world)
         last = st
+    # parity (untimed): the digest of the union of the partitions' committed records must equal the CPU oracle's
+    # closure of the same workload (tests/oracle_lib.py = the checker; SURVEY.md App. A canonical form, sim_obj.hpp:66-77)
+    got_digest = ssb.dist.all_gather_digest(eng.digest(), world)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        t0 = time.perf_counter()
+        want_digest = oracle_lib.phold_closure_digest(n_lp, n_init, args.remote, 1.0)
+        parity = {"checked": True, "equal": tuple(got_digest) == tuple(want_digest), "oracle": "closure (tw_oracle.cc)",
+                  "committed": int(got_digest[0]), "oracle_seconds": round(time.perf_counter() - t0, 2)}
+        log(f"parity: {parity}")
+        if not parity["equal"]:
+            print(json.dumps({"error": "committed digest differs from the oracle", "got": list(got_digest),
+                              "want": list(want_digest)}), file=sys.stderr, flush=True)
+            raise SystemExit(3)
     clocks = sampler.stop() if rank == 0 else None
     total_s = sum(step_ms) / 1000.0
     value = committed_total / total_s
@@ -453,8 +473,9 @@ def main():
                                     else "NCCL send/recv + allreduce-min") if world > 1 else "none (1 GPU)",
                        "committed_per_step": committed_per_step, "rounds_per_step": rounds_total // args.steps,
                        "l2": "inputs larger than L2 (event pool + tables > 600 MB per GPU); no flush between steps",
-                       "rollbacks": last.rollbacks, "antis": last.antis_sent},
-            "gpu_launches": int(rounds_total * launches_per_round(world, last.rollbacks)),
+                       "rollbacks": last.rollbacks, "antis": last.antis_sent, "irregular_turns": last.fix_turns},
+            "parity": parity,
+            "gpu_launches": launches_total,
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "traffic": traffic_res,
         }
         print(json.dumps(line), flush=True)

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 typedef struct ssb_engine ssb_engine;
 
@@ -148,6 +148,8 @@ typedef struct ssb_stats {
   int64_t pool_high_water;   /* peak event-pool slots in use */
   int64_t log_dropped;       /* committed records not kept because max_committed was reached */
   double loop_ms;            /* device time of the window loop (CUDA events) */
+  int64_t fix_rounds;        /* rounds in which some LP's turn was not plain (the k_fix_* kernels ran) */
+  int64_t fix_turns;         /* irregular LP turns (anti-message, duplicate key, straggler, state-mutating handler) */
 } ssb_stats;
 
 int ssb_abi_version(void);

@@ -10,7 +10,7 @@ import numpy as np
 MODEL_PHOLD = 1
 MODEL_TRAFFIC = 2
 MODEL_PHOLD_STATEFUL = 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 #: host mirror of ``ssb_event`` (8 x int64)
 EVENT_DTYPE = np.dtype([
@@ -96,7 +96,7 @@ class _Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "rounds", "processed", "rollbacks", "undone", "antis_sent", "annihilated", "duplicates",
         "committed", "beyond_finish", "remote_sent", "gvt_time", "gvt_id", "pool_high_water", "log_dropped",
-    )] + [("loop_ms", C.c_double)]
+    )] + [("loop_ms", C.c_double), ("fix_rounds", C.c_int64), ("fix_turns", C.c_int64)]
 
 
 @dataclass
@@ -134,6 +134,8 @@ class Stats:
     pool_high_water: int = 0
     log_dropped: int = 0
     loop_ms: float = 0.0
+    fix_rounds: int = 0
+    fix_turns: int = 0
 
 
 def library_path() -> str:

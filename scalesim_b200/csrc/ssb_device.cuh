@@ -3,22 +3,35 @@
 // Layout in HBM:
 //   * event pool   : Ev[max_events], 32-byte records = one DRAM sector each, carved into chunks of
 //                    2^ch_log slots; a calendar bucket (receive_time / bucket_ticks) owns a list of chunks
-//                    (chunk_tab) and is append-only, so "pending set" == the unconsumed tail of the buckets.
-//                    Event records are immutable once routed.
-//   * per-slot meta: Meta[max_events] (32 B: processed-chain link, sent-log entry — what set_cancel keeps in the
-//                    reference, queue.hpp:151-157 — and snapshot index) + pflag[max_events] (1 B: processed / dead).
-//   * per-LP       : lph {arrivals of this round | flags, newest arrival, chain head before the round} (zeroed every
-//                    round), last {chain head slot, its time}, state words.
-//   * per-round    : link records that chain the arrivals of one LP (16 B per arrival), sorted segments for the
-//                    long or irregular LPs only, outboxes. The event records themselves are never copied.
+//                    (chunk_tab) and is append-only, so "pending set" == the unconsumed tail of the buckets and
+//                    "processed events" == the consumed head. Event records are immutable once routed.
+//   * per-slot meta: Meta[max_events] (16 B: the sent-log entry — what set_cancel keeps in the reference,
+//                    queue.hpp:151-157 — and the snapshot index) + pflag[max_events] (1 B: processed / dead / history).
+//   * per-LP       : lpw {time of the newest processed event + 1, irregular-turn ticket of this round}, state words,
+//                    inv (exact-differential repeat only: key from which the recorded history of the LP is invalid).
+//   * per-round    : a hash set of the window's (LP, key) pairs (duplicate detection), outboxes, and — only for the
+//                    LPs whose turn is not plain — sorted (key, slot, arrival) segments. Event records are never
+//                    copied or sorted.
+// There are no per-LP event lists or chains: a rollback finds the processed events of an LP by a coalesced scan over
+// the consumed part of the window's buckets (k_fix_count / k_fix_scatter).
 #pragma once
 #include <cstdint>
+#ifdef SSB_EMU
+#include "cuda_emu.h"      // tools/emu: sequential host emulation of the kernels (developer tool, never shipped)
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace ssb {
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
+
+#ifdef SSB_EMU
+constexpr u32 kWarp = 1;          // the emulation runs every kernel as one block of one thread
+#else
+constexpr u32 kWarp = 32;
+#endif
 
 constexpr u32 NIL = 0xFFFFFFFFu;
 constexpr u64 KEY_MAX = ~0ull;
@@ -33,7 +46,7 @@ constexpr int RQ_LEN = 64;
 // error bits (Ctl::error)
 constexpr u32 E_POOL = 1u;        // event pool exhausted
 constexpr u32 E_RANGE = 2u;       // time / id does not fit the packed record
-constexpr u32 E_BATCH = 4u;       // aux outbox overflow
+constexpr u32 E_BATCH = 4u;       // aux outbox / fix segment overflow
 constexpr u32 E_SNAP = 8u;        // snapshot ring overflow
 constexpr u32 E_HORIZON = 16u;    // bucket index beyond the calendar
 constexpr u32 E_SENDBUF = 32u;    // remote send buffer overflow
@@ -53,21 +66,23 @@ struct __align__(32) Ev {
 };
 static_assert(sizeof(Ev) == 32, "Ev must be one 32-byte sector");
 
-struct __align__(32) Meta {
-  u32 link;      // previous processed event of this LP (slot) or NIL
-  u32 prevtime;  // receive_time of that previous event (so a stale link is never dereferenced)
+struct __align__(16) Meta {
   u32 sent_dst;  // sent-log: destination LP of the event this one produced, NIL = none
   u32 snap;      // index into the snapshot ring of the pre-state, NIL = handler left the state unchanged
   u64 sent_key;  // sent-log: key of the produced event
-  u32 pad0, pad1;
 };
-static_assert(sizeof(Meta) == 32, "Meta must be one 32-byte sector");
+static_assert(sizeof(Meta) == 16, "Meta is one 16-byte access");
 
+// entry of an irregular LP's segment (k_fix_*): sorted by (key, order of arrival)
+constexpr u32 S_ANTI = 0x80000000u;     // the arrival is an anti-message
+constexpr u32 S_UNDONE = 0x40000000u;   // a processed event that the rollback undid (it was in the queue before every arrival)
+constexpr u32 S_IDX = 0x3FFFFFFFu;      // arrival: arrival index + 1; undone: snapshot index + 1 (0 = no snapshot)
 struct __align__(16) Sorted {
   u64 key;
   u32 slot;      // calendar slot of the event
-  u32 seq;       // arrival index (bits 0..30; also the arrival order), bit 31 = anti-message
+  u32 seq;       // S_ANTI | S_UNDONE | S_IDX
 };
+__device__ __forceinline__ u32 sorted_ord(u32 seq) { return (seq & S_UNDONE) ? 0u : (seq & S_IDX); }
 
 struct Ctl {
   u64 local_min;      // min key over this partition's unconsumed events
@@ -75,7 +90,12 @@ struct Ctl {
   u64 beyond_min;     // min key of events dropped because receive_time >= finish_time
   u32 done, error;
   u32 cur_abs, bound_abs, commit_next;
-  u32 n_arr, seg_cursor, n_anti, n_extra, n_heavy, n_vheavy, n_fix, commit_blocks, heavy_blocks;
+  u32 hi_bound;       // largest window bound so far: no event beyond bucket hi_bound has been processed by this run
+  u32 hist_end;       // exact-differential repeat: buckets [0, hist_end) hold recorded history
+  u32 n_touched;      // ... number of LPs whose history has been invalidated from some key on (0 = nothing to re-execute)
+  u32 n_arr, n_anti, n_extra, commit_blocks, exec_blocks;
+  u32 n_fix, n_ent, n_scan, scan_total;
+  u32 hmask_round;    // size - 1 of the hash-set region this round uses
   u32 n_gather, n_commit, commit_total;
   u32 free_top, free_low;
   u32 snap_head, snap_tail;
@@ -86,13 +106,15 @@ struct Ctl {
   u32 recv_count[MAX_WORLD];
   u64 prev_gvt;       // stall detection of the graph's loop
   u32 stall;
-  u32 where;          // first internal invariant that failed (1 commit of an unprocessed event, 2 irregular turn in a
-                      // history replay, 3 arrival list shorter than its count, 4 chunk never published, 5 arrival below GVT)
+  u32 where;          // first internal invariant that failed (1 commit of an unprocessed event, 4 chunk never
+                      // published, 5 arrival below GVT, 6 fix segment longer than counted)
   u32 where_arg;      // its argument (time / LP / bucket)
   u32 epoch;          // number of resets: keeps the GVT-exchange stamps of consecutive simulations apart
   u64 sent_min;       // peer-memory exchange: smallest bucket-start key of the events written to peers this round
   // statistics
   u64 n_processed, n_rollbacks, n_undone, n_antis, n_annihilated, n_dups, n_committed, n_beyond, n_remote;
+  u64 n_fix_total;    // irregular LP turns so far
+  u64 n_fix_rounds;   // rounds with at least one irregular turn
   u64 log_count, log_dropped;
   u64 log_stable;     // log_count at the start of the current round: everything below is completely written
   u64 digest[4];
@@ -109,34 +131,40 @@ struct View {
   u32 ch_log, maxc;       // chunk size log2, chunk-table row length
   u32 route_slots;        // buckets covered by k_route's shared-memory table
   u32 bucket_ticks, finish_time, window;
-  u32 cap_batch, cap_aux, cap_snap, cap_send;
+  u32 cap_batch, cap_aux, cap_snap, cap_send, cap_fix;
   u64 cap_log;
   u32 state_words;
   u32 use_graph;          // 1 = the kernels run inside the window-loop graph and drive its conditional nodes
-  cudaGraphConditionalHandle h_loop, h_vheavy, h_fix;
-  u32 light_max;          // LPs with up to this many arrivals in a round are handled by list walks (<= kLightMax)
+  cudaGraphConditionalHandle h_loop, h_fix;
   // event pool
   Ev* ev;
   Meta* meta;
-  unsigned char* pflag;   // [max_events] P_PROCESSED / P_DEAD
+  unsigned char* pflag;   // [max_events] P_PROCESSED / P_DEAD / P_HISTORY
   u32* chunk_tab;   // [nb * maxc]
   u32* free_stack;  // [n_chunks]
   u32* fill;        // [nb] events appended
   u32* consumed;    // [nb] events already integrated
   // per LP
-  uint4* lph;       // this round (zeroed by a memset at its start): {arrivals (bits 0..27) | PL_* flags (28..31),
-                    //   newest arrival index + 1 (long LP: start of its segment in `sorted`), chain head slot before the round, its time}
-  uint2* last;      // processed-chain head {slot, receive_time}; slot NIL = nothing processed yet
+  uint2* lpw;       // {receive_time of the newest processed event + 1 (0 = none), ticket of an irregular turn in this
+                    //  round: 0 = plain, 0xffffffff = being issued, else index into the fix table + 1}
   u32* state;       // [n_lp_local * state_words]
+  u64* inv;         // exact-differential repeat only (else null): recorded events of the LP with key >= inv[lp] are invalid
   // per round
-  uint4* link;         // [cap_batch] per arrival {key lo, key hi, previous arrival of the same LP | anti << 31, slot}
-  u32* tmp_rank;       // [cap_batch] rank of the arrival among its LP's arrivals (position in a long segment)
-  Sorted* sorted;      // [cap_batch] (key, slot, arrival) segments of the long LPs, and of the irregular LPs sorted
-  u32* fix;            // [cap_batch] LPs that need the sequential turn
-  uint4* heavy;        // [cap_batch / 16] LPs with long segments {lp, seg_start, n, 0}
+  u32* hset;           // [hcap] (LP, key) fingerprints of the window's arrivals: round stamp << 24 | 24-bit fingerprint
+  u32 hmask;           // hcap - 1 (hcap is a power of two >= 2 * cap_batch)
+  // irregular turns (anti-message, duplicate, straggler, state-mutating handler, invalidated history)
+  u32* fixlp;          // [n_lp_local] fix table: LP of ticket f
+  u32* fixcnt;         // [n_lp_local] entries counted for the LP (upper bound)
+  u32* fixstart;       // [n_lp_local] start of its segment in `sorted`
+  u32* fixpos;         // [n_lp_local] fill cursor of the segment
+  u32* fixund;         // [n_lp_local] processed events undone by this round's rollback
+  u64* fixmin;         // [n_lp_local] smallest arrival key = the key the LP rolls back to
+  Sorted* sorted;      // [cap_fix] segments of the irregular LPs
+  uint2* ent_out;      // [cap_fix] per segment entry: {slot of the event that survives the merge under this key, its outbox index}
   Ev* outbox;          // [cap_batch + cap_aux]: entry i = output of arrival i, then re-execution outputs
   Ev* anti_box;        // [cap_aux] anti-messages of this round
   uint4* gather;       // [window] {bucket, start, count, out_off}
+  uint4* scan;         // [nb] consumed parts of the buckets a rollback can reach {bucket, 0, count, off}
   uint4* commit;       // [nb] {bucket, count, off, 0}
   Ev* sendbuf;         // [world * cap_send]
   Ev* recvbuf;         // [world * cap_send]
@@ -158,7 +186,7 @@ struct View {
   Ev* log;             // [cap_log] committed records
   uint4* log_sent;     // [cap_log] history store (--diff_init): sent-log entry of each committed event {dst, key lo, key hi, 0}
   uint4* hist_sent;    // [cap_batch] staging of the sent-log entries while history is loaded (--diff_repeat)
-  u32 replay;          // 1 = history replay: events are linked into the processed chains, handlers do not run
+  u32 replay;          // 1 = a recorded history is being loaded: routed events become processed history events
   u32* snap;           // [cap_snap * state_words]
   Ctl* ctl;
 };
@@ -180,6 +208,7 @@ __device__ __forceinline__ u32 part_local(const View& v, u32 lp) {
 
 // 32-byte records move as ONE 256-bit access per thread (LDG/STG.256 on sm_100a): a warp touches every DRAM sector
 // once, instead of twice with two 128-bit halves.
+#ifndef SSB_EMU
 __device__ __forceinline__ void ld256(const void* p, u32 (&x)[8]) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
@@ -200,6 +229,19 @@ __device__ __forceinline__ void st256_ef(void* p, u32 a, u32 b, u32 c, u32 d, u3
   asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
 }
+__device__ __forceinline__ void st128_ef(void* p, u32 a, u32 b, u32 c, u32 d) {
+  // (the L2::evict_first qualifier exists for 256-bit stores only; a 128-bit store takes the streaming hint)
+  asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+#else
+__device__ __forceinline__ void ld256(const void* p, u32 (&x)[8]) { for (int i = 0; i < 8; ++i) x[i] = static_cast<const u32*>(p)[i]; }
+__device__ __forceinline__ void st256(void* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
+  u32* q = static_cast<u32*>(p); q[0] = a; q[1] = b; q[2] = c; q[3] = d; q[4] = e; q[5] = f; q[6] = g; q[7] = h;
+}
+__device__ __forceinline__ void ld256_ef(const void* p, u32 (&x)[8]) { ld256(p, x); }
+__device__ __forceinline__ void st256_ef(void* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) { st256(p, a, b, c, d, e, f, g, h); }
+__device__ __forceinline__ void st128_ef(void* p, u32 a, u32 b, u32 c, u32 d) { u32* q = static_cast<u32*>(p); q[0] = a; q[1] = b; q[2] = c; q[3] = d; }
+#endif
 __device__ __forceinline__ Ev load_ev_ef(const Ev* p) {
   u32 x[8];
   ld256_ef(p, x);
@@ -211,9 +253,6 @@ __device__ __forceinline__ Ev load_ev_ef(const Ev* p) {
 __device__ __forceinline__ void store_ev_ef(Ev* p, const Ev& e) {
   st256_ef(p, (u32)e.key, (u32)(e.key >> 32), e.dst, e.src, e.send, e.p0, e.p1, e.flags);
 }
-__device__ __forceinline__ void store_meta_ef(Meta* p, const Meta& m) {
-  st256_ef(p, m.link, m.prevtime, m.sent_dst, m.snap, (u32)m.sent_key, (u32)(m.sent_key >> 32), 0u, 0u);
-}
 __device__ __forceinline__ Ev load_ev(const Ev* p) {
   u32 x[8];
   ld256(p, x);
@@ -222,19 +261,21 @@ __device__ __forceinline__ Ev load_ev(const Ev* p) {
   e.send = x[4]; e.p0 = x[5]; e.p1 = x[6]; e.flags = x[7];
   return e;
 }
+__device__ __forceinline__ void store_ev(Ev* p, const Ev& e) {
+  st256(p, (u32)e.key, (u32)(e.key >> 32), e.dst, e.src, e.send, e.p0, e.p1, e.flags);
+}
 __device__ __forceinline__ Meta load_meta(const Meta* p) {
-  u32 x[8];
-  ld256(p, x);
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
   Meta m;
-  m.link = x[0]; m.prevtime = x[1]; m.sent_dst = x[2]; m.snap = x[3];
-  m.sent_key = ((u64)x[5] << 32) | x[4]; m.pad0 = 0; m.pad1 = 0;
+  m.sent_dst = q.x; m.snap = q.y; m.sent_key = ((u64)q.w << 32) | q.z;
   return m;
 }
 __device__ __forceinline__ void store_meta(Meta* p, const Meta& m) {
-  st256(p, m.link, m.prevtime, m.sent_dst, m.snap, (u32)m.sent_key, (u32)(m.sent_key >> 32), 0u, 0u);
+  *reinterpret_cast<uint4*>(p) = make_uint4(m.sent_dst, m.snap, (u32)m.sent_key, (u32)(m.sent_key >> 32));
 }
-__device__ __forceinline__ void store_ev(Ev* p, const Ev& e) {
-  st256(p, (u32)e.key, (u32)(e.key >> 32), e.dst, e.src, e.send, e.p0, e.p1, e.flags);
+// a meta record is not read again unless its LP rolls back (or the history store keeps it): evict-first
+__device__ __forceinline__ void store_meta_ef(Meta* p, const Meta& m) {
+  st128_ef(p, m.sent_dst, m.snap, (u32)m.sent_key, (u32)(m.sent_key >> 32));
 }
 
 __device__ __forceinline__ u32* mb_cnt(const View& v, u32 owner, u32 par, u32 src, u32 kind) {

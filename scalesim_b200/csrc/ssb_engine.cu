@@ -1,5 +1,5 @@
 // ssb_engine.cu — host side of libscalesim_b200.so: owns the device memory, enqueues the per-round kernel
-// sequence on one CUDA stream, and implements the C ABI of include/scalesim_b200.h.
+// sequence on one CUDA stream (or launches it as one CUDA graph), and implements the C ABI of include/scalesim_b200.h.
 // There is no CPU fallback: every entry point that does work needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
@@ -14,6 +14,13 @@
 
 #include "../../include/scalesim_b200.h"
 #include "ssb_kernels.cuh"
+
+// kernel launch: <<<>>> on the device; the developer-only host emulation (tools/emu) calls the kernel body once
+#ifdef SSB_EMU
+#define SSB_LAUNCH(kern, grid, block, smem, stream, ...) do { (void)(grid); (void)(block); (void)(smem); (void)(stream); kern(__VA_ARGS__); } while (0)
+#else
+#define SSB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 
 using namespace ssb;
 
@@ -74,7 +81,7 @@ struct ssb_engine {
   int n_sm = 148;
   u32 n_chunks = 0;
   size_t route_smem = 0;
-  int g_link = 8, g_exec = 8, g_commit = 4, g_heavy = 8;      // blocks per SM of the per-arrival kernels (SSB_GRID=link,exec,commit,heavy)
+  int g_exec = 8, g_commit = 4, g_fix = 8;      // blocks per SM of the per-event kernels (SSB_GRID=exec,commit,fix)
   int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
   std::vector<void*> allocs;
   // partition (host copies)
@@ -96,6 +103,7 @@ struct ssb_engine {
   u64 log_drained = 0;
   double loop_ms = 0.0;
   long long rounds = 0;
+  u64* d_inv = nullptr;                      // exact-differential repeat: per-LP invalid-from keys (View::inv while a history is loaded)
   // comm
   Nccl::Comm comm = nullptr;
   void* mbox_block = nullptr;              // own mailbox (exported with CUDA IPC)
@@ -109,7 +117,8 @@ struct ssb_engine {
   // initial states (for ssb_reset)
   u32* d_state0 = nullptr;
   // kernel timing
-  enum { K_MIN, K_PLAN, K_COMMIT, K_LINK, K_SEGS_HEAVY, K_EXEC, K_SORTHEAVY, K_EXEC_HEAVY, K_FIXUP, K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
+  enum { K_MIN, K_PLAN, K_COMMIT, K_EXEC, K_HIST_FLAG, K_FIX_COUNT, K_FIX_SEGS, K_FIX_SCATTER, K_FIX_SORT, K_FIX_TURN,
+         K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
   struct Timed { int id; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -137,12 +146,11 @@ struct ssb_engine {
     timed.clear();
   }
   int reset_sim();
-  void launch_sortheavy(const View& vv) { k_sortheavy<<<n_sm * 4, kSortThreads, 0, stream>>>(vv); }
-  void launch_fixup(const View& vv);
-  void launch_exec_heavy(const View& vv);
-  // whole window loop as ONE CUDA graph: WHILE(!done) { round }, with IF nodes around the rarely needed kernels
+  // whole window loop as ONE CUDA graph: WHILE(!done) { round }, with an IF node around the irregular-turn kernels
+#ifndef SSB_EMU
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+#endif
   View vg;                       // view baked into the graph's kernel nodes (use_graph = 1 + the conditional handles)
   bool graph_dirty = true;
   bool graph_enabled = true;
@@ -159,6 +167,15 @@ struct ssb_engine {
   }
   TrafficModel::Data traffic_data() const { TrafficModel::Data d; d.route = d_route; d.route_len = route_len; return d; }
 
+  // the ONE place that maps ssb_config.model to a device twin: f(model tag, its data)
+  template <class F> void with_model(F&& f) const {
+    switch (cfg.model) {
+      case SSB_MODEL_PHOLD: f(PholdModel{}, phold_data()); break;
+      case SSB_MODEL_PHOLD_STATEFUL: f(PholdStatefulModel{}, phold_data()); break;
+      case SSB_MODEL_TRAFFIC: f(TrafficModel{}, traffic_data()); break;
+    }
+  }
+
   int grid(size_t n, int threads) const {
     size_t b = (n + threads - 1) / threads;
     size_t cap = (size_t)n_sm * 8;
@@ -171,32 +188,26 @@ struct ssb_engine {
     return SSB_OK;
   }
   int fill32(u32* p, u32 val, size_t n) {
-    if (n) k_fill_u32<<<grid(n, 256), 256, 0, stream>>>(p, val, n);
+    if (n) SSB_LAUNCH(k_fill_u32, grid(n, 256), 256, 0, stream, p, val, n);
     CK(cudaGetLastError());
     return SSB_OK;
   }
   int state_words() const {
-    switch (cfg.model) {
-      case SSB_MODEL_PHOLD: return PholdModel::kStateWords;
-      case SSB_MODEL_PHOLD_STATEFUL: return PholdStatefulModel::kStateWords;
-      case SSB_MODEL_TRAFFIC: return TrafficModel::kStateWords;
-    }
-    return 0;
+    int w = 0;
+    with_model([&](auto m, auto) { w = decltype(m)::kStateWords; });
+    return w;
   }
 
   int init();
   int sync_ctl();
   int check_device_error();
   int model_ready();
-  int model_ready_data();
-  int build_hot();
-  bool hot_built = false;
   u32 epoch = 0;
   int enqueue_round();
-  int enqueue_replay_round();
   int exchange();
   void launch_commit(const View& vv);
   void launch_exec(const View& vv);
+  void launch_fix(const View& vv, bool timed_);
   void launch_route(const View& vv, int which, u32 peer, u32 filter);
   u32 owner_of(long long lp) const { return h_owner.empty() ? (u32)(lp % cfg.world) : h_owner[(size_t)lp]; }
   u32 local_of(long long lp) const { return h_local.empty() ? (u32)(lp / cfg.world) : h_local[(size_t)lp]; }
@@ -238,18 +249,23 @@ int ssb_engine::init() {
   v.maxc = n_chunks;
   v.cap_batch = (u32)cfg.max_batch;
   v.cap_aux = std::max<u32>(1024, v.cap_batch);      // anti-messages, re-execution outputs and re-queued events of a round
+  v.cap_fix = v.cap_batch + v.cap_aux;               // entries of the irregular LPs' segments (arrivals + undone events)
   v.cap_snap = (u32)std::max<int64_t>(cfg.max_snapshots, 1024);
   v.cap_send = cfg.world > 1 ? std::max<u32>(v.cap_batch / 4, 1u << 16) : 1;
   v.cap_anti = cfg.world > 1 ? std::min<u32>(v.cap_send, v.cap_aux) : 1;
   v.cap_log = (u64)cfg.max_committed;
   v.state_words = (u32)state_words();
-  v.light_max = 8;
+  u32 hcap = 1024;
+  while (hcap < 2u * v.cap_batch) hcap <<= 1;
+  v.hmask = hcap - 1u;
   if (getenv("SSB_NO_GRAPH")) graph_enabled = false;
+#ifdef SSB_EMU
+  graph_enabled = false;
+#endif
   if (const char* gs = getenv("SSB_GRID")) {
-    int a = 0, b = 0, c2 = 0, d = 0;
-    if (sscanf(gs, "%d,%d,%d,%d", &a, &b, &c2, &d) == 4 && a > 0 && b > 0 && c2 > 0 && d > 0) { g_link = a; g_exec = b; g_commit = c2; g_heavy = d; }
+    int a = 0, b = 0, c2 = 0;
+    if (sscanf(gs, "%d,%d,%d", &a, &b, &c2) == 3 && a > 0 && b > 0 && c2 > 0) { g_exec = a; g_commit = b; g_fix = c2; }
   }
-  if (const char* lm = getenv("SSB_LIGHT_MAX")) { int x = atoi(lm); if (x >= 1 && x <= (int)kLightMax) v.light_max = (u32)x; }
 
   const size_t n_slots = (size_t)n_chunks << v.ch_log;
   int rc;
@@ -260,17 +276,21 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.free_stack, n_chunks))) return rc;
   if ((rc = alloc(&v.fill, v.nb))) return rc;
   if ((rc = alloc(&v.consumed, v.nb))) return rc;
-  if ((rc = alloc(&v.lph, v.n_lp_local))) return rc;
-  if ((rc = alloc(&v.last, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.lpw, v.n_lp_local))) return rc;
   if ((rc = alloc(&v.state, (size_t)v.n_lp_local * v.state_words))) return rc;
-  if ((rc = alloc(&v.link, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.tmp_rank, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.sorted, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.fix, v.cap_batch))) return rc;
-  if ((rc = alloc(&v.heavy, v.cap_batch / 16 + 64))) return rc;
+  if ((rc = alloc(&v.hset, hcap))) return rc;
+  if ((rc = alloc(&v.fixlp, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.fixcnt, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.fixstart, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.fixpos, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.fixund, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.fixmin, v.n_lp_local))) return rc;
+  if ((rc = alloc(&v.sorted, v.cap_fix))) return rc;
+  if ((rc = alloc(&v.ent_out, v.cap_fix))) return rc;
   if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
   if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
   if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1)))) return rc;
+  if ((rc = alloc(&v.scan, v.nb))) return rc;
   if ((rc = alloc(&v.commit, v.nb))) return rc;
   if ((rc = alloc(&v.sendbuf, (size_t)v.world * v.cap_send))) return rc;
   if ((rc = alloc(&v.recvbuf, (size_t)v.world * v.cap_send))) return rc;
@@ -286,8 +306,10 @@ int ssb_engine::init() {
   if ((rc = reset_sim())) return rc;
   v.route_slots = std::min<u32>(v.nb, 2048);
   route_smem = (size_t)kRouteTile * sizeof(Ev) + (size_t)(v.route_slots + 1 + v.world) * 16;
+#ifndef SSB_EMU
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&route_bps, k_route, kRouteThreads, route_smem));
+#endif
   if (route_bps < 1) route_bps = 1;
   if (const char* rb = getenv("SSB_ROUTE_BPS")) { int x = atoi(rb); if (x >= 1 && x <= route_bps) route_bps = x; }
   CK(cudaStreamSynchronize(stream));
@@ -304,13 +326,20 @@ int ssb_engine::reset_sim() {
   CK(cudaStreamSynchronize(stream));
   CK(cudaMemcpyAsync(v.ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
   CK(cudaStreamSynchronize(stream));   // `init` lives on the stack
-  k_iota_u32<<<grid(n_chunks - 1, 256), 256, 0, stream>>>(v.free_stack, 1u, n_chunks - 1);   // chunks 1..n-1 are free
+  SSB_LAUNCH(k_iota_u32, grid(n_chunks - 1, 256), 256, 0, stream, v.free_stack, 1u, (size_t)(n_chunks - 1));   // chunks 1..n-1 are free
   int rc;
   if ((rc = fill32(v.chunk_tab, NIL, (size_t)v.nb * v.maxc))) return rc;
   CK(cudaMemsetAsync(v.fill, 0, sizeof(u32) * v.nb, stream));
   CK(cudaMemsetAsync(v.consumed, 0, sizeof(u32) * v.nb, stream));
-  k_fill_u2<<<grid(v.n_lp_local, 256), 256, 0, stream>>>(v.last, make_uint2(NIL, 0u), v.n_lp_local);
+  CK(cudaMemsetAsync(v.lpw, 0, sizeof(uint2) * (size_t)v.n_lp_local, stream));
+  CK(cudaMemsetAsync(v.hset, 0, sizeof(u32) * ((size_t)v.hmask + 1), stream));
   CK(cudaMemcpyAsync(v.state, d_state0, sizeof(u32) * (size_t)v.n_lp_local * v.state_words, cudaMemcpyDeviceToDevice, stream));
+  if (v.inv) { v.inv = nullptr; graph_dirty = true; }      // a loaded history goes with the reset
+  if (mbox_block) {
+    // own mailbox: counts and GVT slots of the finished run (all partitions must reset together, before any of them
+    // starts the next run)
+    CK(cudaMemsetAsync(static_cast<char*>(mbox_block) + 256, 0, mbox_cnt_bytes() - 256 + mbox_gvt_bytes(), stream));
+  }
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   log_drained = 0;
@@ -333,7 +362,7 @@ int ssb_engine::check_device_error() {
   std::string s = "device error:";
   if (e & E_POOL) s += " event pool exhausted (raise max_events)";
   if (e & E_RANGE) s += " value out of device record range / destination not owned";
-  if (e & E_BATCH) s += " rollback outbox overflow (raise max_batch)";
+  if (e & E_BATCH) s += " rollback outbox / segment overflow (raise max_batch)";
   if (e & E_SNAP) s += " snapshot ring overflow (raise max_snapshots)";
   if (e & E_HORIZON) s += " calendar horizon exceeded";
   if (e & E_SENDBUF) s += " send buffer overflow (raise max_batch)";
@@ -347,60 +376,7 @@ int ssb_engine::check_device_error() {
   return SSB_ERR_INVALID;
 }
 
-// The randomly accessed words — per-LP round words, chain heads, LP states and the PHOLD table — move into ONE block
-// that is given a persisting L2 access-policy window: the streams of a round (events, meta, outbox: hundreds of MB)
-// then cannot evict what every event gathers from. Called once, before the first round.
-int ssb_engine::build_hot() {
-  if (hot_built) return SSB_OK;
-  hot_built = true;
-  // Measured on B200 (PHOLD 1M LPs): the window's streams already live in L2 between k_link, k_exec and k_route; a
-  // persisting carve-out for the gathered words takes that capacity away and the round gets 8 % slower. Off by default.
-  if (!getenv("SSB_L2_PERSIST")) return SSB_OK;
-  int max_persist = 0, max_window = 0;
-  CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg.device));
-  CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg.device));
-  if (max_persist <= 0 || max_window <= 0) return SSB_OK;
-  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t n = v.n_lp_local, sw = v.state_words;
-  const size_t b_lph = al(n * sizeof(uint4)), b_last = al(n * sizeof(uint2)), b_state = al(n * sw * 4),
-               b_table = al((size_t)phold_table_size * 4);
-  const size_t total = b_lph + b_last + b_state + b_table;
-  if (total > (size_t)max_window) return SSB_OK;      // would not fit one window: keep the separate arrays
-  char* blk = nullptr;
-  int rc = alloc(&blk, total);
-  if (rc) return rc;
-  uint4* n_lph = reinterpret_cast<uint4*>(blk);
-  uint2* n_last = reinterpret_cast<uint2*>(blk + b_lph);
-  u32* n_state = reinterpret_cast<u32*>(blk + b_lph + b_last);
-  u32* n_table = reinterpret_cast<u32*>(blk + b_lph + b_last + b_state);
-  CK(cudaMemsetAsync(n_lph, 0, n * sizeof(uint4), stream));
-  CK(cudaMemcpyAsync(n_last, v.last, n * sizeof(uint2), cudaMemcpyDeviceToDevice, stream));
-  CK(cudaMemcpyAsync(n_state, v.state, n * sw * 4, cudaMemcpyDeviceToDevice, stream));
-  if (d_phold_table) CK(cudaMemcpyAsync(n_table, d_phold_table, (size_t)phold_table_size * 4, cudaMemcpyDeviceToDevice, stream));
-  CK(cudaStreamSynchronize(stream));
-  v.lph = n_lph; v.last = n_last; v.state = n_state;
-  if (d_phold_table) d_phold_table = n_table;
-  const size_t set_aside = std::min<size_t>((size_t)max_persist, total);
-  CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
-  cudaStreamAttrValue attr;
-  std::memset(&attr, 0, sizeof(attr));
-  attr.accessPolicyWindow.base_ptr = blk;
-  attr.accessPolicyWindow.num_bytes = total;
-  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)total);
-  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  CK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-  graph_dirty = true;
-  return SSB_OK;
-}
-
 int ssb_engine::model_ready() {
-  int rc0 = model_ready_data();
-  if (rc0) return rc0;
-  return build_hot();
-}
-
-int ssb_engine::model_ready_data() {
   if (cfg.model == SSB_MODEL_PHOLD || cfg.model == SSB_MODEL_PHOLD_STATEFUL) {
     if (!d_phold_table) {
       if (!(have_lat && have_rem)) { set_error("PHOLD model data slots 0 and 1 not set"); return SSB_ERR_MODEL; }
@@ -412,7 +388,7 @@ int ssb_engine::model_ready_data() {
       if (rc) return rc;
       CK(cudaMemcpyAsync(d_lat, h_lat.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, stream));
       CK(cudaMemcpyAsync(d_rem, h_rem.data(), sizeof(int) * n, cudaMemcpyHostToDevice, stream));
-      k_pack_phold_table<<<grid(n, 256), 256, 0, stream>>>(d_lat, d_rem, d_phold_table, n, v.ctl);
+      SSB_LAUNCH(k_pack_phold_table, grid(n, 256), 256, 0, stream, (const long long*)d_lat, (const int*)d_rem, d_phold_table, n, v.ctl);
       CK(cudaStreamSynchronize(stream));
       CK(cudaFree(d_lat)); CK(cudaFree(d_rem));
       phold_table_size = n;
@@ -427,53 +403,34 @@ int ssb_engine::model_ready_data() {
 
 void ssb_engine::launch_route(const View& vv, int which, u32 peer, u32 filter) {
   t_begin(which == 0 ? K_ROUTE_ANTI : (which == 2 ? K_ROUTE_RECV : K_ROUTE));
-  k_route<<<n_sm * route_bps, kRouteThreads, route_smem, stream>>>(vv, which, peer, filter);
+  SSB_LAUNCH(k_route, n_sm * route_bps, kRouteThreads, route_smem, stream, vv, which, peer, filter);
   t_end();
 }
 
-void ssb_engine::launch_commit(const View& v) {
+void ssb_engine::launch_commit(const View& vv) {
   const int g = n_sm * g_commit;
-  switch (cfg.model) {
-    case SSB_MODEL_PHOLD: k_commit<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_PHOLD_STATEFUL: k_commit<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_TRAFFIC: k_commit<TrafficModel><<<g, 256, 0, stream>>>(v, traffic_data()); break;
-  }
+  with_model([&](auto m, auto md) { SSB_LAUNCH(k_commit<decltype(m)>, g, kCommitThreads, 0, stream, vv, md); });
 }
 
-void ssb_engine::launch_exec(const View& v) {
+void ssb_engine::launch_exec(const View& vv) {
   const int g = n_sm * g_exec;
-  switch (cfg.model) {
-    case SSB_MODEL_PHOLD: k_exec<PholdModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_PHOLD_STATEFUL: k_exec<PholdStatefulModel><<<g, 256, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_TRAFFIC: k_exec<TrafficModel><<<g, 256, 0, stream>>>(v, traffic_data()); break;
-  }
+  with_model([&](auto m, auto md) { SSB_LAUNCH(k_exec<decltype(m)>, g, 256, 0, stream, vv, md); });
 }
 
-void ssb_engine::launch_exec_heavy(const View& v) {
-  k_exec_heavy<<<n_sm * g_heavy, 256, 0, stream>>>(v);
-}
-
-void ssb_engine::launch_fixup(const View& v) {
-  const int g = n_sm * 8;
-  switch (cfg.model) {
-    case SSB_MODEL_PHOLD: k_fixup<PholdModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_PHOLD_STATEFUL: k_fixup<PholdStatefulModel><<<g, 128, 0, stream>>>(v, phold_data()); break;
-    case SSB_MODEL_TRAFFIC: k_fixup<TrafficModel><<<g, 128, 0, stream>>>(v, traffic_data()); break;
-  }
-}
-
-// one round of history replay (--diff_repeat): group the window's recorded events by LP and link them into the
-// processed chains; no handler runs, nothing is committed or sent
-int ssb_engine::enqueue_replay_round() {
-  k_plan<<<1, 1024, 0, stream>>>(v, 0);
-  CK(cudaMemsetAsync(v.lph, 0, sizeof(uint4) * (size_t)v.n_lp_local, stream));
-  k_link<<<n_sm * g_link, 256, 0, stream>>>(v);
-  k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
-  launch_exec(v);
-  launch_sortheavy(v);
-  launch_exec_heavy(v);
-  CK(cudaGetLastError());
-  return SSB_OK;
+// the irregular turns of a round (inside the graph: the body of an IF node)
+void ssb_engine::launch_fix(const View& vv, bool timed_) {
+  const int g = n_sm * g_fix;
+  auto tb = [&](int id) { if (timed_) t_begin(id); };
+  auto te = [&]() { if (timed_) t_end(); };
+  if (vv.inv) { tb(K_HIST_FLAG); SSB_LAUNCH(k_hist_flag, g, 256, 0, stream, vv); te(); }
+  tb(K_FIX_COUNT); SSB_LAUNCH(k_fix_count, g, 256, 0, stream, vv); te();
+  tb(K_FIX_SEGS); SSB_LAUNCH(k_fix_segs, n_sm, 256, 0, stream, vv); te();
+  tb(K_FIX_SCATTER); SSB_LAUNCH(k_fix_scatter, g, 256, 0, stream, vv); te();
+  tb(K_FIX_SORT); SSB_LAUNCH(k_fix_sort, n_sm * 4, kSortThreads, 0, stream, vv); te();
+  tb(K_FIX_TURN);
+  with_model([&](auto m, auto md) { SSB_LAUNCH(k_fix_turn<decltype(m)>, g, 256, 0, stream, vv, md); });
+  te();
+  launch_route(vv, 0, 0, 0);
 }
 
 // counts all-to-all, then payload all-to-all (grouped ncclSend/ncclRecv), then integrate what arrived
@@ -481,8 +438,11 @@ int ssb_engine::exchange() {
   if (cfg.world <= 1 || v.p2p) return SSB_OK;      // peer-memory exchange: the receive side runs at the next round's start
   if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
   Nccl& n = g_nccl;
-  int rc;
-#define NC(call) do { rc = (call); if (rc != 0) { set_error(std::string(#call) + ": " + n.GetErrorString(rc)); return SSB_ERR_COMM; } } while (0)
+  int rc = 0, first_rc = 0;
+  std::string first_call;
+  // inside a group every call is still issued after a failure and the group is always closed: the peers' matching
+  // sends / receives must not be left hanging
+#define NC(call) do { rc = (call); if (rc != 0 && !first_rc) { first_rc = rc; first_call = #call; } } while (0)
   NC(n.GroupStart());
   for (int r = 0; r < cfg.world; ++r) {
     if (r == cfg.rank) continue;
@@ -490,18 +450,24 @@ int ssb_engine::exchange() {
     NC(n.Recv(&v.ctl->recv_count[r], 1, Nccl::kUint32, r, comm, stream));
   }
   NC(n.GroupEnd());
+  if (first_rc) { set_error(first_call + ": " + n.GetErrorString(first_rc)); return SSB_ERR_COMM; }
   int s = sync_ctl();
   if (s) return s;
+  // both ends of a transfer see the same unclamped count (our send count is the peer's receive count), so a transfer
+  // that does not fit is skipped by both, and both report the overflow
+  bool overflow = false;
   NC(n.GroupStart());
   for (int r = 0; r < cfg.world; ++r) {
     if (r == cfg.rank) continue;
-    u32 ns = std::min(h_ctl->send_count[r], v.cap_send), nr = h_ctl->recv_count[r];
-    if (nr > v.cap_send) { set_error("receive buffer overflow (raise max_batch)"); return SSB_ERR_CAPACITY; }
-    if (ns) NC(n.Send(v.sendbuf + (size_t)r * v.cap_send, (size_t)ns * sizeof(Ev), Nccl::kUint8, r, comm, stream));
-    if (nr) NC(n.Recv(v.recvbuf + (size_t)r * v.cap_send, (size_t)nr * sizeof(Ev), Nccl::kUint8, r, comm, stream));
+    const u32 ns = h_ctl->send_count[r], nr = h_ctl->recv_count[r];
+    if (ns > v.cap_send || nr > v.cap_send) overflow = true;
+    if (ns && ns <= v.cap_send) NC(n.Send(v.sendbuf + (size_t)r * v.cap_send, (size_t)ns * sizeof(Ev), Nccl::kUint8, r, comm, stream));
+    if (nr && nr <= v.cap_send) NC(n.Recv(v.recvbuf + (size_t)r * v.cap_send, (size_t)nr * sizeof(Ev), Nccl::kUint8, r, comm, stream));
   }
   NC(n.GroupEnd());
 #undef NC
+  if (first_rc) { set_error(first_call + ": " + n.GetErrorString(first_rc)); return SSB_ERR_COMM; }
+  if (overflow) { set_error("send / receive buffer overflow (raise max_batch)"); return SSB_ERR_CAPACITY; }
   for (int pass = 1; pass <= 2; ++pass)
     for (int r = 0; r < cfg.world; ++r)
       if (r != cfg.rank && h_ctl->recv_count[r]) launch_route(v, 2, (u32)r, (u32)pass);
@@ -515,45 +481,29 @@ int ssb_engine::enqueue_round() {
       // GVT candidates cross through the mailboxes; when all have arrived, what the peers appended to this GPU's
       // mailbox in the previous round is complete: integrate it (anti-messages first) before planning the window
       t_begin(K_MIN);
-      k_gvt<<<1, 256, 0, stream>>>(v);
+      SSB_LAUNCH(k_gvt, 1, 256, 0, stream, v);
       t_end();
       launch_route(v, 2, 1, 0);
       launch_route(v, 2, 0, 0);
     } else {
       if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
       t_begin(K_MIN);
-      k_min<<<1, 1024, 0, stream>>>(v);
+      SSB_LAUNCH(k_min, 1, 1024, 0, stream, v);
       t_end();
       int rc = g_nccl.AllReduce(&v.ctl->local_min, &v.ctl->gvt, 1, Nccl::kUint64, Nccl::kMin, comm, stream);
       if (rc != 0) { set_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
     }
   }
   t_begin(K_PLAN);
-  k_plan<<<1, 1024, 0, stream>>>(v, cfg.world > 1 ? 1 : 0);
+  SSB_LAUNCH(k_plan, 1, 1024, 0, stream, v, cfg.world > 1 ? 1 : 0);
   t_end();
-  CK(cudaMemsetAsync(v.lph, 0, sizeof(uint4) * (size_t)v.n_lp_local, stream));   // per-LP round words
   t_begin(K_COMMIT);
   launch_commit(v);
-  t_end();
-  t_begin(K_LINK);
-  k_link<<<n_sm * g_link, 256, 0, stream>>>(v);
-  t_end();
-  t_begin(K_SEGS_HEAVY);
-  k_segs_heavy<<<n_sm, 256, 0, stream>>>(v);
   t_end();
   t_begin(K_EXEC);
   launch_exec(v);
   t_end();
-  t_begin(K_SORTHEAVY);
-  launch_sortheavy(v);
-  t_end();
-  t_begin(K_EXEC_HEAVY);
-  launch_exec_heavy(v);
-  t_end();
-  t_begin(K_FIXUP);
-  launch_fixup(v);
-  t_end();
-  launch_route(v, 0, 0, 0);
+  launch_fix(v, true);
   launch_route(v, 1, 0, 0);
   CK(cudaGetLastError());
   ++rounds;
@@ -561,14 +511,17 @@ int ssb_engine::enqueue_round() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The window loop as one CUDA graph (single partition): a WHILE node whose condition k_plan keeps at "GVT has not
-// reached finish_time and no device error", and inside it one round. The commit pass runs as a parallel branch next
-// to link/exec (they touch disjoint buckets; both join before k_route, which is the only other user of the chunk
-// free stack). The kernels that only irregular turns need sit in IF nodes: k_sortheavy (a segment longer than
-// kRegSortSmall exists) and k_fixup + k_route(anti) (some LP needs the sequential turn); their
-// conditions are set on the device by k_exec and by the last block of k_exec_heavy. The host launches the graph once
-// per ssb_run and is not involved in the loop at all.
+// The window loop as one CUDA graph: a WHILE node whose condition k_plan keeps at "GVT has not reached finish_time
+// and no device error", and inside it one round. The commit pass runs as a parallel branch next to k_exec (they
+// touch disjoint buckets; both join before k_route, which is the only other user of the chunk free stack). The
+// kernels that only irregular turns need sit in an IF node whose condition the last block of k_exec sets on the
+// device. The host launches the graph once per ssb_run and is not involved in the loop at all — also for N > 1,
+// because GVT and the barrier go through peer memory.
 // ------------------------------------------------------------------------------------------------
+#ifdef SSB_EMU
+void ssb_engine::destroy_graph() {}
+int ssb_engine::build_graph() { return SSB_OK; }
+#else
 void ssb_engine::destroy_graph() {
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
   if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
@@ -582,7 +535,6 @@ int ssb_engine::build_graph() {
   vg = v;
   vg.use_graph = 1;
   CK(cudaGraphConditionalHandleCreate(&vg.h_loop, graph, 1, cudaGraphCondAssignDefault));
-  CK(cudaGraphConditionalHandleCreate(&vg.h_vheavy, graph, 0, cudaGraphCondAssignDefault));
   CK(cudaGraphConditionalHandleCreate(&vg.h_fix, graph, 0, cudaGraphCondAssignDefault));
   auto add_cond = [&](cudaGraph_t parent, cudaGraphConditionalHandle h, cudaGraphConditionalNodeType type,
                       const std::vector<cudaGraphNode_t>& deps, cudaGraphNode_t* node, cudaGraph_t* body) -> cudaError_t {
@@ -611,44 +563,42 @@ int ssb_engine::build_graph() {
     cudaError_t err2 = cudaStreamEndCapture(stream, &out);
     return err != cudaSuccess ? err : err2;
   };
-  cudaGraphNode_t n_while, n_if_vheavy, n_if_fix;
-  cudaGraph_t body, b_vheavy, b_fix;
+  cudaGraphNode_t n_while, n_if_fix;
+  cudaGraph_t body, b_fix;
   CK(add_cond(graph, vg.h_loop, cudaGraphCondTypeWhile, {}, &n_while, &body));
-  std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_heavy;
+  std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec;
   CK(capture(body, {}, &t_plan, [&] {
-    cudaMemsetAsync(vg.lph, 0, sizeof(uint4) * (size_t)vg.n_lp_local, stream);
     if (cfg.world > 1) {      // peer-memory exchange: GVT + barrier, then the receive side of the previous round
-      k_gvt<<<1, 256, 0, stream>>>(vg);
+      SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vg);
       launch_route(vg, 2, 1, 0);
       launch_route(vg, 2, 0, 0);
     }
-    k_plan<<<1, 1024, 0, stream>>>(vg, cfg.world > 1 ? 1 : 0);
+    SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vg, cfg.world > 1 ? 1 : 0);
   }));
   CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));
-  CK(capture(body, t_plan, &t_exec, [&] {
-    k_link<<<n_sm * g_link, 256, 0, stream>>>(vg);
-    k_segs_heavy<<<n_sm, 256, 0, stream>>>(vg);
-    launch_exec(vg);
-  }));
-  CK(add_cond(body, vg.h_vheavy, cudaGraphCondTypeIf, t_exec, &n_if_vheavy, &b_vheavy));
-  CK(capture(b_vheavy, {}, nullptr, [&] {
-    launch_sortheavy(vg);
-  }));
-  CK(capture(body, {n_if_vheavy}, &t_heavy, [&] { launch_exec_heavy(vg); }));
+  CK(capture(body, t_plan, &t_exec, [&] { launch_exec(vg); }));
   // k_route(anti) pops chunks off the free stack that the commit pass pushes to: the IF node waits for both branches
-  std::vector<cudaGraphNode_t> join = t_heavy;
+  std::vector<cudaGraphNode_t> join = t_exec;
   join.insert(join.end(), t_commit.begin(), t_commit.end());
   CK(add_cond(body, vg.h_fix, cudaGraphCondTypeIf, join, &n_if_fix, &b_fix));
-  CK(capture(b_fix, {}, nullptr, [&] {
-    launch_fixup(vg);
-    launch_route(vg, 0, 0, 0);
-  }));
+  CK(capture(b_fix, {}, nullptr, [&] { launch_fix(vg, false); }));
   CK(capture(body, {n_if_fix}, nullptr, [&] { launch_route(vg, 1, 0, 0); }));
   CK(cudaGetLastError());
   CK(cudaGraphInstantiate(&graph_exec, graph, 0));
   graph_dirty = false;
   return SSB_OK;
 }
+#endif
+
+namespace {
+template <class T> bool regrow(ssb_engine* e, T** p, size_t n) {
+  T* q = nullptr;
+  if (dalloc(&q, n) != cudaSuccess) return false;
+  e->allocs.push_back(q);
+  *p = q;
+  return true;
+}
+}  // namespace
 
 // ======================================= C ABI =======================================
 extern "C" {
@@ -662,9 +612,10 @@ void ssb_destroy(ssb_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->destroy_graph();
-  if (e->hot_built) cudaCtxResetPersistingL2Cache();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+#ifndef SSB_EMU
   for (void* p : e->peer_blocks) if (p) cudaIpcCloseMemHandle(p);
+#endif
   if (e->mbox_block) cudaFree(e->mbox_block);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_unpack) cudaFree(e->d_unpack);
@@ -735,14 +686,15 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp) {
   if (mine > e->v.n_lp_local) {
     // per-LP arrays were sized for the modulo partition: grow them
     auto& v = e->v;
-    auto regrow = [&](u32** p, size_t n) -> int { u32* q = nullptr; if (dalloc(&q, n) != cudaSuccess) return 1; e->allocs.push_back(q); *p = q; return 0; };
-    if (regrow((u32**)&v.lph, (size_t)mine * 4) || regrow((u32**)&v.last, (size_t)mine * 2) ||
-        regrow(&v.state, (size_t)mine * v.state_words) || regrow(&e->d_state0, (size_t)mine * v.state_words)) {
+    const size_t sw = v.state_words;
+    if (!(regrow(e, &v.lpw, mine) && regrow(e, &v.state, mine * sw) && regrow(e, &e->d_state0, mine * sw) &&
+          regrow(e, &v.fixlp, mine) && regrow(e, &v.fixcnt, mine) && regrow(e, &v.fixstart, mine) &&
+          regrow(e, &v.fixpos, mine) && regrow(e, &v.fixund, mine) && regrow(e, &v.fixmin, mine))) {
       e->set_error("cudaMalloc failed"); return SSB_ERR_CUDA;
     }
-    cudaMemsetAsync(e->d_state0, 0, sizeof(u32) * (size_t)mine * v.state_words, e->stream);
-    k_fill_u2<<<e->grid(mine, 256), 256, 0, e->stream>>>(v.last, make_uint2(NIL, 0u), mine);
-    cudaMemsetAsync(v.state, 0, sizeof(u32) * (size_t)mine * v.state_words, e->stream);
+    cudaMemsetAsync(e->d_state0, 0, sizeof(u32) * mine * sw, e->stream);
+    cudaMemsetAsync(v.lpw, 0, sizeof(uint2) * (size_t)mine, e->stream);
+    cudaMemsetAsync(v.state, 0, sizeof(u32) * mine * sw, e->stream);
   }
   e->v.n_lp_local = mine;
   u32 *d_o = nullptr, *d_l = nullptr;
@@ -778,7 +730,7 @@ int ssb_set_model_data(ssb_engine* e, int slot, const void* data, size_t bytes) 
     int rc = e->alloc(&e->d_route, n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(d_in, data, n * 8, cudaMemcpyHostToDevice, e->stream));
-    k_narrow_u32<<<e->grid(n, 256), 256, 0, e->stream>>>(d_in, e->d_route, n, e->v.ctl);
+    SSB_LAUNCH(k_narrow_u32, e->grid(n, 256), 256, 0, e->stream, (const long long*)d_in, e->d_route, n, e->v.ctl);
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaFree(d_in));
     e->route_len = (u32)n;
@@ -831,7 +783,7 @@ int ssb_load_events(ssb_engine* e, const ssb_event* ev, int64_t n) {
   while (done < n) {
     u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
     CK(cudaMemcpyAsync(e->d_stage, ev + done, sizeof(HostEvent) * m, cudaMemcpyHostToDevice, e->stream));
-    k_pack<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, e->d_stage, m);
+    SSB_LAUNCH(k_pack, e->grid(m, 256), 256, 0, e->stream, e->v, (const HostEvent*)e->d_stage, m);
     e->launch_route(e->v, 3, 0, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));   // the host buffer may be reused by the caller; staging is single-buffered
@@ -852,7 +804,7 @@ int ssb_load_events_raw(ssb_engine* e, const ssb_raw_record* ev, int64_t n) {
     u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
     // straight into the routing staging area: no unpack pass
     CK(cudaMemcpyAsync(e->v.outbox, ev + done, sizeof(Ev) * m, cudaMemcpyHostToDevice, e->stream));
-    k_check_raw<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, m);
+    SSB_LAUNCH(k_check_raw, e->grid(m, 256), 256, 0, e->stream, e->v, m);
     e->launch_route(e->v, 3, 0, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -874,19 +826,25 @@ int ssb_step(ssb_engine* e, int* done) {
   return e->check_device_error();
 }
 
+static bool use_graph_path(const ssb_engine* e) {
+  return e->graph_enabled && (e->cfg.world == 1 || e->v.p2p) && !e->timing();
+}
+
 int ssb_run(ssb_engine* e, ssb_stats* stats) {
   if (!e) return SSB_ERR_INVALID;
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->model_ready();
   if (rc) return rc;
-  const bool use_graph = e->graph_enabled && (e->cfg.world == 1 || e->v.p2p) && !e->timing();
+  const bool use_graph = use_graph_path(e);
   if (use_graph && e->graph_dirty && (rc = e->build_graph())) return rc;
   CK(cudaEventRecord(e->ev0, e->stream));
   u64 last_gvt = ~0ull;
   long long stalled = 0;
   if (use_graph) {
+#ifndef SSB_EMU
     CK(cudaGraphLaunch(e->graph_exec, e->stream));
+#endif
     if ((rc = e->sync_ctl())) return rc;
     e->rounds = e->h_ctl->round;
     if ((rc = e->check_device_error())) return rc;
@@ -932,6 +890,8 @@ int ssb_get_stats(ssb_engine* e, ssb_stats* s) {
   s->pool_high_water = (int64_t)(e->n_chunks - 1 - c.free_low) << e->v.ch_log;
   s->log_dropped = (int64_t)c.log_dropped;
   s->loop_ms = e->loop_ms;
+  s->fix_rounds = (int64_t)c.n_fix_rounds;
+  s->fix_turns = (int64_t)c.n_fix_total;
   return SSB_OK;
 }
 
@@ -944,12 +904,34 @@ int ssb_committed_digest(ssb_engine* e, uint64_t d[4]) {
   return SSB_OK;
 }
 
+// a committed log that overflowed is an error for every drain call: the caller would otherwise print an incomplete
+// set of result lines with exit status 0
+static int log_overflow(ssb_engine* e) {
+  if (!e->h_ctl->log_dropped) return SSB_OK;
+  e->set_error("committed log overflowed: " + std::to_string(e->h_ctl->log_dropped) +
+               " records dropped (raise max_committed or drain more often)");
+  return SSB_ERR_CAPACITY;
+}
+
+// log fully drained: rewind so that the buffer can be reused by later windows
+static int rewind_log(ssb_engine* e, u64 have) {
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  if (e->log_drained == have && have == e->h_ctl->log_count) {
+    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(&e->v.ctl->log_stable, 0, sizeof(u64), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->log_drained = 0;
+  }
+  return SSB_OK;
+}
+
 int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n) {
   if (!e || !n || (!out && cap) || cap < 0) return SSB_ERR_INVALID;
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->sync_ctl();
   if (rc) return rc;
+  if ((rc = log_overflow(e))) return rc;
   u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
   u64 avail = have - e->log_drained;
   u64 m = std::min<u64>(avail, (u64)cap);
@@ -963,19 +945,13 @@ int ssb_drain_committed(ssb_engine* e, ssb_record* out, int64_t cap, int64_t* n)
   u64 done = 0;
   while (done < m) {
     u32 k = (u32)std::min<u64>(m - done, e->unpack_cap);
-    k_unpack_log<<<e->grid(k, 256), 256, 0, e->stream>>>(e->v.log, e->log_drained + done, k, e->d_unpack);
+    SSB_LAUNCH(k_unpack_log, e->grid(k, 256), 256, 0, e->stream, (const Ev*)e->v.log, e->log_drained + done, k, e->d_unpack);
     CK(cudaMemcpyAsync(out + done, e->d_unpack, (size_t)k * sizeof(ssb_record), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     done += k;
   }
   e->log_drained += m;
-  if (e->log_drained == have && have == e->h_ctl->log_count) {
-    // log fully drained: rewind so that the buffer can be reused by later windows
-    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    e->log_drained = 0;
-  }
-  return SSB_OK;
+  return rewind_log(e, have);
 }
 
 int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int64_t* n) {
@@ -985,6 +961,7 @@ int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->sync_ctl();
   if (rc) return rc;
+  if ((rc = log_overflow(e))) return rc;
   u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
   u64 m = std::min<u64>(have - e->log_drained, (u64)cap);
   *n = (int64_t)m;
@@ -993,10 +970,19 @@ int ssb_drain_committed_raw(ssb_engine* e, ssb_raw_record* out, int64_t cap, int
     CK(cudaStreamSynchronize(e->stream));
   }
   e->log_drained += m;
-  if (e->log_drained == have && have == e->h_ctl->log_count) {
-    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    e->log_drained = 0;
+  return rewind_log(e, have);
+}
+
+static int ensure_pack_buffers(ssb_engine* e) {
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  const u64 kChunk = 1u << 22;
+  if (e->d_pack[0]) return SSB_OK;
+  CK(cudaMalloc(&e->d_pack[0], kChunk * 24));
+  CK(cudaMalloc(&e->d_pack[1], kChunk * 24));
+  CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&e->pack_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->copy_done[i], cudaEventDisableTiming));
   }
   return SSB_OK;
 }
@@ -1008,26 +994,19 @@ int ssb_drain_committed_packed(ssb_engine* e, ssb_packed_record* out, int64_t ca
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->sync_ctl();
   if (rc) return rc;
+  if ((rc = log_overflow(e))) return rc;
   u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
   u64 m = std::min<u64>(have - e->log_drained, (u64)cap);
   *n = (int64_t)m;
   // two staging halves: the pack kernel of chunk k+1 runs while chunk k crosses PCIe
   const u64 kChunk = 1u << 22;
-  if (m && !e->d_pack[0]) {
-    CK(cudaMalloc(&e->d_pack[0], kChunk * 24));
-    CK(cudaMalloc(&e->d_pack[1], kChunk * 24));
-    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&e->pack_done[0], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->pack_done[1], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->copy_done[0], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->copy_done[1], cudaEventDisableTiming));
-  }
+  if (m && (rc = ensure_pack_buffers(e))) return rc;
   u64 done = 0;
   for (int k = 0; done < m; ++k) {
     const int b = k & 1;
     const u32 cnt = (u32)std::min<u64>(m - done, kChunk);
     if (k >= 2) CK(cudaStreamWaitEvent(e->stream, e->copy_done[b], 0));      // the half is free again
-    k_pack_log<<<e->grid(cnt, 256), 256, 0, e->stream>>>(e->v.log, e->log_drained + done, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
+    SSB_LAUNCH(k_pack_log, e->grid(cnt, 256), 256, 0, e->stream, (const Ev*)e->v.log, e->log_drained + done, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
     CK(cudaEventRecord(e->pack_done[b], e->stream));
     CK(cudaStreamWaitEvent(e->copy_stream, e->pack_done[b], 0));
     CK(cudaMemcpyAsync(out + done, e->d_pack[b], (size_t)cnt * 24, cudaMemcpyDeviceToHost, e->copy_stream));
@@ -1036,12 +1015,7 @@ int ssb_drain_committed_packed(ssb_engine* e, ssb_packed_record* out, int64_t ca
   }
   if (m) { CK(cudaStreamSynchronize(e->copy_stream)); CK(cudaStreamSynchronize(e->stream)); }
   e->log_drained += m;
-  if (e->log_drained == have && have == e->h_ctl->log_count) {
-    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    e->log_drained = 0;
-  }
-  return SSB_OK;
+  return rewind_log(e, have);
 }
 
 int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int64_t* n, ssb_stats* stats) {
@@ -1050,22 +1024,18 @@ int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->model_ready();
   if (rc) return rc;
-  const bool use_graph = e->graph_enabled && (e->cfg.world == 1 || e->v.p2p) && !e->timing();
+  const bool use_graph = use_graph_path(e);
   if (!use_graph || e->log_drained != 0) {      // no device-side loop to overlap with: one after the other
-    if ((rc = ssb_run(e, stats))) return rc;
+    ssb_stats local;
+    if ((rc = ssb_run(e, &local))) return rc;
+    if (stats) *stats = local;
+    if (local.committed > cap) { set_error("ssb_run_drain_packed: output buffer too small"); return SSB_ERR_CAPACITY; }
     return ssb_drain_committed_packed(e, out, cap, n);
   }
+#ifndef SSB_EMU
   if (e->graph_dirty && (rc = e->build_graph())) return rc;
   const u64 kChunk = 1u << 22;
-  if (!e->d_pack[0]) {
-    CK(cudaMalloc(&e->d_pack[0], kChunk * 24));
-    CK(cudaMalloc(&e->d_pack[1], kChunk * 24));
-    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&e->pack_done[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&e->copy_done[i], cudaEventDisableTiming));
-    }
-  }
+  if ((rc = ensure_pack_buffers(e))) return rc;
   if (!e->h_poll) CK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_poll), sizeof(u64), cudaHostAllocDefault));
   CK(cudaEventRecord(e->ev0, e->stream));
   CK(cudaGraphLaunch(e->graph_exec, e->stream));
@@ -1079,7 +1049,7 @@ int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int
       const u32 cnt = (u32)std::min<u64>(upto - drained, kChunk);
       if ((u64)cap < drained + cnt) { set_error("ssb_run_drain_packed: output buffer too small"); return SSB_ERR_CAPACITY; }
       const int b = k++ & 1;
-      k_pack_log<<<e->grid(cnt, 256), 256, 0, e->copy_stream>>>(e->v.log, drained, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
+      SSB_LAUNCH(k_pack_log, e->grid(cnt, 256), 256, 0, e->copy_stream, (const Ev*)e->v.log, drained, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
       CK(cudaMemcpyAsync(out + drained, e->d_pack[b], (size_t)cnt * 24, cudaMemcpyDeviceToHost, e->copy_stream));
       drained += cnt;
     }
@@ -1103,12 +1073,14 @@ int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int
   e->rounds = e->h_ctl->round;
   if ((rc = e->check_device_error())) return rc;
   if (!e->h_ctl->done) { set_error("window loop ended before GVT reached finish_time"); return SSB_ERR_INVALID; }
-  if (e->h_ctl->log_dropped) { set_error("committed log overflowed (raise max_committed)"); return SSB_ERR_CAPACITY; }
+  if ((rc = log_overflow(e))) return rc;
   *n = (int64_t)drained;
   CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));      // fully drained: rewind the log
+  CK(cudaMemsetAsync(&e->v.ctl->log_stable, 0, sizeof(u64), e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->log_drained = 0;
   if (stats) return ssb_get_stats(e, stats);
+#endif
   return SSB_OK;
 }
 
@@ -1120,7 +1092,7 @@ int ssb_drain_history(ssb_engine* e, ssb_raw_record* rec, ssb_sent_record* sent,
   if (!e->v.log_sent) { set_error("history was not kept: create the engine with SSB_FLAG_HISTORY and max_committed > 0"); return SSB_ERR_INVALID; }
   int rc = e->sync_ctl();
   if (rc) return rc;
-  if (e->h_ctl->log_dropped) { set_error("history incomplete: committed log overflowed (raise max_committed)"); return SSB_ERR_CAPACITY; }
+  if ((rc = log_overflow(e))) return rc;
   u64 have = std::min<u64>(e->h_ctl->log_count, e->v.cap_log);
   u64 m = std::min<u64>(have - e->log_drained, (u64)cap);
   *n = (int64_t)m;
@@ -1130,14 +1102,15 @@ int ssb_drain_history(ssb_engine* e, ssb_raw_record* rec, ssb_sent_record* sent,
     CK(cudaStreamSynchronize(e->stream));
   }
   e->log_drained += m;
-  if (e->log_drained == have && have == e->h_ctl->log_count) {
-    CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    e->log_drained = 0;
-  }
-  return SSB_OK;
+  return rewind_log(e, have);
 }
 
+// --diff_repeat (R13): the recorded events go back into the calendar as PROCESSED events — their recorded sent-log
+// entries become their meta records, every bucket counts as consumed, every LP's newest processed time is that of its
+// last recorded event. Nothing is executed. What-if events injected afterwards are stragglers at their LPs: the
+// ordinary rollback machinery undoes exactly the recorded events they invalidate (those inside the window at once,
+// the later ones when the window reaches them: View::inv) — the reference's lazy history load
+// (logical_process.hpp:132-153) with the history resident in HBM.
 int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n) {
   if (!e || ((!rec || !sent) && n) || n < 0) return SSB_ERR_INVALID;
   cudaSetDevice(e->cfg.device);
@@ -1147,6 +1120,8 @@ int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_re
   if ((rc = e->sync_ctl())) return rc;
   if (e->h_ctl->round != 0 || e->h_ctl->load_count != 0) { set_error("ssb_load_history must be the first load after create / reset"); return SSB_ERR_INVALID; }
   if (!e->v.hist_sent && (rc = e->alloc(&e->v.hist_sent, e->v.cap_batch))) return rc;
+  if (!e->d_inv && (rc = e->alloc(&e->d_inv, e->v.n_lp_local))) return rc;
+  SSB_LAUNCH(k_fill_u64, e->grid(e->v.n_lp_local, 256), 256, 0, e->stream, e->d_inv, KEY_MAX, (size_t)e->v.n_lp_local);
   e->v.replay = 1;
   Ev* stage = reinterpret_cast<Ev*>(e->d_stage);      // the load staging buffer (64 B per entry) holds a chunk of records
   int64_t done = 0;
@@ -1154,26 +1129,20 @@ int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_re
     u32 m = (u32)std::min<int64_t>(n - done, e->v.cap_batch);
     CK(cudaMemcpyAsync(stage, rec + done, sizeof(Ev) * m, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->v.hist_sent, sent + done, sizeof(uint4) * m, cudaMemcpyHostToDevice, e->stream));
-    k_hist_stage<<<e->grid(m, 256), 256, 0, e->stream>>>(e->v, stage, m);
+    SSB_LAUNCH(k_hist_stage, e->grid(m, 256), 256, 0, e->stream, e->v, (const Ev*)stage, m);
     e->launch_route(e->v, 3, 0, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     done += m;
   }
-  // replay: window after window until every loaded event sits in its LP's processed chain
-  for (long long guard = 0;; ++guard) {
-    for (int i = 0; i < 8; ++i) if ((rc = e->enqueue_replay_round())) { e->v.replay = 0; return rc; }
-    if ((rc = e->sync_ctl())) { e->v.replay = 0; return rc; }
-    if ((rc = e->check_device_error())) { e->v.replay = 0; return rc; }
-    if (e->h_ctl->done) break;
-    if (guard > 1000000) { e->v.replay = 0; set_error("history replay does not terminate"); return SSB_ERR_INVALID; }
-  }
   e->v.replay = 0;
-  e->graph_dirty = true;
-  k_after_replay<<<1, 1, 0, e->stream>>>(e->v);
+  SSB_LAUNCH(k_after_history, e->grid(e->v.nb, 256), 256, 0, e->stream, e->v);
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaGetLastError());
-  return SSB_OK;
+  e->v.inv = e->d_inv;
+  e->graph_dirty = true;
+  if ((rc = e->sync_ctl())) return rc;
+  return e->check_device_error();
 }
 
 int ssb_reset(ssb_engine* e) {
@@ -1193,8 +1162,8 @@ int ssb_set_flags(ssb_engine* e, int32_t flags) {
 
 int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_t* launches, int cap) {
   if (!e || !names || !total_ms || !launches) return 0;
-  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_link", "k_segs_heavy", "k_exec",
-                                                    "k_sortheavy", "k_exec_heavy", "k_fixup",
+  static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_exec", "k_hist_flag", "k_fix_count",
+                                                    "k_fix_segs", "k_fix_scatter", "k_fix_sort", "k_fix_turn",
                                                     "k_route(anti)", "k_route", "k_route(recv)"};
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
@@ -1233,6 +1202,10 @@ int ssb_comm_init(ssb_engine* e, const void* id128) {
 int ssb_comm_export(ssb_engine* e, void* handle64) {
   if (!e || !handle64) return SSB_ERR_INVALID;
   if (e->cfg.world <= 1) { std::memset(handle64, 0, 64); return SSB_OK; }
+#ifdef SSB_EMU
+  e->set_error("the host emulation has no peer-memory exchange");
+  return SSB_ERR_COMM;
+#else
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1247,11 +1220,16 @@ int ssb_comm_export(ssb_engine* e, void* handle64) {
   CK(cudaIpcGetMemHandle(&h, e->mbox_block));
   std::memcpy(handle64, &h, 64);
   return SSB_OK;
+#endif
 }
 
 int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
   if (!e || !handles || world != e->cfg.world) return SSB_ERR_INVALID;
   if (world <= 1) return SSB_OK;
+#ifdef SSB_EMU
+  e->set_error("the host emulation has no peer-memory exchange");
+  return SSB_ERR_COMM;
+#else
   if (!e->mbox_block) { e->set_error("ssb_comm_export must be called first"); return SSB_ERR_INVALID; }
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
@@ -1274,6 +1252,7 @@ int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
   e->v.p2p = 1;
   e->graph_dirty = true;
   return SSB_OK;
+#endif
 }
 
 }  // extern "C"

@@ -3,22 +3,19 @@
 // One round (= one optimistic window step), as the body of the window-loop graph (ssb_engine.cu: build_graph):
 //   [k_gvt      N > 1: GVT min-reduction + barrier through the peers' mailboxes; then k_route of the received
 //               anti-messages and of the received positives]
-//   k_plan      GVT (block min-reduction over the calendar when N = 1), window bounds, gather list, commit list,
-//               loop condition of the graph
+//   k_plan      GVT (block min-reduction over the calendar when N = 1), window bounds, gather list (unconsumed tails
+//               of the window's buckets), scan list (their consumed heads), commit list, loop condition of the graph
 //   k_commit    (parallel branch) stream-compaction of every bucket that fell below GVT into the committed log +
 //               digest (+ sent-log entries for the history store); the last block does the fossil collection
-//   k_link      arrivals of the window, in calendar order: count per LP, chain every arrival to the previous
-//               arrival of its LP (atomic exchange on the LP's list head), note the chain head, list the long LPs
-//   k_segs_heavy  segment allocation for the LPs with more than light_max arrivals
-//   k_exec      one thread per EVENT, in calendar order (coalesced): handler, sent-log, outbox (speculative on the LP
-//               state); an event of a short LP finds its place in the LP's key order by walking the arrival list, an
-//               event of a long LP drops (key, slot, arrival) into the LP's segment
-//   [k_sortheavy  IF a segment longer than kRegSortSmall exists: one block per such LP, hybrid bitonic sort + links]
-//   k_exec_heavy  one warp per long LP: bitonic sort in registers, processed-chain links from the sorted neighbours
-//   [k_fixup + k_route(anti)  IF some LP is not plain (anti-message, duplicate, straggler, state-mutating handler):
-//               annihilate, roll back, re-execute sequentially, re-queue, emit anti-messages]
+//   k_exec      one thread per EVENT of the window, in calendar order (coalesced): irregularity tests (anti-message,
+//               straggler against the LP's newest processed time, duplicate key through the round's hash set),
+//               handler, sent-log, outbox. This single pass is the whole turn of every plain LP.
+//   [k_fix_*    IF some LP is not plain: k_hist_flag (exact-differential repeat only), k_fix_count, k_fix_segs,
+//               k_fix_scatter (collects the LP's arrivals and — by a coalesced scan over the consumed part of the
+//               window's buckets — the processed events its rollback undoes, emitting their anti-messages),
+//               k_fix_sort (segmented bitonic sort), k_fix_turn (merge, annihilate, re-execute; one warp per LP),
+//               k_route(anti)]
 //   k_route     outbox -> calendar buckets / the destination GPU's mailbox (TMA-staged tiles, block-aggregated atomics)
-// The same kernels in replay mode (View::replay) rebuild the processed chains of a recorded history (--diff_repeat).
 // Reference semantics restated per kernel; rule numbers R1..R13 refer to SURVEY.md Appendix A.
 #pragma once
 #include "ssb_device.cuh"
@@ -26,24 +23,28 @@
 
 namespace ssb {
 
+#ifdef SSB_EMU
+constexpr int kRouteThreads = 1;
+constexpr int kRouteItems = 32;
+constexpr u32 kCommitThreads = 1;
+constexpr int kSortThreads = 1;
+#else
 constexpr int kRouteThreads = 256;
 constexpr int kRouteItems = 4;
+constexpr u32 kCommitThreads = 256;
+constexpr int kSortThreads = 256;
+#endif
 constexpr int kRouteTile = kRouteThreads * kRouteItems;   // records staged in shared memory per tile (32 KB)
+constexpr u32 kCommitWarps = (kCommitThreads + 31) / 32;
 
-// flag bits of an LP in this round (lph[lp].x >> kCntBits)
-constexpr u32 PL_IRREGULAR = 1u;   // anti-message, duplicate key or possible straggler in the segment
-constexpr u32 PL_MUTATED = 2u;     // a handler invocation changed the LP state
-constexpr u32 PL_SORTED = 4u;      // the segment is sorted by (key, arrival order)
-constexpr u32 PL_FIX = PL_IRREGULAR | PL_MUTATED;
-constexpr u32 kCntBits = 28;       // lph[lp].x = arrivals of the round (bits 0..27) | PL_* << 28
-constexpr u32 kCntMask = (1u << kCntBits) - 1u;
-constexpr u32 NIL31 = 0x7FFFFFFFu; // end of an LP's arrival list
-constexpr u32 kLightMax = 16;      // upper bound of View::light_max: LPs with more arrivals in a round get a segment
-constexpr u32 kRegSortSmall = 128; // register sort with up to 4 entries per lane (the every-round kernel)
+constexpr u32 TICKET_PENDING = 0xFFFFFFFFu;   // lpw[lp].y while the fix-table entry of the LP is being written
+constexpr u32 kHashProbes = 32;               // longer probe sequences fall back to the irregular turn
+constexpr u32 kWarpSortMax = 128;             // segments up to this size are sorted by one warp in registers
+constexpr u32 kSmemSortMax = 2048;            // ... up to this size by one block in shared memory, longer ones in global memory
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = kWarp / 2; o > 0; o >>= 1) {
     u64 w = __shfl_xor_sync(0xffffffffu, v, o);
     v = w < v ? w : v;
   }
@@ -51,12 +52,27 @@ __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 }
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = kWarp / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 __device__ __forceinline__ u64 warp_xor_u64(u64 v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = kWarp / 2; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ u32 warp_sum_u32(u32 v) {
+#pragma unroll
+  for (int o = kWarp / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ u32 warp_min_u32(u32 v) {
+#pragma unroll
+  for (int o = kWarp / 2; o > 0; o >>= 1) { u32 w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+  return v;
+}
+__device__ __forceinline__ u32 warp_max_u32(u32 v) {
+#pragma unroll
+  for (int o = kWarp / 2; o > 0; o >>= 1) { u32 w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
   return v;
 }
 
@@ -66,6 +82,9 @@ __device__ __forceinline__ u64 warp_xor_u64(u64 v) {
 // buckets; the start time of the first bucket with such a tail is a valid lower bound ("any value <= every LP's
 // local time") and gives the same commit frontier as the exact minimum, because commit works on whole
 // buckets. Events dropped beyond finish_time count as (finish_time, 0). Warp-shuffle + block min-reduction.
+// Exact-differential repeat: once the recorded history of some LP is invalid from a key on, the recorded events
+// behind the window count as unprocessed too (they are re-executed when the window reaches them), so the windows
+// then step through the history bucket by bucket.
 // Replaces scheduler::min_locals (process_scheduler.hpp:83-90) + the local half of mpi_gsync::check_sync
 // (global_sync.hpp:95-150).
 // ------------------------------------------------------------------------------------------------
@@ -74,14 +93,18 @@ __device__ __forceinline__ void block_local_min(const View& v, Ctl* c, u64* sm) 
   for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x)
     if (v.fill[b] != v.consumed[b]) { u64 k = make_key(b * v.bucket_ticks, 0); m = k < m ? k : m; }
   m = warp_min_u64(m);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  if ((threadIdx.x & (kWarp - 1)) == 0) sm[threadIdx.x / kWarp] = m;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : KEY_MAX;
+  if (threadIdx.x < kWarp) {
+    m = threadIdx.x < (blockDim.x + kWarp - 1) / kWarp ? sm[threadIdx.x] : KEY_MAX;
     m = warp_min_u64(m);
     if (threadIdx.x == 0) {
       u64 bm = c->n_beyond ? make_key(v.finish_time, 0) : KEY_MAX;
       m = bm < m ? bm : m;
+      if (c->n_touched && c->bound_abs < c->hist_end) {
+        const u64 hm = make_key(c->bound_abs * v.bucket_ticks, 0);
+        m = hm < m ? hm : m;
+      }
       // peer-memory exchange: events this partition wrote into other partitions' mailboxes are in flight until the
       // receivers integrate them after the all-reduce; the sender accounts for them (the reference folds the
       // timestamp of every sent message into the sender's local minimum the same way, sender_receiver.hpp:63-67)
@@ -140,9 +163,10 @@ __global__ void k_gvt(View v) {
 // ------------------------------------------------------------------------------------------------
 // k_plan — GVT := (all-reduced) local_min. Finish test of runner.hpp:392. Commit list = buckets entirely below GVT
 // (R8/R9). Gather list = unconsumed tails of the buckets inside the optimistic window
-// [bucket(GVT), bucket(GVT) + window). The control block is staged in shared memory (one coalesced load, one
-// coalesced store): the serial bookkeeping of thread 0 then costs no global round trips. Nothing else touches the
-// control block while k_plan runs (it is the first kernel of a round).
+// [bucket(GVT), bucket(GVT) + window); scan list = the consumed heads of the buckets a rollback of this round can
+// reach (everything processed lies below the largest window bound so far). The control block is staged in shared
+// memory (one coalesced load, one coalesced store): the serial bookkeeping of thread 0 then costs no global round
+// trips. Nothing else touches the control block while k_plan runs (it is the first kernel of a round).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_plan(View v, int use_global_gvt) {
   __shared__ u64 sm[32];
@@ -165,24 +189,29 @@ __global__ void k_plan(View v, int use_global_gvt) {
     u32 cur = done ? fin_b : t / v.bucket_ticks;
     if (cur > fin_b) cur = fin_b;
     c->cur_abs = cur;
-    // commit list (history replay commits nothing: the loaded events stay in the calendar as processed events)
+    // commit list (a recorded history that was never re-executed is not committed: k_commit skips P_HISTORY)
     u32 nc = 0, tot = 0;
-    if (!v.replay) {
-      for (u32 b = c->commit_next; b < cur; ++b) {
-        u32 f = v.fill[b];
-        if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
-      }
-      c->commit_next = cur > c->commit_next ? cur : c->commit_next;
+    for (u32 b = c->commit_next; b < cur; ++b) {
+      u32 f = v.fill[b];
+      if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
     }
+    c->commit_next = cur > c->commit_next ? cur : c->commit_next;
     c->n_commit = nc;
     c->commit_total = tot;
     // snapshot ring: rounds whose window lies below GVT are dead (their snapshots can be reused)
     while (c->rq_tail != c->rq_head && c->rq_bound[c->rq_tail % RQ_LEN] <= cur) c->rq_tail++;
     c->snap_tail = c->rq_tail == c->rq_head ? c->snap_head : c->rq_snap[c->rq_tail % RQ_LEN];
-    // gather list
-    u32 ng = 0, total = 0;
+    u32 ng = 0, total = 0, ns = 0, stot = 0;
     u32 bound = cur;
     if (!done) {
+      // scan list: what has been processed in the buckets from the window start on (before this round's gather)
+      u32 shi = cur + v.window < fin_b ? cur + v.window : fin_b;
+      if (c->hi_bound > shi) shi = c->hi_bound < fin_b ? c->hi_bound : fin_b;
+      for (u32 b = cur; b < shi; ++b) {
+        const u32 cons = v.consumed[b];
+        if (cons) { v.scan[ns++] = make_uint4(b, 0u, cons, stot); stot += cons; }
+      }
+      // gather list
       bound = cur + v.window < fin_b ? cur + v.window : fin_b;
       for (u32 b = cur; b < bound; ++b) {
         const u32 cons = v.consumed[b];
@@ -203,17 +232,23 @@ __global__ void k_plan(View v, int use_global_gvt) {
       } else {
         c->rq_bound[(c->rq_head - 1) % RQ_LEN] = bound;
       }
+      if (bound > c->hi_bound) c->hi_bound = bound;
     }
     c->bound_abs = bound;
     c->n_gather = ng;
     c->n_arr = total;
-    c->n_processed += total;   // k_fixup corrects this for the LPs it re-executes
-    c->seg_cursor = 0;
+    {      // hash-set region of this round: the smallest power of two >= 2 * arrivals (at least 1024 slots)
+      u32 hm = 1023u;
+      while (hm < v.hmask && hm + 1u < 2u * total) hm = (hm << 1) | 1u;
+      c->hmask_round = hm < v.hmask ? hm : v.hmask;
+    }
+    c->n_scan = ns;
+    c->scan_total = stot;
+    c->n_processed += total;   // k_fix_turn corrects this for the LPs it re-executes
     c->n_anti = 0;
     c->n_extra = 0;
-    c->n_heavy = 0;
-    c->n_vheavy = 0;
     c->n_fix = 0;
+    c->n_ent = 0;
     c->done = done ? 1u : 0u;
     c->log_stable = c->log_count;      // the commit passes of all earlier rounds are complete
     c->round++;
@@ -243,19 +278,19 @@ __global__ void k_plan(View v, int use_global_gvt) {
 // (replaces eventq::release / release_cancel / stateq::release, queue.hpp:159-177, 292-302).
 // ------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
+__global__ void __launch_bounds__(kCommitThreads) k_commit(View v, typename M::Data md) {
   Ctl* c = v.ctl;
   const u32 total = c->commit_total;
   const u32 nc = c->n_commit;
   if (nc == 0) return;
   u64 cnt = 0, hsum = 0, hxor = 0, hsum2 = 0;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ u32 w_cnt[8];
+  const u32 lane = threadIdx.x & (kWarp - 1), warp = threadIdx.x / kWarp;
+  __shared__ u32 w_cnt[kCommitWarps];
   __shared__ u64 s_pos;
-  __shared__ u64 s_dg[8][4];
+  __shared__ u64 s_dg[kCommitWarps][4];
   __shared__ u32 s_last;
   // every thread of a block iterates the same number of times (block-level compaction inside the loop)
-  for (u32 base = blockIdx.x * 256u; base < total; base += gridDim.x * 256u) {
+  for (u32 base = blockIdx.x * kCommitThreads; base < total; base += gridDim.x * kCommitThreads) {
     u32 i = base + threadIdx.x;
     bool keep = false;
     Ev e;
@@ -288,7 +323,7 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
       if (threadIdx.x == 0) {
         u32 tot = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { u32 a = w_cnt[w]; w_cnt[w] = tot; tot += a; }
+        for (u32 w = 0; w < kCommitWarps; ++w) { u32 a = w_cnt[w]; w_cnt[w] = tot; tot += a; }
         s_pos = tot ? atomicAdd(&c->log_count, (u64)tot) : 0ull;
       }
       __syncthreads();
@@ -314,7 +349,7 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
   if (threadIdx.x == 0) {
     u64 a = 0, b = 0, x = 0, d = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { a += s_dg[w][0]; b += s_dg[w][1]; x ^= s_dg[w][2]; d += s_dg[w][3]; }
+    for (u32 w = 0; w < kCommitWarps; ++w) { a += s_dg[w][0]; b += s_dg[w][1]; x ^= s_dg[w][2]; d += s_dg[w][3]; }
     if (a) {
       atomicAdd(&c->digest[0], a);
       atomicAdd(&c->digest[1], b);
@@ -345,77 +380,209 @@ __global__ void __launch_bounds__(256) k_commit(View v, typename M::Data md) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// calendar slot of the arrival with index i (arrival order = calendar order of the gathered bucket tails)
+// calendar slot of the arrival with index i (arrival order = calendar order of the gathered bucket tails), and of
+// item i of the scan list (the consumed heads)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 slot_of_arrival(const View& v, u32 i) {
-  u32 g = 0, hi = v.ctl->n_gather;
+__device__ __forceinline__ u32 slot_of_list(const View& v, const uint4* list, u32 n, u32 i) {
+  u32 g = 0, hi = n;
   while (hi - g > 1) {
     u32 mid = (g + hi) >> 1;
-    if (v.gather[mid].w <= i) g = mid; else hi = mid;
+    if (list[mid].w <= i) g = mid; else hi = mid;
   }
-  const uint4 ge = v.gather[g];
+  const uint4 ge = list[g];
   return slot_of(v, ge.x, ge.y + (i - ge.w));
+}
+__device__ __forceinline__ u32 slot_of_arrival(const View& v, u32 i) { return slot_of_list(v, v.gather, v.ctl->n_gather, i); }
+
+// ------------------------------------------------------------------------------------------------
+// Irregular turns. An LP whose turn of this round is not plain gets a ticket (index into the fix table); the first
+// flagger issues it. lpw[lp].y: 0 = plain, TICKET_PENDING while the table entry is written, then ticket + 1.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flag_lp(const View& v, u32 lp) {
+  u32* t = &v.lpw[lp].y;
+  if (atomicCAS(t, 0u, TICKET_PENDING) != 0u) return;
+  const u32 f = atomicAdd(&v.ctl->n_fix, 1u);      // < n_lp_local: every LP is issued at most one ticket per round
+  v.fixlp[f] = lp;
+  v.fixcnt[f] = 0;
+  v.fixund[f] = 0;
+  v.fixmin[f] = KEY_MAX;
+  __threadfence();
+  atomicExch(t, f + 1u);
+}
+
+// Duplicate detection (R1: "same key twice at one LP = one event", queue.hpp:92) without per-LP lists: every plain
+// arrival inserts a fingerprint of (LP, key) into the round's hash set (open addressing, linear probing). Entries
+// carry the round number in their top byte, so the table is never cleared: an entry of another round is free.
+// The table region used by a round is sized by the round's arrivals (Ctl::hmask_round), so it stays L2-resident.
+// Returns false when the same fingerprint is already there (duplicate SUSPECT: the LP takes the exact irregular
+// turn) or the probe sequence gets too long. Two arrivals with the same (LP, key) follow the same probe sequence,
+// and occupied slots stay occupied during a round, so at most one of them can return true.
+__device__ __forceinline__ bool hash_insert(const View& v, u32 lp, u64 key, u32 stamp, u32 hmask) {
+  const u64 h = mix64(key ^ ((u64)lp * 0x9E3779B97F4A7C15ULL));
+  const u32 fp = stamp | ((u32)(h >> 40) & 0x00FFFFFEu) | 1u;      // never 0 (0 = slot never used)
+  u32 pos = (u32)h & hmask;
+  for (u32 probe = 0; probe < kHashProbes; ++probe) {
+    u32 cur = *reinterpret_cast<volatile u32*>(v.hset + pos);
+    for (;;) {
+      if (cur == fp) return false;
+      if ((cur & 0xFF000000u) == stamp && cur != 0u) break;          // taken by another arrival of this round
+      const u32 old = atomicCAS(v.hset + pos, cur, fp);
+      if (old == cur) return true;
+      cur = old;
+    }
+    pos = (pos + 1u) & hmask;
+  }
+  return false;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_link — arrivals of this window, in calendar (slot) order: one coalesced pass over the event records. Replaces
-// the inbox append of lp::buffer (logical_process.hpp:115-127) and scheduler::queue (process_scheduler.hpp:55-81,
-// "which LPs have work"): every arrival is counted on its LP and chained to the LP's previous arrival of the round
-// (atomic exchange on the LP's list head), so that afterwards any arrival can see all arrivals of its LP without
-// the events being moved or sorted. The first arrival of an LP notes the LP's processed-chain head as it was before
-// the round; the arrival that makes the LP's count exceed kLightMax puts the LP on the long-segment list.
+// k_exec — one thread per EVENT of the window, in calendar (slot) order, so the event read and the meta / pflag /
+// outbox writes are coalesced streams; only the per-LP word, the hash-set slot and the model's tables are gathered.
+// This is the speculative form of runner::run_lp_aggr (runner.hpp:530-570): every event of an LP is executed against
+// the LP's current state, which is exactly the sequential result as long as no invocation changes the state (neither
+// shipped application ever does) and the LP's turn is plain:
+//   * no anti-message among its arrivals                                   (R4/R6, queue.hpp:87-90)
+//   * no arrival at or before the time of its newest processed event       (straggler, R5, queue.hpp:98-105);
+//     lpw[lp].x is stable during the pass — k_route raises it afterwards, from the send time of every output
+//   * no key twice                                                          (R1, queue.hpp:92)
+// Otherwise the LP is flagged and k_fix_* redo its whole turn exactly (whatever this pass wrote for the LP's other
+// arrivals is overwritten: arrival i owns outbox entry i). Skew-free: a hot LP's events are spread over many threads.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_link(View v) {
+template <class M>
+__device__ __forceinline__ bool run_handler(const View& v, const typename M::Data& md, const Ev& e, u32 lp, Ev& out,
+                                            bool& has, u32& err) {
+  u32 st[M::kStateWords], pre[M::kStateWords];
+#pragma unroll
+  for (int q = 0; q < M::kStateWords; ++q) { st[q] = v.state[(size_t)lp * M::kStateWords + q]; pre[q] = st[q]; }
+  Ev in = e;
+  in.flags = 0;
+  has = M::handle(md, in, st, out, err);
+  bool changed = false;
+#pragma unroll
+  for (int q = 0; q < M::kStateWords; ++q) changed |= (pre[q] != st[q]);
+  return has && changed;
+}
+
+template <class M>
+__global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
   Ctl* c = v.ctl;
-  const u32 n = c->n_arr;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const u32 n_arr = c->n_arr;
+  const u32 stamp = (c->round & 0xFFu) << 24;
+  const u32 hmask = c->hmask_round;
+  u32 err = 0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_arr; i += gridDim.x * blockDim.x) {
     const u32 slot = slot_of_arrival(v, i);
     const Ev e = load_ev(v.ev + slot);
     const u32 lp = part_local(v, e.dst);
-    u32* h = reinterpret_cast<u32*>(v.lph + lp);
-    const u32 rank = atomicAdd(h, 1u) & kCntMask;
-    const u32 prev1 = atomicExch(h + 1, i + 1u);
-    const u32 prev = prev1 ? prev1 - 1u : NIL31;
-    v.link[i] = make_uint4((u32)e.key, (u32)(e.key >> 32), prev | ((e.flags & F_CANCEL) ? 0x80000000u : 0u), slot);
-    v.tmp_rank[i] = rank;
-    if (rank == 0) *reinterpret_cast<uint2*>(h + 2) = v.last[lp];
-    if (rank == v.light_max) v.heavy[atomicAdd(&c->n_heavy, 1u)] = make_uint4(lp, 0, 0, 0);
+    const uint2 w = __ldcg(reinterpret_cast<const uint2*>(v.lpw + lp));
+    if (w.y) continue;                                   // the LP already has a ticket: k_fix_turn runs its turn
+    bool bad = (e.flags & F_CANCEL) != 0 || key_time(e.key) < w.x;
+    if (!bad) bad = !hash_insert(v, lp, e.key, stamp, hmask);
+    if (bad) { flag_lp(v, lp); continue; }
+    Ev out;
+    bool has;
+    if (run_handler<M>(v, md, e, lp, out, has, err)) { flag_lp(v, lp); continue; }      // state-mutating handler
+    Meta m;
+    m.sent_dst = NIL; m.snap = NIL; m.sent_key = 0;
+    if (has) {
+      m.sent_dst = out.dst;
+      m.sent_key = out.key;
+      store_ev(v.outbox + i, out);
+    } else {
+      v.outbox[i].key = KEY_MAX;
+    }
+    store_meta_ef(v.meta + slot, m);
+    v.pflag[slot] = P_PROCESSED;
+  }
+  if (err) atomicOr(&c->error, err);
+  if (v.use_graph) {
+    // the last block to finish knows whether any LP was flagged: it opens or closes the IF node around k_fix_*
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&c->exec_blocks, 1u) == gridDim.x - 1) {
+        c->exec_blocks = 0;
+        const u32 nf = *reinterpret_cast<volatile u32*>(&c->n_fix);
+        cudaGraphSetConditional(v.h_fix, (nf || (v.inv && c->n_touched)) ? 1u : 0u);
+      }
+    }
   }
 }
 
-// k_segs_heavy — the LPs with more than kLightMax arrivals get a segment of `sorted` (one atomic each).
-__global__ void k_segs_heavy(View v) {
+// ------------------------------------------------------------------------------------------------
+// The irregular turns, k_fix_*: what eventq::merge_buffer + lp::flush_buf + the re-execution in run_lp_aggr do for an
+// LP with an anti-message, a duplicate, a straggler or a state-mutating handler (queue.hpp:82-108,
+// logical_process.hpp:129-157, runner.hpp:530-570) — as data-parallel passes:
+//   k_hist_flag    exact-differential repeat only: a recorded event inside the window whose LP's history is invalid
+//                  from an earlier key on must be re-executed: its LP takes a ticket                          (R13)
+//   k_fix_count    per ticket: number of entries (its arrivals + every processed event of the scan list that belongs
+//                  to the LP: an upper bound of what the rollback undoes) and the smallest arrival key m    (R4)
+//   k_fix_segs     one segment of `sorted` per ticket
+//   k_fix_scatter  arrivals -> entries; scan list: every processed event of a ticketed LP with key >= m is UNDONE —
+//                  its recorded output leaves as an anti-message, its processed flag is cleared, it becomes an entry
+//                  of the segment (it was in the queue before every arrival)                                   (R5)
+//   k_fix_sort     segments sorted by (key, arrival order)                                                     (R1)
+//   k_fix_turn     one warp per LP: per key apply the inbox items in arrival order (positive = insert unless
+//                  present, anti = erase if present), restore the state snapshot, execute the survivors        (R2, R4, R6)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 ticket_of(const View& v, u32 lp) {
+  const u32 t = *reinterpret_cast<volatile u32*>(&v.lpw[lp].y);
+  return t;      // 0 = none; TICKET_PENDING cannot be seen after the kernel that issued it
+}
+
+__global__ void __launch_bounds__(256) k_hist_flag(View v) {
   Ctl* c = v.ctl;
-  const u32 nh = c->n_heavy;
-  for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
-    const u32 lp = v.heavy[h].x;
-    const u32 n = v.lph[lp].x & kCntMask;
-    const u32 start = atomicAdd(&c->seg_cursor, n);
-    v.lph[lp].y = start;          // the list head is not needed for a long LP: the word now holds its segment start
-    v.heavy[h] = make_uint4(lp, start, n, 0);
-    if (n > kRegSortSmall) atomicAdd(&c->n_vheavy, 1u);
+  if (!v.inv || !c->n_touched) return;
+  const u32 n = c->scan_total;
+  const u32 tbound = c->bound_abs * v.bucket_ticks;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 slot = slot_of_list(v, v.scan, c->n_scan, i);
+    const unsigned char pf = v.pflag[slot];
+    if ((pf & (P_PROCESSED | P_HISTORY | P_DEAD)) != (P_PROCESSED | P_HISTORY)) continue;
+    const Ev e = load_ev(v.ev + slot);
+    if (key_time(e.key) >= tbound) continue;
+    const u32 lp = part_local(v, e.dst);
+    if (e.key >= v.inv[lp]) flag_lp(v, lp);
   }
 }
 
-// first flagger of an LP puts it on the fix list
-__device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 bit) {
-  if (v.replay) internal_error(v, 2, lp);      // a recorded history has no irregular turns
-  const u32 old = atomicOr(reinterpret_cast<u32*>(v.lph + lp), bit << kCntBits);
-  if (((old >> kCntBits) & PL_FIX) == 0) v.fix[atomicAdd(&v.ctl->n_fix, 1u)] = lp;
+__global__ void __launch_bounds__(256) k_fix_count(View v) {
+  Ctl* c = v.ctl;
+  if (c->n_fix == 0) return;
+  const u32 n_arr = c->n_arr, n = n_arr + c->scan_total;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < n_arr) {
+      const u32 slot = slot_of_arrival(v, i);
+      const Ev e = load_ev(v.ev + slot);
+      const u32 t = ticket_of(v, part_local(v, e.dst));
+      if (!t) continue;
+      atomicAdd(&v.fixcnt[t - 1u], 1u);
+      atomicMin(&v.fixmin[t - 1u], e.key);
+    } else {
+      const u32 slot = slot_of_list(v, v.scan, c->n_scan, i - n_arr);
+      const unsigned char pf = v.pflag[slot];
+      if ((pf & (P_PROCESSED | P_DEAD)) != P_PROCESSED) continue;
+      const Ev e = load_ev(v.ev + slot);
+      const u32 t = ticket_of(v, part_local(v, e.dst));
+      if (t) atomicAdd(&v.fixcnt[t - 1u], 1u);
+    }
+  }
 }
 
-// ------------------------------------------------------------------------------------------------
-// lp_turn — one LP's turn in a round, sequentially: what runner::run_lp_aggr does (runner.hpp:530-570) for every
-// event of the window instead of switch_lp_interval() of them. The segment is sorted by (key, arrival order) (R1).
-//   1. straggler test against the newest processed event; roll back: walk the processed chain, emit the
-//      anti-message of every undone event's output, restore the pre-state from the snapshot ring,
-//      put the undone events back in front of the merge                  — R5 (queue.hpp:98-105, 286-290)
-//   2. merge inbox and undone events in key order; per key apply the inbox items in arrival order:
-//      positive = insert unless present, anti = erase if present           — R4/R6 (queue.hpp:82-96)
-//   3. execute survivors in key order; record sent-log + snapshot          — R2 (runner.hpp:544-568)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool sorted_less(const Sorted& a, const Sorted& b) {
-  return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
+__global__ void k_fix_segs(View v) {
+  Ctl* c = v.ctl;
+  const u32 nf = c->n_fix;
+  for (u32 f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    u32 n = v.fixcnt[f];
+    u32 start = atomicAdd(&c->n_ent, n);
+    if (start + n > v.cap_fix || start + n < start) { atomicOr(&c->error, E_BATCH); start = 0; n = 0; v.fixcnt[f] = 0; }
+    v.fixstart[f] = start;
+    v.fixpos[f] = start;
+  }
+}
+
+__device__ __forceinline__ void store_sorted(Sorted* p, u64 key, u32 slot, u32 seq) {
+  *reinterpret_cast<uint4*>(p) = make_uint4((u32)key, (u32)(key >> 32), slot, seq);
 }
 __device__ __forceinline__ Sorted load_sorted(const Sorted* p) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);
@@ -423,325 +590,89 @@ __device__ __forceinline__ Sorted load_sorted(const Sorted* p) {
   x.key = ((u64)q.y << 32) | q.x; x.slot = q.z; x.seq = q.w;
   return x;
 }
-__device__ __forceinline__ void store_sorted(Sorted* p, const Sorted& x) {
-  *reinterpret_cast<uint4*>(p) = make_uint4((u32)x.key, (u32)(x.key >> 32), x.slot, x.seq);
+// claims the next entry of ticket t's segment
+__device__ __forceinline__ Sorted* claim_entry(const View& v, u32 t) {
+  const u32 f = t - 1u;
+  const u32 p = atomicAdd(&v.fixpos[f], 1u);
+  if (p >= v.fixstart[f] + v.fixcnt[f]) { internal_error(v, 6, v.fixlp[f]); return nullptr; }
+  return v.sorted + p;
 }
 
-template <class M>
-struct Turn {
-  const View& v;
-  const typename M::Data& md;
-  u32 last_slot, last_time;
-  u32 st[M::kStateWords];
-  bool st_dirty;
-  u32 err;
-  u32 n_proc, n_undone, n_anti, n_annih, n_dup, n_requeued;
-  u32 tbound;      // first time beyond the current window
-
-  __device__ Turn(const View& v_, const typename M::Data& md_) : v(v_), md(md_) {}
-
-  __device__ __forceinline__ void emit_anti(u64 key, u32 dst, u32 src, u32 send) {
-    u32 pos = atomicAdd(&v.ctl->n_anti, 1u);
-    if (pos >= v.cap_aux) { err |= E_BATCH; return; }
-    Ev a;
-    a.key = key; a.dst = dst; a.src = src; a.send = send; a.p0 = 0; a.p1 = 0; a.flags = F_CANCEL;
-    store_ev(v.anti_box + pos, a);
-    ++n_anti;
-  }
-
-  // run the handler on the event in `slot`; out_idx = outbox position for its output
-  __device__ __forceinline__ void process(u32 slot, u32 out_idx) {
-    Ev e = load_ev(v.ev + slot);
-    u32 pre[M::kStateWords];
-#pragma unroll
-    for (int w = 0; w < M::kStateWords; ++w) pre[w] = st[w];
-    Ev out;
-    bool has = M::handle(md, e, st, out, err);
-    Meta m;
-    m.link = last_slot;
-    m.prevtime = last_time;
-    m.sent_dst = NIL;
-    m.snap = NIL;
-    m.sent_key = 0;
-    if (has) {
-      bool changed = false;
-#pragma unroll
-      for (int w = 0; w < M::kStateWords; ++w) changed |= (pre[w] != st[w]);
-      if (changed) {
-        // state saving: the pre-state goes to the snapshot ring (copy-on-change)
-        u32 s = atomicAdd(&v.ctl->snap_head, 1u);
-        if (s - v.ctl->snap_tail >= v.cap_snap) err |= E_SNAP;
-        u32 si = s % v.cap_snap;
-#pragma unroll
-        for (int w = 0; w < M::kStateWords; ++w) v.snap[(size_t)si * M::kStateWords + w] = pre[w];
-        m.snap = si;
-        st_dirty = true;
-      }
-      m.sent_dst = out.dst;
-      m.sent_key = out.key;
-      store_ev(v.outbox + out_idx, out);
-    } else {
-      // no event produced: nothing recorded, state update dropped (runner.hpp:552-553, quirk Q2)
-#pragma unroll
-      for (int w = 0; w < M::kStateWords; ++w) st[w] = pre[w];
-      v.outbox[out_idx].key = KEY_MAX;
-    }
-    store_meta(v.meta + slot, m);
-    v.pflag[slot] = P_PROCESSED;
-    last_slot = slot;
-    last_time = key_time(e.key);
-    ++n_proc;
-  }
-
-  // An undone event beyond the current window goes back to PENDING instead of being re-executed at once: a copy is
-  // appended to its calendar bucket (through the outbox) and the recorded slot dies. What lp::flush_buf does by
-  // lowering local_time_ (logical_process.hpp:145-156): the rolled-back events wait in the queue until the
-  // simulation reaches them again. Re-executing them eagerly would let every later arrival at this LP roll the
-  // same future back again (quadratic in a --diff_repeat cascade).
-  __device__ __forceinline__ void requeue(u32 slot) {
-    Ev e = load_ev(v.ev + slot);
-    e.flags = 0;
-    store_ev(v.outbox + extra_idx(), e);
-    v.pflag[slot] = P_DEAD;
-    ++n_requeued;
-  }
-
-  __device__ __forceinline__ u32 extra_idx() {
-    u32 pos = atomicAdd(&v.ctl->n_extra, 1u);
-    if (pos >= v.cap_aux) { err |= E_BATCH; pos = v.cap_aux - 1; }
-    return v.cap_batch + pos;
-  }
-
-  // seg[0..n) = the LP's arrivals of this round, sorted; old_slot/old_time = the LP's chain head before the round.
-  // Arrival i owns outbox entry i, so whatever k_exec may already have written for this LP is overwritten here.
-  __device__ void run(u32 lp, const Sorted* seg, u32 n, u32 old_slot, u32 old_time) {
-    err = 0; n_proc = n_undone = n_anti = n_annih = n_dup = n_requeued = 0;
-    tbound = v.ctl->bound_abs * v.bucket_ticks;
-    st_dirty = false;
-    last_slot = old_slot;
-    last_time = old_time;
-#pragma unroll
-    for (int w = 0; w < M::kStateWords; ++w) st[w] = v.state[(size_t)lp * M::kStateWords + w];
-
-    // 1. rollback
-    u32 U = NIL;   // undone events, ascending key order, linked through Meta::link
-    const u64 m = seg[0].key;
-    const u32 mtime = key_time(m);
-    if (last_slot != NIL && last_time >= mtime) {
-      u32 cur = last_slot, curtime = last_time;
-      bool any = false;
-      while (cur != NIL && curtime >= mtime) {
-        Ev e = load_ev(v.ev + cur);
-        if (e.key < m) break;
-        Meta mt = load_meta(v.meta + cur);
-        if (mt.sent_dst != NIL) emit_anti(mt.sent_key, mt.sent_dst, e.dst, key_time(e.key));
-        if (mt.snap != NIL) {
-#pragma unroll
-          for (int w = 0; w < M::kStateWords; ++w) st[w] = v.snap[(size_t)mt.snap * M::kStateWords + w];
-          st_dirty = true;
-        }
-        v.pflag[cur] = 0;
-        v.meta[cur].link = U;
-        U = cur;
-        cur = mt.link;
-        curtime = mt.prevtime;
-        ++n_undone;
-        any = true;
-      }
-      last_slot = cur;
-      last_time = curtime;
-      if (any) atomicAdd(&v.ctl->n_rollbacks, 1ull);
-    }
-
-    // 2 + 3. merge and execute
-    u32 ia = 0;
-    while (ia < n || U != NIL) {
-      u64 ka = ia < n ? seg[ia].key : KEY_MAX;
-      u64 ku = KEY_MAX;
-      if (U != NIL) ku = v.ev[U].key;
-      u64 k = ka < ku ? ka : ku;
-      u32 present = NIL;      // slot of the event currently in the queue under key k
-      u32 out_idx = NIL;
-      if (ku == k) {
-        present = U;
-        U = v.meta[present].link;
-      }
-      while (ia < n && seg[ia].key == k) {
-        const Sorted a = load_sorted(seg + ia);
-        const u32 my_out = a.seq & 0x7FFFFFFFu;
-        const u32 a_slot = a.slot;
-        if (a.seq & 0x80000000u) {
-          v.pflag[a_slot] = P_DEAD;                     // the anti-message itself is consumed
-          v.outbox[my_out].key = KEY_MAX;
-          if (present != NIL) {                         // erase (queue.hpp:87-90)
-            v.pflag[present] = P_DEAD;
-            present = NIL;
-            if (out_idx != NIL) { v.outbox[out_idx].key = KEY_MAX; out_idx = NIL; }
-            ++n_annih;
-          }
-        } else if (present == NIL) {
-          present = a_slot;                             // insert (queue.hpp:92)
-          out_idx = my_out;
-        } else {
-          v.pflag[a_slot] = P_DEAD;                     // duplicate key: second insert ignored
-          v.outbox[my_out].key = KEY_MAX;
-          ++n_dup;
-        }
-        ++ia;
-      }
-      if (present != NIL) {
-        // a re-executed (rolled back) event has no inbox position: its output goes to the extra region
-        if (key_time(k) < tbound) process(present, out_idx != NIL ? out_idx : extra_idx());
-        else requeue(present);
-      }
-    }
-
-    v.last[lp] = make_uint2(last_slot, last_time);
-    if (st_dirty) {
-#pragma unroll
-      for (int w = 0; w < M::kStateWords; ++w) v.state[(size_t)lp * M::kStateWords + w] = st[w];
-    }
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
-// exec_one — the plain case of an LP turn for ONE event: run the handler on the LP's current state, link the event
-// into the LP's processed chain behind its predecessor in key order, record the sent-log entry, write the produced
-// event to outbox entry i. This is the speculative form of runner::run_lp_aggr (runner.hpp:530-570): all events of
-// an LP are executed against the same state, which is exactly the sequential result as long as no invocation changes
-// the state (neither shipped application ever does). The moment one does, the LP is flagged and k_fixup re-executes
-// its whole turn sequentially — handlers that mutate state keep exact semantics.
-// ------------------------------------------------------------------------------------------------
-template <class M, bool kLinkLater = false>
-__device__ __forceinline__ void exec_one(const View& v, const typename M::Data& md, u32 i, u32 slot, Ev e, u32 lp,
-                                         u32 pred_slot, u32 pred_time, bool is_last, u32& err) {
-  e.flags = 0;
-  if (v.replay) {
-    // history replay (--diff_repeat, R13): the event was processed in the recorded run; its sent-log entry came with
-    // it. Only its place in the LP's processed chain is established, nothing is executed or sent.
-    Meta m = load_meta(v.meta + slot);
-    m.link = pred_slot;
-    m.prevtime = pred_time;
-    store_meta(v.meta + slot, m);
-    v.pflag[slot] = P_PROCESSED | P_HISTORY;
-    v.outbox[i].key = KEY_MAX;
-    if (is_last) v.last[lp] = make_uint2(slot, key_time(e.key));
-    return;
-  }
-  u32 st[M::kStateWords], pre[M::kStateWords];
-#pragma unroll
-  for (int q = 0; q < M::kStateWords; ++q) { st[q] = v.state[(size_t)lp * M::kStateWords + q]; pre[q] = st[q]; }
-  Ev out;
-  const bool has = M::handle(md, e, st, out, err);
-  bool changed = false;
-#pragma unroll
-  for (int q = 0; q < M::kStateWords; ++q) changed |= (pre[q] != st[q]);
-  if (has && changed) { flag_lp(v, lp, PL_MUTATED); return; }   // state-mutating handler
-  Meta m;
-  m.link = pred_slot;
-  m.prevtime = pred_time;
-  m.sent_dst = NIL;
-  m.snap = NIL;
-  m.sent_key = 0;
-  if (has) {
-    m.sent_dst = out.dst;
-    m.sent_key = out.key;
-    store_ev(v.outbox + i, out);
-  } else {
-    v.outbox[i].key = KEY_MAX;
-  }
-  // a meta record is not read again unless its LP rolls back: evict-first. Exception: the record of a long LP's event,
-  // whose chain link k_exec_heavy fills in right afterwards.
-  if (kLinkLater) store_meta(v.meta + slot, m); else store_meta_ef(v.meta + slot, m);
-  v.pflag[slot] = P_PROCESSED;
-  if (is_last) v.last[lp] = make_uint2(slot, key_time(e.key));
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_exec — one thread per EVENT of the window, in calendar (slot) order, so the event read and the meta / pflag /
-// outbox writes are coalesced streams; only the per-LP words are gathered. Skew-free: a hot LP's events are spread
-// over many threads.
-//   * LP with up to kLightMax arrivals: the thread walks the LP's arrival list (link records) to find its place in
-//     the LP's key order (R1): predecessor = largest smaller key, "last" = no larger key. The walk also finds the
-//     irregular turns — an anti-message, a duplicate key, or a key not later than the LP's newest processed event
-//     (straggler, R5) — which are left to the sequential lp_turn of k_fixup.
-//   * LP with more arrivals: the thread only drops (key, slot, arrival) into the LP's segment of `sorted`;
-//     k_sortheavy sorts the segment and k_exec_heavy executes it.
-// ------------------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
+__global__ void __launch_bounds__(256) k_fix_scatter(View v) {
   Ctl* c = v.ctl;
-  const u32 n_arr = c->n_arr;
-  u32 err = 0;
-  if (v.use_graph && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(v.h_vheavy, c->n_vheavy ? 1u : 0u);
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_arr; i += gridDim.x * blockDim.x) {
-    const u32 slot = slot_of_arrival(v, i);
-    const Ev e = load_ev(v.ev + slot);
-    const u32 lp = part_local(v, e.dst);
-    const uint4 h = v.lph[lp];
-    const u32 n = h.x & kCntMask;
-    const u32 anti = (e.flags & F_CANCEL) ? 0x80000000u : 0u;
-    if (n > v.light_max) {
-      // long LP: drop (key, slot, arrival) into the LP's segment and execute speculatively right here, where the
-      // event, meta and outbox accesses are coalesced; k_exec_heavy adds the processed-chain link afterwards
-      Sorted x;
-      x.key = e.key; x.slot = slot; x.seq = i | anti;
-      store_sorted(v.sorted + h.y + v.tmp_rank[i], x);
-      if (anti) { flag_lp(v, lp, PL_IRREGULAR); continue; }
-      if ((h.x >> kCntBits) & PL_FIX) continue;
-      exec_one<M, true>(v, md, i, slot, e, lp, NIL, 0u, false, err);
-      continue;
-    }
-    if ((h.x >> kCntBits) & PL_FIX) continue;             // handled by k_fixup
-    u32 pred_slot = h.z, pred_time = h.w;
-    bool is_last = true;
-    bool bad = anti != 0 || (h.z != NIL && key_time(e.key) <= h.w);
-    if (n > 1) {
-      u64 pk = 0;
-      bool have = false;
-      u32 k = h.y - 1u;
-      for (u32 step = 0; step < n && k != NIL31; ++step) {
-        const uint4 L = v.link[k];
-        if (k != i) {
-          const u64 tk = ((u64)L.y << 32) | L.x;
-          if (L.z >> 31) bad = true;
-          if (tk == e.key) bad = true;
-          else if (tk < e.key) {
-            if (!have || tk > pk) { pk = tk; pred_slot = L.w; have = true; }
-          } else {
-            is_last = false;
-          }
+  if (c->n_fix == 0) return;
+  const u32 n_arr = c->n_arr, n = n_arr + c->scan_total;
+  const u32 tbound = c->bound_abs * v.bucket_ticks;
+  u32 n_und = 0, n_anti = 0, err = 0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < n_arr) {
+      const u32 slot = slot_of_arrival(v, i);
+      const Ev e = load_ev(v.ev + slot);
+      const u32 t = ticket_of(v, part_local(v, e.dst));
+      if (!t) continue;
+      Sorted* p = claim_entry(v, t);
+      if (p) store_sorted(p, e.key, slot, (i + 1u) | ((e.flags & F_CANCEL) ? S_ANTI : 0u));
+    } else {
+      const u32 slot = slot_of_list(v, v.scan, c->n_scan, i - n_arr);
+      const unsigned char pf = v.pflag[slot];
+      if ((pf & (P_PROCESSED | P_DEAD)) != P_PROCESSED) continue;
+      const Ev e = load_ev(v.ev + slot);
+      const u32 lp = part_local(v, e.dst);
+      const u32 t = ticket_of(v, lp);
+      if (!t) continue;
+      // R5: undone = every processed event of the LP with key >= m. A recorded event behind the window is left in
+      // place (its LP's inv key marks it invalid; it is undone when the window reaches it).
+      const bool hist = (pf & P_HISTORY) != 0;
+      if (hist && key_time(e.key) >= tbound) continue;
+      if (!(e.key >= v.fixmin[t - 1u] || (hist && v.inv && e.key >= v.inv[lp]))) continue;
+      const Meta mt = load_meta(v.meta + slot);
+      if (mt.sent_dst != NIL) {      // the sent-log entry leaves as an anti-message (queue.hpp:99-105)
+        const u32 pos = atomicAdd(&c->n_anti, 1u);
+        if (pos >= v.cap_aux) err |= E_BATCH;
+        else {
+          Ev a;
+          a.key = mt.sent_key; a.dst = mt.sent_dst; a.src = e.dst; a.send = key_time(e.key); a.p0 = 0; a.p1 = 0; a.flags = F_CANCEL;
+          store_ev(v.anti_box + pos, a);
+          ++n_anti;
         }
-        k = L.z & 0x7FFFFFFFu;
       }
-      if (have) pred_time = key_time(pk);
+      v.pflag[slot] = 0;
+      atomicAdd(&v.fixund[t - 1u], 1u);
+      ++n_und;
+      Sorted* p = claim_entry(v, t);
+      if (p) store_sorted(p, e.key, slot, S_UNDONE | (mt.snap != NIL ? (mt.snap + 1u) & S_IDX : 0u));
     }
-    if (bad) { flag_lp(v, lp, PL_IRREGULAR); continue; }
-    exec_one<M>(v, md, i, slot, e, lp, pred_slot, pred_time, is_last, err);
+  }
+  n_und = warp_sum_u32(n_und);
+  n_anti = warp_sum_u32(n_anti);
+  if ((threadIdx.x & (kWarp - 1)) == 0) {
+    if (n_und) atomicAdd(&c->n_undone, (u64)n_und);
+    if (n_anti) atomicAdd(&c->n_antis, (u64)n_anti);
   }
   if (err) atomicOr(&c->error, err);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_sortheavy — segments longer than kRegSortSmall (the very hot LPs: at N GPUs PHOLD's hot LPs hold N times as
-// many events): one BLOCK of 256 threads per LP sorts the segment by (key, arrival order) (R1) and classifies it: an
-// anti-message, a duplicate key or a possible straggler makes the turn irregular (-> k_fixup); a plain turn gets its
-// processed-chain links right here, as in k_exec_heavy.
-// Hybrid bitonic network, R = 1, 2, 4 or 8 entries per thread in registers (entry index = tid + 256 r):
-//   partner distance < 32        register shuffle inside the warp
-//   32 <= distance < 256         exchange through a 4 KB shared-memory tile (the only shared-memory traffic:
-//                                3 of the log2(P) steps of a merge level — a pure shared-memory network is bound by
-//                                shared-memory bandwidth, measured 257 us per window for 10 500 segments of ~200)
-//   distance >= 256              the other register of the same thread
-// Longer than kBlockSortCap: one thread sorts in place (not reached by any shipped workload).
+// k_fix_sort — every segment sorted by (key, arrival order) (R1; an undone event precedes the arrivals under its key:
+// it was in the queue before them).
+//   n <= kWarpSortMax : one warp, bitonic network over register shuffles, 1 / 2 / 4 entries per lane
+//   n <= kSmemSortMax : one block, bitonic network in shared memory (all compare-exchanges ascending, so the
+//                       padding up to the next power of two needs no storage: pairs that reach beyond n are skipped)
+//   longer            : the same network in global memory
 // ------------------------------------------------------------------------------------------------
-constexpr u32 kBlockSortCap = 2048;
-constexpr int kSortThreads = 256;
-
-struct KS { u64 key; u32 slot, seq; };      // sort element: key, calendar slot, arrival index | anti << 31
+struct KS { u64 key; u32 slot, seq; };
 __device__ __forceinline__ bool ks_less(const KS& a, const KS& b) {
-  return a.key < b.key || (a.key == b.key && (a.seq & 0x7FFFFFFFu) < (b.seq & 0x7FFFFFFFu));
+  return a.key < b.key || (a.key == b.key && sorted_ord(a.seq) < sorted_ord(b.seq));
 }
+__device__ __forceinline__ KS ks_load(const uint4* p) {
+  const uint4 q = *p;
+  KS x;
+  x.key = ((u64)q.y << 32) | q.x; x.slot = q.z; x.seq = q.w;
+  return x;
+}
+__device__ __forceinline__ void ks_store(uint4* p, const KS& x) { *p = make_uint4((u32)x.key, (u32)(x.key >> 32), x.slot, x.seq); }
+
+#ifndef SSB_EMU
 __device__ __forceinline__ KS ks_shfl_xor(const KS& x, int m) {
   KS y;
   const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)x.key, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(x.key >> 32), m);
@@ -750,181 +681,6 @@ __device__ __forceinline__ KS ks_shfl_xor(const KS& x, int m) {
   y.seq = __shfl_xor_sync(0xffffffffu, x.seq, m);
   return y;
 }
-
-template <int R>
-__device__ __forceinline__ void block_sort_segment(const View& v, u32 lp, Sorted* seg, u32 n, uint4* tile, u64* s_last,
-                                                   u32* s_lslot, u32* s_flag, u64& s_first) {
-  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  KS x[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const u32 e = tid + ((u32)r << 8);
-    if (e < n) { const uint4 q = *reinterpret_cast<const uint4*>(seg + e); x[r].key = ((u64)q.y << 32) | q.x; x[r].slot = q.z; x[r].seq = q.w; }
-    else { x[r].key = KEY_MAX; x[r].slot = NIL; x[r].seq = 0x7FFFFFFFu; }
-  }
-  if (tid == 0) *s_flag = 0;
-#pragma unroll
-  for (u32 k2 = 2; k2 <= 256u * R; k2 <<= 1) {
-#pragma unroll
-    for (u32 j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-      if (j2 >= 256u) {
-        const u32 dr = j2 >> 8;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if ((r & dr) == 0) {
-            const bool asc = (((u32)r << 8) & k2) == 0;
-            const bool sw = asc ? ks_less(x[r | dr], x[r]) : ks_less(x[r], x[r | dr]);
-            if (sw) { const KS t = x[r]; x[r] = x[r | dr]; x[r | dr] = t; }
-          }
-        }
-      } else if (j2 >= 32u) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          tile[tid] = make_uint4((u32)x[r].key, (u32)(x[r].key >> 32), x[r].slot, x[r].seq);
-          __syncthreads();
-          const uint4 q = tile[tid ^ j2];
-          __syncthreads();
-          KS y;
-          y.key = ((u64)q.y << 32) | q.x; y.slot = q.z; y.seq = q.w;
-          const u32 e = tid + ((u32)r << 8);
-          const bool keep_min = ((tid & j2) == 0) == ((e & k2) == 0);
-          if (keep_min ? ks_less(y, x[r]) : ks_less(x[r], y)) x[r] = y;
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const KS y = ks_shfl_xor(x[r], (int)j2);
-          const u32 e = tid + ((u32)r << 8);
-          const bool keep_min = ((lane & j2) == 0) == ((e & k2) == 0);
-          if (keep_min ? ks_less(y, x[r]) : ks_less(x[r], y)) x[r] = y;
-        }
-      }
-    }
-  }
-  // every entry looks at the entry before it: duplicate key, and its predecessor in the LP's processed chain
-#pragma unroll
-  for (int r = 0; r < R; ++r) if (lane == 31) { s_last[r * 8 + warp] = x[r].key; s_lslot[r * 8 + warp] = x[r].slot; }
-  __syncthreads();
-  const uint4 h = v.lph[lp];
-  const bool fixed = ((h.x >> kCntBits) & PL_FIX) != 0;      // k_exec already sent the LP to k_fixup: only sort
-  u32 flag = 0;
-  u64 pkey[R];
-  u32 pslot[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const u32 e = tid + ((u32)r << 8);
-    const u32 lo = __shfl_up_sync(0xffffffffu, (u32)x[r].key, 1), hi = __shfl_up_sync(0xffffffffu, (u32)(x[r].key >> 32), 1);
-    pkey[r] = ((u64)hi << 32) | lo;
-    pslot[r] = __shfl_up_sync(0xffffffffu, x[r].slot, 1);
-    if (lane == 0 && e) {
-      const u32 w = warp ? r * 8 + warp - 1 : (r - 1) * 8 + 7;
-      pkey[r] = s_last[w]; pslot[r] = s_lslot[w];
-    }
-    if (e < n) {
-      flag |= x[r].seq >> 31;
-      if (e && pkey[r] == x[r].key) flag = 1;
-    }
-  }
-  if (tid == 0) s_first = x[0].key;
-  if (flag) *s_flag = 1;
-  __syncthreads();
-  bool irregular = *s_flag != 0;
-  if (h.z != NIL && key_time(s_first) <= h.w) irregular = true;      // possible straggler
-  if (irregular || fixed) {
-    // leave the sorted segment for the sequential lp_turn of k_fixup
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const u32 e = tid + ((u32)r << 8);
-      if (e < n) *reinterpret_cast<uint4*>(seg + e) = make_uint4((u32)x[r].key, (u32)(x[r].key >> 32), x[r].slot, x[r].seq);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
-      if (!fixed) flag_lp(v, lp, PL_IRREGULAR);
-    }
-  } else {
-    // plain turn: k_exec has run the handlers; add every event's place in the processed chain
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const u32 e = tid + ((u32)r << 8);
-      if (e < n) {
-        u32 ps = pslot[r], ptime = key_time(pkey[r]);
-        if (e == 0) { ps = h.z; ptime = h.w; }
-        *reinterpret_cast<uint2*>(v.meta + x[r].slot) = make_uint2(ps, ptime);
-        if (e + 1u == n) v.last[lp] = make_uint2(x[r].slot, key_time(x[r].key));
-      }
-    }
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(kSortThreads) k_sortheavy(View v) {
-  __shared__ uint4 tile[kSortThreads];
-  __shared__ u64 s_last[8 * 8];
-  __shared__ u32 s_lslot[8 * 8];
-  __shared__ u32 s_flag;
-  __shared__ u64 s_first;
-  Ctl* c = v.ctl;
-  const u32 nh = c->n_vheavy ? c->n_heavy : 0u;      // n_vheavy counts the segments longer than kRegSortSmall
-  if (nh == 0) return;
-  for (u32 h = blockIdx.x; h < nh; h += gridDim.x) {
-    const uint4 a = v.heavy[h];
-    const u32 lp = a.x, n = a.z;
-    if (n <= kRegSortSmall) continue;
-    Sorted* seg = v.sorted + a.y;
-    if (n <= 256) block_sort_segment<1>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
-    else if (n <= 512) block_sort_segment<2>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
-    else if (n <= 1024) block_sort_segment<4>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
-    else if (n <= kBlockSortCap) block_sort_segment<8>(v, lp, seg, n, tile, s_last, s_lslot, &s_flag, s_first);
-    else {
-      if (threadIdx.x == 0) {
-        u32 flag = 0;
-        for (u32 i = 1; i < n; ++i) {
-          Sorted x = seg[i];
-          u32 j = i;
-          while (j > 0) {
-            Sorted y = seg[j - 1];
-            if (!sorted_less(x, y)) break;
-            seg[j] = y;
-            --j;
-          }
-          if (j != i) seg[j] = x;
-        }
-        for (u32 i = 0; i < n; ++i) {
-          flag |= seg[i].seq >> 31;
-          if (i && seg[i - 1].key == seg[i].key) flag = 1;
-        }
-        const uint4 hh = v.lph[lp];
-        bool irregular = flag != 0 || (hh.z != NIL && key_time(seg[0].key) <= hh.w);
-        __threadfence();
-        atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
-        if ((hh.x >> kCntBits) & PL_FIX) irregular = false;      // already on the fix list
-        else if (irregular) flag_lp(v, lp, PL_IRREGULAR);
-        if (!irregular && !((hh.x >> kCntBits) & PL_FIX)) {
-          u32 ps = hh.z, pt = hh.w;
-          for (u32 i = 0; i < n; ++i) {
-            *reinterpret_cast<uint2*>(v.meta + seg[i].slot) = make_uint2(ps, pt);
-            ps = seg[i].slot; pt = key_time(seg[i].key);
-          }
-          v.last[lp] = make_uint2(ps, pt);
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_exec_heavy — one WARP per long LP (the hot LPs). k_exec has already run the handler for the LP's events, in the
-// coalesced pass; what is left is each event's place in the LP's key order (R1). The warp loads the segment
-// (key, slot, arrival) into registers — R entries per lane, R = 1, 2 or 4 — sorts it with a bitonic network over register
-// shuffles, and each entry reads its predecessor off its neighbour: processed-chain link -> 8-byte store into the
-// event's meta record, the last entry becomes the LP's chain head. An anti-message, a duplicate key or a possible
-// straggler makes the turn irregular: the sorted segment is written back for the sequential lp_turn of k_fixup
-// (also when k_exec flagged the LP because its handler changed the state). Segments longer than kRegSortSmall are
-// k_sortheavy's (one block per LP).
-// ------------------------------------------------------------------------------------------------
 // entry index = lane + 32 * r. Sorts 32 * R entries ascending.
 template <int R>
 __device__ __forceinline__ void warp_bitonic(KS (&x)[R], u32 lane) {
@@ -954,158 +710,297 @@ __device__ __forceinline__ void warp_bitonic(KS (&x)[R], u32 lane) {
     }
   }
 }
-
 template <int R>
-__device__ __forceinline__ void heavy_turn(const View& v, u32 lp, u32 start, u32 n, const uint4 h, u32 lane) {
-  const bool fixed = ((h.x >> kCntBits) & PL_FIX) != 0;      // k_exec already sent the LP to k_fixup: only sort
+__device__ __forceinline__ void warp_sort_segment(uint4* seg, u32 n, u32 lane) {
   KS x[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const u32 i = lane + ((u32)r << 5);
-    if (i < n) { const uint4 q = *reinterpret_cast<const uint4*>(v.sorted + start + i); x[r].key = ((u64)q.y << 32) | q.x; x[r].slot = q.z; x[r].seq = q.w; }
-    else { x[r].key = KEY_MAX; x[r].slot = NIL; x[r].seq = 0x7FFFFFFFu; }
+    if (i < n) x[r] = ks_load(seg + i);
+    else { x[r].key = KEY_MAX; x[r].slot = NIL; x[r].seq = S_IDX; }
   }
   warp_bitonic<R>(x, lane);
-  // neighbours: the entry before (index - 1) of every entry
-  u32 flag = 0;
-  u64 pkey[R];
-  u32 pslot[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    u32 lo = __shfl_up_sync(0xffffffffu, (u32)x[r].key, 1), hi = __shfl_up_sync(0xffffffffu, (u32)(x[r].key >> 32), 1);
-    u32 sl = __shfl_up_sync(0xffffffffu, x[r].slot, 1);
-    if (r > 0) {      // lane 0 takes the last lane's entry of the previous register
-      const u32 lo2 = __shfl_sync(0xffffffffu, (u32)x[r - 1].key, 31), hi2 = __shfl_sync(0xffffffffu, (u32)(x[r - 1].key >> 32), 31);
-      const u32 sl2 = __shfl_sync(0xffffffffu, x[r - 1].slot, 31);
-      if (lane == 0) { lo = lo2; hi = hi2; sl = sl2; }
-    }
-    pkey[r] = ((u64)hi << 32) | lo;
-    pslot[r] = sl;
-    const u32 i = lane + ((u32)r << 5);
-    if (i < n) {
-      flag |= x[r].seq >> 31;
-      if (i && pkey[r] == x[r].key) flag = 1;
-    }
-  }
-  const u64 first_key = ((u64)__shfl_sync(0xffffffffu, (u32)(x[0].key >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)x[0].key, 0);
-  bool irregular = __any_sync(0xffffffffu, flag != 0);
-  if (h.z != NIL && key_time(first_key) <= h.w) irregular = true;      // possible straggler
-  if (irregular || fixed) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const u32 i = lane + ((u32)r << 5);
-      if (i < n) *reinterpret_cast<uint4*>(v.sorted + start + i) = make_uint4((u32)x[r].key, (u32)(x[r].key >> 32), x[r].slot, x[r].seq);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence();
-      atomicOr(reinterpret_cast<u32*>(v.lph + lp), PL_SORTED << kCntBits);
-      if (!fixed) flag_lp(v, lp, PL_IRREGULAR);
-    }
-    return;
-  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const u32 i = lane + ((u32)r << 5);
-    if (i < n) {
-      u32 ps = pslot[r], ptime = key_time(pkey[r]);
-      if (i == 0) { ps = h.z; ptime = h.w; }
-      *reinterpret_cast<uint2*>(v.meta + x[r].slot) = make_uint2(ps, ptime);
-      if (i + 1u == n) v.last[lp] = make_uint2(x[r].slot, key_time(x[r].key));
-    }
+    if (i < n) ks_store(seg + i, x[r]);
   }
 }
+#endif
 
-__global__ void __launch_bounds__(256) k_exec_heavy(View v) {
-  Ctl* c = v.ctl;
-  const u32 nh = c->n_heavy;
-  const u32 lane = threadIdx.x & 31;
-  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (u32 hi = wid; hi < nh; hi += nw) {
-    const uint4 a = v.heavy[hi];
-    const u32 lp = a.x, start = a.y, n = a.z;
-    if (n > kRegSortSmall) continue;                  // k_sortheavy's
-    const uint4 h = v.lph[lp];
-    if (n <= 32) heavy_turn<1>(v, lp, start, n, h, lane);
-    else if (n <= 64) heavy_turn<2>(v, lp, start, n, h, lane);
-    else heavy_turn<4>(v, lp, start, n, h, lane);
-  }
-  if (v.use_graph) {
-    // the last block to finish knows the final fix list: it opens or closes the IF node around k_fixup
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(&c->heavy_blocks, 1u) == gridDim.x - 1) {
-        c->heavy_blocks = 0;
-        cudaGraphSetConditional(v.h_fix, *reinterpret_cast<volatile u32*>(&c->n_fix) ? 1u : 0u);
+// block-wide bitonic network over a[0..n) (shared or global memory), every compare-exchange ascending: the first
+// step of a merge level pairs i with its mirror inside the 2^k block, the following steps pair i with i ^ j
+__device__ __forceinline__ void block_bitonic(uint4* a, u32 n) {
+  u32 P = 1;
+  while (P < n) P <<= 1;
+  for (u32 k = 2; k <= P; k <<= 1) {
+    for (u32 j = k >> 1; j > 0; j >>= 1) {
+      const u32 mask = (j == (k >> 1)) ? (k - 1u) : j;
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        const u32 l = i ^ mask;
+        if (l > i && l < n) {
+          const KS x = ks_load(a + i), y = ks_load(a + l);
+          if (ks_less(y, x)) { ks_store(a + i, y); ks_store(a + l, x); }
+        }
       }
+      __syncthreads();
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_fixup — the LPs whose turn is not plain (anti-message, duplicate, straggler, state-mutating handler): one thread
-// per LP runs the exact sequential lp_turn. Long segments were sorted by k_sortheavy; a short one is collected
-// from the LP's arrival list and sorted here.
-// ------------------------------------------------------------------------------------------------
-template <class M>
-__global__ void k_fixup(View v, typename M::Data md) {
+__global__ void __launch_bounds__(kSortThreads) k_fix_sort(View v) {
+  __shared__ uint4 s_seg[kSmemSortMax];
   Ctl* c = v.ctl;
   const u32 nf = c->n_fix;
   if (nf == 0) return;
-  u64 n_proc = 0, n_undone = 0, n_anti = 0, n_annih = 0, n_dup = 0, n_redo = 0;
-  u32 err = 0;
-  const u32 lane = threadIdx.x & 31;
-  const u32 nthreads = gridDim.x * blockDim.x;
-  for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nf; base += nthreads) {
-    u32 k = base + lane;
-    if (k < nf) {
-      const u32 lp = v.fix[k];
-      const uint4 h = v.lph[lp];
-      const u32 n = h.x & kCntMask;
-      u32 s0;
-      if ((h.x >> kCntBits) & PL_SORTED) {
-        s0 = h.y;
-      } else {
-        Sorted loc[kLightMax];
-        u32 m = 0;
-        for (u32 a = h.y - 1u; a != NIL31 && m < kLightMax; ++m) {
-          const uint4 L = v.link[a];
-          loc[m].key = ((u64)L.y << 32) | L.x; loc[m].slot = L.w; loc[m].seq = a | (L.z & 0x80000000u);
-          a = L.z & 0x7FFFFFFFu;
-        }
-        if (m != n) internal_error(v, 3, lp);
-        for (u32 q = 1; q < m; ++q) {
-          Sorted x = loc[q];
-          u32 j = q;
-          while (j > 0 && sorted_less(x, loc[j - 1])) { loc[j] = loc[j - 1]; --j; }
-          loc[j] = x;
-        }
-        s0 = atomicAdd(&c->seg_cursor, m);
-        for (u32 q = 0; q < m; ++q) store_sorted(v.sorted + s0 + q, loc[q]);
-      }
-      n_redo += n;
-      Turn<M> t(v, md);
-      t.run(lp, v.sorted + s0, n, h.z, h.w);
-      n_proc += t.n_proc; n_undone += t.n_undone; n_anti += t.n_anti; n_annih += t.n_annih; n_dup += t.n_dup;
-      err |= t.err;
+  uint4* sorted = reinterpret_cast<uint4*>(v.sorted);
+#ifndef SSB_EMU
+  // short segments: one warp each
+  const u32 lane = threadIdx.x & 31u;
+  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 f = wid; f < nf; f += nw) {
+    const u32 start = v.fixstart[f], n = v.fixpos[f] - start;
+    if (n < 2 || n > kWarpSortMax) continue;
+    if (n <= 32) warp_sort_segment<1>(sorted + start, n, lane);
+    else if (n <= 64) warp_sort_segment<2>(sorted + start, n, lane);
+    else warp_sort_segment<4>(sorted + start, n, lane);
+  }
+  const u32 small_max = kWarpSortMax;
+#else
+  const u32 small_max = 1;
+#endif
+  // long segments: one block each
+  for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
+    const u32 start = v.fixstart[f], n = v.fixpos[f] - start;
+    if (n <= small_max) continue;
+    if (n <= kSmemSortMax) {
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) s_seg[i] = sorted[start + i];
+      __syncthreads();
+      block_bitonic(s_seg, n);
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) sorted[start + i] = s_seg[i];
+      __syncthreads();
+    } else {
+      __syncthreads();
+      block_bitonic(sorted + start, n);
     }
   }
-  __syncwarp();
-  n_proc = warp_sum_u64(n_proc);
-  n_redo = warp_sum_u64(n_redo);
-  n_undone = warp_sum_u64(n_undone);
-  n_anti = warp_sum_u64(n_anti);
-  n_annih = warp_sum_u64(n_annih);
-  n_dup = warp_sum_u64(n_dup);
-  if (lane == 0) {
-    if (n_proc != n_redo) atomicAdd(&c->n_processed, n_proc - n_redo);   // k_plan counted every arrival once
-    if (n_undone) atomicAdd(&c->n_undone, n_undone);
-    if (n_anti) atomicAdd(&c->n_antis, n_anti);
-    if (n_annih) atomicAdd(&c->n_annihilated, n_annih);
-    if (n_dup) atomicAdd(&c->n_dups, n_dup);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fix_turn — one warp per irregular LP; its segment holds the arrivals of the round and the undone events, sorted.
+//   A. merge (R4/R6, queue.hpp:82-96): per key, in arrival order: the undone event (if any) is present; a positive is
+//      inserted unless the key is present (else it is a duplicate and dies); an anti-message erases what is present
+//      (annihilation) and is consumed. Lanes work on different keys; a key group longer than one entry is walked by
+//      the lane of its first entry. Result per key: the surviving event and its outbox entry.
+//   B. state restore (R5, queue.hpp:286-290): the pre-state of the smallest undone event that changed the state.
+//   C. execute the survivors (R2, runner.hpp:544-568): speculatively in parallel against that state — exact unless an
+//      invocation changes the state; if one does, lane 0 redoes the turn sequentially with copy-on-change snapshots.
+//      A survivor behind the window (an undone event of a later bucket) goes back to PENDING: a copy is appended to
+//      its bucket through the outbox, the recorded slot dies — what lp::flush_buf achieves by lowering local_time_
+//      (logical_process.hpp:145-156).
+// ------------------------------------------------------------------------------------------------
+template <class M>
+struct TurnExec {
+  const View& v;
+  const typename M::Data& md;
+  u32 err;
+  __device__ TurnExec(const View& v_, const typename M::Data& md_) : v(v_), md(md_), err(0) {}
+
+  __device__ __forceinline__ u32 extra_idx() {
+    u32 pos = atomicAdd(&v.ctl->n_extra, 1u);
+    if (pos >= v.cap_aux) { err |= E_BATCH; pos = v.cap_aux - 1; }
+    return v.cap_batch + pos;
   }
-  if (err) atomicOr(&c->error, err);
+  // handler on a copy of `st`; returns true when the invocation changed the state (nothing is written then)
+  __device__ __forceinline__ bool try_process(u32 slot, u32 out_idx, const u32* st) {
+    const Ev e0 = load_ev(v.ev + slot);
+    Ev e = e0;
+    e.flags = 0;
+    u32 ls[M::kStateWords];
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) ls[w] = st[w];
+    Ev out;
+    const bool has = M::handle(md, e, ls, out, err);
+    if (has) {
+      bool changed = false;
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) changed |= (ls[w] != st[w]);
+      if (changed) return true;
+    }
+    Meta m;
+    m.sent_dst = NIL; m.snap = NIL; m.sent_key = 0;
+    if (has) { m.sent_dst = out.dst; m.sent_key = out.key; store_ev(v.outbox + out_idx, out); }
+    else v.outbox[out_idx].key = KEY_MAX;
+    store_meta(v.meta + slot, m);
+    v.pflag[slot] = P_PROCESSED;
+    return false;
+  }
+  // sequential form: the state evolves, the pre-state of a changing invocation goes to the snapshot ring
+  __device__ __forceinline__ void process_seq(u32 slot, u32 out_idx, u32* st, bool& dirty) {
+    Ev e = load_ev(v.ev + slot);
+    e.flags = 0;
+    u32 pre[M::kStateWords];
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) pre[w] = st[w];
+    Ev out;
+    const bool has = M::handle(md, e, st, out, err);
+    Meta m;
+    m.sent_dst = NIL; m.snap = NIL; m.sent_key = 0;
+    if (has) {
+      bool changed = false;
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) changed |= (pre[w] != st[w]);
+      if (changed) {
+        const u32 s = atomicAdd(&v.ctl->snap_head, 1u);
+        if (s - v.ctl->snap_tail >= v.cap_snap) err |= E_SNAP;
+        const u32 si = s % v.cap_snap;
+#pragma unroll
+        for (int w = 0; w < M::kStateWords; ++w) v.snap[(size_t)si * M::kStateWords + w] = pre[w];
+        m.snap = si;
+        dirty = true;
+      }
+      m.sent_dst = out.dst;
+      m.sent_key = out.key;
+      store_ev(v.outbox + out_idx, out);
+    } else {
+      // no event produced: nothing recorded, state update dropped (runner.hpp:552-553, quirk Q2)
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) st[w] = pre[w];
+      v.outbox[out_idx].key = KEY_MAX;
+    }
+    store_meta(v.meta + slot, m);
+    v.pflag[slot] = P_PROCESSED;
+  }
+  __device__ __forceinline__ void requeue(u32 slot) {
+    Ev e = load_ev(v.ev + slot);
+    e.flags = 0;
+    store_ev(v.outbox + extra_idx(), e);
+    v.pflag[slot] = P_DEAD;
+  }
+};
+
+template <class M>
+__global__ void __launch_bounds__(256) k_fix_turn(View v, typename M::Data md) {
+  Ctl* c = v.ctl;
+  const u32 nf = c->n_fix;
+  if (nf == 0) return;
+  const u32 lane = threadIdx.x & (kWarp - 1);
+  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = (gridDim.x * blockDim.x) / kWarp;
+  const u32 tbound = c->bound_abs * v.bucket_ticks;
+  TurnExec<M> T(v, md);
+  u32 s_proc = 0, s_arr = 0, s_annih = 0, s_dup = 0, s_rb = 0;
+  for (u32 f = wid; f < nf; f += nw) {
+    const u32 lp = v.fixlp[f];
+    const u32 start = v.fixstart[f], n = v.fixpos[f] - start;
+    const u64 m = v.fixmin[f];
+    const u32 n_und = v.fixund[f];
+    const Sorted* seg = v.sorted + start;
+    uint2* eo = v.ent_out + start;
+    // --- A. merge ---
+    u32 snap_pos = NIL;      // first (smallest key) undone entry that carries a snapshot
+    for (u32 i = lane; i < n; i += kWarp) {
+      const Sorted a = load_sorted(seg + i);
+      if (!(a.seq & S_UNDONE)) ++s_arr;
+      else if ((a.seq & S_IDX) && i < snap_pos) snap_pos = i;
+      if (i > 0 && seg[i - 1].key == a.key) { eo[i] = make_uint2(NIL, NIL); continue; }      // not the first entry of its key
+      u32 present = NIL, out_idx = NIL;
+      for (u32 j = i; j < n; ++j) {
+        const Sorted b = j == i ? a : load_sorted(seg + j);
+        if (b.key != a.key) break;
+        if (b.seq & S_UNDONE) {
+          present = b.slot;                               // was in the queue before the arrivals
+        } else if (b.seq & S_ANTI) {
+          v.pflag[b.slot] = P_DEAD;                       // the anti-message itself is consumed
+          v.outbox[(b.seq & S_IDX) - 1u].key = KEY_MAX;
+          if (present != NIL) {                           // erase (queue.hpp:87-90)
+            v.pflag[present] = P_DEAD;
+            if (out_idx != NIL) v.outbox[out_idx].key = KEY_MAX;
+            present = NIL; out_idx = NIL;
+            ++s_annih;
+          }
+        } else if (present == NIL) {
+          present = b.slot;                               // insert (queue.hpp:92)
+          out_idx = (b.seq & S_IDX) - 1u;
+        } else {
+          v.pflag[b.slot] = P_DEAD;                       // duplicate key: second insert ignored
+          v.outbox[(b.seq & S_IDX) - 1u].key = KEY_MAX;
+          ++s_dup;
+        }
+      }
+      eo[i] = make_uint2(present, out_idx);
+    }
+    __syncwarp();
+    // --- B. state restore ---
+    u32 st[M::kStateWords];
+#pragma unroll
+    for (int w = 0; w < M::kStateWords; ++w) st[w] = v.state[(size_t)lp * M::kStateWords + w];
+    bool dirty = false;
+    snap_pos = warp_min_u32(snap_pos);
+    if (snap_pos != NIL) {
+      const u32 si = (seg[snap_pos].seq & S_IDX) - 1u;
+#pragma unroll
+      for (int w = 0; w < M::kStateWords; ++w) st[w] = v.snap[(size_t)si * M::kStateWords + w];
+      dirty = true;
+    }
+    // --- C. execute ---
+    bool mutated = false;
+    u32 maxt1 = 0, n_exec = 0;
+    for (u32 i = lane; i < n; i += kWarp) {
+      const uint2 s = eo[i];
+      if (s.x == NIL) continue;
+      const u32 t = key_time(seg[i].key);
+      if (t >= tbound) { T.requeue(s.x); continue; }
+      u32 out_idx = s.y;
+      if (out_idx == NIL) { out_idx = T.extra_idx(); eo[i].y = out_idx; }      // a re-executed event has no inbox position
+      if (T.try_process(s.x, out_idx, st)) mutated = true;
+      ++n_exec;
+      maxt1 = t + 1u > maxt1 ? t + 1u : maxt1;
+    }
+    if (__any_sync(0xffffffffu, mutated)) {
+      __syncwarp();
+      if (lane == 0) {
+        for (u32 i = 0; i < n; ++i) {
+          const uint2 s = eo[i];
+          if (s.x == NIL || key_time(seg[i].key) >= tbound) continue;
+          T.process_seq(s.x, s.y, st, dirty);
+        }
+      }
+    }
+    s_proc += n_exec;
+    maxt1 = warp_max_u32(maxt1);
+    // --- finish: newest processed time, state, ticket, history validity ---
+    if (lane == 0) {
+      const u32 lt_old = v.lpw[lp].x;
+      const u64 inv_old = v.inv ? v.inv[lp] : KEY_MAX;
+      // recorded events behind the window that were valid so far: the rollback to m reaches them too (lazily)
+      const bool behind = v.inv && m < inv_old && lt_old > tbound;
+      const u64 low = m < inv_old ? m : inv_old;      // everything at or above `low` inside the window was undone
+      u32 base = lt_old;
+      if ((n_und || behind) && low != KEY_MAX) {
+        const u32 lt1 = key_time(low) + 1u;          // what is still processed lies below `low`
+        base = lt1 < lt_old ? lt1 : lt_old;
+      }
+      if (n_und) ++s_rb;
+      if (v.inv && m < inv_old && (n_und || behind)) {      // the recorded history of this LP is invalid from m on (R13)
+        if (inv_old == KEY_MAX) atomicAdd(&c->n_touched, 1u);
+        v.inv[lp] = m;
+      }
+      v.lpw[lp] = make_uint2(maxt1 > base ? maxt1 : base, 0u);
+      if (dirty) {
+#pragma unroll
+        for (int w = 0; w < M::kStateWords; ++w) v.state[(size_t)lp * M::kStateWords + w] = st[w];
+      }
+    }
+  }
+  s_proc = warp_sum_u32(s_proc); s_arr = warp_sum_u32(s_arr); s_annih = warp_sum_u32(s_annih); s_dup = warp_sum_u32(s_dup);
+  if (lane == 0) {
+    if (s_proc != s_arr) atomicAdd(&c->n_processed, (u64)s_proc - (u64)s_arr);   // k_plan counted every arrival once
+    if (s_annih) atomicAdd(&c->n_annihilated, (u64)s_annih);
+    if (s_dup) atomicAdd(&c->n_dups, (u64)s_dup);
+    if (s_rb) atomicAdd(&c->n_rollbacks, (u64)s_rb);
+  }
+  if (T.err) atomicOr(&c->error, T.err);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&c->n_fix_total, (u64)nf); atomicAdd(&c->n_fix_rounds, 1ull); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1115,6 +1010,8 @@ __global__ void k_fixup(View v, typename M::Data md) {
 // (block-aggregated). The appended event is at once part of the bucket's unconsumed tail, which is what the GVT
 // reduction looks at (R3: the destination's local time drops at once). Events at or beyond finish_time are never
 // executed nor committed (R8), so they are counted and dropped (GVT treats them as (finish_time, 0)).
+// Routing the output of arrival i also raises the sender's newest processed time (lpw[src].x) to the output's send
+// time = the receive time of the event that produced it: the straggler test of the next round's k_exec reads it.
 //   which: 0 = anti box, 1 = main + extra outbox, 2 = receive buffer, 3 = host-loaded staging (outbox[0..load_count))
 //   filter: 0 = all, 1 = anti-messages only, 2 = positives only (the receive side keeps antis ahead of positives)
 // ------------------------------------------------------------------------------------------------
@@ -1138,6 +1035,7 @@ __device__ __forceinline__ u32 wait_chunk(const View& v, const u32* entry) {
   return ch;
 }
 
+#ifndef SSB_EMU
 // --- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+/sm_100a) ---
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
@@ -1156,24 +1054,36 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
       "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
       :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#else
+__device__ __forceinline__ void mbar_init(u64*, u32) {}
+__device__ __forceinline__ void mbar_expect_tx(u64*, u32) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(u64*, u32) {}
+#endif
 
 // Each block stages one tile of the source (a contiguous run of 32-byte records) in shared memory with ONE TMA bulk
 // copy, builds the per-target histogram from the staged records, claims one range per target with a single global
 // atomic, and scatters the records from shared memory with 256-bit stores. Tiles are sized so that every block of
 // the persistent grid gets the same number of equally large tiles (no tail wave).
 __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 peer, u32 filter) {
+#ifdef SSB_EMU
+  alignas(128) static unsigned char smem_route[1 << 20];
+#else
   extern __shared__ __align__(128) unsigned char smem_route[];
+#endif
   __shared__ u64 s_bar;
   __shared__ u64 s_sent_min;
   __shared__ const Ev* s_seg[MAX_WORLD + 2];     // the source = a concatenation of up to world + 1 record runs
   __shared__ u32 s_off[MAX_WORLD + 3];
   __shared__ u32 s_nseg;
+  __shared__ u32 s_main;                         // which == 1: records [0, s_main) are outputs of arrivals
   Ctl* c = v.ctl;
   if (threadIdx.x == 0) {
     u32 ns = 0, tot = 0;
     auto add = [&](const Ev* p, u32 n) { if (n) { s_seg[ns] = p; s_off[ns] = tot; tot += n; ++ns; } };
+    s_main = 0;
     if (which == 0) add(v.anti_box, c->n_anti < v.cap_aux ? c->n_anti : v.cap_aux);
-    else if (which == 1) { add(v.outbox, c->n_arr); add(v.outbox + v.cap_batch, c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux); }
+    else if (which == 1) { s_main = c->n_arr; add(v.outbox, c->n_arr); add(v.outbox + v.cap_batch, c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux); }
     else if (which == 2) {
       if (v.p2p) {
         // own mailbox, all sources; `peer` = kind (1 = anti-message regions, integrated first; 0 = positives)
@@ -1197,6 +1107,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   __syncthreads();
   const u32 total = s_off[s_nseg];
   if (total == 0) return;
+  const u32 main_n = s_main;
   // equal tiles for all blocks: `passes` tiles of `tile` records each (tile is a multiple of 32 records = 1 KB)
   const u32 passes = (total + gridDim.x * kRouteTile - 1) / (gridDim.x * kRouteTile);
   u32 tile = (total + gridDim.x * passes - 1) / (gridDim.x * passes);
@@ -1251,6 +1162,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
           const u32 dst = h.z;
           if (dst >= v.n_lp) { atomicOr(&c->error, E_RANGE); continue; }
           const u32 tm = key_time(key);
+          // the output of arrival i: its sender has now processed an event at the output's send time
+          if (t0 + i < main_n) atomicMax(&v.lpw[part_local(v, h.w)].x, s_tile[i].send + 1u);
           const u32 owner = v.world > 1 ? part_owner(v, dst) : v.rank;
           u32 t;
           if (owner != v.rank) {
@@ -1344,10 +1257,15 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         if (ch == NIL) continue;
         const size_t slot = ((size_t)ch << v.ch_log) | (p & chm);
         st256_ef(v.ev + slot, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
-        v.pflag[slot] = 0;
-        if (which == 3 && v.replay) {      // history load: the recorded sent-log entry becomes the event's meta record
+        if (which == 3 && v.replay) {
+          // history load (--diff_repeat, R13): the event was processed in the recorded run; its recorded sent-log
+          // entry becomes its meta record
           const uint4 sr = v.hist_sent[t0 + i];
-          st256(v.meta + slot, NIL, 0u, sr.x, NIL, sr.y, sr.z, 0u, 0u);
+          store_meta(v.meta + slot, Meta{sr.x, NIL, ((u64)sr.z << 32) | sr.y});
+          v.pflag[slot] = P_PROCESSED | P_HISTORY;
+          atomicMax(&v.lpw[part_local(v, qa.z)].x, tm + 1u);
+        } else {
+          v.pflag[slot] = 0;
         }
       } else {
         const u32 r = t - rs - 1;
@@ -1435,12 +1353,15 @@ __global__ void k_hist_stage(View v, const Ev* in, u32 n) {
   if (blockIdx.x == 0 && threadIdx.x == 0) v.ctl->load_count = n;
 }
 
-// after the history replay: back to "nothing has run yet", with the history in place as processed events
-__global__ void k_after_replay(View v) {
+// after the history load: every recorded event counts as consumed (processed); the last bucket with history
+__global__ void k_after_history(View v) {
   Ctl* c = v.ctl;
-  c->gvt = 0; c->local_min = KEY_MAX; c->prev_gvt = KEY_MAX; c->stall = 0;
-  c->done = 0; c->round = 0; c->n_processed = 0; c->load_count = 0;
-  c->rq_head = 0; c->rq_tail = 0;
+  for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < v.nb; b += gridDim.x * blockDim.x) {
+    const u32 f = v.fill[b];
+    v.consumed[b] = f;
+    if (f) atomicMax(&c->hist_end, b + 1u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = 0;
 }
 
 // committed log record (device Ev with flags = tag) -> ssb_record (6 x int64)
@@ -1460,7 +1381,7 @@ __global__ void k_unpack_log(const Ev* log, u64 first, u32 n, long long* out) {
 __global__ void k_fill_u32(u32* p, u32 val, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
 }
-__global__ void k_fill_u2(uint2* p, uint2 val, size_t n) {
+__global__ void k_fill_u64(u64* p, u64 val, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
 }
 __global__ void k_iota_u32(u32* p, u32 start, size_t n) {

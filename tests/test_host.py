@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = ssb.load_library()
     for n in sorted(names):
         assert hasattr(lib, n), f"libscalesim_b200.so does not export {n}"
-    assert lib.ssb_abi_version() == 1
+    assert lib.ssb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

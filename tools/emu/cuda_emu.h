@@ -1,0 +1,89 @@
+// cuda_emu.h — DEVELOPER TOOL, never shipped and never loadable by the product (scalesim_b200/capi.py has no switch
+// for it): a sequential host emulation of the CUDA constructs the kernels in scalesim_b200/csrc use, so that their
+// LOGIC can be exercised with gdb / asan on a machine without a GPU (tools/emu/build.sh compiles ssb_engine.cu with
+// g++ -DSSB_EMU into tools/emu/libssb_emu.so). Every kernel runs as ONE block of ONE thread ("warp" of one lane):
+// grid-stride loops visit every element, atomics are plain read-modify-writes, barriers and fences are no-ops.
+// It finds logic errors, not races; parity claims are made on the B200 only.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+#define __launch_bounds__(...)
+
+struct uint2 { unsigned int x, y; };
+struct alignas(16) uint4 { unsigned int x, y, z, w; };
+inline uint2 make_uint2(unsigned int x, unsigned int y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
+struct dim3 { unsigned int x = 1, y = 1, z = 1; };
+inline dim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
+
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { T o = *p; *p = o - v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicXor(T* p, T v) { T o = *p; *p = o ^ v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <class T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+template <class T> inline T atomicAdd_system(T* p, T v) { return atomicAdd(p, v); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T> inline T __shfl_sync(unsigned, T v, int) { return v; }
+inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+inline bool __any_sync(unsigned, bool p) { return p; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline void __syncthreads() {}
+inline void __syncwarp() {}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline void __nanosleep(unsigned) {}
+
+typedef unsigned long long cudaGraphConditionalHandle;
+inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
+
+// ---- the slice of the runtime API that ssb_engine.cu uses: host memory, no streams ----
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated runtime error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+typedef void* cudaStream_t;
+struct cudaEmuEvent { std::chrono::steady_clock::time_point t; };
+typedef cudaEmuEvent* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+constexpr unsigned cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDisableTiming = 2;
+struct cudaDeviceProp { int multiProcessorCount; };
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 1; return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new cudaEmuEvent(); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
