@@ -50,11 +50,11 @@ CONFIG2 = dict(n_lp=1_000_000, n_init=16_000_000, remote=0.1, committed=72_823_2
 CONFIG4 = dict(n_lp=16_000_000, n_init=256_000_000, remote=0.5, committed=1_165_396_484, name="BASELINE.json config 4")
 
 
-# kernels per round inside the window-loop graph: plan, commit, exec, route = 4; N > 1 adds k_gvt and the two
+# kernels per round inside the window-loop graph: plan, commit, exec, route, post = 5; N > 1 adds k_gvt and the two
 # receive-side routes; a round with an irregular LP turn (ssb_stats.fix_rounds) adds the IF node's six kernels:
 # k_fix_count, k_fix_segs, k_fix_scatter, k_fix_sort, k_fix_turn, k_route(anti).
 def launches(st, world):
-    return int(st.rounds * (4 + (3 if world > 1 else 0)) + st.fix_rounds * 6)
+    return int(st.rounds * (5 + (3 if world > 1 else 0)) + st.fix_rounds * 6)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -150,7 +150,7 @@ struct View {
   u32* state;       // [n_lp_local * state_words]
   u64* inv;         // exact-differential repeat only (else null): recorded events of the LP with key >= inv[lp] are invalid
   // per round
-  u32* hset;           // [hcap] (LP, key) fingerprints of the window's arrivals: round stamp << 24 | 24-bit fingerprint
+  u32* hset;           // [hcap] 32-bit fingerprints of the window's (LP, key) pairs; all zero between rounds
   u32 hmask;           // hcap - 1 (hcap is a power of two >= 2 * cap_batch)
   // irregular turns (anti-message, duplicate, straggler, state-mutating handler, invalidated history)
   u32* fixlp;          // [n_lp_local] fix table: LP of ticket f

@@ -118,7 +118,7 @@ struct ssb_engine {
   u32* d_state0 = nullptr;
   // kernel timing
   enum { K_MIN, K_PLAN, K_COMMIT, K_EXEC, K_HIST_FLAG, K_FIX_COUNT, K_FIX_SEGS, K_FIX_SCATTER, K_FIX_SORT, K_FIX_TURN,
-         K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_COUNT };
+         K_ROUTE_ANTI, K_ROUTE, K_ROUTE_RECV, K_POST, K_COUNT };
   struct Timed { int id; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -505,6 +505,9 @@ int ssb_engine::enqueue_round() {
   t_end();
   launch_fix(v, true);
   launch_route(v, 1, 0, 0);
+  t_begin(K_POST);
+  SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, v);
+  t_end();
   CK(cudaGetLastError());
   ++rounds;
   return exchange();
@@ -583,6 +586,7 @@ int ssb_engine::build_graph() {
   CK(add_cond(body, vg.h_fix, cudaGraphCondTypeIf, join, &n_if_fix, &b_fix));
   CK(capture(b_fix, {}, nullptr, [&] { launch_fix(vg, false); }));
   CK(capture(body, {n_if_fix}, nullptr, [&] { launch_route(vg, 1, 0, 0); }));
+  CK(capture(body, {n_if_fix}, nullptr, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vg); }));      // next to k_route
   CK(cudaGetLastError());
   CK(cudaGraphInstantiate(&graph_exec, graph, 0));
   graph_dirty = false;
@@ -1164,7 +1168,7 @@ int ssb_kernel_times(ssb_engine* e, const char** names, double* total_ms, int64_
   if (!e || !names || !total_ms || !launches) return 0;
   static const char* kNames[ssb_engine::K_COUNT] = {"k_min", "k_plan", "k_commit", "k_exec", "k_hist_flag", "k_fix_count",
                                                     "k_fix_segs", "k_fix_scatter", "k_fix_sort", "k_fix_turn",
-                                                    "k_route(anti)", "k_route", "k_route(recv)"};
+                                                    "k_route(anti)", "k_route", "k_route(recv)", "k_post"};
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   e->t_collect();

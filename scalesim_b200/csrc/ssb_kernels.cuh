@@ -88,10 +88,15 @@ __device__ __forceinline__ u32 warp_max_u32(u32 v) {
 // Replaces scheduler::min_locals (process_scheduler.hpp:83-90) + the local half of mpi_gsync::check_sync
 // (global_sync.hpp:95-150).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_local_min(const View& v, Ctl* c, u64* sm) {
+constexpr u32 kPlanBuckets = 2048;      // calendars up to this size are staged in shared memory by k_plan
+// s_fill / s_cons: optional shared-memory copies of the calendar counters (null = not staged)
+__device__ __forceinline__ void block_local_min(const View& v, Ctl* c, u64* sm, u32* s_fill = nullptr, u32* s_cons = nullptr) {
   u64 m = KEY_MAX;
-  for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x)
-    if (v.fill[b] != v.consumed[b]) { u64 k = make_key(b * v.bucket_ticks, 0); m = k < m ? k : m; }
+  for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x) {
+    const u32 f = v.fill[b], cs = v.consumed[b];
+    if (s_fill) { s_fill[b] = f; s_cons[b] = cs; }
+    if (f != cs) { u64 k = make_key(b * v.bucket_ticks, 0); m = k < m ? k : m; }
+  }
   m = warp_min_u64(m);
   if ((threadIdx.x & (kWarp - 1)) == 0) sm[threadIdx.x / kWarp] = m;
   __syncthreads();
@@ -171,14 +176,23 @@ __global__ void k_gvt(View v) {
 __global__ void k_plan(View v, int use_global_gvt) {
   __shared__ u64 sm[32];
   __shared__ __align__(16) u32 s_words[(sizeof(Ctl) + 3) / 4];
+  __shared__ u32 s_fill[kPlanBuckets], s_cons[kPlanBuckets];
   Ctl* c = reinterpret_cast<Ctl*>(s_words);
   constexpr u32 kWords = (u32)(sizeof(Ctl) / 4);
   static_assert(sizeof(Ctl) % 4 == 0, "Ctl is copied word-wise");
   for (u32 w = threadIdx.x; w < kWords; w += blockDim.x) s_words[w] = reinterpret_cast<const u32*>(v.ctl)[w];
+  // the calendar counters come into shared memory with one coalesced pass, so that the serial bookkeeping below does
+  // not pay a global round trip per bucket it looks at
+  const bool staged = v.nb <= kPlanBuckets;
   __syncthreads();
   if (!use_global_gvt) {     // single partition: the min-reduction is fused here
-    block_local_min(v, c, sm);
+    block_local_min(v, c, sm, staged ? s_fill : nullptr, staged ? s_cons : nullptr);
+  } else if (staged) {
+    for (u32 b = threadIdx.x; b < v.nb; b += blockDim.x) { s_fill[b] = v.fill[b]; s_cons[b] = v.consumed[b]; }
   }
+  __syncthreads();
+  const u32* fillp = staged ? s_fill : v.fill;
+  const u32* consp = staged ? s_cons : v.consumed;
   if (threadIdx.x == 0) {
     u64 gvt = use_global_gvt ? c->gvt : c->local_min;
     c->gvt = gvt;
@@ -192,7 +206,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     // commit list (a recorded history that was never re-executed is not committed: k_commit skips P_HISTORY)
     u32 nc = 0, tot = 0;
     for (u32 b = c->commit_next; b < cur; ++b) {
-      u32 f = v.fill[b];
+      u32 f = fillp[b];
       if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
     }
     c->commit_next = cur > c->commit_next ? cur : c->commit_next;
@@ -208,14 +222,14 @@ __global__ void k_plan(View v, int use_global_gvt) {
       u32 shi = cur + v.window < fin_b ? cur + v.window : fin_b;
       if (c->hi_bound > shi) shi = c->hi_bound < fin_b ? c->hi_bound : fin_b;
       for (u32 b = cur; b < shi; ++b) {
-        const u32 cons = v.consumed[b];
+        const u32 cons = consp[b];
         if (cons) { v.scan[ns++] = make_uint4(b, 0u, cons, stot); stot += cons; }
       }
       // gather list
       bound = cur + v.window < fin_b ? cur + v.window : fin_b;
       for (u32 b = cur; b < bound; ++b) {
-        const u32 cons = v.consumed[b];
-        u32 avail = v.fill[b] - cons;
+        const u32 cons = consp[b];
+        u32 avail = fillp[b] - cons;
         if (!avail) continue;
         u32 take = avail < v.cap_batch - total ? avail : v.cap_batch - total;
         if (take) {
@@ -411,25 +425,20 @@ __device__ __forceinline__ void flag_lp(const View& v, u32 lp) {
 }
 
 // Duplicate detection (R1: "same key twice at one LP = one event", queue.hpp:92) without per-LP lists: every plain
-// arrival inserts a fingerprint of (LP, key) into the round's hash set (open addressing, linear probing). Entries
-// carry the round number in their top byte, so the table is never cleared: an entry of another round is free.
-// The table region used by a round is sized by the round's arrivals (Ctl::hmask_round), so it stays L2-resident.
+// arrival inserts a 32-bit fingerprint of (LP, key) into the round's hash set (open addressing, linear probing, ONE
+// atomic per probe). The table region used by a round is sized by the round's arrivals (Ctl::hmask_round), so it stays
+// L2-resident; k_post clears it again behind k_exec, off the critical path.
 // Returns false when the same fingerprint is already there (duplicate SUSPECT: the LP takes the exact irregular
 // turn) or the probe sequence gets too long. Two arrivals with the same (LP, key) follow the same probe sequence,
 // and occupied slots stay occupied during a round, so at most one of them can return true.
-__device__ __forceinline__ bool hash_insert(const View& v, u32 lp, u64 key, u32 stamp, u32 hmask) {
+__device__ __forceinline__ bool hash_insert(const View& v, u32 lp, u64 key, u32 hmask) {
   const u64 h = mix64(key ^ ((u64)lp * 0x9E3779B97F4A7C15ULL));
-  const u32 fp = stamp | ((u32)(h >> 40) & 0x00FFFFFEu) | 1u;      // never 0 (0 = slot never used)
+  const u32 fp = (u32)(h >> 32) | 1u;      // never 0 (0 = free slot)
   u32 pos = (u32)h & hmask;
   for (u32 probe = 0; probe < kHashProbes; ++probe) {
-    u32 cur = *reinterpret_cast<volatile u32*>(v.hset + pos);
-    for (;;) {
-      if (cur == fp) return false;
-      if ((cur & 0xFF000000u) == stamp && cur != 0u) break;          // taken by another arrival of this round
-      const u32 old = atomicCAS(v.hset + pos, cur, fp);
-      if (old == cur) return true;
-      cur = old;
-    }
+    const u32 old = atomicCAS(v.hset + pos, 0u, fp);
+    if (old == 0u) return true;
+    if (old == fp) return false;
     pos = (pos + 1u) & hmask;
   }
   return false;
@@ -443,7 +452,7 @@ __device__ __forceinline__ bool hash_insert(const View& v, u32 lp, u64 key, u32 
 // shipped application ever does) and the LP's turn is plain:
 //   * no anti-message among its arrivals                                   (R4/R6, queue.hpp:87-90)
 //   * no arrival at or before the time of its newest processed event       (straggler, R5, queue.hpp:98-105);
-//     lpw[lp].x is stable during the pass — k_route raises it afterwards, from the send time of every output
+//     lpw[lp].x is stable during the pass — k_post raises it afterwards, from the send time of every output
 //   * no key twice                                                          (R1, queue.hpp:92)
 // Otherwise the LP is flagged and k_fix_* redo its whole turn exactly (whatever this pass wrote for the LP's other
 // arrivals is overwritten: arrival i owns outbox entry i). Skew-free: a hot LP's events are spread over many threads.
@@ -467,7 +476,6 @@ template <class M>
 __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
   Ctl* c = v.ctl;
   const u32 n_arr = c->n_arr;
-  const u32 stamp = (c->round & 0xFFu) << 24;
   const u32 hmask = c->hmask_round;
   u32 err = 0;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_arr; i += gridDim.x * blockDim.x) {
@@ -477,7 +485,7 @@ __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
     const uint2 w = __ldcg(reinterpret_cast<const uint2*>(v.lpw + lp));
     if (w.y) continue;                                   // the LP already has a ticket: k_fix_turn runs its turn
     bool bad = (e.flags & F_CANCEL) != 0 || key_time(e.key) < w.x;
-    if (!bad) bad = !hash_insert(v, lp, e.key, stamp, hmask);
+    if (!bad) bad = !hash_insert(v, lp, e.key, hmask);
     if (bad) { flag_lp(v, lp); continue; }
     Ev out;
     bool has;
@@ -506,6 +514,31 @@ __global__ void __launch_bounds__(256) k_exec(View v, typename M::Data md) {
         cudaGraphSetConditional(v.h_fix, (nf || (v.inv && c->n_touched)) ? 1u : 0u);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_post — bookkeeping behind k_exec, off the critical path (in the graph it runs next to k_route):
+//   * the output of arrival i raises its sender's newest processed time (lpw[src].x) to the output's send time = the
+//     receive time of the event that produced it; the straggler test of the next round's k_exec reads it. (An event
+//     whose handler produced nothing leaves no trace here: it had no effect, so nothing ever needs to undo it. The
+//     LPs of irregular turns got their value from k_fix_turn.)
+//   * the hash-set region the round used is cleared again.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_post(View v) {
+  Ctl* c = v.ctl;
+  const u32 n_arr = c->n_arr;
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (u32 i = tid; i < n_arr; i += nth) {
+    const uint4 h = *reinterpret_cast<const uint4*>(v.outbox + i);      // key lo, key hi, dst, src
+    if ((h.x & h.y) == 0xFFFFFFFFu) continue;                            // KEY_MAX: no output
+    const u32 send = v.outbox[i].send;
+    atomicMax(&v.lpw[part_local(v, h.w)].x, send + 1u);
+  }
+  if (n_arr) {
+    uint4* hs = reinterpret_cast<uint4*>(v.hset);
+    const u32 nq = (c->hmask_round + 1u) >> 2;
+    for (u32 i = tid; i < nq; i += nth) hs[i] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -1010,8 +1043,6 @@ __global__ void __launch_bounds__(256) k_fix_turn(View v, typename M::Data md) {
 // (block-aggregated). The appended event is at once part of the bucket's unconsumed tail, which is what the GVT
 // reduction looks at (R3: the destination's local time drops at once). Events at or beyond finish_time are never
 // executed nor committed (R8), so they are counted and dropped (GVT treats them as (finish_time, 0)).
-// Routing the output of arrival i also raises the sender's newest processed time (lpw[src].x) to the output's send
-// time = the receive time of the event that produced it: the straggler test of the next round's k_exec reads it.
 //   which: 0 = anti box, 1 = main + extra outbox, 2 = receive buffer, 3 = host-loaded staging (outbox[0..load_count))
 //   filter: 0 = all, 1 = anti-messages only, 2 = positives only (the receive side keeps antis ahead of positives)
 // ------------------------------------------------------------------------------------------------
@@ -1076,14 +1107,12 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   __shared__ const Ev* s_seg[MAX_WORLD + 2];     // the source = a concatenation of up to world + 1 record runs
   __shared__ u32 s_off[MAX_WORLD + 3];
   __shared__ u32 s_nseg;
-  __shared__ u32 s_main;                         // which == 1: records [0, s_main) are outputs of arrivals
   Ctl* c = v.ctl;
   if (threadIdx.x == 0) {
     u32 ns = 0, tot = 0;
     auto add = [&](const Ev* p, u32 n) { if (n) { s_seg[ns] = p; s_off[ns] = tot; tot += n; ++ns; } };
-    s_main = 0;
     if (which == 0) add(v.anti_box, c->n_anti < v.cap_aux ? c->n_anti : v.cap_aux);
-    else if (which == 1) { s_main = c->n_arr; add(v.outbox, c->n_arr); add(v.outbox + v.cap_batch, c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux); }
+    else if (which == 1) { add(v.outbox, c->n_arr); add(v.outbox + v.cap_batch, c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux); }
     else if (which == 2) {
       if (v.p2p) {
         // own mailbox, all sources; `peer` = kind (1 = anti-message regions, integrated first; 0 = positives)
@@ -1107,7 +1136,6 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   __syncthreads();
   const u32 total = s_off[s_nseg];
   if (total == 0) return;
-  const u32 main_n = s_main;
   // equal tiles for all blocks: `passes` tiles of `tile` records each (tile is a multiple of 32 records = 1 KB)
   const u32 passes = (total + gridDim.x * kRouteTile - 1) / (gridDim.x * kRouteTile);
   u32 tile = (total + gridDim.x * passes - 1) / (gridDim.x * passes);
@@ -1162,8 +1190,6 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
           const u32 dst = h.z;
           if (dst >= v.n_lp) { atomicOr(&c->error, E_RANGE); continue; }
           const u32 tm = key_time(key);
-          // the output of arrival i: its sender has now processed an event at the output's send time
-          if (t0 + i < main_n) atomicMax(&v.lpw[part_local(v, h.w)].x, s_tile[i].send + 1u);
           const u32 owner = v.world > 1 ? part_owner(v, dst) : v.rank;
           u32 t;
           if (owner != v.rank) {
