@@ -19,7 +19,7 @@ struct device_model<phold> {
     out.p0 = e.num_hops(); out.p1 = 0; out.flags = e.is_cancel() ? 1 : 0;
   }
   static int state_words() { return 2; }
-  static void pack_state(const phold::State& s, uint32_t* w) {
+  static void pack_state(const phold::State& s, uint32_t* w, context&) {
     w[0] = (uint32_t)((uint64_t)s.id() & 0xFFFFFFFFull); w[1] = (uint32_t)((uint64_t)s.id() >> 32);
   }
   // exact-differential store: PHOLD events carry no references into model data

@@ -12,8 +12,8 @@
 namespace scalesim {
 template <>
 struct device_model<traffic_sim> {
-  static const int kMaxRoads = 4;   // TrafficModel::kMaxRoads
-  struct context { std::vector<int64_t> route_pool; };
+  static const int kInlineRoads = 2;   // TrafficModel::kInlineRoads
+  struct context { std::vector<int64_t> route_pool, road_table; };
   static int model_id() { return SSB_MODEL_TRAFFIC; }
   // shortest possible hop: length >= 1 m, so len*3600/speed/1000 >= 0, plus the fixed 5 s (traffic_sim.hpp:314-316)
   static long default_bucket_ticks() { return 5; }
@@ -28,16 +28,25 @@ struct device_model<traffic_sim> {
     out.flags = e.is_cancel() ? 1 : 0;
     cx.route_pool.insert(cx.route_pool.end(), route.begin(), route.end());
   }
-  static int state_words() { return 2 + 3 * kMaxRoads; }
-  static void pack_state(const traffic_sim::State& s, uint32_t* w) {
+  static int state_words() { return 2 + 3 * kInlineRoads; }
+  // up to kInlineRoads out-roads sit in the state words; a junction with more keeps them in the road table (model
+  // data slot 1) and its state holds the index of its first road there — any junction degree (the reference's State
+  // holds unbounded vectors, traffic_sim.hpp:99-142)
+  static void pack_state(const traffic_sim::State& s, uint32_t* w, context& cx) {
     // serialize order: id_, destinations_, speed_limit_, num_lanes_, road_length_
     field_capture fc = capture_fields(s);
     const std::vector<long>&dst = fc.vectors.at(0), &speed = fc.vectors.at(1), &len = fc.vectors.at(3);
-    if (dst.size() > (size_t)kMaxRoads) throw std::runtime_error("junction with more out-roads than the device model supports");
     for (int i = 0; i < state_words(); ++i) w[i] = 0;
     w[0] = (uint32_t)s.id(); w[1] = (uint32_t)dst.size();
-    for (size_t i = 0; i < dst.size(); ++i) {
-      w[2 + 3 * i] = (uint32_t)dst[i]; w[3 + 3 * i] = (uint32_t)speed[i]; w[4 + 3 * i] = (uint32_t)len[i];
+    if (dst.size() <= (size_t)kInlineRoads) {
+      for (size_t i = 0; i < dst.size(); ++i) {
+        w[2 + 3 * i] = (uint32_t)dst[i]; w[3 + 3 * i] = (uint32_t)speed[i]; w[4 + 3 * i] = (uint32_t)len[i];
+      }
+    } else {
+      w[2] = (uint32_t)(cx.road_table.size() / 3);
+      for (size_t i = 0; i < dst.size(); ++i) {
+        cx.road_table.push_back(dst[i]); cx.road_table.push_back(speed[i]); cx.road_table.push_back(len[i]);
+      }
     }
   }
   // exact-differential store: the recorded events index into the route pool, so it travels with the history
@@ -45,7 +54,9 @@ struct device_model<traffic_sim> {
   static void restore_model_data(context& cx, const std::vector<int64_t>& blob) { cx.route_pool = blob; }
   static int upload_model_data(ssb_engine* e, context& cx) {
     if (cx.route_pool.empty()) cx.route_pool.push_back(0);
-    return ssb_set_model_data(e, 0, cx.route_pool.data(), cx.route_pool.size() * sizeof(int64_t));
+    int rc = ssb_set_model_data(e, 0, cx.route_pool.data(), cx.route_pool.size() * sizeof(int64_t));
+    if (rc || cx.road_table.empty()) return rc;
+    return ssb_set_model_data(e, 1, cx.road_table.data(), cx.road_table.size() * sizeof(int64_t));
   }
 };
 }  // namespace scalesim

@@ -8,7 +8,7 @@
 //     static int model_id();                                     // ssb_model_id
 //     static long default_bucket_ticks();                         // window granularity (the app's lookahead)
 //     static void pack_event(const App::Event&, ssb_event&, context&);
-//     static int state_words();  static void pack_state(const App::State&, uint32_t* words);
+//     static int state_words();  static void pack_state(const App::State&, uint32_t* words, context&);
 //     static int upload_model_data(ssb_engine*, context&);        // ssb_set_model_data calls
 //   };
 //

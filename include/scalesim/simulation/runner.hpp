@@ -279,15 +279,15 @@ void runner<App>::run() {
   std::vector<int64_t> part64(part.begin(), part.end());
   for (size_t i = 0; i < part64.size(); ++i) part64[i] %= world_;
   if ((rc = ssb_set_partition(engine_, part64.data(), (int64_t)part64.size()))) fail("ssb_set_partition", rc);
-  if ((rc = model::upload_model_data(engine_, cx))) fail("ssb_set_model_data", rc);
   {
     const int sw = model::state_words();
     std::vector<int64_t> ids(states.size());
     std::vector<uint32_t> words(states.size() * (size_t)sw);
     for (size_t i = 0; i < states.size(); ++i) {
       ids[i] = states[i]->id();
-      model::pack_state(*states[i], &words[i * (size_t)sw]);
+      model::pack_state(*states[i], &words[i * (size_t)sw], cx);      // may add to the model data (TrafficSim road table)
     }
+    if ((rc = model::upload_model_data(engine_, cx))) fail("ssb_set_model_data", rc);
     if ((rc = ssb_load_states(engine_, ids.data(), words.data(), (int64_t)ids.size()))) fail("ssb_load_states", rc);
   }
   if (FLAGS_diff_repeat &&

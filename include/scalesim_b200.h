@@ -166,6 +166,10 @@ int ssb_set_partition(ssb_engine* e, const int64_t* lp_to_part, int64_t n_lp);
  *   PHOLD   slot 0: LATENCY_TABLE  int64[n]   slot 1: REMOTE_COM_TABLE int32[n]   (phold.hpp:56-58)
  *           slot 2: int64[2] = { LOOK_AHEAD, NUM_LP }
  *   TRAFFIC slot 0: route pool int64[n] (all route nodes, concatenated; events index into it)
+ *           slot 1: road table int64[3k] = {destination, speed km/h, length m} per road, for the junctions with more
+ *                   than 2 out-roads (state word 2 = index of the junction's first road; see the state layout below)
+ * TRAFFIC LP state (8 words): [0] id, [1] n = number of out-roads; n <= 2: words 2.. = n x {dst, speed, length} inline;
+ *   n > 2: word 2 = index (in roads) of the LP's first road in the slot-1 table, its n roads contiguous there.
  */
 int ssb_set_model_data(ssb_engine* e, int slot, const void* data, size_t bytes);
 

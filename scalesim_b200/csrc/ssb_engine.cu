@@ -93,6 +93,7 @@ struct ssb_engine {
   std::vector<long long> h_lat; std::vector<int> h_rem;
   bool have_lat = false, have_rem = false;
   u32* d_route = nullptr; u32 route_len = 0;
+  u32* d_roads = nullptr; u32 roads_len = 0;
   // staging
   HostEvent* d_stage = nullptr;
   long long* d_unpack = nullptr; size_t unpack_cap = 0;
@@ -165,7 +166,11 @@ struct ssb_engine {
     d.lookahead = (u32)h_phold_params[0]; d.num_lp = (u32)h_phold_params[1];
     return d;
   }
-  TrafficModel::Data traffic_data() const { TrafficModel::Data d; d.route = d_route; d.route_len = route_len; return d; }
+  TrafficModel::Data traffic_data() const {
+    TrafficModel::Data d;
+    d.route = d_route; d.route_len = route_len; d.roads = d_roads; d.roads_len = roads_len;
+    return d;
+  }
 
   // the ONE place that maps ssb_config.model to a device twin: f(model tag, its data)
   template <class F> void with_model(F&& f) const {
@@ -726,18 +731,20 @@ int ssb_set_model_data(ssb_engine* e, int slot, const void* data, size_t bytes) 
     return SSB_ERR_MODEL;
   }
   if (e->cfg.model == SSB_MODEL_TRAFFIC) {
-    if (slot != 0) { set_error("TrafficSim: unknown model data slot"); return SSB_ERR_MODEL; }
+    if (slot != 0 && slot != 1) { set_error("TrafficSim: unknown model data slot"); return SSB_ERR_MODEL; }
     size_t n = bytes / 8;
-    if (n >= 0xFFFFFFFFull) { set_error("route pool too large"); return SSB_ERR_RANGE; }
+    if (n >= 0xFFFFFFFFull) { set_error(slot == 0 ? "route pool too large" : "road table too large"); return SSB_ERR_RANGE; }
+    if (slot == 1 && n % 3) { set_error("road table: {dst, speed, length} triples expected"); return SSB_ERR_MODEL; }
     long long* d_in = nullptr;
     CK(dalloc(&d_in, n));
-    int rc = e->alloc(&e->d_route, n);
+    u32** dst = slot == 0 ? &e->d_route : &e->d_roads;
+    int rc = e->alloc(dst, n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(d_in, data, n * 8, cudaMemcpyHostToDevice, e->stream));
-    SSB_LAUNCH(k_narrow_u32, e->grid(n, 256), 256, 0, e->stream, (const long long*)d_in, e->d_route, n, e->v.ctl);
+    SSB_LAUNCH(k_narrow_u32, e->grid(n, 256), 256, 0, e->stream, (const long long*)d_in, *dst, n, e->v.ctl);
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaFree(d_in));
-    e->route_len = (u32)n;
+    (slot == 0 ? e->route_len : e->roads_len) = (u32)n;
     return SSB_OK;
   }
   return SSB_ERR_MODEL;

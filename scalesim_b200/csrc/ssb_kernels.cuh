@@ -457,12 +457,28 @@ __device__ __forceinline__ bool hash_insert(const View& v, u32 lp, u64 key, u32 
 // Otherwise the LP is flagged and k_fix_* redo its whole turn exactly (whatever this pass wrote for the LP's other
 // arrivals is overwritten: arrival i owns outbox entry i). Skew-free: a hot LP's events are spread over many threads.
 // ------------------------------------------------------------------------------------------------
+// LP state -> registers with the widest loads the record size allows (8 words = two 128-bit loads of one sector)
+template <int W>
+__device__ __forceinline__ void load_state(const u32* p, u32 (&st)[W]) {
+  if (W % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) { const uint4 x = reinterpret_cast<const uint4*>(p)[q]; st[4 * q] = x.x; st[4 * q + 1] = x.y; st[4 * q + 2] = x.z; st[4 * q + 3] = x.w; }
+  } else if (W % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < W / 2; ++q) { const uint2 x = reinterpret_cast<const uint2*>(p)[q]; st[2 * q] = x.x; st[2 * q + 1] = x.y; }
+  } else {
+#pragma unroll
+    for (int q = 0; q < W; ++q) st[q] = p[q];
+  }
+}
+
 template <class M>
 __device__ __forceinline__ bool run_handler(const View& v, const typename M::Data& md, const Ev& e, u32 lp, Ev& out,
                                             bool& has, u32& err) {
   u32 st[M::kStateWords], pre[M::kStateWords];
+  load_state<M::kStateWords>(v.state + (size_t)lp * M::kStateWords, st);
 #pragma unroll
-  for (int q = 0; q < M::kStateWords; ++q) { st[q] = v.state[(size_t)lp * M::kStateWords + q]; pre[q] = st[q]; }
+  for (int q = 0; q < M::kStateWords; ++q) pre[q] = st[q];
   Ev in = e;
   in.flags = 0;
   has = M::handle(md, in, st, out, err);
@@ -965,8 +981,7 @@ __global__ void __launch_bounds__(256) k_fix_turn(View v, typename M::Data md) {
     __syncwarp();
     // --- B. state restore ---
     u32 st[M::kStateWords];
-#pragma unroll
-    for (int w = 0; w < M::kStateWords; ++w) st[w] = v.state[(size_t)lp * M::kStateWords + w];
+    load_state<M::kStateWords>(v.state + (size_t)lp * M::kStateWords, st);
     bool dirty = false;
     snap_pos = warp_min_u32(snap_pos);
     if (snap_pos != NIL) {

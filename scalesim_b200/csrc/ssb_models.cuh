@@ -89,34 +89,48 @@ struct PholdStatefulModel {
 // ---------------------------------------------------------------------------------------------
 // TrafficSim — src/trafficsim/traffic_sim.hpp:279-342
 // Event payload: p0 = offset of destination() in the route pool, p1 = route nodes left (>= 1).
-// LP state words: [0] = id, [1] = number of out-roads n (<= kMaxRoads), then n x {dst, speed km/h, length m}.
+// LP state: 8 words = one 32-byte sector: [0] = id, [1] = number of out-roads n, then
+//   n <= 2 : the roads inline, n x {dst, speed km/h, length m}            (grids: one gather per event)
+//   n >  2 : [2] = index of the LP's first road in the road table (model data slot 1: {dst, speed, length} triples,
+//            the LP's roads contiguous, in the order of the state's vectors) — any junction degree
 //   no event when the route is exhausted (p1 == 1) or no road leads to the next node (:286-306)
 //   arrival' = len*3600/speed/1000 + arrival + 5   (speed != 0, left-to-right truncating division, :314-316)
 //            = len*3600 + arrival                   (speed == 0, :318-319)
 //   departure' = arrival; source' = this node; the state is returned unchanged.
 // ---------------------------------------------------------------------------------------------
 struct TrafficModel {
-  static constexpr int kMaxRoads = 4;
-  static constexpr int kStateWords = 2 + 3 * kMaxRoads;
+  static constexpr int kInlineRoads = 2;
+  static constexpr int kStateWords = 2 + 3 * kInlineRoads;
   struct Data {
     const u32* route;   // route pool
     u32 route_len;
+    const u32* roads;   // road table of the junctions with more than kInlineRoads out-roads
+    u32 roads_len;      // in words
   };
   __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
     if (e.p1 <= 1u) return false;
     if (e.p0 + 1u >= d.route_len) { err |= E_INTERNAL; return false; }
     u32 next = __ldg(d.route + e.p0 + 1u);
     const u32 n = state[1];
-    // first road that leads to `next`, as std::find (traffic_sim.hpp:299-306); static indices only, so the state
-    // words stay in registers
+    // first road that leads to `next`, as std::find (traffic_sim.hpp:299-306)
     bool found = false;
     u64 speed = 0, len = 0;
+    if (n <= (u32)kInlineRoads) {
+      // static indices only, so the state words stay in registers
 #pragma unroll
-    for (int r = 0; r < kMaxRoads; ++r) {
-      if (!found && (u32)r < n && state[2 + 3 * r] == next) {
-        found = true;
-        speed = state[2 + 3 * r + 1];
-        len = state[2 + 3 * r + 2];
+      for (int r = 0; r < kInlineRoads; ++r) {
+        if (!found && (u32)r < n && state[2 + 3 * r] == next) {
+          found = true;
+          speed = state[2 + 3 * r + 1];
+          len = state[2 + 3 * r + 2];
+        }
+      }
+    } else {
+      const u32 first = state[2];
+      if ((u64)3 * ((u64)first + n) > d.roads_len) { err |= E_INTERNAL; return false; }
+      for (u32 r = 0; r < n && !found; ++r) {
+        const u32* rd = d.roads + 3u * (first + r);
+        if (__ldg(rd) == next) { found = true; speed = __ldg(rd + 1); len = __ldg(rd + 2); }
       }
     }
     if (!found) return false;

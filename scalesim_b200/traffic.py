@@ -11,8 +11,8 @@ import numpy as np
 from .capi import EVENT_DTYPE, FLAG_HISTORY, MODEL_TRAFFIC, Config, Engine
 
 FINISH_TIME = 10800      # traffic_sim.hpp:240-247
-MAX_ROADS = 4            # TrafficModel::kMaxRoads
-STATE_WORDS = 2 + 3 * MAX_ROADS
+INLINE_ROADS = 2         # TrafficModel::kInlineRoads: junctions with more out-roads keep them in the road table
+STATE_WORDS = 2 + 3 * INLINE_ROADS
 
 
 @dataclass
@@ -207,21 +207,30 @@ def stripe_partition(width: int, height: int, world: int) -> np.ndarray:
 # packing
 # ---------------------------------------------------------------------------------------
 def pack_states(sc: Scenario):
-    """LP state words: [id, n_roads, (dst, speed, length) x n_roads], padded to MAX_ROADS."""
+    """LP state words [id, n_roads, ...]: up to INLINE_ROADS roads inline as (dst, speed, length) triples; a junction
+    with more keeps the index of its first road in the road table (model data slot 1) in word 2.
+    Returns (state LP ids, words, road table as int64 triples)."""
     n = sc.state_ids.size
     deg = np.diff(sc.road_start)
-    if deg.size and deg.max() > MAX_ROADS:
-        raise ValueError(f"an LP has {int(deg.max())} out-roads; the device model supports {MAX_ROADS}")
     words = np.zeros((n, STATE_WORDS), dtype=np.uint32)
     words[:, 0] = sc.state_ids.astype(np.uint32)
     words[:, 1] = deg.astype(np.uint32)
-    for k in range(MAX_ROADS):
-        has = deg > k
+    small = deg <= INLINE_ROADS
+    for k in range(INLINE_ROADS):
+        has = small & (deg > k)
         j = sc.road_start[:-1][has] + k
         words[has, 2 + 3 * k] = sc.road_dst[j].astype(np.uint32)
         words[has, 3 + 3 * k] = sc.road_speed[j].astype(np.uint32)
         words[has, 4 + 3 * k] = sc.road_len[j].astype(np.uint32)
-    return sc.state_ids.astype(np.int64), words
+    big = np.nonzero(~small)[0]
+    table = np.zeros((0, 3), dtype=np.int64)
+    if big.size:
+        first = np.zeros(big.size, dtype=np.int64)
+        np.cumsum(deg[big][:-1], out=first[1:])
+        words[big, 2] = first.astype(np.uint32)
+        rows = np.concatenate([np.arange(sc.road_start[i], sc.road_start[i + 1]) for i in big])
+        table = np.stack([sc.road_dst[rows], sc.road_speed[rows], sc.road_len[rows]], axis=1).astype(np.int64)
+    return sc.state_ids.astype(np.int64), words, table
 
 
 def pack_events(sc: Scenario) -> np.ndarray:
@@ -265,7 +274,9 @@ def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1,
     if extra_routes is not None and len(extra_routes):
         pool = np.concatenate([pool, np.asarray(extra_routes, dtype=np.int64)])      # what-if trips: routes appended
     eng.set_model_data(0, pool)
-    ids, words = pack_states(sc)
+    ids, words, road_table = pack_states(sc)
+    if road_table.size:
+        eng.set_model_data(1, road_table.reshape(-1))
     owner = (part[ids] % world) if part is not None else (ids % world)
     mine = owner == rank
     eng.load_states(ids[mine], words[mine])

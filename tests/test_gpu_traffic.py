@@ -52,3 +52,45 @@ def test_grid_trips_that_outlive_finish_time():
     assert eng.digest() == s.digest()
     assert st.beyond_finish > 0
     eng.close()
+
+
+def _random_network(n_nodes, max_degree, n_trips, seed):
+    """random directed road network with 1..max_degree out-roads per junction (duplicate destinations allowed: the
+    handler takes the first match, traffic_sim.hpp:299-306) and random walks over it as trips"""
+    rng = np.random.default_rng(seed)
+    deg = rng.integers(1, max_degree + 1, n_nodes)
+    road_start = np.zeros(n_nodes + 1, dtype=np.int64)
+    np.cumsum(deg, out=road_start[1:])
+    road_dst = rng.integers(0, n_nodes, road_start[-1])
+    road_speed = rng.integers(0, 61, road_start[-1])          # 0 = the reference's "speed unknown" branch (:318-319)
+    road_len = rng.integers(1, 1200, road_start[-1])
+    trip_id, trip_dep, route_start, nodes = [], [], [0], []
+    for t in range(n_trips):
+        cur = int(rng.integers(0, n_nodes))
+        route = [cur]
+        for _ in range(int(rng.integers(1, 12))):
+            cur = int(road_dst[road_start[cur] + rng.integers(0, deg[cur])])
+            route.append(cur)
+        if rng.random() < 0.1:
+            route.append(int(rng.integers(0, n_nodes)))          # most likely no road leads there: the trip ends early
+        trip_id.append(t); trip_dep.append(int(rng.integers(0, 3000)))
+        nodes.extend(route); route_start.append(len(nodes))
+    a = lambda x: np.array(x, dtype=np.int64)
+    return traffic.Scenario(n_nodes, np.arange(n_nodes, dtype=np.int64), road_start, a(road_dst), a(road_speed), a(road_len),
+                            a(trip_id), a(trip_dep), a(route_start), a(nodes))
+
+
+@pytest.mark.parametrize("bucket,window", [(5, 1), (40, 4)])
+def test_any_junction_degree_equals_oracle(bucket, window):
+    """Junctions with more out-roads than fit the inline state words (road table, model data slot 1): the reference's
+    State holds unbounded vectors (traffic_sim.hpp:99-142)."""
+    sc = _random_network(300, 9, 4000, seed=5)
+    assert np.diff(sc.road_start).max() > traffic.INLINE_ROADS
+    s = O.Sim.traffic_scenario(sc)
+    s.run_closure(4)
+    eng = traffic.make_engine(sc, bucket_ticks=bucket, window_buckets=window, keep_records=True)
+    st = eng.run()
+    assert eng.digest() == s.digest()
+    rec = eng.drain_committed()
+    assert sorted(ssb.records_to_lines(rec)) == sorted(O.records_to_lines(s.committed()))
+    eng.close()

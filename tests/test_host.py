@@ -114,9 +114,17 @@ def test_traffic_reader_quirks(tmp_path):
 
 def test_traffic_packing():
     sc, _ = ring_scenario()
-    ids, words = traffic.pack_states(sc)
-    assert words.shape == (10, traffic.STATE_WORDS)
+    ids, words, table = traffic.pack_states(sc)
+    assert words.shape == (10, traffic.STATE_WORDS) and table.size == 0
     assert words[3].tolist()[:5] == [3, 1, 4, 10, 100]
+    # a junction with more out-roads than fit inline keeps them in the road table, in the order of the state's vectors
+    big = traffic.Scenario(3, np.array([0, 1, 2]), np.array([0, 1, 5, 6]), np.array([1, 0, 2, 0, 2, 0]),
+                           np.array([10, 20, 30, 40, 50, 60]), np.array([100, 200, 300, 400, 500, 600]),
+                           np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64),
+                           np.zeros(0, dtype=np.int64))
+    ids, words, table = traffic.pack_states(big)
+    assert words[1].tolist()[:3] == [1, 4, 0] and words[0].tolist()[:5] == [0, 1, 1, 10, 100]
+    assert table.tolist() == [[0, 20, 200], [2, 30, 300], [0, 40, 400], [2, 50, 500]]
     ev = traffic.pack_events(sc)
     assert ev["src"].tolist() == [-1, -1, -1]
     assert ev["dst"].tolist() == [0, 1, 0]
