@@ -4,6 +4,7 @@
 // Device twin of phold::event_handler: PholdModel in csrc/ssb_models.cuh.
 #ifndef SCALESIM_B200_MODELS_PHOLD_MODEL_HPP_
 #define SCALESIM_B200_MODELS_PHOLD_MODEL_HPP_
+#include <algorithm>
 #include "scalesim/simulation/device_model.hpp"
 
 namespace scalesim {
@@ -17,6 +18,11 @@ struct device_model<phold> {
     out.id = e.id(); out.src = e.source(); out.dst = e.destination();
     out.recv_time = e.receive_time(); out.send_time = e.send_time();
     out.p0 = e.num_hops(); out.p1 = 0; out.flags = e.is_cancel() ? 1 : 0;
+  }
+  // upper bound of the committed events of a run, for sizing the device log: a chain advances by >= LOOK_AHEAD per hop
+  static long committed_bound(const std::vector<ssb_event>& initial, long finish_time) {
+    const long hops = LOOK_AHEAD > 0 ? finish_time / LOOK_AHEAD + 1 : 64;
+    return (long)initial.size() * std::min<long>(hops, 8);      // ~4.6 hops per chain at lambda 1.0; SCALESIM_B200_MAX_COMMITTED overrides
   }
   static int state_words() { return 2; }
   static void pack_state(const phold::State& s, uint32_t* w, context&) {

@@ -28,6 +28,12 @@ struct device_model<traffic_sim> {
     out.flags = e.is_cancel() ? 1 : 0;
     cx.route_pool.insert(cx.route_pool.end(), route.begin(), route.end());
   }
+  // upper bound of the committed events of a run, for sizing the device log: one event per route node
+  static long committed_bound(const std::vector<ssb_event>& initial, long) {
+    long n = 0;
+    for (size_t i = 0; i < initial.size(); ++i) n += (long)initial[i].p1 + 1;
+    return n;
+  }
   static int state_words() { return 2 + 3 * kInlineRoads; }
   // up to kInlineRoads out-roads sit in the state words; a junction with more keeps them in the road table (model
   // data slot 1) and its state holds the index of its first road there — any junction degree (the reference's State

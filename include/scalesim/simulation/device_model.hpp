@@ -10,6 +10,7 @@
 //     static void pack_event(const App::Event&, ssb_event&, context&);
 //     static int state_words();  static void pack_state(const App::State&, uint32_t* words, context&);
 //     static int upload_model_data(ssb_engine*, context&);        // ssb_set_model_data calls
+//     static long committed_bound(const std::vector<ssb_event>&, long finish_time);   // sizes the device log
 //   };
 //
 // Adapters for the two shipped applications live in scalesim/models/; a translation unit that wants the drop-in

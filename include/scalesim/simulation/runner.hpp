@@ -5,8 +5,12 @@
 //           App::init_partition_index(world)  -> ssb_set_partition            (runner.hpp:98)
 //           App::init_states_in_this_rank     -> ssb_load_states              (runner.hpp:108-118)
 //           App::init_events + shuffle by partition[destination] -> ssb_load_events   (runner.hpp:131-147)
-//           ssb_run                           = runner::loop                   (runner.hpp:350-396)
-//           ssb_drain_committed -> "RE,..." lines on stdout                     (queue.hpp:203-211, sim_obj.hpp:66-77)
+//           ssb_run_stream_packed             = runner::loop (runner.hpp:350-396): the window loop runs as one CUDA
+//                                               graph while the committed records stream out through pinned staging
+//                                               buffers and are printed as "RE,..." lines (queue.hpp:203-211,
+//                                               sim_obj.hpp:66-77) — the reference prints while it simulates, too
+//           --diff_init: ssb_run_stream_history — the same with every event's sent-log entry; a writer thread appends
+//                                               the chunks to the history store (logical_process.hpp:187-203)
 //           report on stderr                                                    (runner.hpp:482-507)
 //
 // The application's host event_handler is not on the hot path: its device twin runs in the kernels. It is still
@@ -23,12 +27,15 @@
 #define SCALESIM_B200_SIMULATION_RUNNER_HPP_
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <filesystem>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -76,10 +83,113 @@ class runner {
     std::vector<ssb_sent_record> sent;
     std::vector<int64_t> state_lps, pool;
   };
+  // Appends (records, sent-log entries) chunks to the history file from a background thread while the simulation
+  // runs: the reference keeps every put in one in-memory WriteBatch until finish() (leveldb_store.hpp:132-141, quirk
+  // Q15); here host memory is bounded by the queue depth. File = "SSBHIST3", n_state, n_pool, state LPs, model data
+  // pool, then chunks {n, rec[n], sent[n]} closed by n = 0 and the total (same format as scalesim_b200/store.py).
+  class history_writer {
+   public:
+    history_writer() : f_(NULL), total_(0), bytes_(0), stop_(false), failed_(false) {}
+    bool open(const std::string& path, const std::vector<int64_t>& state_lps, const std::vector<int64_t>& pool) {
+      path_ = path;
+      f_ = std::fopen((path + ".tmp").c_str(), "wb");
+      if (!f_) return false;
+      const int64_t hdr[2] = {(int64_t)state_lps.size(), (int64_t)pool.size()};
+      put("SSBHIST3", 8); put(hdr, sizeof(hdr));
+      put(state_lps.data(), state_lps.size() * 8); put(pool.data(), pool.size() * 8);
+      thr_ = std::thread(&history_writer::loop, this);
+      return !failed_;
+    }
+    // called from the drain sink: the staging buffer is reused at once, so the chunk is copied into the queue
+    void push(const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n) {
+      chunk c;
+      c.rec.assign(rec, rec + n); c.sent.assign(sent, sent + n);
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return q_.size() < 4; });      // back-pressure: at most 4 chunks in flight
+      q_.push_back(std::move(c));
+      cv_.notify_all();
+    }
+    bool close() {
+      { std::unique_lock<std::mutex> lk(m_); stop_ = true; cv_.notify_all(); }
+      if (thr_.joinable()) thr_.join();
+      if (!f_) return false;
+      const int64_t tail[2] = {0, total_};
+      put(tail, sizeof(tail));
+      const bool ok = std::fclose(f_) == 0 && !failed_;
+      f_ = NULL;
+      return ok && std::rename((path_ + ".tmp").c_str(), path_.c_str()) == 0;
+    }
+    int64_t records() const { return total_; }
+    int64_t bytes() const { return bytes_; }
+   private:
+    struct chunk { std::vector<ssb_raw_record> rec; std::vector<ssb_sent_record> sent; };
+    void put(const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f_) != n) failed_ = true; bytes_ += (int64_t)n; }
+    void loop() {
+      for (;;) {
+        chunk c;
+        {
+          std::unique_lock<std::mutex> lk(m_);
+          cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+          if (q_.empty()) return;
+          c = std::move(q_.front());
+          q_.pop_front();
+          cv_.notify_all();
+        }
+        const int64_t n = (int64_t)c.rec.size();
+        put(&n, 8); put(c.rec.data(), c.rec.size() * sizeof(ssb_raw_record)); put(c.sent.data(), c.sent.size() * sizeof(ssb_sent_record));
+        total_ += n;
+      }
+    }
+    std::FILE* f_;
+    std::string path_;
+    std::thread thr_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<chunk> q_;
+    int64_t total_, bytes_;
+    bool stop_, failed_;
+  };
+  // "RE,id,src,send,dst,recv[,START|,END]\n" (sim_obj.hpp:66-77) for a chunk of records, formatted by a few threads
+  // into per-thread buffers and written in order
+  struct line_printer {
+    static char* num(char* p, uint32_t v) {
+      char t[10]; int n = 0;
+      do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+      while (n) *p++ = t[--n];
+      return p;
+    }
+    static char* line(char* p, uint32_t id, uint32_t src, uint32_t send, uint32_t dst, uint32_t recv, uint32_t tag) {
+      *p++ = 'R'; *p++ = 'E'; *p++ = ',';
+      p = num(p, id); *p++ = ',';
+      if (src == 0xffffffffu) { *p++ = '-'; *p++ = '1'; } else p = num(p, src);
+      *p++ = ','; p = num(p, send); *p++ = ','; p = num(p, dst); *p++ = ','; p = num(p, recv);
+      if (tag == 1) { std::memcpy(p, ",START", 6); p += 6; } else if (tag == 2) { std::memcpy(p, ",END", 4); p += 4; }
+      *p++ = '\n';
+      return p;
+    }
+    std::vector<std::vector<char> > bufs;
+    template <class Get> void print(int64_t n, Get get) {
+      const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(8, std::min<int64_t>(n / 65536 + 1, std::thread::hardware_concurrency())));
+      bufs.resize((size_t)nt);
+      std::vector<size_t> used((size_t)nt, 0);
+      auto work = [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        std::vector<char>& buf = bufs[(size_t)t];
+        buf.resize((size_t)(b - a) * 64 + 64);
+        char* p = buf.data();
+        for (int64_t i = a; i < b; ++i) p = get(i, p);
+        used[(size_t)t] = (size_t)(p - buf.data());
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+      work(0);
+      for (size_t t = 0; t < th.size(); ++t) th[t].join();
+      for (int t = 0; t < nt; ++t) std::fwrite(bufs[(size_t)t].data(), 1, used[(size_t)t], stdout);
+    }
+  };
   std::string history_path() const {
     return (FLAGS_store_dir.empty() ? std::string(".") : FLAGS_store_dir) + "/" + FLAGS_sim_id + "/history" + std::to_string(rank_) + ".ssb";
   }
-  void write_history(const history& h);
   void read_history(history& h);
   void verify_twin(const ev_vec<App>& initial, const std::vector<ssb_record>& committed, long k);
 };
@@ -153,41 +263,35 @@ void runner<App>::comm_init() {
 }
 
 template <class App>
-void runner<App>::write_history(const history& h) {
-  const std::string p = history_path(), dir = p.substr(0, p.find_last_of('/'));
-  std::error_code ec;
-  std::filesystem::create_directories(dir, ec);
-  if (ec) { LOG(ERROR) << "cannot create " << dir << ": " << ec.message(); std::exit(1); }
-  std::ofstream f((p + ".tmp").c_str(), std::ios::binary);
-  const int64_t hdr[3] = {(int64_t)h.rec.size(), (int64_t)h.state_lps.size(), (int64_t)h.pool.size()};
-  f.write("SSBHIST2", 8);
-  f.write((const char*)hdr, sizeof(hdr));
-  f.write((const char*)h.rec.data(), (std::streamsize)(h.rec.size() * sizeof(ssb_raw_record)));
-  f.write((const char*)h.sent.data(), (std::streamsize)(h.sent.size() * sizeof(ssb_sent_record)));
-  f.write((const char*)h.state_lps.data(), (std::streamsize)(h.state_lps.size() * 8));
-  f.write((const char*)h.pool.data(), (std::streamsize)(h.pool.size() * 8));
-  f.close();
-  if (!f || std::rename((p + ".tmp").c_str(), p.c_str()) != 0) { LOG(ERROR) << "cannot write " << p; std::exit(1); }
-  LOG(INFO) << " Stored objects size : " << (h.rec.size() * (sizeof(ssb_raw_record) + sizeof(ssb_sent_record)) + h.state_lps.size() * 8)
-            << " byte (" << h.rec.size() << " events with their sent-log entries, " << h.state_lps.size() << " initial states) -> " << p;
-}
-
-template <class App>
 void runner<App>::read_history(history& h) {
   const std::string p = history_path();
   std::ifstream f(p.c_str(), std::ios::binary);
   char magic[8];
-  int64_t hdr[3];
-  if (!f || !f.read(magic, 8) || std::memcmp(magic, "SSBHIST2", 8) != 0 || !f.read((char*)hdr, sizeof(hdr))) {
+  int64_t hdr[2];
+  if (!f || !f.read(magic, 8) || std::memcmp(magic, "SSBHIST3", 8) != 0 || !f.read((char*)hdr, sizeof(hdr))) {
     LOG(ERROR) << "no history store at " << p << " (run with --diff_init first)";
     std::exit(1);
   }
-  h.rec.resize((size_t)hdr[0]); h.sent.resize((size_t)hdr[0]); h.state_lps.resize((size_t)hdr[1]); h.pool.resize((size_t)hdr[2]);
-  f.read((char*)h.rec.data(), (std::streamsize)(h.rec.size() * sizeof(ssb_raw_record)));
-  f.read((char*)h.sent.data(), (std::streamsize)(h.sent.size() * sizeof(ssb_sent_record)));
+  std::error_code ec;
+  const int64_t fsize = (int64_t)std::filesystem::file_size(p, ec);
+  auto bad = [&](const char* why) { LOG(ERROR) << p << ": " << why; std::exit(1); };
+  if (hdr[0] < 0 || hdr[1] < 0 || (hdr[0] + hdr[1]) * 8 > fsize) bad("header counts do not fit the file");
+  h.state_lps.resize((size_t)hdr[0]); h.pool.resize((size_t)hdr[1]);
   f.read((char*)h.state_lps.data(), (std::streamsize)(h.state_lps.size() * 8));
   f.read((char*)h.pool.data(), (std::streamsize)(h.pool.size() * 8));
-  if (!f) { LOG(ERROR) << p << " is truncated"; std::exit(1); }
+  for (;;) {
+    int64_t n = -1;
+    if (!f.read((char*)&n, 8)) bad("truncated (no closing chunk)");
+    if (n == 0) break;
+    if (n < 0 || n * 48 > fsize) bad("bad chunk size");
+    const size_t at = h.rec.size();
+    h.rec.resize(at + (size_t)n); h.sent.resize(at + (size_t)n);
+    f.read((char*)&h.rec[at], (std::streamsize)((size_t)n * sizeof(ssb_raw_record)));
+    f.read((char*)&h.sent[at], (std::streamsize)((size_t)n * sizeof(ssb_sent_record)));
+    if (!f) bad("truncated chunk");
+  }
+  int64_t total = -1;
+  if (!f.read((char*)&total, 8) || total != (int64_t)h.rec.size()) bad("record count does not match the chunks");
 }
 
 template <class App>
@@ -269,7 +373,10 @@ void runner<App>::run() {
   cfg.max_events = env_long("SCALESIM_B200_MAX_EVENTS", (long)(n_resident * (FLAGS_diff_repeat ? 3.0 : 1.6)) + (1 << 18));
   cfg.max_batch = env_long("SCALESIM_B200_MAX_BATCH", (long)n_resident / 2 + (1 << 16));
   const bool quiet = env_long("SCALESIM_B200_QUIET", 0) != 0 && !FLAGS_diff_init;
-  cfg.max_committed = quiet ? 0 : (1 << 24);
+  // the device log holds the whole run (it streams out while the loop runs, but the device is never throttled by the
+  // host): sized from the workload; an overflow is a loud SSB_ERR_CAPACITY, never a silently shorter output
+  cfg.max_committed = quiet ? 0 : env_long("SCALESIM_B200_MAX_COMMITTED",
+                                           (long)hist.rec.size() + model::committed_bound(pod, App::finish_time()) + (1 << 16));
   if (FLAGS_diff_init) cfg.flags |= SSB_FLAG_HISTORY;
   cfg.max_snapshots = 1 << 20;
   cfg.rounds_per_sync = 4;
@@ -293,9 +400,6 @@ void runner<App>::run() {
   if (FLAGS_diff_repeat &&
       (rc = ssb_load_history(engine_, hist.rec.data(), hist.sent.data(), (int64_t)hist.rec.size()))) fail("ssb_load_history", rc);
   if ((rc = ssb_load_events(engine_, pod.data(), (int64_t)pod.size()))) fail("ssb_load_events", rc);
-  if (FLAGS_diff_init) {
-    for (size_t i = 0; i < states.size(); ++i) hist.state_lps.push_back(states[i]->id());
-  }
   double init_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   LOG_IF(INFO, rank_ == 0)
       << "\n====================================================================\n"
@@ -306,66 +410,89 @@ void runner<App>::run() {
       << "====================================================================\n";
 
   LOG_IF(INFO, rank_ == 0) << "Start Simulation";
-  // the committed log is drained while the simulation advances: a window of rounds, then the records so far
-  std::vector<ssb_record> buf(1 << 22);
   std::vector<ssb_record> kept;
   const long verify_k = env_long("SCALESIM_B200_VERIFY", 0);
+  const bool keep = verify_k > 0 && !quiet && !FLAGS_diff_init && !FLAGS_diff_repeat;
   clk::time_point t1 = clk::now();
   ssb_stats st;
   std::memset(&st, 0, sizeof(st));
-  std::vector<char> line(1 << 16);
   std::setvbuf(stdout, NULL, _IOFBF, 1 << 22);
-  for (;;) {
-    int done = 0;
-    for (int i = 0; i < 4 && !done; ++i)
-      if ((rc = ssb_step(engine_, &done))) fail("ssb_step", rc);
-    if (FLAGS_diff_init) {
-      // --diff_init: the committed events leave the device together with their sent-log entries; the lines are printed
-      // from the same records and the history accumulates on the host (written to the store after the loop)
-      for (;;) {
-        const size_t at = hist.rec.size(), cap = 1 << 20;
-        hist.rec.resize(at + cap); hist.sent.resize(at + cap);
-        int64_t n = 0;
-        if ((rc = ssb_drain_history(engine_, &hist.rec[at], &hist.sent[at], (int64_t)cap, &n))) fail("ssb_drain_history", rc);
-        hist.rec.resize(at + (size_t)n); hist.sent.resize(at + (size_t)n);
-        for (size_t i = at; i < hist.rec.size(); ++i) {
-          const ssb_raw_record& r = hist.rec[i];
-          std::printf("RE,%ld,%ld,%ld,%ld,%ld%s\n", (long)(r.key & 0xffffffffu), r.src == 0xffffffffu ? -1L : (long)r.src,
-                      (long)r.send_time, (long)r.dst, (long)(r.key >> 32), r.tag == 1 ? ",START" : (r.tag == 2 ? ",END" : ""));
-        }
-        if (n < (int64_t)cap) break;
+  line_printer lp;
+  history_writer hw;
+  double print_ms = 0.0;
+  struct sink_ctx { runner* self; line_printer* lp; history_writer* hw; std::vector<ssb_record>* kept; bool keep; double* print_ms; };
+  sink_ctx sc = {this, &lp, &hw, &kept, keep, &print_ms};
+  if (FLAGS_diff_init) {
+    // --diff_init: the committed events leave the device together with their sent-log entries while the loop runs;
+    // the lines are printed from the same records, the store file grows on a writer thread
+    for (size_t i = 0; i < states.size(); ++i) hist.state_lps.push_back(states[i]->id());
+    hist.pool = model::model_data_blob(cx);
+    const std::string p = history_path(), dir = p.substr(0, p.find_last_of('/'));
+    std::error_code ec;
+    std::filesystem::create_directories(dir, ec);
+    if (ec || !hw.open(p, hist.state_lps, hist.pool)) { LOG(ERROR) << "cannot write " << p; std::exit(1); }
+    struct fn {
+      static int sink(void* u, const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n) {
+        sink_ctx* c = (sink_ctx*)u;
+        clk::time_point a = clk::now();
+        c->lp->print(n, [&](int64_t i, char* p) {
+          const ssb_raw_record& r = rec[i];
+          return line_printer::line(p, (uint32_t)(r.key & 0xffffffffu), r.src, r.send_time, r.dst, (uint32_t)(r.key >> 32), r.tag);
+        });
+        c->hw->push(rec, sent, n);
+        *c->print_ms += std::chrono::duration<double, std::milli>(clk::now() - a).count();
+        return 0;
       }
-    } else if (!quiet) {
-      for (;;) {
-        int64_t n = 0;
-        if ((rc = ssb_drain_committed(engine_, buf.data(), (int64_t)buf.size(), &n))) fail("ssb_drain_committed", rc);
-        for (int64_t i = 0; i < n; ++i) {
-          const ssb_record& r = buf[(size_t)i];
-          std::printf("RE,%ld,%ld,%ld,%ld,%ld%s\n", (long)r.id, (long)r.src, (long)r.send_time, (long)r.dst,
-                      (long)r.recv_time, r.tag == 1 ? ",START" : (r.tag == 2 ? ",END" : ""));
+    };
+    if ((rc = ssb_run_stream_history(engine_, &fn::sink, &sc, &st))) fail("ssb_run_stream_history", rc);
+  } else if (!quiet) {
+    struct fn {
+      static int sink(void* u, const ssb_packed_record* rec, int64_t n) {
+        sink_ctx* c = (sink_ctx*)u;
+        clk::time_point a = clk::now();
+        c->lp->print(n, [&](int64_t i, char* p) {
+          const ssb_packed_record& r = rec[i];
+          return line_printer::line(p, r.id, r.src, r.send_time, r.dst, r.recv_time, r.tag);
+        });
+        if (c->keep) {
+          for (int64_t i = 0; i < n; ++i) {
+            const ssb_packed_record& r = rec[i];
+            ssb_record w = {(int64_t)r.id, r.src == 0xffffffffu ? -1 : (int64_t)r.src, (int64_t)r.send_time, (int64_t)r.dst,
+                            (int64_t)r.recv_time, (int64_t)r.tag};
+            c->kept->push_back(w);
+          }
         }
-        if (verify_k > 0) kept.insert(kept.end(), buf.begin(), buf.begin() + n);
-        if (n < (int64_t)buf.size()) break;
+        *c->print_ms += std::chrono::duration<double, std::milli>(clk::now() - a).count();
+        return 0;
       }
-    }
-    if (done) break;
+    };
+    if ((rc = ssb_run_stream_packed(engine_, &fn::sink, &sc, &st))) fail("ssb_run_stream_packed", rc);
+  } else {
+    if ((rc = ssb_run(engine_, &st))) fail("ssb_run", rc);
   }
   std::fflush(stdout);
   double sim_ms = std::chrono::duration<double, std::milli>(clk::now() - t1).count();
-  if ((rc = ssb_get_stats(engine_, &st))) fail("ssb_get_stats", rc);
   uint64_t dg[4];
   ssb_committed_digest(engine_, dg);
-  if (verify_k > 0 && !quiet && !FLAGS_diff_init && !FLAGS_diff_repeat) verify_twin(mine, kept, verify_k);
+  if (keep) verify_twin(mine, kept, verify_k);
+  double store_ms = 0.0;
   if (FLAGS_diff_init) {
-    hist.pool = model::model_data_blob(cx);
-    write_history(hist);
+    clk::time_point a = clk::now();
+    if (!hw.close()) { LOG(ERROR) << "cannot write " << history_path(); std::exit(1); }
+    store_ms = std::chrono::duration<double, std::milli>(clk::now() - a).count();
+    LOG(INFO) << " Stored objects size : " << hw.bytes() << " byte (" << hw.records() << " events with their sent-log entries, "
+              << hist.state_lps.size() << " initial states) -> " << history_path();
   }
 
   LOG(INFO) << "Finish Simulation";
   LOG(INFO)
       << "\n====================================================================\n"
       << " Partition " << rank_ << " of " << world_ << "\n"
-      << " Simulation elapsed time: " << (long)sim_ms << " ms (window loop + draining " << (quiet ? "nothing" : "the result lines") << ")\n"
+      << " Simulation elapsed time: " << (long)sim_ms << " ms (window loop + streaming out " << (quiet ? "nothing" : "and printing the result lines") << ")\n"
+      << "   Window loop on the device        : " << st.loop_ms << " ms\n"
+      << "   Init (parse, pack, load)         : " << (long)init_ms << " ms\n"
+      << "   OutPutResult (format + print)    : " << (long)print_ms << " ms (inside the elapsed time, overlapped with the loop)\n"
+      << "   DBWrite (flush the history store): " << (long)store_ms << " ms\n"
       << "\n"
       << " # of global synchronizations   : " << st.rounds << "\n"
       << " # of processing events         : " << st.processed << "\n"
@@ -374,7 +501,7 @@ void runner<App>::run() {
       << " Rollback efficiency            : "
       << (st.processed ? ((float)(st.processed - st.antis_sent)) / ((float)st.processed) : 1.0f) << "\n"
       << " rollbacks " << st.rollbacks << ", undone " << st.undone << ", annihilated " << st.annihilated
-      << ", duplicates " << st.duplicates << ", sent to other partitions " << st.remote_sent << "\n"
+      << ", duplicates " << st.duplicates << ", irregular LP turns " << st.fix_turns << ", sent to other partitions " << st.remote_sent << "\n"
       << " committed digest: " << dg[0] << " " << dg[1] << " " << dg[2] << " " << dg[3] << "\n"
       << "====================================================================\n";
   ssb_destroy(engine_);

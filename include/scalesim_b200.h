@@ -22,7 +22,13 @@
  *   ssb_run / ssb_step            runner::loop — run_lp/run_lp_aggr, GVT, std_out, clear
  *                                 (runner.hpp:350-396, 517-583)
  *   ssb_committed_digest,         eventq::std_out + sim_event::result_out — the "RE,..." lines
- *   ssb_drain_committed           (queue.hpp:203-211, sim_obj.hpp:66-77)
+ *   ssb_drain_committed*,         (queue.hpp:203-211, sim_obj.hpp:66-77); the reference prints them while it simulates
+ *   ssb_run_stream_packed         (runner.hpp:369-380)
+ *   ssb_drain_history,            lp::clear_old_ev / clear_old_st -> eventq::store_* / stateq::store_state ->
+ *   ssb_run_stream_history        leveldb_store::put (logical_process.hpp:187-203, queue.hpp:179-201, 304-323,
+ *                                 leveldb_store.hpp:132-185)
+ *   ssb_load_history              lp::flush_buf lazy load -> load_events / load_cancels / load_prev_st
+ *                                 (logical_process.hpp:132-153, queue.hpp:213-241, 325-331)
  *   ssb_get_stats, ssb_kernel_times  runner::finish report + the stopwatch phases (runner.hpp:482-507,
  *                                 util/stopwatch.hpp)
  *   ssb_reset                     (no reference equivalent: the reference is one simulation per process)
@@ -207,6 +213,19 @@ int ssb_drain_committed_packed(ssb_engine* e, ssb_packed_record* out, int64_t ca
  * (the reference prints its result lines while it simulates, runner.hpp:369-380). Returns when the simulation has
  * finished and every record is in `out` (*n of them; cap must hold them all). */
 int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int64_t* n, ssb_stats* stats);
+
+/* Streaming forms of the two calls above and of ssb_drain_history: the records leave through two bounded pinned
+ * staging buffers owned by the engine (2 x 2M records) while the window loop runs, and are handed to `sink` chunk
+ * by chunk on the calling thread (the next chunk is already crossing PCIe meanwhile) — host memory stays bounded
+ * whatever the run commits. This is what the reference's store does NOT do (leveldb_store.hpp:132-141 keeps every
+ * put in one in-memory WriteBatch until finish()). A sink returns 0 to go on; anything else
+ * stops the draining and the call fails with SSB_ERR_INVALID once the loop has ended. The device log must hold the
+ * whole run (max_committed >= committed events): it is not a ring, the device is never throttled by the host.
+ * ssb_run_stream_history needs SSB_FLAG_HISTORY. */
+typedef int (*ssb_packed_sink)(void* user, const ssb_packed_record* rec, int64_t n);
+typedef int (*ssb_history_sink)(void* user, const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n);
+int ssb_run_stream_packed(ssb_engine* e, ssb_packed_sink sink, void* user, ssb_stats* stats);
+int ssb_run_stream_history(ssb_engine* e, ssb_history_sink sink, void* user, ssb_stats* stats);
 
 /* ---- exact-differential simulation (reference --diff_init / --diff_repeat; runner.hpp:178-348, queue.hpp:179-241,
  * logical_process.hpp:132-153, leveldb_store.hpp) ----

@@ -138,6 +138,11 @@ class Stats:
     fix_turns: int = 0
 
 
+#: ssb_packed_sink / ssb_history_sink
+PACKED_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+HISTORY_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+
 def library_path() -> str:
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libscalesim_b200.so")
 
@@ -178,6 +183,8 @@ def load_library() -> C.CDLL:
     lib.ssb_drain_committed_packed.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.ssb_run_drain_packed.argtypes = [vp, vp, i64, C.POINTER(i64), C.POINTER(_Stats)]
     lib.ssb_drain_history.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    lib.ssb_run_stream_packed.argtypes = [vp, PACKED_SINK, vp, C.POINTER(_Stats)]
+    lib.ssb_run_stream_history.argtypes = [vp, HISTORY_SINK, vp, C.POINTER(_Stats)]
     lib.ssb_load_history.argtypes = [vp, vp, vp, i64]
     lib.ssb_reset.argtypes = [vp]
     lib.ssb_set_flags.argtypes = [vp, C.c_int32]
@@ -358,6 +365,28 @@ class Engine:
         out = np.empty(cap, dtype=PACKED_RECORD_DTYPE)
         st, n = self.run_drain_packed_ptr(out.ctypes.data, cap)
         return st, out[:n]
+
+    def run_stream_packed(self, on_chunk) -> Stats:
+        """ssb_run_stream_packed: ``on_chunk(records)`` gets every committed record (``PACKED_RECORD_DTYPE`` view of the
+        engine's pinned staging buffer — copy what you keep) while the window loop runs."""
+        def sink(_user, rec, n):
+            buf = (C.c_char * (n * PACKED_RECORD_DTYPE.itemsize)).from_address(rec)
+            return int(on_chunk(np.frombuffer(buf, dtype=PACKED_RECORD_DTYPE, count=n)) or 0)
+        s = _Stats()
+        self._check(self._lib.ssb_run_stream_packed(self._h, PACKED_SINK(sink), None, C.byref(s)))
+        return self._stats(s)
+
+    def run_stream_history(self, on_chunk) -> Stats:
+        """ssb_run_stream_history (--diff_init): ``on_chunk(rec, sent)`` gets every committed event with its sent-log
+        entry, chunk by chunk, while the window loop runs (views of the pinned staging buffers)."""
+        def sink(_user, rec, sent, n):
+            a = (C.c_char * (n * RAW_RECORD_DTYPE.itemsize)).from_address(rec)
+            b = (C.c_char * (n * SENT_RECORD_DTYPE.itemsize)).from_address(sent)
+            return int(on_chunk(np.frombuffer(a, dtype=RAW_RECORD_DTYPE, count=n),
+                                np.frombuffer(b, dtype=SENT_RECORD_DTYPE, count=n)) or 0)
+        s = _Stats()
+        self._check(self._lib.ssb_run_stream_history(self._h, HISTORY_SINK(sink), None, C.byref(s)))
+        return self._stats(s)
 
     def drain_history(self, cap: int | None = None):
         """--diff_init: every committed event (``ssb_raw_record``) with its sent-log entry (``ssb_sent_record``).

@@ -100,6 +100,7 @@ struct ssb_engine {
   void* d_pack[2] = {nullptr, nullptr};      // staging halves of ssb_drain_committed_packed
   cudaStream_t copy_stream = nullptr;
   u64* h_poll = nullptr;                     // pinned: progress of the committed log while the loop graph runs
+  char* h_stage[2] = {nullptr, nullptr};     // pinned staging halves of the streaming drains (ssb_run_stream_*)
   cudaEvent_t pack_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   u64 log_drained = 0;
   double loop_ms = 0.0;
@@ -635,6 +636,7 @@ void ssb_destroy(ssb_engine* e) {
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->h_poll) cudaFreeHost(e->h_poll);
+  for (int i = 0; i < 2; ++i) if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
   e->t_collect();
   for (cudaEvent_t x : e->event_pool) cudaEventDestroy(x);
@@ -1093,6 +1095,109 @@ int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int
   if (stats) return ssb_get_stats(e, stats);
 #endif
   return SSB_OK;
+}
+
+// ssb_run with the committed records streaming out through two pinned staging halves; packed != 0: 24-byte records
+// (k_pack_log on the copy stream), else the raw record + its sent-log entry (two plain copies per chunk)
+static int stream_run(ssb_engine* e, ssb_packed_sink psink, ssb_history_sink hsink, void* user, ssb_stats* stats) {
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  constexpr u64 kStreamChunk = 1u << 21;
+  const bool packed = psink != nullptr;
+  if (!packed && !e->v.log_sent) { set_error("history was not kept: create the engine with SSB_FLAG_HISTORY and max_committed > 0"); return SSB_ERR_INVALID; }
+  if (!e->v.cap_log) { set_error("streaming drain needs max_committed > 0"); return SSB_ERR_INVALID; }
+  int rc = e->model_ready();
+  if (rc) return rc;
+  if (e->log_drained != 0) { set_error("streaming drain: the committed log is partly drained already"); return SSB_ERR_INVALID; }
+  if ((rc = ensure_pack_buffers(e))) return rc;
+  for (int i = 0; i < 2; ++i)
+    if (!e->h_stage[i]) CK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_stage[i]), kStreamChunk * 48, cudaHostAllocDefault));
+  if (!e->h_poll) CK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_poll), sizeof(u64), cudaHostAllocDefault));
+  bool overlapped = false;
+#ifndef SSB_EMU
+  overlapped = use_graph_path(e);
+  if (overlapped) {
+    if (e->graph_dirty && (rc = e->build_graph())) return rc;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    CK(cudaGraphLaunch(e->graph_exec, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+  }
+#endif
+  if (!overlapped && (rc = ssb_run(e, nullptr))) return rc;      // no device-side loop to overlap with: run, then stream out
+  u64 drained = 0;
+  int k = 0, sink_rc = 0;
+  struct { u32 cnt; bool live; } pend[2] = {{0, false}, {0, false}};
+  auto flush = [&](int b) -> int {
+    if (!pend[b].live) return SSB_OK;
+    CK(cudaEventSynchronize(e->copy_done[b]));
+    pend[b].live = false;
+    if (sink_rc) return SSB_OK;
+    if (packed) sink_rc = psink(user, reinterpret_cast<const ssb_packed_record*>(e->h_stage[b]), (int64_t)pend[b].cnt);
+    else sink_rc = hsink(user, reinterpret_cast<const ssb_raw_record*>(e->h_stage[b]),
+                         reinterpret_cast<const ssb_sent_record*>(e->h_stage[b] + kStreamChunk * 32), (int64_t)pend[b].cnt);
+    return SSB_OK;
+  };
+  auto issue = [&](u64 upto, bool all) -> int {
+    while (drained < upto && (all || upto - drained >= (kStreamChunk >> 2)) && !sink_rc) {
+      const u32 cnt = (u32)std::min<u64>(upto - drained, kStreamChunk);
+      const int b = k++ & 1;
+      int r = flush(b);      // the half is free once its previous chunk has been handed to the sink
+      if (r) return r;
+      if (packed) {
+        SSB_LAUNCH(k_pack_log, e->grid(cnt, 256), 256, 0, e->copy_stream, (const Ev*)e->v.log, drained, cnt, reinterpret_cast<u32*>(e->d_pack[b]));
+        CK(cudaMemcpyAsync(e->h_stage[b], e->d_pack[b], (size_t)cnt * 24, cudaMemcpyDeviceToHost, e->copy_stream));
+      } else {
+        CK(cudaMemcpyAsync(e->h_stage[b], e->v.log + drained, (size_t)cnt * sizeof(Ev), cudaMemcpyDeviceToHost, e->copy_stream));
+        CK(cudaMemcpyAsync(e->h_stage[b] + kStreamChunk * 32, e->v.log_sent + drained, (size_t)cnt * sizeof(uint4), cudaMemcpyDeviceToHost, e->copy_stream));
+      }
+      CK(cudaEventRecord(e->copy_done[b], e->copy_stream));
+      pend[b].cnt = cnt; pend[b].live = true;
+      drained += cnt;
+    }
+    return SSB_OK;
+  };
+  for (bool finished = false; !finished;) {
+    finished = !overlapped || cudaEventQuery(e->ev1) == cudaSuccess;
+    CK(cudaMemcpyAsync(e->h_poll, finished ? &e->v.ctl->log_count : &e->v.ctl->log_stable, sizeof(u64), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaStreamSynchronize(e->copy_stream));
+    const u64 upto = std::min<u64>(*e->h_poll, e->v.cap_log);
+    const u64 before = drained;
+    if ((rc = issue(upto, finished))) { cudaStreamSynchronize(e->stream); return rc; }
+    if (!finished && drained == before) {
+      if ((rc = flush(k & 1)) || (rc = flush((k + 1) & 1))) { cudaStreamSynchronize(e->stream); return rc; }   // idle: hand over what is ready
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  }
+  if ((rc = flush(k & 1)) || (rc = flush((k + 1) & 1))) return rc;      // in issue order
+  CK(cudaStreamSynchronize(e->copy_stream));
+  if (overlapped) {
+    CK(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->loop_ms += ms;
+  }
+  if ((rc = e->sync_ctl())) return rc;
+  e->rounds = e->h_ctl->round;
+  if ((rc = e->check_device_error())) return rc;
+  if (!e->h_ctl->done) { set_error("window loop ended before GVT reached finish_time"); return SSB_ERR_INVALID; }
+  if ((rc = log_overflow(e))) return rc;
+  if (sink_rc) { set_error("streaming drain: the sink returned " + std::to_string(sink_rc)); return SSB_ERR_INVALID; }
+  CK(cudaMemsetAsync(&e->v.ctl->log_count, 0, sizeof(u64), e->stream));      // fully drained: rewind the log
+  CK(cudaMemsetAsync(&e->v.ctl->log_stable, 0, sizeof(u64), e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->log_drained = 0;
+  if (stats) return ssb_get_stats(e, stats);
+  return SSB_OK;
+}
+
+int ssb_run_stream_packed(ssb_engine* e, ssb_packed_sink sink, void* user, ssb_stats* stats) {
+  if (!e || !sink) return SSB_ERR_INVALID;
+  return stream_run(e, sink, nullptr, user, stats);
+}
+
+int ssb_run_stream_history(ssb_engine* e, ssb_history_sink sink, void* user, ssb_stats* stats) {
+  if (!e || !sink) return SSB_ERR_INVALID;
+  return stream_run(e, nullptr, sink, user, stats);
 }
 
 int ssb_drain_history(ssb_engine* e, ssb_raw_record* rec, ssb_sent_record* sent, int64_t cap, int64_t* n) {

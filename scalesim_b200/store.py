@@ -18,7 +18,8 @@ which is the logical content of all three reference stores:
 ``key60`` renders the reference's 60-byte LevelDB key (leveldb_store.hpp:336-368) so that stores can be compared
 record by record. The value bytes of the reference (Boost binary archives) are not reproduced (unpinned).
 
-Files are written by a background thread from the (pinned) host arrays while the caller goes on (``save_async``).
+``HistoryWriter`` streams the store to its file from a background thread while the simulation runs
+(``Engine.run_stream_history`` hands it the chunks from the engine's pinned staging buffers).
 """
 from __future__ import annotations
 
@@ -29,7 +30,7 @@ import numpy as np
 
 from .capi import RAW_RECORD_DTYPE, SENT_RECORD_DTYPE
 
-MAGIC = b"SSBHIST2"
+MAGIC = b"SSBHIST3"
 NONE = 0xFFFFFFFF
 
 
@@ -77,17 +78,9 @@ class HistoryStore:
         return os.path.join(store_dir, str(sim_id), f"history{rank}.ssb")
 
     def save(self, store_dir: str, sim_id, rank: int = 0) -> str:
-        p = self.path(store_dir, sim_id, rank)
-        os.makedirs(os.path.dirname(p), exist_ok=True)
-        with open(p + ".tmp", "wb") as f:
-            f.write(MAGIC)
-            np.array([self.rec.size, self.state_lps.size, self.pool.size], dtype="<i8").tofile(f)
-            self.rec.tofile(f)
-            self.sent.tofile(f)
-            self.state_lps.astype("<i8").tofile(f)
-            self.pool.astype("<i8").tofile(f)
-        os.replace(p + ".tmp", p)
-        return p
+        w = HistoryWriter(self.path(store_dir, sim_id, rank), self.state_lps, self.pool)
+        w.append(self.rec, self.sent)
+        return w.close()
 
     def save_async(self, store_dir: str, sim_id, rank: int = 0) -> threading.Thread:
         """Write the store from a background thread (the arrays must stay untouched until ``join()``)."""
@@ -98,14 +91,92 @@ class HistoryStore:
     @classmethod
     def load(cls, store_dir: str, sim_id, rank: int = 0) -> "HistoryStore":
         p = cls.path(store_dir, sim_id, rank)
+        size = os.path.getsize(p)
         with open(p, "rb") as f:
             if f.read(8) != MAGIC:
                 raise ValueError(f"{p}: not a scalesim_b200 history store")
-            n, ns, npool = (int(x) for x in np.fromfile(f, dtype="<i8", count=3))
-            rec = np.fromfile(f, dtype=RAW_RECORD_DTYPE, count=n)
-            sent = np.fromfile(f, dtype=SENT_RECORD_DTYPE, count=n)
+            ns, npool = (int(x) for x in np.fromfile(f, dtype="<i8", count=2))
+            if ns < 0 or npool < 0 or (ns + npool) * 8 > size:
+                raise ValueError(f"{p}: header counts do not fit the file")
             lps = np.fromfile(f, dtype="<i8", count=ns)
             pool = np.fromfile(f, dtype="<i8", count=npool)
-        if rec.size != n or sent.size != n or lps.size != ns or pool.size != npool:
+            recs, sents = [], []
+            while True:
+                hdr = np.fromfile(f, dtype="<i8", count=1)
+                if hdr.size != 1:
+                    raise ValueError(f"{p}: truncated (no closing chunk)")
+                n = int(hdr[0])
+                if n == 0:
+                    break
+                if n < 0 or n * 48 > size:
+                    raise ValueError(f"{p}: bad chunk size")
+                r = np.fromfile(f, dtype=RAW_RECORD_DTYPE, count=n)
+                t = np.fromfile(f, dtype=SENT_RECORD_DTYPE, count=n)
+                if r.size != n or t.size != n:
+                    raise ValueError(f"{p}: truncated chunk")
+                recs.append(r)
+                sents.append(t)
+            total = np.fromfile(f, dtype="<i8", count=1)
+        rec = np.concatenate(recs) if recs else np.zeros(0, dtype=RAW_RECORD_DTYPE)
+        sent = np.concatenate(sents) if sents else np.zeros(0, dtype=SENT_RECORD_DTYPE)
+        if lps.size != ns or pool.size != npool or total.size != 1 or int(total[0]) != rec.size:
             raise ValueError(f"{p}: truncated")
         return cls(rec, sent, lps, pool)
+
+
+class HistoryWriter:
+    """Appends (records, sent-log entries) chunks to a history file from a background thread while the simulation
+    runs (``Engine.run_stream_history``): host memory stays bounded by the queue depth, where the reference keeps
+    every put in one in-memory WriteBatch until finish() (leveldb_store.hpp:132-141).
+    File layout (same as include/scalesim/simulation/runner.hpp): "SSBHIST3", n_state, n_pool, state LPs, model data
+    pool, then chunks {n, rec[n], sent[n]}, closed by n = 0 and the total record count."""
+
+    def __init__(self, path: str, state_lps=None, pool=None, queue_depth: int = 4):
+        import queue
+        self.path = path
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        self.f = open(path + ".tmp", "wb")
+        lps = np.ascontiguousarray(state_lps if state_lps is not None else np.zeros(0), dtype="<i8")
+        pl = np.ascontiguousarray(pool if pool is not None else np.zeros(0), dtype="<i8")
+        self.f.write(MAGIC)
+        np.array([lps.size, pl.size], dtype="<i8").tofile(self.f)
+        lps.tofile(self.f)
+        pl.tofile(self.f)
+        self.total = 0
+        self.error = None
+        self.q = queue.Queue(maxsize=queue_depth)
+        self.thr = threading.Thread(target=self._loop, daemon=True)
+        self.thr.start()
+
+    def _loop(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            try:
+                rec, sent = item
+                np.array([rec.size], dtype="<i8").tofile(self.f)
+                rec.tofile(self.f)
+                sent.tofile(self.f)
+                self.total += rec.size
+            except Exception as exc:      # reported by close()
+                self.error = exc
+
+    def append(self, rec: np.ndarray, sent: np.ndarray, copy: bool = True):
+        """Queue one chunk (copied: a staging-buffer view is reused by the engine as soon as the sink returns)."""
+        if rec.size == 0:
+            return
+        r = np.array(rec, dtype=RAW_RECORD_DTYPE, copy=copy)
+        t = np.array(sent, dtype=SENT_RECORD_DTYPE, copy=copy)
+        self.q.put((r, t))
+
+    def close(self) -> str:
+        self.q.put(None)
+        self.thr.join()
+        if self.error is not None:
+            self.f.close()
+            raise self.error
+        np.array([0, self.total], dtype="<i8").tofile(self.f)
+        self.f.close()
+        os.replace(self.path + ".tmp", self.path)
+        return self.path

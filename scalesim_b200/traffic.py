@@ -303,6 +303,21 @@ def run_diff_init(sc: Scenario, **kw):
     return st, rec, HistoryStore(rec, sent, sc.state_ids[owner == rank], sc.route_nodes)
 
 
+def run_diff_init_streaming(sc: Scenario, store_dir: str, sim_id, **kw):
+    """--diff_init with the history leaving the device WHILE the window loop runs (ssb_run_stream_history): chunks go
+    from the engine's pinned staging buffers to a writer thread that appends them to the store file. Returns
+    (engine stats, path of the store)."""
+    from .store import HistoryStore, HistoryWriter
+    rank, world = kw.get("rank", 0), kw.get("world", 1)
+    eng = make_engine(sc, history=True, **kw)
+    part = sc.partition
+    owner = (part[sc.state_ids] % world) if part is not None else (sc.state_ids % world)
+    w = HistoryWriter(HistoryStore.path(store_dir, sim_id, rank), sc.state_ids[owner == rank], sc.route_nodes)
+    st = eng.run_stream_history(lambda rec, sent: w.append(rec, sent))
+    eng.close()
+    return st, w.close()
+
+
 def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
     """--diff_repeat (runner::init_repeat, runner.hpp:178-348): the recorded history goes back into the engine as
     processed events, then the AE queries are injected. ``sc`` provides the road network and the ORIGINAL route pool

@@ -136,3 +136,23 @@ def test_history_needs_the_flag():
     with pytest.raises(ssb.EngineError):
         eng.drain_history()
     eng.close()
+
+
+def test_streaming_history_store_equals_the_drained_one(tmp_path):
+    """ssb_run_stream_history: the history leaves through the pinned staging buffers while the loop runs and a writer
+    thread appends it to the store file — same records as ssb_drain_history after the run."""
+    sc = traffic.synthetic_grid(48, 48, 30000, seed=4)
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=11)
+    st2, path = traffic.run_diff_init_streaming(sc, str(tmp_path), 5, bucket_ticks=11)
+    hs2 = store.HistoryStore.load(str(tmp_path), 5, 0)
+    assert st2.committed == st.committed == hs2.rec.size
+    a = np.sort(np.stack([hs.rec["key"], hs.rec["dst"].astype(np.uint64), hs.sent["dst"].astype(np.uint64)], axis=1), axis=0)
+    k1 = np.lexsort((hs.sent["recv_time"], hs.sent["dst"], hs.rec["dst"], hs.rec["key"]))
+    k2 = np.lexsort((hs2.sent["recv_time"], hs2.sent["dst"], hs2.rec["dst"], hs2.rec["key"]))
+    assert np.array_equal(hs.rec[k1], hs2.rec[k2]) and np.array_equal(hs.sent[k1], hs2.sent[k2])
+    assert np.array_equal(hs2.pool, sc.route_nodes) and hs2.state_lps.size == sc.state_ids.size
+    # a sink that fails stops the run loudly
+    eng = traffic.make_engine(sc, bucket_ticks=11, history=True)
+    with pytest.raises(ssb.EngineError):
+        eng.run_stream_history(lambda rec, sent: 7)
+    eng.close()

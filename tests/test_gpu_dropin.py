@@ -10,10 +10,11 @@ from fixtures import golden, golden_lines, sha256_lines, write_ring_files
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APPS = os.environ.get("SCALESIM_B200_APPS_DIR", os.path.join(ROOT, "apps"))      # (tools/emu builds its own copies)
 
 
 def _run(exe, args, env=None):
-    path = os.path.join(ROOT, "apps", exe)
+    path = os.path.join(APPS, exe)
     if not os.path.exists(path):
         pytest.skip(f"{path} not built (needs the reference tree at build time)")
     p = subprocess.run([path] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
@@ -86,7 +87,7 @@ def test_phold_dropin_diff_init_and_repeat_equal_reference(tmp_path):
 
 
 def test_dropin_repeat_without_store_fails_loudly(tmp_path):
-    path = os.path.join(ROOT, "apps", "PHOLD")
+    path = os.path.join(APPS, "PHOLD")
     if not os.path.exists(path):
         pytest.skip("not built")
     p = subprocess.run([path, "--diff_repeat", "--sim_id=1", f"--store_dir={tmp_path}/none", "100", "1600", "0.1", "1.0", "1", "50"],

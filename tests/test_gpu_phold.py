@@ -255,4 +255,25 @@ def test_compact_load_and_packed_drain_equal_the_wide_forms(phold_tables_01):
         eng.reset()
         eng.load_events_raw(ssb.events_to_raw(ev))
         eng.run_drain_packed(10)          # output buffer too small: fails loudly
+    # ... and through the bounded staging buffers of the streaming form
+    eng.reset()
+    eng.load_events_raw(ssb.events_to_raw(ev))
+    chunks = []
+    st = eng.run_stream_packed(lambda rec: chunks.append(rec.copy()))
+    rec = np.concatenate(chunks)
+    assert st.committed == rec.size == len(want) and eng.digest() == want_digest
+    assert sorted(ssb.records_to_lines(ssb.packed_to_records(rec))) == sorted(want)
+    eng.close()
+
+
+def test_committed_log_overflow_fails_loudly(phold_tables_01):
+    """A committed log that is too small must not yield a silently shorter output: every drain call fails."""
+    from scalesim_b200 import phold
+    eng = phold.make_engine(1000, 16000, 0.1, 1.0, tables=phold_tables_01, max_committed=1000)
+    st = eng.run()
+    assert st.log_dropped == st.committed - 1000 > 0
+    for call in (eng.drain_committed, eng.drain_committed_raw, eng.drain_committed_packed):
+        with pytest.raises(ssb.EngineError) as ei:
+            call()
+        assert ei.value.status == 4      # SSB_ERR_CAPACITY
     eng.close()
