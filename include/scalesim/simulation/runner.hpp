@@ -314,6 +314,8 @@ void runner<App>::run() {
   ev_vec<App> mine;
   history hist;
   std::vector<ssb_event> deletes;      // anti-messages of the DE / RE what-if queries
+  struct state_change { long lp, time; std::vector<uint32_t> words; };
+  std::vector<state_change> state_changes;      // SC what-if queries
   if (!FLAGS_diff_repeat) {
     for (int r = 0; r < world_; ++r) {
       ev_vec<App> parsed;
@@ -332,12 +334,17 @@ void runner<App>::run() {
       std::vector<boost::shared_ptr<const what_if<App> > > wi;
       app_.init_what_if(wi, r, world_);
       for (size_t i = 0; i < wi.size(); ++i) {
-        if (wi[i]->update_state_.id() != -1) {
-          LOG(ERROR) << "what-if queries of type SC (state change) are not part of this build yet";
-          std::exit(2);
-        }
         long d = wi[i]->lp_id_;
         if (!(d >= 0 && d < n_lp && part[d] % world_ == rank_)) continue;
+        if (wi[i]->update_state_.id() != -1) {
+          // state change (runner.hpp:217-245): the LP gets this state at (time, 0); its recorded events and sent
+          // events from there on are re-armed -> ssb_set_state_from after the history is loaded
+          state_change sc;
+          sc.lp = d; sc.time = wi[i]->time_;
+          sc.words.resize((size_t)model::state_words());
+          model::pack_state(wi[i]->update_state_, sc.words.data(), cx);
+          state_changes.push_back(sc);
+        }
         if (wi[i]->delete_event_id_ != -1) {
           // delete event (runner.hpp:246-276): the recorded event loses its sent-log entry — eventq::delete_can: its
           // output is NOT cancelled — and an anti-message goes into the LP's inbox (eventq::delete_ev,
@@ -399,6 +406,8 @@ void runner<App>::run() {
   }
   if (FLAGS_diff_repeat &&
       (rc = ssb_load_history(engine_, hist.rec.data(), hist.sent.data(), (int64_t)hist.rec.size()))) fail("ssb_load_history", rc);
+  for (size_t i = 0; i < state_changes.size(); ++i)
+    if ((rc = ssb_set_state_from(engine_, state_changes[i].lp, state_changes[i].time, state_changes[i].words.data()))) fail("ssb_set_state_from", rc);
   if ((rc = ssb_load_events(engine_, pod.data(), (int64_t)pod.size()))) fail("ssb_load_events", rc);
   double init_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   LOG_IF(INFO, rank_ == 0)

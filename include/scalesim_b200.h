@@ -240,6 +240,11 @@ int ssb_run_stream_history(ssb_engine* e, ssb_history_sink sink, void* user, ssb
  * Only events (re-)executed by the repeat run are committed (output / digest). */
 int ssb_drain_history(ssb_engine* e, ssb_raw_record* rec, ssb_sent_record* sent, int64_t cap, int64_t* n);
 int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_record* sent, int64_t n);
+/* --diff_repeat, state change (SC) what-if query (runner.hpp:217-245: init_state(new state, (time, 0)), then the LP's
+ * recorded events and sent events from (time, 0) on are re-armed): after ssb_load_history, LP `lp_id` (owned by this
+ * rank) gets the state `words` and its recorded history with key >= (time, 0) becomes invalid — the repeat run
+ * re-executes it with the new state and cancels what it had sent. */
+int ssb_set_state_from(ssb_engine* e, int64_t lp_id, int64_t time, const uint32_t* words);
 
 /* Back to the state right after ssb_load_states: empty calendar, zero statistics; model data, partition and the
  * loaded initial states are kept. Lets one engine run many simulations (bench steps) without re-allocating. */

@@ -186,6 +186,7 @@ def load_library() -> C.CDLL:
     lib.ssb_run_stream_packed.argtypes = [vp, PACKED_SINK, vp, C.POINTER(_Stats)]
     lib.ssb_run_stream_history.argtypes = [vp, HISTORY_SINK, vp, C.POINTER(_Stats)]
     lib.ssb_load_history.argtypes = [vp, vp, vp, i64]
+    lib.ssb_set_state_from.argtypes = [vp, i64, i64, vp]
     lib.ssb_reset.argtypes = [vp]
     lib.ssb_set_flags.argtypes = [vp, C.c_int32]
     lib.ssb_kernel_times.argtypes = [vp, vp, vp, vp, i32]
@@ -406,6 +407,11 @@ class Engine:
         if rec.size != sent.size:
             raise ValueError("history arrays differ in length")
         self._check(self._lib.ssb_load_history(self._h, _ptr(rec), _ptr(sent), rec.size))
+
+    def set_state_from(self, lp_id: int, time: int, words):
+        """--diff_repeat SC query: LP ``lp_id`` gets the state ``words``; its recorded history from ``time`` on is invalid."""
+        w = np.ascontiguousarray(words, dtype=np.uint32).reshape(self.state_words)
+        self._check(self._lib.ssb_set_state_from(self._h, lp_id, time, _ptr(w)))
 
     def reset(self):
         self._check(self._lib.ssb_reset(self._h))

@@ -1261,6 +1261,22 @@ int ssb_load_history(ssb_engine* e, const ssb_raw_record* rec, const ssb_sent_re
   return e->check_device_error();
 }
 
+int ssb_set_state_from(ssb_engine* e, int64_t lp_id, int64_t time, const uint32_t* words) {
+  if (!e || !words) return SSB_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  auto set_error = [&](const std::string& s) { e->set_error(s); };
+  if (!e->v.inv) { set_error("ssb_set_state_from needs a loaded history (ssb_load_history first)"); return SSB_ERR_INVALID; }
+  if (lp_id < 0 || lp_id >= e->cfg.n_lp || e->owner_of(lp_id) != (u32)e->cfg.rank) { set_error("state change for an LP this rank does not own"); return SSB_ERR_INVALID; }
+  if (time < 0 || time >= 0x80000000ll) { set_error("state change time out of range"); return SSB_ERR_RANGE; }
+  const u32 l = e->local_of(lp_id);
+  const int sw = e->state_words();
+  CK(cudaMemcpyAsync(e->v.state + (size_t)l * sw, words, (size_t)sw * 4, cudaMemcpyHostToDevice, e->stream));
+  SSB_LAUNCH(k_invalidate_from, 1, 1, 0, e->stream, e->v, l, (u64)time << 32);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  return SSB_OK;
+}
+
 int ssb_reset(ssb_engine* e) {
   if (!e) return SSB_ERR_INVALID;
   cudaSetDevice(e->cfg.device);

@@ -1394,6 +1394,15 @@ __global__ void k_hist_stage(View v, const Ev* in, u32 n) {
   if (blockIdx.x == 0 && threadIdx.x == 0) v.ctl->load_count = n;
 }
 
+// state-change what-if query: the LP's recorded history is invalid from `key` on
+__global__ void k_invalidate_from(View v, u32 lp, u64 key) {
+  if (blockIdx.x || threadIdx.x) return;
+  if (key < v.inv[lp]) {
+    if (v.inv[lp] == KEY_MAX) v.ctl->n_touched += 1u;
+    v.inv[lp] = key;
+  }
+}
+
 // after the history load: every recorded event counts as consumed (processed); the last bucket with history
 __global__ void k_after_history(View v) {
   Ctl* c = v.ctl;

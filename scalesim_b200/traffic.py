@@ -97,6 +97,7 @@ class WhatIf:
     route_start: np.ndarray
     route_nodes: np.ndarray
     deletes: np.ndarray          # rows (lp, time, event id)
+    state_changes: list = None   # SC queries: (lp, time, road dst[], speed[], length[])
 
     def __iter__(self):          # unpacks like the (trip_id, trip_dep, route_start, route_nodes) tuple of the AE part
         return iter((self.trip_id, self.trip_dep, self.route_start, self.route_nodes))
@@ -107,8 +108,9 @@ def read_what_if(path: str) -> WhatIf:
     ``AE,{event id},0,{departure},{1st node},{2nd node},...`` add event: query LP = first node, time = departure (:522-558)
     ``DE,{lp id},{time},{event id}``                           delete event (:559-580)
     ``RE,{event id},{source},{send time},{destination},{receive time}``   delete the event of that result line (:581-596)
-    SC (state change) queries are not supported by this build and raise."""
-    tid, dep, start, nodes, dels = [], [], [0], [], []
+    ``SC,{lp id},{time};{road};{road};...``                    state change: the LP's roads from ``time`` on (:473-521);
+                                                               road = ``R,{id},{lp},{dst},{speed},{length},{lanes}``"""
+    tid, dep, start, nodes, dels, scs = [], [], [0], [], [], []
     with open(path) as f:
         for line in f.read().splitlines():
             fld = line.split(",")
@@ -122,9 +124,14 @@ def read_what_if(path: str) -> WhatIf:
             elif line[:2] == "RE":
                 dels.append((_atol(fld[4]), _atol(fld[5]), _atol(fld[1])))
             elif line[:2] == "SC":
-                raise NotImplementedError("what-if query type SC (state change) is not supported")
+                parts = line.split(";")
+                head = parts[0].split(",")
+                roads = [r.split(",") for r in parts[1:]]
+                ln = [_atol(r[5]) for r in roads]
+                scs.append((_atol(head[1]), _atol(head[2]), [_atol(r[3]) for r in roads], [_atol(r[4]) for r in roads],
+                            [x if x != 0 else 1 for x in ln]))
     return WhatIf(np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
-                  np.array(nodes, dtype=np.int64), np.array(dels, dtype=np.int64).reshape(-1, 3))
+                  np.array(nodes, dtype=np.int64), np.array(dels, dtype=np.int64).reshape(-1, 3), scs)
 
 
 def read_scenario(road_csv: str, trip_csv: str, partition_file: str | None = None) -> Scenario:
@@ -251,7 +258,8 @@ def pack_events(sc: Scenario) -> np.ndarray:
 def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1, keep_records: bool = False,
                 rank: int = 0, world: int = 1, device: int = 0, max_events: int | None = None,
                 max_batch: int | None = None, max_committed: int | None = None, finish_time: int = FINISH_TIME,
-                rounds_per_sync: int = 8, load: bool = True, history: bool = False, extra_routes=None) -> Engine:
+                rounds_per_sync: int = 8, load: bool = True, history: bool = False, extra_routes=None,
+                extra_roads=None) -> Engine:
     """Build a TrafficSim engine the way runner<traffic_sim>::init does (runner.hpp:79-176)."""
     n_trips = sc.trip_id.size
     n_nodes = sc.route_nodes.size
@@ -275,6 +283,8 @@ def make_engine(sc: Scenario, *, bucket_ticks: int = 8, window_buckets: int = 1,
         pool = np.concatenate([pool, np.asarray(extra_routes, dtype=np.int64)])      # what-if trips: routes appended
     eng.set_model_data(0, pool)
     ids, words, road_table = pack_states(sc)
+    if extra_roads is not None and len(extra_roads):
+        road_table = np.concatenate([road_table, np.asarray(extra_roads, dtype=np.int64).reshape(-1, 3)])
     if road_table.size:
         eng.set_model_data(1, road_table.reshape(-1))
     owner = (part[ids] % world) if part is not None else (ids % world)
@@ -326,11 +336,29 @@ def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
     rank, world = kw.get("rank", 0), kw.get("world", 1)
     tid, dep, rstart, rnodes = what_if
     deletes = getattr(what_if, "deletes", np.zeros((0, 3), dtype=np.int64))
+    state_changes = getattr(what_if, "state_changes", None) or []
     n_hist = store.rec.size
     # re-executed history is re-sent: until a bucket is fossil-collected it holds the recorded copy AND the new one
     kw.setdefault("max_events", int((n_hist + rnodes.size) * 3) + (1 << 16))
     kw.setdefault("max_batch", max(1 << 14, (n_hist + tid.size) // 2 + (1 << 14)))
     kw.setdefault("max_committed", n_hist + int(rnodes.size) + 1024)
+    # state-change queries: the new road sets are packed like states (junctions with more than INLINE_ROADS roads go
+    # to the road table, behind the scenario's own entries)
+    sc_words = []
+    if state_changes:
+        _, base_words, base_table = pack_states(sc)
+        extra_rows = []
+        for lp, t, dst, speed, length in state_changes:
+            w = np.zeros(STATE_WORDS, dtype=np.uint32)
+            w[0], w[1] = lp, len(dst)
+            if len(dst) <= INLINE_ROADS:
+                for k in range(len(dst)):
+                    w[2 + 3 * k: 5 + 3 * k] = (dst[k], speed[k], length[k])
+            else:
+                w[2] = base_table.shape[0] + len(extra_rows)
+                extra_rows.extend(zip(dst, speed, length))
+            sc_words.append(w)
+        kw = dict(kw, extra_roads=np.array(extra_rows, dtype=np.int64).reshape(-1, 3))
     eng = make_engine(sc, load=False, extra_routes=rnodes, **kw)
     sent = store.sent
     if deletes.size:
@@ -343,6 +371,10 @@ def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
             hit = np.nonzero((store.rec["key"] == key) & (store.rec["dst"] == lp))[0]
             sent["dst"][hit] = 0xFFFFFFFF
     eng.load_history(store.rec, sent)
+    part = sc.partition
+    for (lp, t, *_), w in zip(state_changes, sc_words):
+        if ((part[lp] % world) if part is not None else (lp % world)) == rank:
+            eng.set_state_from(lp, t, w)
     ev = np.zeros(tid.size, dtype=EVENT_DTYPE)
     ev["id"] = tid
     ev["src"] = -1
@@ -351,7 +383,6 @@ def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
     ev["send_time"] = dep
     ev["p0"] = sc.route_nodes.size + rstart[:-1]
     ev["p1"] = np.diff(rstart)
-    part = sc.partition
     if deletes.size:
         anti = np.zeros(deletes.shape[0], dtype=EVENT_DTYPE)
         anti["id"] = deletes[:, 2]

@@ -156,3 +156,48 @@ def test_streaming_history_store_equals_the_drained_one(tmp_path):
     with pytest.raises(ssb.EngineError):
         eng.run_stream_history(lambda rec, sent: 7)
     eng.close()
+
+
+def ring_changed_network_lines():
+    """one plain run (oracle closure) of the ring example on the network of change_state.csv: LP 1's road = 200 m"""
+    sc, _ = ring_scenario()
+    changed = traffic.Scenario(sc.n_lp, sc.state_ids, sc.road_start, sc.road_dst, sc.road_speed, sc.road_len.copy(),
+                               sc.trip_id, sc.trip_dep, sc.route_start, sc.route_nodes)
+    changed.road_len[changed.road_start[1]] = 200
+    o = O.Sim.traffic_scenario(changed)
+    o.run_closure(2)
+    return sorted(O.records_to_lines(o.committed()))
+
+
+def test_state_change_query_on_the_ring(tmp_path):
+    """SC what-if (traffic/ring/change_state.csv: LP 1's road gets 200 m from t = 5, before any event reaches LP 1).
+    Exactness (the definition of exact-differential simulation): init output minus what the change supersedes, plus
+    the new lines of the repeat run, must equal ONE run on the changed network.
+    The reference's own SC output is not a parity target as a whole: it drops every anti-message that reaches an LP
+    before that LP's lazy history load (logical_process.hpp:132-138, queue.hpp:87-90), so it keeps the stale
+    trajectories (30 / 31 stale lines, 69 lines at 2 worker threads, 70 at 3 / 4 / 8) and even re-executes a stale
+    arrival at LP 1 with the new state (a 6-line trajectory no run on the changed network has). What IS checked against
+    it: this engine's output is contained in every reference variant, and its new lines are exactly the reference's
+    new lines that are right (= also lines of the run on the changed network)."""
+    g = golden("ring_diff")
+    sc, _ = ring_scenario()
+    sc.partition = None
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=8)
+    init_lines = sorted(ssb.records_to_lines(ssb.raw_to_records(rec)))
+    assert init_lines == g["init_lines"]
+    wi = _what_if(g["sc_lines"], tmp_path)
+    assert len(wi.state_changes) == 1 and wi.state_changes[0][:2] == (1, 5) and wi.state_changes[0][4] == [200]
+    full = ring_changed_network_lines()
+    superseded = set(init_lines) - set(full)
+    for bucket, window in ((8, 1), (41, 3)):
+        eng = traffic.make_repeat_engine(sc, hs, wi, bucket_ticks=bucket, window_buckets=window, keep_records=True)
+        st2 = eng.run()
+        lines = sorted(ssb.records_to_lines(eng.drain_committed()))
+        eng.close()
+        new = sorted(l for l in lines if l not in set(init_lines))
+        assert sorted((set(init_lines) - superseded) | set(new)) == full                  # exact
+        assert new == sorted(set(g["sc_new_lines"]) & set(full))                          # the reference's right new lines
+        assert len(set(g["sc_new_lines"]) - set(full)) == 6                               # ... its artefact trajectory
+        for v in g["sc_variants"]:
+            assert set(lines) <= set(v["lines"])
+        assert st2.rollbacks > 0 and st2.antis_sent >= len(superseded)

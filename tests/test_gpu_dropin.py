@@ -74,6 +74,16 @@ def test_trafficsim_dropin_diff_init_and_repeat_equal_reference(tmp_path):
         f.write("".join(l + "\n" for l in g["de_lines"]))
     lines, err = _run("TrafficSim", flags + ["--diff_repeat", part1, rd, de])
     assert sorted(lines) == g["delete_union"]
+    scq = str(tmp_path / "change_state.csv")       # traffic/ring/change_state.csv: the SC query
+    with open(scq, "w") as f:
+        f.write("".join(l + "\n" for l in g["sc_lines"]))
+    lines, err = _run("TrafficSim", flags + ["--diff_repeat", part1, rd, scq])
+    from test_gpu_diff import ring_changed_network_lines
+    init, full = set(g["init_lines"]), set(ring_changed_network_lines())
+    new = set(l for l in lines if l not in init)
+    assert sorted((init - (init - full)) | new) == sorted(full)                          # init + repeat == one run on the changed network
+    assert new == set(g["sc_new_lines"]) & full                                          # the reference's (right) new lines
+    assert all(set(lines) <= set(v["lines"]) for v in g["sc_variants"])                 # ... and nothing it does not print
 
 
 def test_phold_dropin_diff_init_and_repeat_equal_reference(tmp_path):
