@@ -484,6 +484,91 @@ def traffic_measure(env):
 
 
 # ------------------------------------------------------------------------------------------------
+# Exact-differential simulation at scale (BASELINE.json config 5): --diff_init on the config-3 grid with the history
+# streaming out while the loop runs, then --diff_repeat with added trips (AE queries)
+# ------------------------------------------------------------------------------------------------
+def exact_diff_measure(env):
+    import numpy as np
+    import scalesim_b200 as ssb
+    from scalesim_b200 import traffic
+    from scalesim_b200.store import HistoryStore
+    args = env.args
+    g, n_trips, n_add = args.traffic_grid, args.diff_trips, args.diff_added
+    sc = traffic.synthetic_grid(g, g, n_trips, seed=1)
+    extra = traffic.synthetic_grid(g, g, n_add, seed=9, max_departure=6000)
+    extra_ids = 100_000_000 + np.arange(n_add, dtype=np.int64)
+    n_nodes = int(sc.route_nodes.size)
+    # --diff_init: every committed event + its sent-log entry leaves through the pinned staging buffers while the
+    # graph loop runs (ssb_run_stream_history); the sink appends to the host arrays the repeat run loads from
+    eng = traffic.make_engine(sc, bucket_ticks=args.traffic_bucket, history=True, max_events=2 * n_trips + (1 << 20),
+                              max_batch=n_trips + (1 << 16), max_committed=n_nodes + 1024)
+    rec = np.empty(n_nodes, dtype=ssb.RAW_RECORD_DTYPE)
+    sent = np.empty(n_nodes, dtype=ssb.SENT_RECORD_DTYPE)
+    fill = [0]
+
+    def sink(r, s):
+        rec[fill[0]:fill[0] + r.size] = r
+        sent[fill[0]:fill[0] + s.size] = s
+        fill[0] += r.size
+
+    t0 = time.perf_counter()
+    st = eng.run_stream_history(sink)
+    init_wall = time.perf_counter() - t0
+    init_digest = eng.digest()
+    eng.close()
+    n_hist = fill[0]
+    hs = HistoryStore(rec[:n_hist], sent[:n_hist], None, sc.route_nodes)
+    # --diff_repeat
+    t0 = time.perf_counter()
+    eng = traffic.make_repeat_engine(sc, hs, (extra_ids, extra.trip_dep, extra.route_start, extra.route_nodes),
+                                     bucket_ticks=args.traffic_bucket, keep_records=True)
+    load_wall = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    st2 = eng.run()
+    rep = eng.drain_committed_packed()
+    repeat_wall = time.perf_counter() - t0
+    eng.close()
+    # exactness: vehicles do not interact, so ONE run over trips + added trips = init + the added trips' lines; the
+    # rest of the repeat output is recorded history that had to be re-executed (it must reproduce recorded lines)
+    new = rep[rep["id"] >= 100_000_000]
+    redone = rep[rep["id"] < 100_000_000]
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        full = traffic.Scenario(sc.n_lp, sc.state_ids, sc.road_start, sc.road_dst, sc.road_speed, sc.road_len,
+                                np.concatenate([sc.trip_id, extra_ids]), np.concatenate([sc.trip_dep, extra.trip_dep]),
+                                np.concatenate([sc.route_start, sc.route_start[-1] + extra.route_start[1:]]),
+                                np.concatenate([sc.route_nodes, extra.route_nodes]))
+        o = oracle_lib.Sim.traffic_scenario(full)
+        o.run_closure(max(4, cpu_threads()), keep_records=False)
+        want = tuple(int(x) for x in o.digest())
+        o.close()
+        got = ssb.dist.combine_digests([init_digest, ssb.digest_records(ssb.packed_to_records(new))])
+        # re-executed history: every such record is one of the recorded ones (same key, destination, source, send time)
+        hk = np.sort(rec[:n_hist]["key"])
+        rk = (redone["recv_time"].astype(np.uint64) << np.uint64(32)) | redone["id"].astype(np.uint64)
+        pos = np.searchsorted(hk, rk)
+        pos[pos >= hk.size] = hk.size - 1
+        redone_ok = bool(np.all(hk[pos] == rk)) if redone.size else True
+        parity = {"checked": True, "equal": tuple(got) == want and redone_ok, "rule": "digest(init) + digest(new lines) == oracle closure of trips + added trips; re-executed records are recorded ones"}
+        if not parity["equal"]:
+            print(json.dumps({"error": "exact-differential run is not exact", "got": list(got), "want": list(want), "redone_ok": redone_ok}),
+                  file=sys.stderr, flush=True)
+            raise SystemExit(3)
+    return {"workload": f"TrafficSim {g}x{g} torus grid, {n_trips} trips; --diff_init, then --diff_repeat with {n_add} added trips "
+                        f"(BASELINE.json config 5)",
+            "init": {"committed": st.committed, "loop_ms": st.loop_ms, "wall_ms": 1000 * init_wall,
+                     "history_bytes": int(n_hist) * 48, "events_per_s": st.committed / init_wall,
+                     "note": "wall = window loop + D2H of every (event, sent-log entry) pair through 2 pinned staging buffers + host sink"},
+            "repeat": {"load_history_wall_ms": 1000 * load_wall, "run_and_drain_wall_ms": 1000 * repeat_wall, "loop_ms": st2.loop_ms,
+                       "rounds": st2.rounds, "committed": st2.committed, "new_lines": int(new.size), "reexecuted_history": int(redone.size),
+                       "rollbacks": st2.rollbacks, "antis": st2.antis_sent,
+                       "fraction_of_full_run_reexecuted": st2.committed / max(1, st.committed + int(new.size))},
+            "parity": parity}
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -508,6 +593,9 @@ def main():
     ap.add_argument("--traffic-trips", type=int, default=10_000_000)
     ap.add_argument("--traffic-bucket", type=int, default=11)
     ap.add_argument("--traffic-window", type=int, default=1)
+    ap.add_argument("--no-exact-diff", action="store_true", help="skip the exact-differential (config 5) measurement")
+    ap.add_argument("--diff-trips", type=int, default=2_000_000)
+    ap.add_argument("--diff-added", type=int, default=1000)
     args = ap.parse_args()
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line and nothing else
@@ -576,6 +664,10 @@ def main():
     if not args.no_traffic:
         traffic_res = traffic_measure(env)
 
+    exact_diff = None
+    if world == 1 and not args.no_exact_diff and not args.no_traffic:
+        exact_diff = exact_diff_measure(env)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -595,7 +687,7 @@ def main():
             "parity_checked": bool(main_res["parity"] and main_res["parity"]["equal"]), "parity": main_res["parity"],
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"], "roofline": main_res.get("roofline"), "e2e": main_res.get("e2e"),
-            "cpu_baseline": cpu, "optimistic": optimistic, "weak_config2": weak, "traffic": traffic_res,
+            "cpu_baseline": cpu, "optimistic": optimistic, "weak_config2": weak, "traffic": traffic_res, "exact_diff": exact_diff,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

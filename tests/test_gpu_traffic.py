@@ -94,3 +94,22 @@ def test_any_junction_degree_equals_oracle(bucket, window):
     rec = eng.drain_committed()
     assert sorted(ssb.records_to_lines(rec)) == sorted(O.records_to_lines(s.committed()))
     eng.close()
+
+
+def test_traffic_config3_full_size_count_and_digest():
+    """BASELINE.json config 3 at full size: 1024 x 1024 torus grid, 10M trips -> 367 737 881 committed events, digest =
+    the oracle's closure (every trip advanced hop by hop on the CPU). Also the size-independent property of a window
+    within the lookahead: every event is processed exactly once, no rollback."""
+    sc = traffic.synthetic_grid(1024, 1024, 10_000_000, seed=1)
+    s = O.Sim.traffic_scenario(sc)
+    s.run_closure(8, keep_records=False)
+    want = s.digest()
+    s.close()
+    n = sc.trip_id.size
+    eng = traffic.make_engine(sc, bucket_ticks=11, window_buckets=1, max_events=2 * n + (1 << 20), max_batch=n + (1 << 16))
+    del sc
+    st = eng.run()
+    assert st.committed == 367_737_881 == want[0]
+    assert st.processed == st.committed and st.rollbacks == 0
+    assert eng.digest() == want
+    eng.close()
