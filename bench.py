@@ -54,7 +54,8 @@ CONFIG4 = dict(n_lp=16_000_000, n_init=256_000_000, remote=0.5, committed=1_165_
 # receive-side routes; a round with an irregular LP turn (ssb_stats.fix_rounds) adds the IF node's six kernels:
 # k_fix_count, k_fix_segs, k_fix_scatter, k_fix_sort, k_fix_turn, k_route(anti).
 def launches(st, world):
-    return int(st.rounds * (5 + (3 if world > 1 else 0)) + st.fix_rounds * 6)
+    # (N > 1: k_gvt + the receive-side route of the positives; the one of the anti-messages sits in an IF node)
+    return int(st.rounds * 5 + (st.exchanges * 2 if world > 1 else 0) + st.fix_rounds * 6)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -442,6 +443,8 @@ def traffic_measure(env):
                               device=env.local_rank, max_events=int(per * 2.0) + (1 << 20), max_batch=per + (1 << 16),
                               rounds_per_sync=32, load=False)
     ssb.dist.init_engine_comm(eng, rank, world, p2p=args.exchange == "p2p")
+    if world > 1 and args.exchange == "p2p":
+        eng.set_sync_interval(args.traffic_sync)
     ev = traffic.pack_events(sc)
     if world > 1:
         ev = ev[sc.partition[ev["dst"]] % world == rank]
@@ -476,6 +479,7 @@ def traffic_measure(env):
     return {"metric": "committed events/sec, grid TrafficSim", "value": value, "unit": UNIT, "ms_per_step": sum(ms) / n,
             "committed_per_step": committed // n, "rounds_per_step": rounds // n, "rollbacks": last.rollbacks,
             "antis": last.antis_sent, "bucket_ticks": args.traffic_bucket, "window_buckets": args.traffic_window,
+            "windows_per_synchronisation": args.traffic_sync if world > 1 else 1,
             "parity": parity, "scaling": "strong",
             "workload": f"TrafficSim {args.traffic_grid}x{args.traffic_grid} torus grid, {args.traffic_trips} trips "
                         f"(8..64 hops), finish 10800 s, {world} row-stripe partition(s) (BASELINE.json config 3)",
@@ -593,6 +597,7 @@ def main():
     ap.add_argument("--traffic-trips", type=int, default=10_000_000)
     ap.add_argument("--traffic-bucket", type=int, default=11)
     ap.add_argument("--traffic-window", type=int, default=1)
+    ap.add_argument("--traffic-sync", type=int, default=8, help="N > 1: local windows per global synchronisation (TrafficSim)")
     ap.add_argument("--no-exact-diff", action="store_true", help="skip the exact-differential (config 5) measurement")
     ap.add_argument("--diff-trips", type=int, default=2_000_000)
     ap.add_argument("--diff-added", type=int, default=1000)

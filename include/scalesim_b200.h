@@ -156,6 +156,7 @@ typedef struct ssb_stats {
   double loop_ms;            /* device time of the window loop (CUDA events) */
   int64_t fix_rounds;        /* rounds in which some LP's turn was not plain (the k_fix_* kernels ran) */
   int64_t fix_turns;         /* irregular LP turns (anti-message, duplicate key, straggler, state-mutating handler) */
+  int64_t exchanges;         /* global synchronisations (GVT + mailbox exchange); = rounds unless ssb_set_sync_interval > 1 */
 } ssb_stats;
 
 int ssb_abi_version(void);
@@ -270,6 +271,13 @@ int ssb_comm_init(ssb_engine* e, const void* id128);
  * choice. One process per GPU (the exchange waits on the peers; ranks sharing a GPU could deadlock). */
 int ssb_comm_export(ssb_engine* e, void* handle64);
 int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world);
+/* Peer-memory exchange, ssb_run (graph loop) only: `windows` local windows per global synchronisation (default 1).
+ * Between two synchronisations a partition keeps executing — window j covers window_buckets + j buckets from GVT on —
+ * while what it sends to peers accumulates in their mailboxes; the peers integrate it at the next synchronisation, and
+ * whatever arrives behind a partition's progress is a straggler there: the ordinary rollback machinery repairs it
+ * (optimism ACROSS partitions, conservative windows inside one). Pays when few events cross partitions (TrafficSim
+ * stripes: < 1 %) and a window is short (the GVT exchange then dominates); results do not depend on it. 1..64. */
+int ssb_set_sync_interval(ssb_engine* e, int32_t windows);
 
 /* ---- host helpers of the PHOLD app mirror (no device work) ---- */
 /* phold.hpp:144-164: the two 10M-entry tables, libstdc++ default_random_engine streams */

@@ -96,7 +96,8 @@ class _Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "rounds", "processed", "rollbacks", "undone", "antis_sent", "annihilated", "duplicates",
         "committed", "beyond_finish", "remote_sent", "gvt_time", "gvt_id", "pool_high_water", "log_dropped",
-    )] + [("loop_ms", C.c_double), ("fix_rounds", C.c_int64), ("fix_turns", C.c_int64)]
+    )] + [("loop_ms", C.c_double), ("fix_rounds", C.c_int64), ("fix_turns", C.c_int64),
+                                                                                ("exchanges", C.c_int64)]
 
 
 @dataclass
@@ -136,6 +137,7 @@ class Stats:
     loop_ms: float = 0.0
     fix_rounds: int = 0
     fix_turns: int = 0
+    exchanges: int = 0
 
 
 #: ssb_packed_sink / ssb_history_sink
@@ -194,6 +196,7 @@ def load_library() -> C.CDLL:
     lib.ssb_comm_init.argtypes = [vp, vp]
     lib.ssb_comm_export.argtypes = [vp, vp]
     lib.ssb_comm_import.argtypes = [vp, vp, C.c_int32]
+    lib.ssb_set_sync_interval.argtypes = [vp, C.c_int32]
     lib.ssb_phold_build_tables.argtypes = [i64, C.c_double, C.c_double, i64, vp, vp]
     lib.ssb_phold_init_events.argtypes = [i64, i64, vp, i64, i64, i64, vp, i64]
     lib.ssb_phold_init_events.restype = i64
@@ -447,6 +450,10 @@ class Engine:
         buf = C.create_string_buffer(64)
         self._check(self._lib.ssb_comm_export(self._h, buf))
         return buf.raw
+
+    def set_sync_interval(self, windows: int):
+        """Local windows per global synchronisation (peer-memory exchange, ``run()`` only); see ssb_set_sync_interval."""
+        self._check(self._lib.ssb_set_sync_interval(self._h, windows))
 
     def comm_import(self, handles: bytes):
         world = len(handles) // 64

@@ -102,6 +102,7 @@ struct Ctl {
   u32 rq_head, rq_tail;
   u32 rq_bound[RQ_LEN], rq_snap[RQ_LEN];
   u32 round, load_count;
+  u32 xround;         // exchange rounds (global synchronisations) so far: parity of the mailbox halves and GVT slots
   u32 send_count[MAX_WORLD];
   u32 recv_count[MAX_WORLD];
   u64 prev_gvt;       // stall detection of the graph's loop
@@ -135,7 +136,8 @@ struct View {
   u64 cap_log;
   u32 state_words;
   u32 use_graph;          // 1 = the kernels run inside the window-loop graph and drive its conditional nodes
-  cudaGraphConditionalHandle h_loop, h_fix;
+  u32 sub;                // window index since the last global synchronisation (0 = the first; see ssb_set_sync_interval)
+  cudaGraphConditionalHandle h_loop, h_fix, h_ranti;
   // event pool
   Ev* ev;
   Meta* meta;

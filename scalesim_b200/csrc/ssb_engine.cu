@@ -83,6 +83,7 @@ struct ssb_engine {
   size_t route_smem = 0;
   int g_exec = 8, g_commit = 4, g_fix = 8;      // blocks per SM of the per-event kernels (SSB_GRID=exec,commit,fix)
   int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
+  int sync_interval = 1;         // local windows per global synchronisation (peer-memory exchange, graph loop)
   std::vector<void*> allocs;
   // partition (host copies)
   std::vector<u32> h_owner, h_local;
@@ -295,7 +296,7 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.ent_out, v.cap_fix))) return rc;
   if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
   if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
-  if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1)))) return rc;
+  if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1) + 64))) return rc;      // + the windows of a synchronisation interval
   if ((rc = alloc(&v.scan, v.nb))) return rc;
   if ((rc = alloc(&v.commit, v.nb))) return rc;
   if ((rc = alloc(&v.sendbuf, (size_t)v.world * v.cap_send))) return rc;
@@ -545,6 +546,7 @@ int ssb_engine::build_graph() {
   vg.use_graph = 1;
   CK(cudaGraphConditionalHandleCreate(&vg.h_loop, graph, 1, cudaGraphCondAssignDefault));
   CK(cudaGraphConditionalHandleCreate(&vg.h_fix, graph, 0, cudaGraphCondAssignDefault));
+  if (cfg.world > 1) CK(cudaGraphConditionalHandleCreate(&vg.h_ranti, graph, 0, cudaGraphCondAssignDefault));
   auto add_cond = [&](cudaGraph_t parent, cudaGraphConditionalHandle h, cudaGraphConditionalNodeType type,
                       const std::vector<cudaGraphNode_t>& deps, cudaGraphNode_t* node, cudaGraph_t* body) -> cudaError_t {
     cudaGraphNodeParams p = {};
@@ -575,13 +577,19 @@ int ssb_engine::build_graph() {
   cudaGraphNode_t n_while, n_if_fix;
   cudaGraph_t body, b_fix;
   CK(add_cond(graph, vg.h_loop, cudaGraphCondTypeWhile, {}, &n_while, &body));
-  std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec;
-  CK(capture(body, {}, &t_plan, [&] {
-    if (cfg.world > 1) {      // peer-memory exchange: GVT + barrier, then the receive side of the previous round
-      SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vg);
-      launch_route(vg, 2, 1, 0);
-      launch_route(vg, 2, 0, 0);
-    }
+  std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_gvt, t_tail;
+  if (cfg.world > 1) {
+    // peer-memory exchange: GVT + barrier, then the receive side of the previous round — anti-messages first (an IF
+    // node: k_gvt opens it only when a peer sent any), then the positives
+    cudaGraphNode_t n_if_ranti;
+    cudaGraph_t b_ranti;
+    CK(capture(body, {}, &t_gvt, [&] { SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vg); }));
+    CK(add_cond(body, vg.h_ranti, cudaGraphCondTypeIf, t_gvt, &n_if_ranti, &b_ranti));
+    CK(capture(b_ranti, {}, nullptr, [&] { launch_route(vg, 2, 1, 0); }));
+    t_gvt.assign(1, n_if_ranti);
+  }
+  CK(capture(body, t_gvt, &t_plan, [&] {
+    if (cfg.world > 1) launch_route(vg, 2, 0, 0);
     SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vg, cfg.world > 1 ? 1 : 0);
   }));
   CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));
@@ -591,8 +599,28 @@ int ssb_engine::build_graph() {
   join.insert(join.end(), t_commit.begin(), t_commit.end());
   CK(add_cond(body, vg.h_fix, cudaGraphCondTypeIf, join, &n_if_fix, &b_fix));
   CK(capture(b_fix, {}, nullptr, [&] { launch_fix(vg, false); }));
-  CK(capture(body, {n_if_fix}, nullptr, [&] { launch_route(vg, 1, 0, 0); }));
-  CK(capture(body, {n_if_fix}, nullptr, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vg); }));      // next to k_route
+  std::vector<cudaGraphNode_t> t_route, t_post;
+  CK(capture(body, {n_if_fix}, &t_route, [&] { launch_route(vg, 1, 0, 0); }));
+  CK(capture(body, {n_if_fix}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vg); }));      // next to k_route
+  // further local windows before the next global synchronisation (ssb_set_sync_interval): the same kernels on a
+  // window one bucket longer each time; GVT stays, nothing new to commit
+  const int subs = cfg.world > 1 ? sync_interval : 1;
+  for (int j = 1; j < subs; ++j) {
+    View vj = vg;
+    vj.sub = (u32)j;
+    vj.window = vg.window + (u32)j;
+    CK(cudaGraphConditionalHandleCreate(&vj.h_fix, graph, 0, cudaGraphCondAssignDefault));
+    std::vector<cudaGraphNode_t> deps = t_route, t_p, t_e;
+    deps.insert(deps.end(), t_post.begin(), t_post.end());
+    CK(capture(body, deps, &t_p, [&] { SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vj, 1); }));
+    CK(capture(body, t_p, &t_e, [&] { launch_exec(vj); }));
+    cudaGraphNode_t n_if;
+    cudaGraph_t b_if;
+    CK(add_cond(body, vj.h_fix, cudaGraphCondTypeIf, t_e, &n_if, &b_if));
+    CK(capture(b_if, {}, nullptr, [&] { launch_fix(vj, false); }));
+    CK(capture(body, {n_if}, &t_route, [&] { launch_route(vj, 1, 0, 0); }));
+    CK(capture(body, {n_if}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vj); }));
+  }
   CK(cudaGetLastError());
   CK(cudaGraphInstantiate(&graph_exec, graph, 0));
   graph_dirty = false;
@@ -905,6 +933,7 @@ int ssb_get_stats(ssb_engine* e, ssb_stats* s) {
   s->loop_ms = e->loop_ms;
   s->fix_rounds = (int64_t)c.n_fix_rounds;
   s->fix_turns = (int64_t)c.n_fix_total;
+  s->exchanges = (int64_t)c.xround;
   return SSB_OK;
 }
 
@@ -1328,6 +1357,14 @@ int ssb_comm_init(ssb_engine* e, const void* id128) {
   std::memcpy(&id, id128, 128);
   int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, id, e->cfg.rank);
   if (rc != 0) { e->set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); return SSB_ERR_COMM; }
+  return SSB_OK;
+}
+
+int ssb_set_sync_interval(ssb_engine* e, int32_t windows) {
+  if (!e) return SSB_ERR_INVALID;
+  if (windows < 1 || windows > 64) { e->set_error("sync interval out of range (1..64)"); return SSB_ERR_INVALID; }
+  e->sync_interval = windows;
+  e->graph_dirty = true;
   return SSB_OK;
 }
 

@@ -138,8 +138,8 @@ __global__ void k_gvt(View v) {
   Ctl* c = v.ctl;
   block_local_min(v, c, sm);
   __syncthreads();
-  const u32 par = (c->round + 1u) & 1u;
-  const u32 R = c->round + 1u + (c->epoch << 24);      // stamp of the round that is about to start
+  const u32 par = (c->xround + 1u) & 1u;
+  const u32 R = c->xround + 1u + (c->epoch << 24);      // stamp of the exchange round that is about to start
   const u64 lm = c->local_min;
   const u32 my_t = lm == KEY_MAX ? 0xFFFFFFFFu : key_time(lm);
   if (threadIdx.x < v.world) {
@@ -162,6 +162,12 @@ __global__ void k_gvt(View v) {
     u32 t = 0xFFFFFFFFu;
     for (u32 r = 0; r < v.world; ++r) t = s_t[r] < t ? s_t[r] : t;
     c->gvt = t == 0xFFFFFFFFu ? KEY_MAX : make_key(t, 0);
+    if (v.use_graph) {
+      // anti-messages from peers are rare: the launch that integrates them sits in an IF node
+      u32 any = 0;
+      for (u32 r = 0; r < v.world; ++r) if (r != v.rank) any |= *reinterpret_cast<volatile u32*>(mb_cnt(v, v.rank, par, r, 1));
+      cudaGraphSetConditional(v.h_ranti, any ? 1u : 0u);
+    }
   }
 }
 
@@ -266,16 +272,21 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->done = done ? 1u : 0u;
     c->log_stable = c->log_count;      // the commit passes of all earlier rounds are complete
     c->round++;
-    for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
-    c->sent_min = KEY_MAX;
+    if (v.sub == 0) {
+      // first window after a global synchronisation: a new exchange round starts (what this partition sends until the
+      // next synchronisation accumulates in one mailbox half and in sent_min)
+      c->xround++;
+      for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
+      c->sent_min = KEY_MAX;
+    }
     if (v.use_graph) {
       // GVT must keep advancing (every round commits or integrates something): give up instead of spinning forever
-      if (gvt == c->prev_gvt) { if (++c->stall > kStallRounds) c->error |= E_STALL; } else { c->stall = 0; c->prev_gvt = gvt; }
+      if (v.sub == 0) { if (gvt == c->prev_gvt) { if (++c->stall > kStallRounds) c->error |= E_STALL; } else { c->stall = 0; c->prev_gvt = gvt; } }
       cudaGraphSetConditional(v.h_loop, (done || c->error) ? 0u : 1u);
     }
-    if (v.p2p) {
-      // the mailbox half that was just integrated (parity of the round that ended) is free again
-      const u32 par = (c->round - 1) & 1u;
+    if (v.p2p && v.sub == 0) {
+      // the mailbox half that was just integrated (parity of the exchange round that ended) is free again
+      const u32 par = (c->xround - 1) & 1u;
       for (u32 r = 0; r < v.world; ++r) { *mb_cnt(v, v.rank, par, r, 0) = 0; *mb_cnt(v, v.rank, par, r, 1) = 0; }
     }
   }
@@ -1170,7 +1181,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
     else if (which == 2) {
       if (v.p2p) {
         // own mailbox, all sources; `peer` = kind (1 = anti-message regions, integrated first; 0 = positives)
-        const u32 par = c->round & 1u, kind = peer, cap = kind ? v.mb_cap_anti[v.rank] : v.mb_cap_send[v.rank];
+        const u32 par = c->xround & 1u, kind = peer, cap = kind ? v.mb_cap_anti[v.rank] : v.mb_cap_send[v.rank];
         for (u32 r = 0; r < v.world; ++r) {
           if (r == v.rank) continue;
           u32 n = *mb_cnt(v, v.rank, par, r, kind);
@@ -1287,7 +1298,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         atomicAdd(&c->n_beyond, (u64)n);
       } else {
         const u32 r = t - rs - 1;
-        if (v.p2p) s_base[t] = atomicAdd_system(mb_cnt(v, r, c->round & 1u, v.rank, send_kind), n);
+        if (v.p2p) s_base[t] = atomicAdd_system(mb_cnt(v, r, c->xround & 1u, v.rank, send_kind), n);
         else s_base[t] = atomicAdd(&c->send_count[r], n);
         atomicAdd(&c->n_remote, (u64)n);
       }
@@ -1353,7 +1364,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         if (p >= (v.p2p ? (send_kind ? v.mb_cap_anti[r] : v.mb_cap_send[r]) : v.cap_send)) { atomicOr(&c->error, E_SENDBUF); continue; }
         if (v.p2p) {
           // straight into the destination GPU's mailbox over NVLink
-          st256(mb_data(v, r, c->round & 1u, v.rank, send_kind) + p, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
+          st256(mb_data(v, r, c->xround & 1u, v.rank, send_kind) + p, qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, fl);
           const u64 k = make_key(tm >= v.finish_time ? v.finish_time : tm / v.bucket_ticks * v.bucket_ticks, 0);
           if (k < s_sent_min) atomicMin(&s_sent_min, k);
         } else {

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, q, p2p=True):
+def _worker(rank, world, port, case, q, p2p=True, sync=1):
     import torch.distributed as dist
     from scalesim_b200 import phold, traffic
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -36,10 +36,12 @@ def _worker(rank, world, port, case, q, p2p=True):
             sc.partition = traffic.stripe_partition(32, 32, world)
             eng = traffic.make_engine(sc, bucket_ticks=8, window_buckets=window, rank=rank, world=world, device=rank)
         ssb.dist.init_engine_comm(eng, rank, world, p2p=p2p)
+        if sync > 1:
+            eng.set_sync_interval(sync)
         dist.barrier()
         st = eng.run()
         d = ssb.dist.all_gather_digest(eng.digest(), world)
-        q.put((rank, d, st.committed, st.remote_sent, st.rollbacks))
+        q.put((rank, d, st.committed, st.remote_sent, st.rollbacks, st.rounds, st.exchanges))
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -125,14 +127,14 @@ def test_diff_init_and_repeat_on_two_gpus_equal_reference():
     assert res[0][3] + res[1][3] > 0
 
 
-def _run(case, world=2, p2p=True):
+def _run(case, world=2, p2p=True, sync=1):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q, p2p)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q, p2p, sync)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
@@ -177,6 +179,30 @@ def test_grid_two_gpus_equals_oracle():
     s.run_closure(4, keep_records=False)
     res = _run(("traffic", None, 2))
     assert all(r[1] == s.digest() for r in res)
+
+
+@pytest.mark.parametrize("kind,sync", [("traffic", 4), ("traffic", 16), ("phold", 3)])
+def test_several_windows_per_synchronisation(kind, sync):
+    """ssb_set_sync_interval: the partitions synchronise (GVT, mailboxes) only every `sync` windows and run ahead in
+    between; events from the peer that arrive behind a partition's progress are stragglers — rolled back and redone.
+    The committed result must not change; the number of global synchronisations drops."""
+    import oracle_lib as O
+    from scalesim_b200 import traffic
+    if kind == "traffic":
+        sc = traffic.synthetic_grid(32, 32, 20000, seed=1)
+        s = O.Sim.traffic_scenario(sc)
+        s.run_closure(4, keep_records=False)
+        want = s.digest()
+        case = ("traffic", None, 1)
+    else:
+        want = golden("phold_10000_160000")["digest"]
+        case = ("phold", (10000, 160000, 0.1, 1.0), 1)
+    base = _run(case)
+    res = _run(case, sync=sync)
+    assert all(r[1] == want for r in res) and all(r[1] == want for r in base)
+    assert sum(r[4] for r in res) > 0                       # late remote events were rolled back ...
+    assert max(r[6] for r in res) < max(r[6] for r in base) # ... and the partitions synchronised less often
+    assert all(r[6] <= r[5] for r in res)
 
 
 def test_dropin_binaries_two_processes(tmp_path):

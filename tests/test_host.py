@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ssb.EVENT_DTYPE.itemsize == 64 and ssb.RECORD_DTYPE.itemsize == 48
     assert ctypes.sizeof(ssb.capi._Config) == 88
-    assert ctypes.sizeof(ssb.capi._Stats) == 14 * 8 + 8 + 2 * 8
+    assert ctypes.sizeof(ssb.capi._Stats) == 14 * 8 + 8 + 3 * 8
 
 
 def test_create_fails_loudly_without_gpu():
