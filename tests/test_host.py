@@ -182,9 +182,10 @@ def test_what_if_reader_parses_the_reference_query_types(tmp_path):
     assert wi.deletes.tolist() == [[4, 165, 0], [3, 135, 2]]          # (lp, time, event id)
     tid, dep, start, nodes = wi                                       # unpacks like the AE tuple
     assert nodes.size == 6
-    p.write_text("SC,1,5;R,1,1,2,10,200,1\n")
-    with pytest.raises(NotImplementedError):
-        traffic.read_what_if(str(p))
+    # state change (traffic/ring/change_state.csv + the README's three-road example; length 0 -> 1 as in road_read)
+    p.write_text("SC,1,5;R,1,1,2,10,200,1\nSC,10,555;R,0,10,1,10,100,2;R,1,10,1,10,0,1;R,3,10,3,10,200,100\n")
+    wi = traffic.read_what_if(str(p))
+    assert wi.state_changes == [(1, 5, [2], [10], [200]), (10, 555, [1, 1, 3], [10, 10, 10], [100, 1, 200])]
 
 
 def test_history_store_keeps_the_model_data(tmp_path):
