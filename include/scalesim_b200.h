@@ -272,8 +272,9 @@ int ssb_comm_init(ssb_engine* e, const void* id128);
 int ssb_comm_export(ssb_engine* e, void* handle64);
 int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world);
 /* Peer-memory exchange, ssb_run (graph loop) only: `windows` local windows per global synchronisation (default 1).
- * Between two synchronisations a partition keeps executing — window j covers window_buckets + j buckets from GVT on —
- * while what it sends to peers accumulates in their mailboxes; the peers integrate it at the next synchronisation, and
+ * Between two synchronisations a partition keeps executing — every window covers the buckets from GVT up to one
+ * bucket beyond its progress so far (at most 4 x `windows` buckets ahead of GVT) — while what it sends to peers
+ * accumulates in their mailboxes; the peers integrate it at the next synchronisation, and
  * whatever arrives behind a partition's progress is a straggler there: the ordinary rollback machinery repairs it
  * (optimism ACROSS partitions, conservative windows inside one). Pays when few events cross partitions (TrafficSim
  * stripes: < 1 %) and a window is short (the GVT exchange then dominates); results do not depend on it. 1..64. */

@@ -96,6 +96,8 @@ struct Ctl {
   u32 n_arr, n_anti, n_extra, commit_blocks, exec_blocks;
   u32 n_fix, n_ent, n_scan, scan_total;
   u32 hmask_round;    // size - 1 of the hash-set region this round uses
+  u32 fix_min_t;      // smallest receive time among the arrivals that flagged an LP this round: no rollback of the round
+                      // reaches below it, so the scans of the consumed bucket heads start at its bucket
   u32 n_gather, n_commit, commit_total;
   u32 free_top, free_low;
   u32 snap_head, snap_tail;
@@ -137,6 +139,7 @@ struct View {
   u32 state_words;
   u32 use_graph;          // 1 = the kernels run inside the window-loop graph and drive its conditional nodes
   u32 sub;                // window index since the last global synchronisation (0 = the first; see ssb_set_sync_interval)
+  u32 sync;               // windows per global synchronisation (1 = every window is synchronised)
   cudaGraphConditionalHandle h_loop, h_fix, h_ranti;
   // event pool
   Ev* ev;

@@ -296,7 +296,7 @@ int ssb_engine::init() {
   if ((rc = alloc(&v.ent_out, v.cap_fix))) return rc;
   if ((rc = alloc(&v.outbox, (size_t)v.cap_batch + v.cap_aux))) return rc;
   if ((rc = alloc(&v.anti_box, v.cap_aux))) return rc;
-  if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1) + 64))) return rc;      // + the windows of a synchronisation interval
+  if ((rc = alloc(&v.gather, std::max<u32>(v.window, 1) + 4 * 64 + 2))) return rc;      // + the lead of a synchronisation interval (k_plan: kLeadMax)
   if ((rc = alloc(&v.scan, v.nb))) return rc;
   if ((rc = alloc(&v.commit, v.nb))) return rc;
   if ((rc = alloc(&v.sendbuf, (size_t)v.world * v.cap_send))) return rc;
@@ -544,6 +544,7 @@ int ssb_engine::build_graph() {
   CK(cudaGraphCreate(&graph, 0));
   vg = v;
   vg.use_graph = 1;
+  vg.sync = cfg.world > 1 ? (u32)sync_interval : 1u;
   CK(cudaGraphConditionalHandleCreate(&vg.h_loop, graph, 1, cudaGraphCondAssignDefault));
   CK(cudaGraphConditionalHandleCreate(&vg.h_fix, graph, 0, cudaGraphCondAssignDefault));
   if (cfg.world > 1) CK(cudaGraphConditionalHandleCreate(&vg.h_ranti, graph, 0, cudaGraphCondAssignDefault));
@@ -602,13 +603,12 @@ int ssb_engine::build_graph() {
   std::vector<cudaGraphNode_t> t_route, t_post;
   CK(capture(body, {n_if_fix}, &t_route, [&] { launch_route(vg, 1, 0, 0); }));
   CK(capture(body, {n_if_fix}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vg); }));      // next to k_route
-  // further local windows before the next global synchronisation (ssb_set_sync_interval): the same kernels on a
-  // window one bucket longer each time; GVT stays, nothing new to commit
+  // further local windows before the next global synchronisation (ssb_set_sync_interval): the same kernels, each
+  // window reaches one bucket further than the partition's progress so far; GVT stays, nothing new to commit
   const int subs = cfg.world > 1 ? sync_interval : 1;
   for (int j = 1; j < subs; ++j) {
     View vj = vg;
     vj.sub = (u32)j;
-    vj.window = vg.window + (u32)j;
     CK(cudaGraphConditionalHandleCreate(&vj.h_fix, graph, 0, cudaGraphCondAssignDefault));
     std::vector<cudaGraphNode_t> deps = t_route, t_p, t_e;
     deps.insert(deps.end(), t_post.begin(), t_post.end());

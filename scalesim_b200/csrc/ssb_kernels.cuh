@@ -233,6 +233,15 @@ __global__ void k_plan(View v, int use_global_gvt) {
       }
       // gather list
       bound = cur + v.window < fin_b ? cur + v.window : fin_b;
+      if (v.sync > 1) {
+        // several windows per global synchronisation: GVT lags behind the partition's progress (it only moves at a
+        // synchronisation), so a window is [GVT bucket, progress frontier + 1): whatever arrived late below the
+        // frontier (stragglers) plus ONE new bucket — unless the partition is already kLeadMax buckets ahead of GVT
+        const u32 kLeadMax = 4u * v.sync;
+        u32 nb2 = c->hi_bound + 1u;
+        if (c->hi_bound >= cur + kLeadMax) nb2 = c->hi_bound;
+        if (nb2 > bound) bound = nb2 < fin_b ? nb2 : fin_b;
+      }
       for (u32 b = cur; b < bound; ++b) {
         const u32 cons = consp[b];
         u32 avail = fillp[b] - cons;
@@ -269,6 +278,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->n_extra = 0;
     c->n_fix = 0;
     c->n_ent = 0;
+    c->fix_min_t = 0xFFFFFFFFu;
     c->done = done ? 1u : 0u;
     c->log_stable = c->log_count;      // the commit passes of all earlier rounds are complete
     c->round++;
@@ -423,7 +433,8 @@ __device__ __forceinline__ u32 slot_of_arrival(const View& v, u32 i) { return sl
 // Irregular turns. An LP whose turn of this round is not plain gets a ticket (index into the fix table); the first
 // flagger issues it. lpw[lp].y: 0 = plain, TICKET_PENDING while the table entry is written, then ticket + 1.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flag_lp(const View& v, u32 lp) {
+__device__ __forceinline__ void flag_lp(const View& v, u32 lp, u32 time) {
+  atomicMin(&v.ctl->fix_min_t, time);
   u32* t = &v.lpw[lp].y;
   if (atomicCAS(t, 0u, TICKET_PENDING) != 0u) return;
   const u32 f = atomicAdd(&v.ctl->n_fix, 1u);      // < n_lp_local: every LP is issued at most one ticket per round
@@ -537,8 +548,14 @@ __global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M:
 #pragma unroll
     for (int u = 0; u < kExecUnroll; ++u) {
       if (!live[u]) continue;
-      if (w[u].y) { live[u] = false; continue; }           // the LP already has a ticket: k_fix_turn runs its turn
       bad[u] = (e[u].flags & F_CANCEL) != 0 || key_time(e[u].key) < w[u].x;
+      if (w[u].y) {
+        // the LP already has a ticket: k_fix_turn runs its turn. Every arrival that can undo something still lowers
+        // the bucket from which the rollback scans start
+        if (bad[u]) atomicMin(&c->fix_min_t, key_time(e[u].key));
+        live[u] = false;
+        continue;
+      }
       if (!bad[u]) {
         const u64 h = hash_of(lp[u], e[u].key);
         hfp[u] = (u32)(h >> 32) | 1u;
@@ -551,10 +568,10 @@ __global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M:
       if (!live[u]) continue;
       const u32 i = i0 + (u32)u * nth;
       if (!bad[u] && hold[u] != 0u) bad[u] = hold[u] == hfp[u] || !hash_insert_from(v, hfp[u], (hpos[u] + 1u) & hmask, hmask);
-      if (bad[u]) { flag_lp(v, lp[u]); continue; }
+      if (bad[u]) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }
       Ev out;
       bool has;
-      if (run_handler<M>(v, md, e[u], lp[u], out, has, err)) { flag_lp(v, lp[u]); continue; }      // state-mutating handler
+      if (run_handler<M>(v, md, e[u], lp[u], out, has, err)) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }      // state-mutating handler
       Meta m;
       m.sent_dst = NIL; m.snap = NIL; m.sent_key = 0;
       if (has) {
@@ -641,14 +658,27 @@ __global__ void __launch_bounds__(256) k_hist_flag(View v) {
     const Ev e = load_ev(v.ev + slot);
     if (key_time(e.key) >= tbound) continue;
     const u32 lp = part_local(v, e.dst);
-    if (e.key >= v.inv[lp]) flag_lp(v, lp);
+    if (e.key >= v.inv[lp]) flag_lp(v, lp, key_time(e.key));
   }
+}
+
+// first item of the scan list that a rollback of this round can reach: the scan entries are in bucket order, and
+// nothing below the bucket of the earliest flagging arrival is undone
+__device__ __forceinline__ u32 scan_begin(const View& v, const Ctl* c) {
+  const u32 bmin = c->fix_min_t / v.bucket_ticks;
+  u32 off = c->scan_total;
+  for (u32 k = 0; k < c->n_scan; ++k) {
+    const uint4 se = v.scan[k];
+    if (se.x >= bmin) { off = se.w; break; }
+  }
+  return off;
 }
 
 __global__ void __launch_bounds__(256) k_fix_count(View v) {
   Ctl* c = v.ctl;
   if (c->n_fix == 0) return;
-  const u32 n_arr = c->n_arr, n = n_arr + c->scan_total;
+  const u32 s0 = scan_begin(v, c);
+  const u32 n_arr = c->n_arr, n = n_arr + c->scan_total - s0;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (i < n_arr) {
       const u32 slot = slot_of_arrival(v, i);
@@ -658,7 +688,7 @@ __global__ void __launch_bounds__(256) k_fix_count(View v) {
       atomicAdd(&v.fixcnt[t - 1u], 1u);
       atomicMin(&v.fixmin[t - 1u], e.key);
     } else {
-      const u32 slot = slot_of_list(v, v.scan, c->n_scan, i - n_arr);
+      const u32 slot = slot_of_list(v, v.scan, c->n_scan, s0 + (i - n_arr));
       const unsigned char pf = v.pflag[slot];
       if ((pf & (P_PROCESSED | P_DEAD)) != P_PROCESSED) continue;
       const Ev e = load_ev(v.ev + slot);
@@ -700,7 +730,8 @@ __device__ __forceinline__ Sorted* claim_entry(const View& v, u32 t) {
 __global__ void __launch_bounds__(256) k_fix_scatter(View v) {
   Ctl* c = v.ctl;
   if (c->n_fix == 0) return;
-  const u32 n_arr = c->n_arr, n = n_arr + c->scan_total;
+  const u32 s0 = scan_begin(v, c);
+  const u32 n_arr = c->n_arr, n = n_arr + c->scan_total - s0;
   const u32 tbound = c->bound_abs * v.bucket_ticks;
   u32 n_und = 0, n_anti = 0, err = 0;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -712,7 +743,7 @@ __global__ void __launch_bounds__(256) k_fix_scatter(View v) {
       Sorted* p = claim_entry(v, t);
       if (p) store_sorted(p, e.key, slot, (i + 1u) | ((e.flags & F_CANCEL) ? S_ANTI : 0u));
     } else {
-      const u32 slot = slot_of_list(v, v.scan, c->n_scan, i - n_arr);
+      const u32 slot = slot_of_list(v, v.scan, c->n_scan, s0 + (i - n_arr));
       const unsigned char pf = v.pflag[slot];
       if ((pf & (P_PROCESSED | P_DEAD)) != P_PROCESSED) continue;
       const Ev e = load_ev(v.ev + slot);
