@@ -597,7 +597,7 @@ def main():
     ap.add_argument("--traffic-trips", type=int, default=10_000_000)
     ap.add_argument("--traffic-bucket", type=int, default=11)
     ap.add_argument("--traffic-window", type=int, default=1)
-    ap.add_argument("--traffic-sync", type=int, default=8, help="N > 1: local windows per global synchronisation (TrafficSim)")
+    ap.add_argument("--traffic-sync", type=int, default=2, help="N > 1: local windows per global synchronisation (TrafficSim)")
     ap.add_argument("--no-exact-diff", action="store_true", help="skip the exact-differential (config 5) measurement")
     ap.add_argument("--diff-trips", type=int, default=2_000_000)
     ap.add_argument("--diff-added", type=int, default=1000)
