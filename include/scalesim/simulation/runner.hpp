@@ -38,6 +38,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 #include <boost/make_shared.hpp>
 #include <boost/optional.hpp>
@@ -75,6 +76,7 @@ class runner {
     std::exit(1);
   }
   void comm_init();
+  std::vector<std::string> comm_files_;      // rendezvous files this rank wrote (removed at the end of run())
   // exact-differential history store of this rank: <store_dir>/<sim_id>/history<rank>.ssb (same file format as
   // scalesim_b200/store.py): the committed events with their sent-log entries, the LPs that had an initial state and
   // the model data the events refer to (TrafficSim: the route pool)
@@ -220,45 +222,45 @@ void runner<App>::comm_init() {
   const char* path = std::getenv("SCALESIM_B200_COMM_FILE");
   if (!path) { LOG(ERROR) << "SCALESIM_B200_COMM_FILE must be set when SCALESIM_B200_WORLD > 1"; std::exit(1); }
   const bool p2p = env_long("SCALESIM_B200_P2P", 1) != 0;
-  int rc = 0;
-  if (!p2p) {      // events travel by ncclSend/ncclRecv, GVT by ncclAllReduce: the ranks join one NCCL communicator
-  char id[128];
-  if (rank_ == 0) {
-    rc = ssb_comm_unique_id(id);
-    if (rc) fail("ssb_comm_unique_id", rc);
-    std::string tmp = std::string(path) + ".tmp";
-    { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(id, 128); }
-    std::rename(tmp.c_str(), path);
-  } else {
-    for (int tries = 0;; ++tries) {
-      std::ifstream f(path, std::ios::binary);
-      if (f && f.read(id, 128) && f.gcount() == 128) break;
-      if (tries > 600) { LOG(ERROR) << "timed out waiting for " << path; std::exit(1); }
-      std::this_thread::sleep_for(std::chrono::milliseconds(100));
-    }
-  }
-  rc = ssb_comm_init(engine_, id);
-  if (rc) fail("ssb_comm_init", rc);
-  return;
-  }
-  // peer-memory exchange (default; events AND the GVT reduction cross through the mailboxes, no NCCL): swap the CUDA IPC handles of the engines' mailboxes through files next to the id file
-  char mine[64];
-  if ((rc = ssb_comm_export(engine_, mine))) fail("ssb_comm_export", rc);
-  {
-    std::string f = std::string(path) + ".h" + std::to_string(rank_), tmp = f + ".tmp";
-    { std::ofstream o(tmp.c_str(), std::ios::binary); o.write(mine, 64); }
+  // Rendezvous through files next to COMM_FILE. Every file starts with the id of THIS launch (SCALESIM_B200_RUN_ID,
+  // default: the parent process id, which the ranks of one launch share), so that a file left behind by an earlier
+  // run with the same COMM_FILE is never taken for a peer's: a reader polls until the id matches. Each rank removes
+  // its own file when it is done.
+  const uint64_t run_id = (uint64_t)env_long("SCALESIM_B200_RUN_ID", (long)getppid());
+  auto publish = [&](const std::string& f, const char* data, size_t n) {
+    std::string tmp = f + ".tmp" + std::to_string(rank_);
+    { std::ofstream o(tmp.c_str(), std::ios::binary); o.write((const char*)&run_id, 8); o.write(data, (std::streamsize)n); }
     std::rename(tmp.c_str(), f.c_str());
-  }
-  std::vector<char> all((size_t)world_ * 64);
-  for (int r = 0; r < world_; ++r) {
-    std::string f = std::string(path) + ".h" + std::to_string(r);
+    comm_files_.push_back(f);
+  };
+  auto fetch = [&](const std::string& f, char* data, size_t n) {
     for (int tries = 0;; ++tries) {
       std::ifstream in(f.c_str(), std::ios::binary);
-      if (in && in.read(&all[(size_t)r * 64], 64) && in.gcount() == 64) break;
-      if (tries > 600) { LOG(ERROR) << "timed out waiting for " << f; std::exit(1); }
+      uint64_t id = 0;
+      if (in && in.read((char*)&id, 8) && id == run_id && in.read(data, (std::streamsize)n) && (size_t)in.gcount() == n) return;
+      if (tries > 600) { LOG(ERROR) << "timed out waiting for " << f << " (run id " << run_id << ")"; std::exit(1); }
       std::this_thread::sleep_for(std::chrono::milliseconds(100));
     }
+  };
+  int rc = 0;
+  if (!p2p) {      // events travel by ncclSend/ncclRecv, GVT by ncclAllReduce: the ranks join one NCCL communicator
+    char id[128];
+    if (rank_ == 0) {
+      if ((rc = ssb_comm_unique_id(id))) fail("ssb_comm_unique_id", rc);
+      publish(path, id, 128);
+    } else {
+      fetch(path, id, 128);
+    }
+    if ((rc = ssb_comm_init(engine_, id))) fail("ssb_comm_init", rc);
+    return;
   }
+  // peer-memory exchange (default; events AND the GVT reduction cross through the mailboxes, no NCCL): swap the CUDA
+  // IPC handles of the engines' mailboxes
+  char mine[64];
+  if ((rc = ssb_comm_export(engine_, mine))) fail("ssb_comm_export", rc);
+  publish(std::string(path) + ".h" + std::to_string(rank_), mine, 64);
+  std::vector<char> all((size_t)world_ * 64);
+  for (int r = 0; r < world_; ++r) fetch(std::string(path) + ".h" + std::to_string(r), &all[(size_t)r * 64], 64);
   if ((rc = ssb_comm_import(engine_, all.data(), world_))) fail("ssb_comm_import", rc);
 }
 
@@ -515,6 +517,7 @@ void runner<App>::run() {
       << "====================================================================\n";
   ssb_destroy(engine_);
   engine_ = NULL;
+  for (size_t i = 0; i < comm_files_.size(); ++i) std::remove(comm_files_[i].c_str());      // peers imported them long ago
 }
 
 // host handler vs device twin: advance the chains of the first k initial events with App::event_handler on the host

@@ -139,7 +139,7 @@ __global__ void k_gvt(View v) {
   block_local_min(v, c, sm);
   __syncthreads();
   const u32 par = (c->xround + 1u) & 1u;
-  const u32 R = c->xround + 1u + (c->epoch << 24);      // stamp of the exchange round that is about to start
+  const u32 R = c->xround + 1u + (c->epoch << 20);      // stamp of the exchange round that is about to start (2^20 rounds per run, 4096 resets)
   const u64 lm = c->local_min;
   const u32 my_t = lm == KEY_MAX ? 0xFFFFFFFFu : key_time(lm);
   if (threadIdx.x < v.world) {
@@ -1288,7 +1288,9 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
           const u32 tm = key_time(key);
           const u32 owner = v.world > 1 ? part_owner(v, dst) : v.rank;
           u32 t;
-          if (owner != v.rank) {
+          if (tm >= v.finish_time && which != 3) {
+            t = rs;      // never executed nor committed (R8): dropped where it is produced, not shipped to its owner
+          } else if (owner != v.rank) {
             if (which == 3) { atomicOr(&c->error, E_RANGE); continue; }   // loaded events must be owned by this rank
             t = rs + 1 + owner;
           } else if (tm >= v.finish_time) {
