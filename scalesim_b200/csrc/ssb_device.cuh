@@ -105,7 +105,8 @@ struct Ctl {
   u32 rq_bound[RQ_LEN], rq_snap[RQ_LEN];
   u32 round, load_count;
   u32 xround;         // exchange rounds (global synchronisations) so far: parity of the mailbox halves and GVT slots
-  u32 send_count[MAX_WORLD];
+  u32 send_count[MAX_WORLD];      // events sent to each partition since the last global synchronisation
+  u32 send_anti[MAX_WORLD];       // ... anti-messages (peer-memory exchange: they travel in their own mailbox region)
   u32 recv_count[MAX_WORLD];
   u64 prev_gvt;       // stall detection of the graph's loop
   u32 stall;
@@ -179,10 +180,10 @@ struct View {
   //   counts   [2 parities][world sources][2 kinds]  one 128-byte line each (kind 0 = positives, 1 = anti-messages)
   //   GVT slot [2 parities][world sources]           u64 = round << 32 | local minimum time
   //   records  [2 parities][world sources] x { cap_send positives, cap_anti anti-messages }
-  // A sender appends straight into its region of the destination's mailbox (system-scope atomic on the count, then
-  // plain stores over NVLink). At the start of the next round every partition writes its GVT candidate into all
-  // peers' slots and waits for theirs (k_gvt): that exchange is the GVT min-reduction AND the barrier that makes the
-  // appended events visible.
+  // A sender appends straight into its region of the destination's mailbox (a region has ONE writer, so positions
+  // are claimed with a LOCAL atomic on the sender's own counter; plain stores over NVLink). At the start of the next
+  // round every partition publishes its counts, writes its GVT candidate into all peers' slots and waits for theirs
+  // (k_gvt): that exchange is the GVT min-reduction AND the barrier that makes the appended events visible.
   u32 p2p;                       // 0 = NCCL send/recv exchange, 1 = peer-memory exchange
   u32 cap_anti;                  // anti-message records per (parity, source) of the own mailbox
   u32 mb_cap_send[MAX_WORLD], mb_cap_anti[MAX_WORLD];     // geometry of every partition's mailbox (from its header)

@@ -146,6 +146,11 @@ __global__ void k_gvt(View v) {
     const u32 r = threadIdx.x;
     u32 t = my_t;
     if (r != v.rank) {
+      // how many records this partition appended to r's mailbox since the last synchronisation (both kinds), ahead of
+      // the GVT slot: when r sees the slot, the counts and the records are there
+      const u32 spar = c->xround & 1u;
+      *reinterpret_cast<volatile u32*>(mb_cnt(v, r, spar, v.rank, 0)) = c->send_count[r];
+      *reinterpret_cast<volatile u32*>(mb_cnt(v, r, spar, v.rank, 1)) = c->send_anti[r];
       __threadfence_system();
       *reinterpret_cast<volatile u64*>(mb_gvt(v, r, par, v.rank)) = ((u64)R << 32) | my_t;
       const volatile u64* mine = mb_gvt(v, v.rank, par, r);
@@ -164,8 +169,9 @@ __global__ void k_gvt(View v) {
     c->gvt = t == 0xFFFFFFFFu ? KEY_MAX : make_key(t, 0);
     if (v.use_graph) {
       // anti-messages from peers are rare: the launch that integrates them sits in an IF node
+      // (the mailbox half the peers filled during the exchange round that just ended: parity of xround, as in k_route)
       u32 any = 0;
-      for (u32 r = 0; r < v.world; ++r) if (r != v.rank) any |= *reinterpret_cast<volatile u32*>(mb_cnt(v, v.rank, par, r, 1));
+      for (u32 r = 0; r < v.world; ++r) if (r != v.rank) any |= *reinterpret_cast<volatile u32*>(mb_cnt(v, v.rank, c->xround & 1u, r, 1));
       cudaGraphSetConditional(v.h_ranti, any ? 1u : 0u);
     }
   }
@@ -286,7 +292,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
       // first window after a global synchronisation: a new exchange round starts (what this partition sends until the
       // next synchronisation accumulates in one mailbox half and in sent_min)
       c->xround++;
-      for (int i = 0; i < MAX_WORLD; ++i) c->send_count[i] = 0;
+      for (int i = 0; i < MAX_WORLD; ++i) { c->send_count[i] = 0; c->send_anti[i] = 0; }
       c->sent_min = KEY_MAX;
     }
     if (v.use_graph) {
@@ -294,11 +300,8 @@ __global__ void k_plan(View v, int use_global_gvt) {
       if (v.sub == 0) { if (gvt == c->prev_gvt) { if (++c->stall > kStallRounds) c->error |= E_STALL; } else { c->stall = 0; c->prev_gvt = gvt; } }
       cudaGraphSetConditional(v.h_loop, (done || c->error) ? 0u : 1u);
     }
-    if (v.p2p && v.sub == 0) {
-      // the mailbox half that was just integrated (parity of the exchange round that ended) is free again
-      const u32 par = (c->xround - 1) & 1u;
-      for (u32 r = 0; r < v.world; ++r) { *mb_cnt(v, v.rank, par, r, 0) = 0; *mb_cnt(v, v.rank, par, r, 1) = 0; }
-    }
+    // (the mailbox half that was just integrated needs no clearing: its counts are overwritten by the senders before
+    // the half is read again)
   }
   __syncthreads();
   for (u32 w = threadIdx.x; w < kWords; w += blockDim.x) reinterpret_cast<u32*>(v.ctl)[w] = s_words[w];
@@ -1331,8 +1334,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         atomicAdd(&c->n_beyond, (u64)n);
       } else {
         const u32 r = t - rs - 1;
-        if (v.p2p) s_base[t] = atomicAdd_system(mb_cnt(v, r, c->xround & 1u, v.rank, send_kind), n);
-        else s_base[t] = atomicAdd(&c->send_count[r], n);
+        // the region of the peer's mailbox (or send buffer) this partition fills has one writer: a local counter
+        s_base[t] = atomicAdd(send_kind && v.p2p ? &c->send_anti[r] : &c->send_count[r], n);
         atomicAdd(&c->n_remote, (u64)n);
       }
     }

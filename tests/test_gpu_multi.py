@@ -28,9 +28,10 @@ def _worker(rank, world, port, case, q, p2p=True, sync=1):
     try:
         torch.cuda.set_device(rank)
         kind, args, window = case
-        if kind == "phold":
+        if kind in ("phold", "stateful"):
             n_lp, n_init, ratio, lam = args
-            eng = phold.make_engine(n_lp, n_init, ratio, lam, window_buckets=window, rank=rank, world=world, device=rank)
+            eng = phold.make_engine(n_lp, n_init, ratio, lam, window_buckets=window, rank=rank, world=world, device=rank,
+                                    stateful=kind == "stateful")
         else:
             sc = traffic.synthetic_grid(32, 32, 20000, seed=1)
             sc.partition = traffic.stripe_partition(32, 32, world)
@@ -41,7 +42,11 @@ def _worker(rank, world, port, case, q, p2p=True, sync=1):
         dist.barrier()
         st = eng.run()
         d = ssb.dist.all_gather_digest(eng.digest(), world)
-        q.put((rank, d, st.committed, st.remote_sent, st.rollbacks, st.rounds, st.exchanges))
+        states = None
+        if kind == "stateful":
+            ids = np.arange(rank, args[0], world, dtype=np.int64)
+            states = (ids, eng.read_states(ids))
+        q.put((rank, d, st.committed, st.remote_sent, st.rollbacks, st.rounds, st.exchanges, states))
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -203,6 +208,28 @@ def test_several_windows_per_synchronisation(kind, sync):
     assert sum(r[4] for r in res) > 0                       # late remote events were rolled back ...
     assert max(r[6] for r in res) < max(r[6] for r in base) # ... and the partitions synchronised less often
     assert all(r[6] <= r[5] for r in res)
+
+
+@pytest.mark.parametrize("window,sync", [(1, 1), (3, 1), (1, 4)])
+def test_stateful_model_two_gpus_equals_sequential_oracle(window, sync):
+    """Mutable LP state that feeds back into the events, LPs split over two GPUs: a rollback's anti-messages that
+    cross partitions MUST arrive and annihilate (with the shipped, state-independent handlers a lost anti-message is
+    masked: the identical re-sent event is dropped as a duplicate). Oracle: plain sequential DES; records' digest and
+    every final LP state."""
+    import oracle_lib as O
+    n_lp, n_init = 500, 4000
+    s = O.Sim.phold(n_lp, n_init, 0.1, 1.0, stateful=True)
+    s.run_sequential()
+    want_ids, want_words = s.final_states(n_lp)
+    res = _run(("stateful", (n_lp, n_init, 0.1, 1.0), window), sync=sync)
+    assert all(r[1] == s.digest() for r in res)
+    got = np.zeros((n_lp, 2), dtype=np.uint32)
+    for r in res:
+        ids, words = r[7]
+        got[ids] = words
+    assert np.array_equal(got[want_ids], want_words)
+    if window > 1 or sync > 1:
+        assert sum(r[4] for r in res) > 0
 
 
 def test_dropin_binaries_two_processes(tmp_path):
