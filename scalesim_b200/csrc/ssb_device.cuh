@@ -36,6 +36,11 @@ constexpr u32 kWarp = 32;
 constexpr u32 NIL = 0xFFFFFFFFu;
 constexpr u64 KEY_MAX = ~0ull;
 constexpr u32 F_CANCEL = 1u;      // anti-message (sim_event_base::is_cancel_, sim_obj.hpp:30)
+// Ev::flags bits 4..31 = sequence stamp, given by the partition that first routes the record (0 = not routed yet): the
+// order in which its sender emitted things. The merge applies the inbox items of one key in stamp order — the FIFO
+// property rule R4 relies on ("a sender's positive always precedes its anti-message") — so it does not matter in
+// which order records are appended to a bucket or cross between GPUs.
+constexpr u32 F_STAMP_SHIFT = 4;
 constexpr unsigned char P_PROCESSED = 1;   // pflag: handler has run and the result stands
 constexpr unsigned char P_DEAD = 2;        // pflag: annihilated, duplicate, or a consumed anti-message
 constexpr unsigned char P_HISTORY = 4;     // pflag: loaded from the exact-differential history store and not re-executed since
@@ -104,6 +109,7 @@ struct Ctl {
   u32 rq_head, rq_tail;
   u32 rq_bound[RQ_LEN], rq_snap[RQ_LEN];
   u32 round, load_count;
+  u32 stamp_base;     // sequence stamps: +2 per round and per load; k_route(anti) stamps with it, k_route(main) with +1
   u32 xround;         // exchange rounds (global synchronisations) so far: parity of the mailbox halves and GVT slots
   u32 send_count[MAX_WORLD];      // events sent to each partition since the last global synchronisation
   u32 send_anti[MAX_WORLD];       // ... anti-messages (peer-memory exchange: they travel in their own mailbox region)
@@ -141,7 +147,7 @@ struct View {
   u32 use_graph;          // 1 = the kernels run inside the window-loop graph and drive its conditional nodes
   u32 sub;                // window index since the last global synchronisation (0 = the first; see ssb_set_sync_interval)
   u32 sync;               // windows per global synchronisation (1 = every window is synchronised)
-  cudaGraphConditionalHandle h_loop, h_fix, h_ranti;
+  cudaGraphConditionalHandle h_loop, h_fix;
   // event pool
   Ev* ev;
   Meta* meta;

@@ -475,9 +475,8 @@ int ssb_engine::exchange() {
 #undef NC
   if (first_rc) { set_error(first_call + ": " + n.GetErrorString(first_rc)); return SSB_ERR_COMM; }
   if (overflow) { set_error("send / receive buffer overflow (raise max_batch)"); return SSB_ERR_CAPACITY; }
-  for (int pass = 1; pass <= 2; ++pass)
-    for (int r = 0; r < cfg.world; ++r)
-      if (r != cfg.rank && h_ctl->recv_count[r]) launch_route(v, 2, (u32)r, (u32)pass);
+  for (int r = 0; r < cfg.world; ++r)
+    if (r != cfg.rank && h_ctl->recv_count[r]) launch_route(v, 2, (u32)r, 0);
   CK(cudaGetLastError());
   return SSB_OK;
 }
@@ -490,7 +489,6 @@ int ssb_engine::enqueue_round() {
       t_begin(K_MIN);
       SSB_LAUNCH(k_gvt, 1, 256, 0, stream, v);
       t_end();
-      launch_route(v, 2, 1, 0);
       launch_route(v, 2, 0, 0);
     } else {
       if (!comm) { set_error("world > 1 but ssb_comm_init was not called"); return SSB_ERR_COMM; }
@@ -547,7 +545,6 @@ int ssb_engine::build_graph() {
   vg.sync = cfg.world > 1 ? (u32)sync_interval : 1u;
   CK(cudaGraphConditionalHandleCreate(&vg.h_loop, graph, 1, cudaGraphCondAssignDefault));
   CK(cudaGraphConditionalHandleCreate(&vg.h_fix, graph, 0, cudaGraphCondAssignDefault));
-  if (cfg.world > 1) CK(cudaGraphConditionalHandleCreate(&vg.h_ranti, graph, 0, cudaGraphCondAssignDefault));
   auto add_cond = [&](cudaGraph_t parent, cudaGraphConditionalHandle h, cudaGraphConditionalNodeType type,
                       const std::vector<cudaGraphNode_t>& deps, cudaGraphNode_t* node, cudaGraph_t* body) -> cudaError_t {
     cudaGraphNodeParams p = {};
@@ -579,18 +576,13 @@ int ssb_engine::build_graph() {
   cudaGraph_t body, b_fix;
   CK(add_cond(graph, vg.h_loop, cudaGraphCondTypeWhile, {}, &n_while, &body));
   std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_gvt, t_tail;
-  if (cfg.world > 1) {
-    // peer-memory exchange: GVT + barrier, then the receive side of the previous round — anti-messages first (an IF
-    // node: k_gvt opens it only when a peer sent any), then the positives
-    cudaGraphNode_t n_if_ranti;
-    cudaGraph_t b_ranti;
-    CK(capture(body, {}, &t_gvt, [&] { SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vg); }));
-    CK(add_cond(body, vg.h_ranti, cudaGraphCondTypeIf, t_gvt, &n_if_ranti, &b_ranti));
-    CK(capture(b_ranti, {}, nullptr, [&] { launch_route(vg, 2, 1, 0); }));
-    t_gvt.assign(1, n_if_ranti);
-  }
-  CK(capture(body, t_gvt, &t_plan, [&] {
-    if (cfg.world > 1) launch_route(vg, 2, 0, 0);
+  CK(capture(body, {}, &t_plan, [&] {
+    if (cfg.world > 1) {
+      // peer-memory exchange: GVT + barrier, then the receive side of the previous exchange round (one launch over
+      // the anti-messages and the positives of all peers)
+      SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vg);
+      launch_route(vg, 2, 0, 0);
+    }
     SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vg, cfg.world > 1 ? 1 : 0);
   }));
   CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));

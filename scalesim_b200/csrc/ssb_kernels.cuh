@@ -167,13 +167,6 @@ __global__ void k_gvt(View v) {
     u32 t = 0xFFFFFFFFu;
     for (u32 r = 0; r < v.world; ++r) t = s_t[r] < t ? s_t[r] : t;
     c->gvt = t == 0xFFFFFFFFu ? KEY_MAX : make_key(t, 0);
-    if (v.use_graph) {
-      // anti-messages from peers are rare: the launch that integrates them sits in an IF node
-      // (the mailbox half the peers filled during the exchange round that just ended: parity of xround, as in k_route)
-      u32 any = 0;
-      for (u32 r = 0; r < v.world; ++r) if (r != v.rank) any |= *reinterpret_cast<volatile u32*>(mb_cnt(v, v.rank, c->xround & 1u, r, 1));
-      cudaGraphSetConditional(v.h_ranti, any ? 1u : 0u);
-    }
   }
 }
 
@@ -288,6 +281,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->done = done ? 1u : 0u;
     c->log_stable = c->log_count;      // the commit passes of all earlier rounds are complete
     c->round++;
+    c->stamp_base += 2u;
     if (v.sub == 0) {
       // first window after a global synchronisation: a new exchange round starts (what this partition sends until the
       // next synchronisation accumulates in one mailbox half and in sent_min)
@@ -1006,7 +1000,7 @@ struct TurnExec {
   }
   __device__ __forceinline__ void requeue(u32 slot) {
     Ev e = load_ev(v.ev + slot);
-    e.flags = 0;
+    e.flags &= ~((1u << F_STAMP_SHIFT) - 1u);      // still the same event: it keeps its place in its sender's sequence
     store_ev(v.outbox + extra_idx(), e);
     v.pflag[slot] = P_DEAD;
   }
@@ -1037,9 +1031,23 @@ __global__ void __launch_bounds__(256) k_fix_turn(View v, typename M::Data md) {
       else if ((a.seq & S_IDX) && i < snap_pos) snap_pos = i;
       if (i > 0 && seg[i - 1].key == a.key) { eo[i] = make_uint2(NIL, NIL); continue; }      // not the first entry of its key
       u32 present = NIL, out_idx = NIL;
-      for (u32 j = i; j < n; ++j) {
-        const Sorted b = j == i ? a : load_sorted(seg + j);
-        if (b.key != a.key) break;
+      // the entries of this key: [i, jend). A lone entry (the rule) needs no order; several are applied in the order
+      // their sender emitted them (sequence stamp, then arrival index), the undone event first
+      u32 jend = i + 1u;
+      while (jend < n && seg[jend].key == a.key) ++jend;
+      u64 last = 0;                                       // (stamp, arrival index + 1) of the entry applied last
+      for (u32 step = i; step < jend; ++step) {
+        Sorted b = a;
+        if (jend - i > 1u) {
+          u64 best = ~0ull;
+          for (u32 j = i; j < jend; ++j) {
+            const Sorted x = load_sorted(seg + j);
+            const u64 ord = (x.seq & S_UNDONE) ? 1ull
+                                               : (((u64)(v.ev[x.slot].flags >> F_STAMP_SHIFT) + 1ull) << 32) | (x.seq & S_IDX);
+            if (ord > last && ord < best) { best = ord; b = x; }
+          }
+          last = best;
+        }
         if (b.seq & S_UNDONE) {
           present = b.slot;                               // was in the queue before the arrivals
         } else if (b.seq & S_ANTI) {
@@ -1203,8 +1211,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
 #endif
   __shared__ u64 s_bar;
   __shared__ u64 s_sent_min;
-  __shared__ const Ev* s_seg[MAX_WORLD + 2];     // the source = a concatenation of up to world + 1 record runs
-  __shared__ u32 s_off[MAX_WORLD + 3];
+  __shared__ const Ev* s_seg[2 * MAX_WORLD + 2];     // the source = a concatenation of up to 2 * world record runs
+  __shared__ u32 s_off[2 * MAX_WORLD + 3];
   __shared__ u32 s_nseg;
   Ctl* c = v.ctl;
   if (threadIdx.x == 0) {
@@ -1214,13 +1222,17 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
     else if (which == 1) { add(v.outbox, c->n_arr); add(v.outbox + v.cap_batch, c->n_extra < v.cap_aux ? c->n_extra : v.cap_aux); }
     else if (which == 2) {
       if (v.p2p) {
-        // own mailbox, all sources; `peer` = kind (1 = anti-message regions, integrated first; 0 = positives)
-        const u32 par = c->xround & 1u, kind = peer, cap = kind ? v.mb_cap_anti[v.rank] : v.mb_cap_send[v.rank];
-        for (u32 r = 0; r < v.world; ++r) {
-          if (r == v.rank) continue;
-          u32 n = *mb_cnt(v, v.rank, par, r, kind);
-          if (n > cap) { n = cap; if (blockIdx.x == 0) atomicOr(&c->error, E_SENDBUF); }
-          add(mb_data(v, v.rank, par, r, kind), n);
+        // own mailbox, all sources, both kinds in one launch (the records carry their senders' sequence stamps: the
+        // order of integration does not matter)
+        const u32 par = c->xround & 1u;
+        for (u32 kind = 0; kind < 2; ++kind) {
+          const u32 cap = kind ? v.mb_cap_anti[v.rank] : v.mb_cap_send[v.rank];
+          for (u32 r = 0; r < v.world; ++r) {
+            if (r == v.rank) continue;
+            u32 n = *mb_cnt(v, v.rank, par, r, kind);
+            if (n > cap) { n = cap; if (blockIdx.x == 0) atomicOr(&c->error, E_SENDBUF); }
+            add(mb_data(v, v.rank, par, r, kind), n);
+          }
         }
       } else {
         add(v.recvbuf + (size_t)peer * v.cap_send, c->recv_count[peer]);
@@ -1252,6 +1264,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   const u32 chm = (1u << v.ch_log) - 1u;
   const u32 T_NONE = NIL, T_DIRECT = NIL - 1u;
   const u32 send_kind = which == 0 ? 1u : 0u;      // anti-messages travel in their own mailbox region
+  // sequence stamp of what this launch routes for the first time (records that were routed before keep theirs)
+  const u32 my_stamp = (c->stamp_base + (which == 1 ? 1u : 0u)) << F_STAMP_SHIFT;
   u32 phase = 0;
   for (u32 t0 = blockIdx.x * tile; t0 < total; t0 += gridDim.x * tile) {
     const u32 cnt = total - t0 < tile ? total - t0 : tile;
@@ -1367,7 +1381,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
       const u32 i = it * kRouteThreads + threadIdx.x;
       const uint4* q = reinterpret_cast<const uint4*>(s_tile + i);
       const uint4 qa = q[0], qb = q[1];
-      const u32 fl = qb.w & F_CANCEL;
+      const u32 fl = (qb.w & F_CANCEL) | ((qb.w >> F_STAMP_SHIFT) ? (qb.w & ~((1u << F_STAMP_SHIFT) - 1u)) : my_stamp);
       const u32 tm = qa.y;                       // key hi = receive_time
       if (t < rs || t == T_DIRECT) {
         u32 p, ch;
@@ -1440,7 +1454,7 @@ __global__ void k_pack(View v, const HostEvent* in, u32 n) {
     }
     store_ev(v.outbox + i, e);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { c->load_count = n; c->stamp_base += 2u; }
 }
 
 // events loaded in the compact layout (ssb_load_events_raw): validated in place in the outbox staging area
@@ -1455,7 +1469,7 @@ __global__ void k_check_raw(View v, u32 n) {
       v.outbox[i].flags = e.flags & F_CANCEL;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) c->load_count = n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { c->load_count = n; c->stamp_base += 2u; }
 }
 
 // committed log record -> ssb_packed_record (6 x u32)
@@ -1477,7 +1491,7 @@ __global__ void k_hist_stage(View v, const Ev* in, u32 n) {
     e.flags = 0;
     store_ev(v.outbox + i, e);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) v.ctl->load_count = n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { v.ctl->load_count = n; v.ctl->stamp_base += 2u; }
 }
 
 // state-change what-if query: the LP's recorded history is invalid from `key` on
