@@ -266,8 +266,9 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->n_gather = ng;
     c->n_arr = total;
     {      // hash-set region of this round: the smallest power of two >= 2 * arrivals (at least 1024 slots)
+      // at least 2 x the arrivals; 4 x while the region stays below 8 MB (fewer second probes, still L2-resident)
       u32 hm = 1023u;
-      while (hm < v.hmask && hm + 1u < 2u * total) hm = (hm << 1) | 1u;
+      while (hm < v.hmask && (hm + 1u < 2u * total || (hm + 1u < 4u * total && hm + 1u < (1u << 21)))) hm = (hm << 1) | 1u;
       c->hmask_round = hm < v.hmask ? hm : v.hmask;
     }
     c->n_scan = ns;
@@ -490,16 +491,16 @@ __device__ __forceinline__ void load_state(const u32* p, u32 (&st)[W]) {
   }
 }
 
+// handler on state words that are already in registers; returns true when the invocation changed the state
 template <class M>
-__device__ __forceinline__ bool run_handler(const View& v, const typename M::Data& md, const Ev& e, u32 lp, Ev& out,
-                                            bool& has, u32& err) {
-  u32 st[M::kStateWords], pre[M::kStateWords];
-  load_state<M::kStateWords>(v.state + (size_t)lp * M::kStateWords, st);
+__device__ __forceinline__ bool run_handler(const typename M::Data& md, const Ev& e, u32 (&st)[M::kStateWords], u32 early,
+                                            Ev& out, bool& has, u32& err) {
+  u32 pre[M::kStateWords];
 #pragma unroll
   for (int q = 0; q < M::kStateWords; ++q) pre[q] = st[q];
   Ev in = e;
   in.flags = 0;
-  has = M::handle(md, in, st, out, err);
+  has = M::handle(md, in, st, early, out, err);
   bool changed = false;
 #pragma unroll
   for (int q = 0; q < M::kStateWords; ++q) changed |= (pre[q] != st[q]);
@@ -524,12 +525,15 @@ __global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M:
   const u32 nth = gridDim.x * blockDim.x;
   u32 err = 0;
   for (u32 i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_arr; i0 += kExecUnroll * nth) {
-    // kExecUnroll independent events per iteration, phase by phase, so that their dependent loads overlap:
-    // (1) event records, (2) per-LP words, (3) first hash probes, (4) handlers + stores
-    u32 slot[kExecUnroll], lp[kExecUnroll], hpos[kExecUnroll], hfp[kExecUnroll], hold[kExecUnroll];
+    // Per event two dependent levels of memory latency instead of a chain: (1) the event record; (2) everything the
+    // turn needs, issued together — the per-LP word, the LP state, the model's gather (M::early) and the first probe
+    // of the hash set (inserting the fingerprint of an arrival that turns out to be irregular is harmless: its LP takes
+    // a ticket anyway); then decisions, handler arithmetic and the coalesced stores. kExecUnroll events per thread.
+    u32 slot[kExecUnroll], lp[kExecUnroll], hpos[kExecUnroll], hfp[kExecUnroll], hold[kExecUnroll], early[kExecUnroll];
+    u32 st[kExecUnroll][M::kStateWords];
     Ev e[kExecUnroll];
     uint2 w[kExecUnroll];
-    bool live[kExecUnroll], bad[kExecUnroll];
+    bool live[kExecUnroll];
 #pragma unroll
     for (int u = 0; u < kExecUnroll; ++u) {
       const u32 i = i0 + (u32)u * nth;
@@ -541,19 +545,10 @@ __global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M:
       if (!live[u]) continue;
       lp[u] = part_local(v, e[u].dst);
       w[u] = __ldcg(reinterpret_cast<const uint2*>(v.lpw + lp[u]));
-    }
-#pragma unroll
-    for (int u = 0; u < kExecUnroll; ++u) {
-      if (!live[u]) continue;
-      bad[u] = (e[u].flags & F_CANCEL) != 0 || key_time(e[u].key) < w[u].x;
-      if (w[u].y) {
-        // the LP already has a ticket: k_fix_turn runs its turn. Every arrival that can undo something still lowers
-        // the bucket from which the rollback scans start
-        if (bad[u]) atomicMin(&c->fix_min_t, key_time(e[u].key));
-        live[u] = false;
-        continue;
-      }
-      if (!bad[u]) {
+      load_state<M::kStateWords>(v.state + (size_t)lp[u] * M::kStateWords, st[u]);
+      early[u] = M::early(md, e[u]);
+      hold[u] = 0u;
+      if (!(e[u].flags & F_CANCEL)) {
         const u64 h = hash_of(lp[u], e[u].key);
         hfp[u] = (u32)(h >> 32) | 1u;
         hpos[u] = (u32)h & hmask;
@@ -564,11 +559,18 @@ __global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M:
     for (int u = 0; u < kExecUnroll; ++u) {
       if (!live[u]) continue;
       const u32 i = i0 + (u32)u * nth;
-      if (!bad[u] && hold[u] != 0u) bad[u] = hold[u] == hfp[u] || !hash_insert_from(v, hfp[u], (hpos[u] + 1u) & hmask, hmask);
-      if (bad[u]) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }
+      bool bad = (e[u].flags & F_CANCEL) != 0 || key_time(e[u].key) < w[u].x;
+      if (w[u].y) {
+        // the LP already has a ticket: k_fix_turn runs its turn. Every arrival that can undo something still lowers
+        // the bucket from which the rollback scans start
+        if (bad) atomicMin(&c->fix_min_t, key_time(e[u].key));
+        continue;
+      }
+      if (!bad && hold[u] != 0u) bad = hold[u] == hfp[u] || !hash_insert_from(v, hfp[u], (hpos[u] + 1u) & hmask, hmask);
+      if (bad) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }
       Ev out;
       bool has;
-      if (run_handler<M>(v, md, e[u], lp[u], out, has, err)) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }      // state-mutating handler
+      if (run_handler<M>(md, e[u], st[u], early[u], out, has, err)) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }      // state-mutating handler
       Meta m;
       m.sent_dst = NIL; m.snap = NIL; m.sent_key = 0;
       if (has) {
@@ -947,7 +949,7 @@ struct TurnExec {
 #pragma unroll
     for (int w = 0; w < M::kStateWords; ++w) ls[w] = st[w];
     Ev out;
-    const bool has = M::handle(md, e, ls, out, err);
+    const bool has = M::handle(md, e, ls, M::early(md, e), out, err);
     if (has) {
       bool changed = false;
 #pragma unroll
@@ -970,7 +972,7 @@ struct TurnExec {
 #pragma unroll
     for (int w = 0; w < M::kStateWords; ++w) pre[w] = st[w];
     Ev out;
-    const bool has = M::handle(md, e, st, out, err);
+    const bool has = M::handle(md, e, st, M::early(md, e), out, err);
     Meta m;
     m.sent_dst = NIL; m.snap = NIL; m.sent_key = 0;
     if (has) {

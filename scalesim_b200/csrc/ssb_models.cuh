@@ -3,7 +3,10 @@
 // A model provides
 //   kStateWords              size of the LP state in 32-bit words
 //   struct Data              read-only model data (device pointers)
-//   handle(d, e, state, out) App::event_handler: returns true and fills `out` when one new event is
+//   early(d, e)              the ONE word of model data the handler gathers that depends on the event alone (PHOLD: the
+//                            table entry; TrafficSim: the next route node). k_exec issues it together with the other
+//                            gathers of the event, before anything else is known, so that the latencies overlap.
+//   handle(d, e, state, early, out) App::event_handler: returns true and fills `out` when one new event is
 //                            produced; may modify `state` (kept only when an event is produced, which
 //                            is what runner.hpp:552-558 does — quirk Q2 of SURVEY.md)
 //   tag(e)                   START / END suffix of the committed line (sim_obj.hpp:73-75)
@@ -29,12 +32,13 @@ struct PholdModel {
     u32 lookahead;
     u32 num_lp;
   };
-  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
+  __device__ static __forceinline__ u32 early(const Data& d, const Ev& e) {
+    // (int)(ev_id + (long)num_hops) % RAND_TABLE_SIZE — id + hops < 2^31 is asserted at load (quirk Q8)
+    return __ldg(d.table + (key_id(e.key) + e.p0 + 1u) % d.table_size);
+  }
+  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, u32 t, Ev& out, u32& err) {
     (void)state;
     u32 hops = e.p0 + 1u;
-    // (int)(ev_id + (long)num_hops) % RAND_TABLE_SIZE — id + hops < 2^31 is asserted at load (quirk Q8)
-    u32 idx = (key_id(e.key) + hops) % d.table_size;
-    u32 t = __ldg(d.table + idx);
     u32 lat = t >> 1;
     u64 recv = (u64)key_time(e.key) + lat + d.lookahead;
     if (recv >= 0x80000000ull) { err |= E_RANGE; recv = 0x7FFFFFFFull; }
@@ -63,7 +67,8 @@ struct PholdModel {
 struct PholdStatefulModel {
   static constexpr int kStateWords = 2;
   typedef PholdModel::Data Data;
-  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
+  __device__ static __forceinline__ u32 early(const Data&, const Ev&) { return 0u; }      // its gather depends on the state
+  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, u32, Ev& out, u32& err) {
     u32 count = state[0] + 1u;
     u32 chain = (u32)mix64(((u64)state[1] << 32) ^ e.key);
     state[0] = count;
@@ -107,10 +112,12 @@ struct TrafficModel {
     const u32* roads;   // road table of the junctions with more than kInlineRoads out-roads
     u32 roads_len;      // in words
   };
-  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, Ev& out, u32& err) {
+  __device__ static __forceinline__ u32 early(const Data& d, const Ev& e) {
+    return (e.p1 > 1u && e.p0 + 1u < d.route_len) ? __ldg(d.route + e.p0 + 1u) : 0u;      // the next route node
+  }
+  __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, u32 next, Ev& out, u32& err) {
     if (e.p1 <= 1u) return false;
     if (e.p0 + 1u >= d.route_len) { err |= E_INTERNAL; return false; }
-    u32 next = __ldg(d.route + e.p0 + 1u);
     const u32 n = state[1];
     // first road that leads to `next`, as std::find (traffic_sim.hpp:299-306)
     bool found = false;
