@@ -84,6 +84,7 @@ struct ssb_engine {
   int g_exec = 8, g_commit = 4, g_fix = 8;      // blocks per SM of the per-event kernels (SSB_GRID=exec,commit,fix)
   int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
   int sync_interval = 1;         // local windows per global synchronisation (peer-memory exchange, graph loop)
+  int loop_unroll = 4;           // rounds per iteration of the graph's WHILE node (SSB_UNROLL)
   std::vector<void*> allocs;
   // partition (host copies)
   std::vector<u32> h_owner, h_local;
@@ -266,6 +267,7 @@ int ssb_engine::init() {
   while (hcap < 2u * v.cap_batch) hcap <<= 1;
   v.hmask = hcap - 1u;
   if (getenv("SSB_NO_GRAPH")) graph_enabled = false;
+  if (const char* u = getenv("SSB_UNROLL")) { int x = atoi(u); if (x >= 1 && x <= 16) loop_unroll = x; }
 #ifdef SSB_EMU
   graph_enabled = false;
 #endif
@@ -572,46 +574,48 @@ int ssb_engine::build_graph() {
     cudaError_t err2 = cudaStreamEndCapture(stream, &out);
     return err != cudaSuccess ? err : err2;
   };
-  cudaGraphNode_t n_while, n_if_fix;
-  cudaGraph_t body, b_fix;
+  cudaGraphNode_t n_while;
+  cudaGraph_t body;
   CK(add_cond(graph, vg.h_loop, cudaGraphCondTypeWhile, {}, &n_while, &body));
-  std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_gvt, t_tail;
-  CK(capture(body, {}, &t_plan, [&] {
-    if (cfg.world > 1) {
-      // peer-memory exchange: GVT + barrier, then the receive side of the previous exchange round (one launch over
-      // the anti-messages and the positives of all peers)
-      SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vg);
-      launch_route(vg, 2, 0, 0);
-    }
-    SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vg, cfg.world > 1 ? 1 : 0);
-  }));
-  CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vg); }));
-  CK(capture(body, t_plan, &t_exec, [&] { launch_exec(vg); }));
-  // k_route(anti) pops chunks off the free stack that the commit pass pushes to: the IF node waits for both branches
-  std::vector<cudaGraphNode_t> join = t_exec;
-  join.insert(join.end(), t_commit.begin(), t_commit.end());
-  CK(add_cond(body, vg.h_fix, cudaGraphCondTypeIf, join, &n_if_fix, &b_fix));
-  CK(capture(b_fix, {}, nullptr, [&] { launch_fix(vg, false); }));
-  std::vector<cudaGraphNode_t> t_route, t_post;
-  CK(capture(body, {n_if_fix}, &t_route, [&] { launch_route(vg, 1, 0, 0); }));
-  CK(capture(body, {n_if_fix}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vg); }));      // next to k_route
-  // further local windows before the next global synchronisation (ssb_set_sync_interval): the same kernels, each
-  // window reaches one bucket further than the partition's progress so far; GVT stays, nothing new to commit
+  // The WHILE body holds `unroll` rounds back to back (a loop iteration costs ~4.7 us on B200, a kernel node ~0.9 us:
+  // tools/mb_graph.cu): every round's k_plan writes the loop condition, and once GVT has reached finish_time the
+  // remaining rounds of the iteration find nothing to do. Inside a round: [N > 1: k_gvt, k_route(recv)] k_plan,
+  // then k_commit next to k_exec, the IF node of the irregular turns, k_route next to k_post; with
+  // ssb_set_sync_interval further windows without a global synchronisation follow (k_plan .. k_post only).
   const int subs = cfg.world > 1 ? sync_interval : 1;
-  for (int j = 1; j < subs; ++j) {
-    View vj = vg;
-    vj.sub = (u32)j;
-    CK(cudaGraphConditionalHandleCreate(&vj.h_fix, graph, 0, cudaGraphCondAssignDefault));
-    std::vector<cudaGraphNode_t> deps = t_route, t_p, t_e;
-    deps.insert(deps.end(), t_post.begin(), t_post.end());
-    CK(capture(body, deps, &t_p, [&] { SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vj, 1); }));
-    CK(capture(body, t_p, &t_e, [&] { launch_exec(vj); }));
-    cudaGraphNode_t n_if;
-    cudaGraph_t b_if;
-    CK(add_cond(body, vj.h_fix, cudaGraphCondTypeIf, t_e, &n_if, &b_if));
-    CK(capture(b_if, {}, nullptr, [&] { launch_fix(vj, false); }));
-    CK(capture(body, {n_if}, &t_route, [&] { launch_route(vj, 1, 0, 0); }));
-    CK(capture(body, {n_if}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vj); }));
+  std::vector<cudaGraphNode_t> tail;      // what the next round has to wait for
+  for (int rep = 0; rep < loop_unroll; ++rep) {
+    for (int j = 0; j < subs; ++j) {
+      View vj = vg;
+      vj.sub = (u32)j;
+      CK(cudaGraphConditionalHandleCreate(&vj.h_fix, graph, 0, cudaGraphCondAssignDefault));
+      std::vector<cudaGraphNode_t> t_plan, t_commit, t_exec, t_route, t_post;
+      CK(capture(body, tail, &t_plan, [&] {
+        if (cfg.world > 1 && j == 0) {
+          // peer-memory exchange: GVT + barrier, then the receive side of the previous exchange round (one launch
+          // over the anti-messages and the positives of all peers)
+          SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vj);
+          launch_route(vj, 2, 0, 0);
+        }
+        SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vj, cfg.world > 1 ? 1 : 0);
+      }));
+      std::vector<cudaGraphNode_t> join;
+      if (j == 0) {      // GVT only moves at a global synchronisation: later windows have nothing new to commit
+        CK(capture(body, t_plan, &t_commit, [&] { launch_commit(vj); }));
+        join = t_commit;
+      }
+      CK(capture(body, t_plan, &t_exec, [&] { launch_exec(vj); }));
+      // k_route(anti) pops chunks off the free stack that the commit pass pushes to: the IF node waits for both branches
+      join.insert(join.end(), t_exec.begin(), t_exec.end());
+      cudaGraphNode_t n_if;
+      cudaGraph_t b_if;
+      CK(add_cond(body, vj.h_fix, cudaGraphCondTypeIf, join, &n_if, &b_if));
+      CK(capture(b_if, {}, nullptr, [&] { launch_fix(vj, false); }));
+      CK(capture(body, {n_if}, &t_route, [&] { launch_route(vj, 1, 0, 0); }));
+      CK(capture(body, {n_if}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vj); }));      // next to k_route
+      tail = t_route;
+      tail.insert(tail.end(), t_post.begin(), t_post.end());
+    }
   }
   CK(cudaGetLastError());
   CK(cudaGraphInstantiate(&graph_exec, graph, 0));
