@@ -546,7 +546,6 @@ int ssb_engine::build_graph() {
   vg.use_graph = 1;
   vg.sync = cfg.world > 1 ? (u32)sync_interval : 1u;
   CK(cudaGraphConditionalHandleCreate(&vg.h_loop, graph, 1, cudaGraphCondAssignDefault));
-  CK(cudaGraphConditionalHandleCreate(&vg.h_fix, graph, 0, cudaGraphCondAssignDefault));
   auto add_cond = [&](cudaGraph_t parent, cudaGraphConditionalHandle h, cudaGraphConditionalNodeType type,
                       const std::vector<cudaGraphNode_t>& deps, cudaGraphNode_t* node, cudaGraph_t* body) -> cudaError_t {
     cudaGraphNodeParams p = {};
