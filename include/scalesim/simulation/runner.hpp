@@ -319,22 +319,24 @@ void runner<App>::run() {
   struct state_change { long lp, time; std::vector<uint32_t> words; };
   std::vector<state_change> state_changes;      // SC what-if queries
   if (!FLAGS_diff_repeat) {
-    for (int r = 0; r < world_; ++r) {
-      ev_vec<App> parsed;
-      app_.init_events(parsed, r, world_);
-      for (typename ev_vec<App>::iterator it = parsed.begin(); it != parsed.end(); ++it) {
-        long d = (*it)->destination();
-        if (d >= 0 && d < n_lp && part[d] % world_ == rank_) mine.push_back(*it);
-      }
+    // ONE pass over the scenario: the application shards its input by "index % rank_size == rank" and "any way of
+    // reading is fine, the events are shuffled to their LPs afterwards" (phold.hpp:190-209, traffic_sim.hpp:410-451),
+    // so asking for shard 0 of 1 yields every event; this rank keeps the ones whose LP it owns (the reference shuffles
+    // instead, runner.hpp:131-147). No rank parses the input `world` times.
+    ev_vec<App> parsed;
+    app_.init_events(parsed, 0, 1);
+    for (typename ev_vec<App>::iterator it = parsed.begin(); it != parsed.end(); ++it) {
+      long d = (*it)->destination();
+      if (d >= 0 && d < n_lp && part[d] % world_ == rank_) mine.push_back(*it);
     }
   } else {
     // --diff_repeat (runner::init_repeat, runner.hpp:178-348): no events are read from the scenario. The recorded
     // history of this rank comes back from the store, the what-if queries (App::init_what_if) are injected on top.
     read_history(hist);
     model::restore_model_data(cx, hist.pool);
-    for (int r = 0; r < world_; ++r) {
+    {
       std::vector<boost::shared_ptr<const what_if<App> > > wi;
-      app_.init_what_if(wi, r, world_);
+      app_.init_what_if(wi, 0, 1);      // every query in one pass (same sharding contract as init_events)
       for (size_t i = 0; i < wi.size(); ++i) {
         long d = wi[i]->lp_id_;
         if (!(d >= 0 && d < n_lp && part[d] % world_ == rank_)) continue;

@@ -84,7 +84,7 @@ struct ssb_engine {
   int g_exec = 8, g_commit = 4, g_fix = 8;      // blocks per SM of the per-event kernels (SSB_GRID=exec,commit,fix)
   int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
   int sync_interval = 1;         // local windows per global synchronisation (peer-memory exchange, graph loop)
-  int loop_unroll = 4;           // rounds per iteration of the graph's WHILE node (SSB_UNROLL)
+  int loop_unroll = 8;           // rounds per iteration of the graph's WHILE node (SSB_UNROLL)
   std::vector<void*> allocs;
   // partition (host copies)
   std::vector<u32> h_owner, h_local;
@@ -317,9 +317,11 @@ int ssb_engine::init() {
   route_smem = (size_t)kRouteTile * sizeof(Ev) + (size_t)(v.route_slots + 1 + v.world) * 16;
 #ifndef SSB_EMU
   CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)route_smem));
+  CK(cudaFuncSetAttribute(k_route, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&route_bps, k_route, kRouteThreads, route_smem));
 #endif
   if (route_bps < 1) route_bps = 1;
+  if (getenv("SSB_VERBOSE")) fprintf(stderr, "[ssb] k_route: %zu B shared memory per block, %d blocks per SM\n", route_smem, route_bps);
   if (const char* rb = getenv("SSB_ROUTE_BPS")) { int x = atoi(rb); if (x >= 1 && x <= route_bps) route_bps = x; }
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
