@@ -506,8 +506,12 @@ def exact_diff_measure(env):
     # graph loop runs (ssb_run_stream_history); the sink appends to the host arrays the repeat run loads from
     eng = traffic.make_engine(sc, bucket_ticks=args.traffic_bucket, history=True, max_events=2 * n_trips + (1 << 20),
                               max_batch=n_trips + (1 << 16), max_committed=n_nodes + 1024)
-    rec = np.empty(n_nodes, dtype=ssb.RAW_RECORD_DTYPE)
-    sent = np.empty(n_nodes, dtype=ssb.SENT_RECORD_DTYPE)
+    # destination of the sink: pinned host memory (page-locked, already faulted in), as a writer thread's queue would be
+    import torch
+    rec_t = torch.empty(n_nodes * ssb.RAW_RECORD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    sent_t = torch.empty(n_nodes * ssb.SENT_RECORD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    rec = rec_t.numpy().view(ssb.RAW_RECORD_DTYPE)
+    sent = sent_t.numpy().view(ssb.SENT_RECORD_DTYPE)
     fill = [0]
 
     def sink(r, s):
