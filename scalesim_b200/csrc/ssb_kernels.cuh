@@ -545,7 +545,11 @@ __global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M:
       if (!live[u]) continue;
       lp[u] = part_local(v, e[u].dst);
       w[u] = __ldcg(reinterpret_cast<const uint2*>(v.lpw + lp[u]));
-      load_state<M::kStateWords>(v.state + (size_t)lp[u] * M::kStateWords, st[u]);
+      if (M::kUsesState) load_state<M::kStateWords>(v.state + (size_t)lp[u] * M::kStateWords, st[u]);
+      else {
+#pragma unroll
+        for (int q = 0; q < M::kStateWords; ++q) st[u][q] = 0u;
+      }
       early[u] = M::early(md, e[u]);
       hold[u] = 0u;
       if (!(e[u].flags & F_CANCEL)) {
