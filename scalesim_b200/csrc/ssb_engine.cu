@@ -82,6 +82,7 @@ struct ssb_engine {
   u32 n_chunks = 0;
   size_t route_smem = 0;
   int g_exec = 8, g_commit = 4, g_fix = 8;      // blocks per SM of the per-event kernels (SSB_GRID=exec,commit,fix)
+  int g_post = 8, g_count = 8, g_scatter = 8, g_turn = 8;      // ... of k_post and the irregular-turn kernels (g_fix unless sized by occupancy)
   int route_bps = 4;             // resident k_route blocks per SM (shared-memory bound)
   int sync_interval = 1;         // local windows per global synchronisation (peer-memory exchange, graph loop)
   int loop_unroll = 8;           // rounds per iteration of the graph's WHILE node (SSB_UNROLL)
@@ -321,6 +322,32 @@ int ssb_engine::init() {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&route_bps, k_route, kRouteThreads, route_smem));
 #endif
   if (route_bps < 1) route_bps = 1;
+#ifndef SSB_EMU
+  if (!getenv("SSB_GRID")) {
+    // persistent grids of exactly one wave: resident blocks per SM of the model's instantiation (a grid sized for
+    // more blocks than fit leaves a nearly empty second wave: measured +20 % on k_exec at 33 registers)
+    int be = g_exec, bc = g_commit, bt = g_fix, bp = g_fix, bn = g_fix, bs = g_fix;
+    with_model([&](auto m, auto) {
+      typedef decltype(m) M;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_exec<M>, 256, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_commit<M>, (int)kCommitThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_fix_turn<M>, 256, 0);
+    });
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp, k_post, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bn, k_fix_count, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_fix_scatter, 256, 0);
+    if (be >= 1) g_exec = be;
+    if (bc >= 1) g_commit = bc;
+    if (bt >= 1) g_turn = bt;
+    if (bp >= 1) g_post = bp;
+    if (bn >= 1) g_count = bn;
+    if (bs >= 1) g_scatter = bs;
+  } else {
+    g_post = g_count = g_scatter = g_turn = g_fix;
+  }
+#endif
+  if (getenv("SSB_VERBOSE")) fprintf(stderr, "[ssb] blocks per SM: k_exec %d, k_commit %d, k_post %d, k_fix_count %d, k_fix_scatter %d, k_fix_turn %d\n",
+                                     g_exec, g_commit, g_post, g_count, g_scatter, g_turn);
   if (getenv("SSB_VERBOSE")) fprintf(stderr, "[ssb] k_route: %zu B shared memory per block, %d blocks per SM\n", route_smem, route_bps);
   if (const char* rb = getenv("SSB_ROUTE_BPS")) { int x = atoi(rb); if (x >= 1 && x <= route_bps) route_bps = x; }
   CK(cudaStreamSynchronize(stream));
@@ -430,16 +457,15 @@ void ssb_engine::launch_exec(const View& vv) {
 
 // the irregular turns of a round (inside the graph: the body of an IF node)
 void ssb_engine::launch_fix(const View& vv, bool timed_) {
-  const int g = n_sm * g_fix;
   auto tb = [&](int id) { if (timed_) t_begin(id); };
   auto te = [&]() { if (timed_) t_end(); };
-  if (vv.inv) { tb(K_HIST_FLAG); SSB_LAUNCH(k_hist_flag, g, 256, 0, stream, vv); te(); }
-  tb(K_FIX_COUNT); SSB_LAUNCH(k_fix_count, g, 256, 0, stream, vv); te();
+  if (vv.inv) { tb(K_HIST_FLAG); SSB_LAUNCH(k_hist_flag, n_sm * g_count, 256, 0, stream, vv); te(); }
+  tb(K_FIX_COUNT); SSB_LAUNCH(k_fix_count, n_sm * g_count, 256, 0, stream, vv); te();
   tb(K_FIX_SEGS); SSB_LAUNCH(k_fix_segs, n_sm, 256, 0, stream, vv); te();
-  tb(K_FIX_SCATTER); SSB_LAUNCH(k_fix_scatter, g, 256, 0, stream, vv); te();
+  tb(K_FIX_SCATTER); SSB_LAUNCH(k_fix_scatter, n_sm * g_scatter, 256, 0, stream, vv); te();
   tb(K_FIX_SORT); SSB_LAUNCH(k_fix_sort, n_sm * 4, kSortThreads, 0, stream, vv); te();
   tb(K_FIX_TURN);
-  with_model([&](auto m, auto md) { SSB_LAUNCH(k_fix_turn<decltype(m)>, g, 256, 0, stream, vv, md); });
+  with_model([&](auto m, auto md) { SSB_LAUNCH(k_fix_turn<decltype(m)>, n_sm * g_turn, 256, 0, stream, vv, md); });
   te();
   launch_route(vv, 0, 0, 0);
 }
@@ -515,7 +541,7 @@ int ssb_engine::enqueue_round() {
   launch_fix(v, true);
   launch_route(v, 1, 0, 0);
   t_begin(K_POST);
-  SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, v);
+  SSB_LAUNCH(k_post, n_sm * g_post, 256, 0, stream, v);
   t_end();
   CK(cudaGetLastError());
   ++rounds;
@@ -613,7 +639,7 @@ int ssb_engine::build_graph() {
       CK(add_cond(body, vj.h_fix, cudaGraphCondTypeIf, join, &n_if, &b_if));
       CK(capture(b_if, {}, nullptr, [&] { launch_fix(vj, false); }));
       CK(capture(body, {n_if}, &t_route, [&] { launch_route(vj, 1, 0, 0); }));
-      CK(capture(body, {n_if}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_fix, 256, 0, stream, vj); }));      // next to k_route
+      CK(capture(body, {n_if}, &t_post, [&] { SSB_LAUNCH(k_post, n_sm * g_post, 256, 0, stream, vj); }));      // next to k_route
       tail = t_route;
       tail.insert(tail.end(), t_post.begin(), t_post.end());
     }
