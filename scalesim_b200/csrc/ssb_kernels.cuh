@@ -512,13 +512,10 @@ __device__ __forceinline__ bool run_handler(const typename M::Data& md, const Ev
 #ifndef SSB_EXEC_UNROLL
 #define SSB_EXEC_UNROLL 1
 #endif
-#ifndef SSB_EXEC_MINB
-#define SSB_EXEC_MINB 1
-#endif
 constexpr int kExecUnroll = SSB_EXEC_UNROLL;      // events in flight per thread: the pass is bound by memory latency, not by issue slots
 
 template <class M>
-__global__ void __launch_bounds__(256, SSB_EXEC_MINB) k_exec(View v, typename M::Data md) {
+__global__ void __launch_bounds__(256, M::kExecMinBlocks) k_exec(View v, typename M::Data md) {
   Ctl* c = v.ctl;
   const u32 n_arr = c->n_arr;
   const u32 hmask = c->hmask_round;

@@ -3,6 +3,7 @@
 // A model provides
 //   kStateWords              size of the LP state in 32-bit words
 //   kUsesState               false: the handler neither reads nor writes the state (k_exec then skips its gather)
+//   kExecMinBlocks           __launch_bounds__ hint of k_exec for this handler (resident blocks per SM to aim for)
 //   struct Data              read-only model data (device pointers)
 //   early(d, e)              the ONE word of model data the handler gathers that depends on the event alone (PHOLD: the
 //                            table entry; TrafficSim: the next route node). k_exec issues it together with the other
@@ -28,6 +29,7 @@ namespace ssb {
 struct PholdModel {
   static constexpr int kStateWords = 2;
   static constexpr bool kUsesState = false;      // phold::event_handler returns the state it was given (phold.hpp:279-280)
+  static constexpr int kExecMinBlocks = 8;       // k_exec fits 32 registers with this handler: 8 resident blocks per SM
   struct Data {
     const u32* table;
     u32 table_size;
@@ -69,6 +71,7 @@ struct PholdModel {
 struct PholdStatefulModel {
   static constexpr int kStateWords = 2;
   static constexpr bool kUsesState = true;
+  static constexpr int kExecMinBlocks = 1;
   typedef PholdModel::Data Data;
   __device__ static __forceinline__ u32 early(const Data&, const Ev&) { return 0u; }      // its gather depends on the state
   __device__ static __forceinline__ bool handle(const Data& d, const Ev& e, u32* state, u32, Ev& out, u32& err) {
@@ -110,6 +113,7 @@ struct TrafficModel {
   static constexpr int kInlineRoads = 2;
   static constexpr int kStateWords = 2 + 3 * kInlineRoads;
   static constexpr bool kUsesState = true;
+  static constexpr int kExecMinBlocks = 1;
   struct Data {
     const u32* route;   // route pool
     u32 route_len;
