@@ -514,10 +514,13 @@ def exact_diff_measure(env):
     sent = sent_t.numpy().view(ssb.SENT_RECORD_DTYPE)
     fill = [0]
 
+    rec_b, sent_b = rec_t.numpy(), sent_t.numpy()      # byte views: structured-dtype assignment is not a plain memcpy in numpy
+
     def sink(r, s):
-        rec[fill[0]:fill[0] + r.size] = r
-        sent[fill[0]:fill[0] + s.size] = s
-        fill[0] += r.size
+        k = fill[0]
+        rec_b[k * 32:(k + r.size) * 32] = r.view(np.uint8)
+        sent_b[k * 16:(k + s.size) * 16] = s.view(np.uint8)
+        fill[0] = k + r.size
 
     t0 = time.perf_counter()
     st = eng.run_stream_history(sink)
