@@ -50,11 +50,10 @@ CONFIG2 = dict(n_lp=1_000_000, n_init=16_000_000, remote=0.1, committed=72_823_2
 CONFIG4 = dict(n_lp=16_000_000, n_init=256_000_000, remote=0.5, committed=1_165_396_484, name="BASELINE.json config 4")
 
 
-# kernels per round inside the window-loop graph: plan, commit, exec, route, post = 5; N > 1 adds k_gvt and the two
-# receive-side routes; a round with an irregular LP turn (ssb_stats.fix_rounds) adds the IF node's six kernels:
-# k_fix_count, k_fix_segs, k_fix_scatter, k_fix_sort, k_fix_turn, k_route(anti).
+# kernels per round inside the window-loop graph: plan, commit, exec, route, post = 5; N > 1 adds k_gvt and the
+# receive-side route once per global synchronisation; a round with an irregular LP turn (ssb_stats.fix_rounds) adds the
+# IF node's six kernels: k_fix_count, k_fix_segs, k_fix_scatter, k_fix_sort, k_fix_turn, k_route(anti).
 def launches(st, world):
-    # (N > 1: k_gvt + the receive-side route of the positives; the one of the anti-messages sits in an IF node)
     return int(st.rounds * 5 + (st.exchanges * 2 if world > 1 else 0) + st.fix_rounds * 6)
 
 
@@ -475,12 +474,24 @@ def traffic_measure(env):
             raise SystemExit(3)
     n = len(ms)
     value = committed / (sum(ms) / 1000.0)
+    # per-kernel device time of one more (untimed) step on the stream path, CUDA events around every launch
+    eng.set_flags(ssb.FLAG_KERNEL_TIMING)
+    env.barrier()
+    eng.reset()
+    env.barrier()
+    eng.load_events(ev)
+    env.barrier()
+    eng.run()
+    env.barrier()
+    kt = eng.kernel_times()
+    eng.set_flags(0)
     eng.close()
     return {"metric": "committed events/sec, grid TrafficSim", "value": value, "unit": UNIT, "ms_per_step": sum(ms) / n,
             "committed_per_step": committed // n, "rounds_per_step": rounds // n, "rollbacks": last.rollbacks,
             "antis": last.antis_sent, "bucket_ticks": args.traffic_bucket, "window_buckets": args.traffic_window,
             "windows_per_synchronisation": args.traffic_sync if world > 1 else 1,
             "parity": parity, "scaling": "strong",
+            "kernel_ms": {k: round(v[0], 4) for k, v in kt.items()}, "kernel_launches": {k: int(v[1]) for k, v in kt.items()},
             "workload": f"TrafficSim {args.traffic_grid}x{args.traffic_grid} torus grid, {args.traffic_trips} trips "
                         f"(8..64 hops), finish 10800 s, {world} row-stripe partition(s) (BASELINE.json config 3)",
             "whole_path_roofline": {"alg_bytes_per_event": B_ALG_TRAFFIC, "achieved_gbs": value / world * B_ALG_TRAFFIC / 1e9,
@@ -600,6 +611,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-partition event exchange")
     ap.add_argument("--no-traffic", action="store_true", help="skip the secondary grid TrafficSim measurement")
     ap.add_argument("--traffic-only", action="store_true")
+    ap.add_argument("--exact-diff-only", action="store_true")
     ap.add_argument("--traffic-grid", type=int, default=1024)
     ap.add_argument("--traffic-trips", type=int, default=10_000_000)
     ap.add_argument("--traffic-bucket", type=int, default=11)
@@ -638,6 +650,10 @@ def main():
             print(json.dumps(t), flush=True)
         if world > 1:
             dist.destroy_process_group()
+        return
+
+    if args.exact_diff_only:
+        print(json.dumps(exact_diff_measure(env)), flush=True)
         return
 
     which = args.workload if args.workload != "auto" else ("config2" if world == 1 else "config4")
