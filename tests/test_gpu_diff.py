@@ -201,3 +201,25 @@ def test_state_change_query_on_the_ring(tmp_path):
         for v in g["sc_variants"]:
             assert set(lines) <= set(v["lines"])
         assert st2.rollbacks > 0 and st2.antis_sent >= len(superseded)
+
+
+def test_state_change_query_with_more_roads_than_fit_inline(tmp_path):
+    """An SC query whose new road set has more out-roads than the state record holds inline: the roads go to the road
+    table behind the scenario's own entries (make_repeat_engine: extra_roads). Four dead-end roads in front of the one
+    the routes use (std::find takes the first road that leads to the next node, traffic_sim.hpp:299-306): the result
+    is the run on the network where LP 1's road is 200 m long."""
+    sc, _ = ring_scenario()
+    sc.partition = None
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=8)
+    init_lines = sorted(ssb.records_to_lines(ssb.raw_to_records(rec)))
+    wi = _what_if(["SC,1,5;R,1,1,5,10,50,1;R,1,1,6,10,60,1;R,1,1,7,10,70,1;R,1,1,8,10,80,1;R,1,1,2,10,200,1"], tmp_path)
+    assert len(wi.state_changes[0][2]) == 5 > traffic.INLINE_ROADS
+    full = ring_changed_network_lines()
+    superseded = set(init_lines) - set(full)
+    for bucket, window in ((8, 1), (41, 3)):
+        eng = traffic.make_repeat_engine(sc, hs, wi, bucket_ticks=bucket, window_buckets=window, keep_records=True)
+        eng.run()
+        lines = sorted(ssb.records_to_lines(eng.drain_committed()))
+        eng.close()
+        new = set(l for l in lines if l not in set(init_lines))
+        assert sorted((set(init_lines) - superseded) | new) == full
