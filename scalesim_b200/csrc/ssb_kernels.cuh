@@ -514,13 +514,24 @@ __device__ __forceinline__ bool run_handler(const typename M::Data& md, const Ev
 #endif
 constexpr int kExecUnroll = SSB_EXEC_UNROLL;      // events in flight per thread: the pass is bound by memory latency, not by issue slots
 
+// An arrival whose first hash probe hits a slot that another key occupies is executed like a plain one, and the rest of
+// its probe sequence is parked in shared memory: the block walks all parked sequences together at the end, so that the
+// dependent atomics of a collision cost one round trip chain per BLOCK instead of one per warp and loop iteration
+// (measured: the in-loop probes were a third of the kernel's stall samples). If the sequence ends in a duplicate
+// suspect, the LP takes its ticket then — k_fix_turn redoes the whole turn and overwrites what this pass wrote.
+constexpr u32 kExecParked = 512;
+
 template <class M>
 __global__ void __launch_bounds__(256, M::kExecMinBlocks) k_exec(View v, typename M::Data md) {
+  __shared__ uint4 s_parked[kExecParked];      // {next probe position, fingerprint, LP, receive time}
+  __shared__ u32 s_nparked;
   Ctl* c = v.ctl;
   const u32 n_arr = c->n_arr;
   const u32 hmask = c->hmask_round;
   const u32 nth = gridDim.x * blockDim.x;
   u32 err = 0;
+  if (threadIdx.x == 0) s_nparked = 0;
+  __syncthreads();
   for (u32 i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_arr; i0 += kExecUnroll * nth) {
     // Per event two dependent levels of memory latency instead of a chain: (1) the event record; (2) everything the
     // turn needs, issued together — the per-LP word, the LP state, the model's gather (M::early) and the first probe
@@ -567,7 +578,14 @@ __global__ void __launch_bounds__(256, M::kExecMinBlocks) k_exec(View v, typenam
         if (bad) atomicMin(&c->fix_min_t, key_time(e[u].key));
         continue;
       }
-      if (!bad && hold[u] != 0u) bad = hold[u] == hfp[u] || !hash_insert_from(v, hfp[u], (hpos[u] + 1u) & hmask, hmask);
+      if (!bad && hold[u] != 0u) {
+        if (hold[u] == hfp[u]) bad = true;
+        else {
+          const u32 d = atomicAdd(&s_nparked, 1u);
+          if (d < kExecParked) s_parked[d] = make_uint4((hpos[u] + 1u) & hmask, hfp[u], lp[u], key_time(e[u].key));
+          else bad = !hash_insert_from(v, hfp[u], (hpos[u] + 1u) & hmask, hmask);
+        }
+      }
       if (bad) { flag_lp(v, lp[u], key_time(e[u].key)); continue; }
       Ev out;
       bool has;
@@ -583,6 +601,14 @@ __global__ void __launch_bounds__(256, M::kExecMinBlocks) k_exec(View v, typenam
       }
       store_meta_ef(v.meta + slot[u], m);
       v.pflag[slot[u]] = P_PROCESSED;
+    }
+  }
+  __syncthreads();
+  {
+    const u32 np = s_nparked < kExecParked ? s_nparked : kExecParked;
+    for (u32 j = threadIdx.x; j < np; j += blockDim.x) {
+      const uint4 q = s_parked[j];
+      if (!hash_insert_from(v, q.y, q.x, hmask)) flag_lp(v, q.z, q.w);
     }
   }
   if (err) atomicOr(&c->error, err);

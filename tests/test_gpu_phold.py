@@ -169,6 +169,42 @@ def test_crafted_duplicate_and_unmatched_anti():
     eng.close()
 
 
+def test_duplicates_in_a_crowded_hash_set():
+    """R1 (queue.hpp:92) when the round's fingerprint set is as full as it gets (max_batch = the number of arrivals,
+    so the set has 2 slots per arrival): most probe sequences collide, their tails are walked at the end of k_exec
+    (parked in shared memory), and every duplicate must still be found there. Every event lands beyond finish_time
+    after one hop, so the committed set is exactly the set of distinct (LP, time, id) triples that were loaded."""
+    n_lp = 64
+    lat = np.full(16, 5000, dtype=np.int64)
+    rem = np.zeros(16, dtype=np.int32)
+    cfg = ssb.Config(model=ssb.MODEL_PHOLD, n_lp=n_lp, finish_time=1000, bucket_ticks=100, window_buckets=1,
+                     max_events=1 << 13, max_batch=1024, max_committed=1 << 12)
+    eng = ssb.Engine(cfg)
+    eng.set_partition(None)
+    eng.set_model_data(0, lat)
+    eng.set_model_data(1, rem)
+    eng.set_model_data(2, np.array([0, n_lp], dtype=np.int64))
+    ids, words = phold.init_states(n_lp)
+    eng.load_states(ids, words)
+    rng = np.random.default_rng(11)
+    uniq = set()
+    while len(uniq) < 900:
+        uniq.add((int(rng.integers(0, n_lp)), int(rng.integers(0, 100)), int(rng.integers(0, 50))))
+    uniq = sorted(uniq)
+    dup = [uniq[i] for i in rng.choice(len(uniq), 124, replace=False)]
+    allev = uniq + dup
+    ev = np.zeros(len(allev), dtype=ssb.EVENT_DTYPE)
+    for k, (dst, t, i) in enumerate(allev):
+        ev[k] = (i, dst, dst, t, t, 0, 0, 0)
+    eng.load_events(ev[rng.permutation(len(allev))])
+    eng.run()
+    st = eng.stats()
+    assert st.duplicates == 124 and st.committed == 900
+    rec = eng.drain_committed()
+    assert sorted((int(r["dst"]), int(r["recv_time"]), int(r["id"])) for r in rec) == uniq
+    eng.close()
+
+
 @pytest.mark.parametrize("window", [1, 10])
 def test_crafted_scenario_result_is_window_invariant(window):
     eng = _crafted_engine(window)
