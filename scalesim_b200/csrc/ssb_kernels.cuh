@@ -546,7 +546,10 @@ __global__ void __launch_bounds__(256, M::kExecMinBlocks) k_exec(View v, typenam
     for (int u = 0; u < kExecUnroll; ++u) {
       const u32 i = i0 + (u32)u * nth;
       live[u] = i < n_arr;
-      if (live[u]) { slot[u] = slot_of_arrival(v, i); e[u] = load_ev(v.ev + slot[u]); }
+      // (evict-first: the record is not read again before its bucket is committed; measured 1 % on the whole loop.
+      // An evict-LAST policy on the gathered tables — per-LP word, state, lookup table — changed nothing: they stay in
+      // L2 as it is)
+      if (live[u]) { slot[u] = slot_of_arrival(v, i); e[u] = load_ev_ef(v.ev + slot[u]); }
     }
 #pragma unroll
     for (int u = 0; u < kExecUnroll; ++u) {
