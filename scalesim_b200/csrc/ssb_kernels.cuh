@@ -471,7 +471,7 @@ __device__ __forceinline__ bool hash_insert_from(const View& v, u32 fp, u32 pos,
 // shipped application ever does) and the LP's turn is plain:
 //   * no anti-message among its arrivals                                   (R4/R6, queue.hpp:87-90)
 //   * no arrival at or before the time of its newest processed event       (straggler, R5, queue.hpp:98-105);
-//     lpw[lp].x is stable during the pass — k_post raises it afterwards, from the send time of every output
+//     lpw[lp].x is stable during the pass — k_route raises it afterwards, from the send time of every output
 //   * no key twice                                                          (R1, queue.hpp:92)
 // Otherwise the LP is flagged and k_fix_* redo its whole turn exactly (whatever this pass wrote for the LP's other
 // arrivals is overwritten: arrival i owns outbox entry i). Skew-free: a hot LP's events are spread over many threads.
@@ -630,28 +630,19 @@ __global__ void __launch_bounds__(256, M::kExecMinBlocks) k_exec(View v, typenam
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_post — bookkeeping behind k_exec, off the critical path (in the graph it runs next to k_route):
-//   * the output of arrival i raises its sender's newest processed time (lpw[src].x) to the output's send time = the
-//     receive time of the event that produced it; the straggler test of the next round's k_exec reads it. (An event
-//     whose handler produced nothing leaves no trace here: it had no effect, so nothing ever needs to undo it. The
-//     LPs of irregular turns got their value from k_fix_turn.)
-//   * the hash-set region the round used is cleared again.
+// k_post — behind k_exec, off the critical path (in the graph it runs next to k_route): the hash-set region the round
+// used is cleared again. (The other piece of bookkeeping after a pass — the output of arrival i raises its sender's
+// newest processed time lpw[src].x, which the straggler test of the next round's k_exec reads — is done by k_route,
+// which has the outputs staged in shared memory anyway: a separate pass over the outbox cost 46 MB of reads per
+// round.)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_post(View v) {
   Ctl* c = v.ctl;
-  const u32 n_arr = c->n_arr;
+  if (!c->n_arr) return;
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (u32 i = tid; i < n_arr; i += nth) {
-    const uint4 h = *reinterpret_cast<const uint4*>(v.outbox + i);      // key lo, key hi, dst, src
-    if ((h.x & h.y) == 0xFFFFFFFFu) continue;                            // KEY_MAX: no output
-    const u32 send = v.outbox[i].send;
-    atomicMax(&v.lpw[part_local(v, h.w)].x, send + 1u);
-  }
-  if (n_arr) {
-    uint4* hs = reinterpret_cast<uint4*>(v.hset);
-    const u32 nq = (c->hmask_round + 1u) >> 2;
-    for (u32 i = tid; i < nq; i += nth) hs[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  uint4* hs = reinterpret_cast<uint4*>(v.hset);
+  const u32 nq = (c->hmask_round + 1u) >> 2;
+  for (u32 i = tid; i < nq; i += nth) hs[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1279,6 +1270,11 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
   __syncthreads();
   const u32 total = s_off[s_nseg];
   if (total == 0) return;
+  // records [0, n_main) are the handler outputs of this round's arrivals: each raises its sender's newest processed
+  // time to its send time + 1 = the receive time of the event that produced it + 1. (An event whose handler produced
+  // nothing leaves no trace: it had no effect, so nothing ever needs to undo it. The LPs of irregular turns got their
+  // value from k_fix_turn; their outputs' send times lie below it.)
+  const u32 n_main = which == 1 ? c->n_arr : 0u;
   // equal tiles for all blocks: `passes` tiles of `tile` records each (tile is a multiple of 32 records = 1 KB)
   const u32 passes = (total + gridDim.x * kRouteTile - 1) / (gridDim.x * kRouteTile);
   u32 tile = (total + gridDim.x * passes - 1) / (gridDim.x * passes);
@@ -1333,6 +1329,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 
         }
         if (take) {
           const u32 dst = h.z;
+          if (t0 + i < n_main) atomicMax(&v.lpw[part_local(v, h.w)].x, s_tile[i].send + 1u);
           if (dst >= v.n_lp) { atomicOr(&c->error, E_RANGE); continue; }
           const u32 tm = key_time(key);
           const u32 owner = v.world > 1 ? part_owner(v, dst) : v.rank;
