@@ -147,6 +147,7 @@ struct View {
   u32 use_graph;          // 1 = the kernels run inside the window-loop graph and drive its conditional nodes
   u32 sub;                // window index since the last global synchronisation (0 = the first; see ssb_set_sync_interval)
   u32 sync;               // windows per global synchronisation (1 = every window is synchronised)
+  u32 hash_hi, hash_cap;  // hash-set region of a round: >= 2 x arrivals, hash_hi x while the region stays below hash_cap slots
   cudaGraphConditionalHandle h_loop, h_fix;
   // event pool
   Ev* ev;

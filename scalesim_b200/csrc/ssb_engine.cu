@@ -264,8 +264,12 @@ int ssb_engine::init() {
   v.cap_anti = cfg.world > 1 ? std::min<u32>(v.cap_send, v.cap_aux) : 1;
   v.cap_log = (u64)cfg.max_committed;
   v.state_words = (u32)state_words();
+  v.hash_hi = 4u;
+  v.hash_cap = 1u << 21;
+  if (const char* h = getenv("SSB_HASH_HI")) v.hash_hi = (u32)atoi(h);
+  if (const char* h = getenv("SSB_HASH_CAP_LOG")) v.hash_cap = 1u << atoi(h);
   u32 hcap = 1024;
-  while (hcap < 2u * v.cap_batch) hcap <<= 1;
+  while (hcap < 2u * v.cap_batch || (hcap < v.hash_hi * v.cap_batch && hcap < v.hash_cap)) hcap <<= 1;
   v.hmask = hcap - 1u;
   if (getenv("SSB_NO_GRAPH")) graph_enabled = false;
   if (const char* u = getenv("SSB_UNROLL")) { int x = atoi(u); if (x >= 1 && x <= 16) loop_unroll = x; }

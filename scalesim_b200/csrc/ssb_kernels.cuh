@@ -268,7 +268,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     {      // hash-set region of this round: the smallest power of two >= 2 * arrivals (at least 1024 slots)
       // at least 2 x the arrivals; 4 x while the region stays below 8 MB (fewer second probes, still L2-resident)
       u32 hm = 1023u;
-      while (hm < v.hmask && (hm + 1u < 2u * total || (hm + 1u < 4u * total && hm + 1u < (1u << 21)))) hm = (hm << 1) | 1u;
+      while (hm < v.hmask && (hm + 1u < 2u * total || (hm + 1u < v.hash_hi * total && hm + 1u < v.hash_cap))) hm = (hm << 1) | 1u;
       c->hmask_round = hm < v.hmask ? hm : v.hmask;
     }
     c->n_scan = ns;
