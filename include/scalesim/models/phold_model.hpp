@@ -24,6 +24,9 @@ struct device_model<phold> {
     const long hops = LOOK_AHEAD > 0 ? finish_time / LOOK_AHEAD + 1 : 64;
     return (long)initial.size() * std::min<long>(hops, 8);      // ~4.6 hops per chain at lambda 1.0; SCALESIM_B200_MAX_COMMITTED overrides
   }
+  static long committed_bound_one(const ssb_raw_record&, long finish_time) {
+    return std::min<long>(LOOK_AHEAD > 0 ? finish_time / LOOK_AHEAD + 1 : 64, 8);
+  }
   static int state_words() { return 2; }
   static void pack_state(const phold::State& s, uint32_t* w, context&) {
     w[0] = (uint32_t)((uint64_t)s.id() & 0xFFFFFFFFull); w[1] = (uint32_t)((uint64_t)s.id() >> 32);
@@ -31,6 +34,15 @@ struct device_model<phold> {
   // exact-differential store: PHOLD events carry no references into model data
   static std::vector<int64_t> model_data_blob(const context&) { return std::vector<int64_t>(); }
   static void restore_model_data(context&, const std::vector<int64_t>&) {}
+  // scenario image (ssb_scenario): the three slots upload_model_data sends
+  static void image_slots(context&, ssb_scenario& sc) {
+    static int64_t params[2];
+    params[0] = LOOK_AHEAD; params[1] = NUM_LP;
+    sc.slot_data[0] = LATENCY_TABLE; sc.slot_bytes[0] = (int64_t)(sizeof(long) * (size_t)RAND_TABLE_SIZE);
+    sc.slot_data[1] = REMOTE_COM_TABLE; sc.slot_bytes[1] = (int64_t)(sizeof(int) * (size_t)RAND_TABLE_SIZE);
+    sc.slot_data[2] = params; sc.slot_bytes[2] = (int64_t)sizeof(params);
+  }
+  static std::vector<int64_t> model_data_blob_of(const ssb_scenario&) { return std::vector<int64_t>(); }
   static int upload_model_data(ssb_engine* e, context&) {
     static_assert(sizeof(long) == 8 && sizeof(int) == 4, "LP64 expected");
     int rc = ssb_set_model_data(e, 0, LATENCY_TABLE, sizeof(long) * (size_t)RAND_TABLE_SIZE);

@@ -34,6 +34,7 @@ struct device_model<traffic_sim> {
     for (size_t i = 0; i < initial.size(); ++i) n += (long)initial[i].p1 + 1;
     return n;
   }
+  static long committed_bound_one(const ssb_raw_record& e, long) { return (long)e.p1 + 1; }
   static int state_words() { return 2 + 3 * kInlineRoads; }
   // up to kInlineRoads out-roads sit in the state words; a junction with more keeps them in the road table (model
   // data slot 1) and its state holds the index of its first road there — any junction degree (the reference's State
@@ -58,6 +59,16 @@ struct device_model<traffic_sim> {
   // exact-differential store: the recorded events index into the route pool, so it travels with the history
   static std::vector<int64_t> model_data_blob(const context& cx) { return cx.route_pool; }
   static void restore_model_data(context& cx, const std::vector<int64_t>& blob) { cx.route_pool = blob; }
+  // scenario image (ssb_scenario): slot 0 = route pool, slot 1 = road table — what upload_model_data sends
+  static void image_slots(context& cx, ssb_scenario& sc) {
+    if (cx.route_pool.empty()) cx.route_pool.push_back(0);
+    sc.slot_data[0] = cx.route_pool.data(); sc.slot_bytes[0] = (int64_t)(cx.route_pool.size() * sizeof(int64_t));
+    if (!cx.road_table.empty()) { sc.slot_data[1] = cx.road_table.data(); sc.slot_bytes[1] = (int64_t)(cx.road_table.size() * sizeof(int64_t)); }
+  }
+  static std::vector<int64_t> model_data_blob_of(const ssb_scenario& sc) {
+    const int64_t* p = (const int64_t*)sc.slot_data[0];
+    return std::vector<int64_t>(p, p + sc.slot_bytes[0] / 8);
+  }
   static int upload_model_data(ssb_engine* e, context& cx) {
     if (cx.route_pool.empty()) cx.route_pool.push_back(0);
     int rc = ssb_set_model_data(e, 0, cx.route_pool.data(), cx.route_pool.size() * sizeof(int64_t));

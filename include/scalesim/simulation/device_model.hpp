@@ -11,6 +11,9 @@
 //     static int state_words();  static void pack_state(const App::State&, uint32_t* words, context&);
 //     static int upload_model_data(ssb_engine*, context&);        // ssb_set_model_data calls
 //     static long committed_bound(const std::vector<ssb_event>&, long finish_time);   // sizes the device log
+//     static long committed_bound_one(const ssb_raw_record&, long finish_time);       // ... for a scenario image's events
+//     static void image_slots(context&, ssb_scenario&);           // model data slots of a scenario image to write
+//     static std::vector<int64_t> model_data_blob_of(const ssb_scenario&);   // what the history store keeps of them
 //   };
 //
 // Adapters for the two shipped applications live in scalesim/models/; a translation unit that wants the drop-in

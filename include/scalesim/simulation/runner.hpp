@@ -23,6 +23,12 @@
 // Tunables: SCALESIM_B200_BUCKET (ticks), SCALESIM_B200_WINDOW (buckets), SCALESIM_B200_MAX_EVENTS,
 // SCALESIM_B200_MAX_BATCH, SCALESIM_B200_QUIET=1 (digest instead of result lines), SCALESIM_B200_P2P=0 (exchange by
 // ncclSend/ncclRecv instead of peer-memory writes).
+// Input at scale: SCALESIM_B200_SCENARIO_OUT=<file> (one partition) writes what the application's readers / generators
+// produced — partition table, packed states, model data, initial events as device records — as a scenario image
+// (ssb_scenario_save); SCALESIM_B200_SCENARIO=<file> starts from such an image instead (ssb_scenario_open +
+// ssb_scenario_load: one mapping, no parse, no per-event object; any rank / world), e.g. one made from CSV files by
+// ssb_traffic_compile. The application's init() still runs; its init_partition_index / init_states_in_this_rank /
+// init_events do not.
 #ifndef SCALESIM_B200_SIMULATION_RUNNER_HPP_
 #define SCALESIM_B200_SIMULATION_RUNNER_HPP_
 
@@ -304,21 +310,42 @@ void runner<App>::run() {
   app_.init();
   LOG_IF(INFO, rank_ == 0) << "Initiate application";
 
-  std::pair<parti_ptr, parti_indx_ptr> parti = app_.init_partition_index(world_);
-  const std::vector<long>& part = *parti.first;
-  const long n_lp = model::n_lp(parti.first);
+  // a scenario image replaces the application's readers (not for --diff_repeat: that run starts from the history store)
+  const char* image_path = std::getenv("SCALESIM_B200_SCENARIO");
+  const bool from_image = image_path && *image_path && !FLAGS_diff_repeat;
+  ssb_scenario img;
+  std::memset(&img, 0, sizeof(img));
+  if (from_image) {
+    int irc = ssb_scenario_open(image_path, &img);
+    if (irc) { LOG(ERROR) << "ssb_scenario_open failed (status " << irc << "): " << ssb_last_error(NULL); std::exit(1); }
+    if (img.model != model::model_id()) { LOG(ERROR) << image_path << " is a scenario of another application (model " << img.model << ")"; std::exit(1); }
+    if (img.finish_time != App::finish_time())
+      LOG(WARNING) << image_path << ": finish time " << img.finish_time << " differs from the application's " << App::finish_time() << "; the application's is used";
+    LOG_IF(INFO, rank_ == 0) << "Scenario image " << image_path << ": " << img.n_lp << " LPs, " << img.n_states << " states, " << img.n_events << " events";
+  }
+  auto image_owner = [&](long lp) -> int {
+    return img.n_part ? (lp < img.n_part ? (int)(img.lp_to_part[lp] % world_) : 0) : (int)(lp % world_);
+  };
+
+  std::pair<parti_ptr, parti_indx_ptr> parti;
+  if (!from_image) parti = app_.init_partition_index(world_);
+  static const std::vector<long> no_part;
+  const std::vector<long>& part = from_image ? no_part : *parti.first;
+  const long n_lp = from_image ? (long)img.n_lp : model::n_lp(parti.first);
   typename model::context cx;
 
   // states of this rank
   st_vec<App> states;
-  app_.init_states_in_this_rank(states, rank_, world_, parti.first);
+  if (!from_image) app_.init_states_in_this_rank(states, rank_, world_, parti.first);
   // events: every rank reads the whole scenario and keeps what it owns (the reference shuffles instead, runner.hpp:131-147)
   ev_vec<App> mine;
   history hist;
   std::vector<ssb_event> deletes;      // anti-messages of the DE / RE what-if queries
   struct state_change { long lp, time; std::vector<uint32_t> words; };
   std::vector<state_change> state_changes;      // SC what-if queries
-  if (!FLAGS_diff_repeat) {
+  if (from_image) {
+    // nothing to read: the image holds the events as device records
+  } else if (!FLAGS_diff_repeat) {
     // ONE pass over the scenario: the application shards its input by "index % rank_size == rank" and "any way of
     // reading is fine, the events are shuffled to their LPs afterwards" (phold.hpp:190-209, traffic_sim.hpp:410-451),
     // so asking for shard 0 of 1 yields every event; this rank keeps the ones whose LP it owns (the reference shuffles
@@ -368,7 +395,19 @@ void runner<App>::run() {
   std::vector<ssb_event> pod(mine.size());
   for (size_t i = 0; i < mine.size(); ++i) model::pack_event(*mine[i], pod[i], cx);
   pod.insert(pod.end(), deletes.begin(), deletes.end());
-  const size_t n_resident = pod.size() + hist.rec.size();
+  // from an image: the events of this rank's LPs are counted (and the committed log sized) in one pass over the mapping
+  size_t n_image_events = 0, n_image_states = 0;
+  long image_committed_bound = 0;
+  if (from_image) {
+    for (int64_t i = 0; i < img.n_events; ++i) {
+      if (world_ > 1 && image_owner((long)img.events[i].dst) != rank_) continue;
+      ++n_image_events;
+      image_committed_bound += model::committed_bound_one(img.events[i], App::finish_time());
+    }
+    for (int64_t i = 0; i < img.n_states; ++i)
+      if (world_ == 1 || image_owner((long)img.state_lps[i]) == rank_) { ++n_image_states; if (FLAGS_diff_init) hist.state_lps.push_back(img.state_lps[i]); }
+  }
+  const size_t n_resident = pod.size() + hist.rec.size() + n_image_events;
 
   ssb_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
@@ -387,13 +426,20 @@ void runner<App>::run() {
   // the device log holds the whole run (it streams out while the loop runs, but the device is never throttled by the
   // host): sized from the workload; an overflow is a loud SSB_ERR_CAPACITY, never a silently shorter output
   cfg.max_committed = quiet ? 0 : env_long("SCALESIM_B200_MAX_COMMITTED",
-                                           (long)hist.rec.size() + model::committed_bound(pod, App::finish_time()) + (1 << 16));
+                                           (long)hist.rec.size() + model::committed_bound(pod, App::finish_time()) + image_committed_bound + (1 << 16));
   if (FLAGS_diff_init) cfg.flags |= SSB_FLAG_HISTORY;
   cfg.max_snapshots = 1 << 20;
   cfg.rounds_per_sync = 4;
   int rc = ssb_create(&cfg, &engine_);
   if (rc) { LOG(ERROR) << "ssb_create failed (status " << rc << "): " << ssb_last_error(NULL); std::exit(1); }
   comm_init();
+  const char* image_out = std::getenv("SCALESIM_B200_SCENARIO_OUT");
+  if (from_image) {
+    // partition, model data, this rank's states and events straight from the mapping
+    if ((rc = ssb_scenario_load(engine_, &img))) fail("ssb_scenario_load", rc);
+    if (FLAGS_diff_init) hist.pool = model::model_data_blob_of(img);
+    ssb_scenario_close(&img);
+  } else {
   std::vector<int64_t> part64(part.begin(), part.end());
   for (size_t i = 0; i < part64.size(); ++i) part64[i] %= world_;
   if ((rc = ssb_set_partition(engine_, part64.data(), (int64_t)part64.size()))) fail("ssb_set_partition", rc);
@@ -407,6 +453,33 @@ void runner<App>::run() {
     }
     if ((rc = model::upload_model_data(engine_, cx))) fail("ssb_set_model_data", rc);
     if ((rc = ssb_load_states(engine_, ids.data(), words.data(), (int64_t)ids.size()))) fail("ssb_load_states", rc);
+    if (image_out && *image_out && !FLAGS_diff_repeat) {
+      // keep what the application's readers / generators produced as a scenario image for later runs
+      if (world_ != 1) { LOG(ERROR) << "SCALESIM_B200_SCENARIO_OUT needs a single partition (the image holds every partition's share)"; std::exit(1); }
+      std::vector<ssb_raw_record> raw(pod.size());
+      for (size_t i = 0; i < pod.size(); ++i) {
+        const ssb_event& e = pod[i];
+        if (e.recv_time < 0 || e.recv_time >= (1ll << 31) || e.send_time < 0 || e.send_time >= (1ll << 31) || e.id < 0 || e.id >= 0xffffffffll ||
+            e.dst < 0 || e.dst >= 0xffffffffll || e.src < -1 || e.src >= 0xffffffffll || e.p0 < 0 || e.p0 > 0xffffffffll || e.p1 < 0 || e.p1 > 0xffffffffll) {
+          LOG(ERROR) << "event " << e.id << " does not fit the device record (see the limits in scalesim_b200.h)"; std::exit(1);
+        }
+        ssb_raw_record& r = raw[i];
+        r.key = ((uint64_t)e.recv_time << 32) | (uint64_t)e.id;
+        r.dst = (uint32_t)e.dst; r.src = e.src < 0 ? 0xffffffffu : (uint32_t)e.src; r.send_time = (uint32_t)e.send_time;
+        r.p0 = (uint32_t)e.p0; r.p1 = (uint32_t)e.p1; r.tag = (uint32_t)(e.flags & 1);
+      }
+      std::vector<int64_t> part_raw(part.begin(), part.end());
+      ssb_scenario out;
+      std::memset(&out, 0, sizeof(out));
+      out.model = model::model_id(); out.state_words = sw; out.n_lp = n_lp; out.finish_time = App::finish_time();
+      out.n_part = (int64_t)part_raw.size(); out.lp_to_part = part_raw.data();
+      out.n_states = (int64_t)ids.size(); out.state_lps = ids.data(); out.states = words.data();
+      out.n_events = (int64_t)raw.size(); out.events = raw.data();
+      model::image_slots(cx, out);
+      if ((rc = ssb_scenario_save(image_out, &out))) { LOG(ERROR) << "ssb_scenario_save failed (status " << rc << "): " << ssb_last_error(NULL); std::exit(1); }
+      LOG(INFO) << "Scenario image written: " << image_out;
+    }
+  }
   }
   if (FLAGS_diff_repeat &&
       (rc = ssb_load_history(engine_, hist.rec.data(), hist.sent.data(), (int64_t)hist.rec.size()))) fail("ssb_load_history", rc);
@@ -417,15 +490,16 @@ void runner<App>::run() {
   LOG_IF(INFO, rank_ == 0)
       << "\n====================================================================\n"
       << " Number of partitions: " << world_ << " (one B200 each)\n"
-      << "     Total events num (this partition): " << pod.size() << "\n"
-      << "     Total states num (this partition): " << states.size() << "\n"
+      << "     Total events num (this partition): " << pod.size() + n_image_events << "\n"
+      << "     Total states num (this partition): " << states.size() + n_image_states << "\n"
       << " Total init time: " << (long)init_ms << " ms\n"
       << "====================================================================\n";
 
   LOG_IF(INFO, rank_ == 0) << "Start Simulation";
   std::vector<ssb_record> kept;
   const long verify_k = env_long("SCALESIM_B200_VERIFY", 0);
-  const bool keep = verify_k > 0 && !quiet && !FLAGS_diff_init && !FLAGS_diff_repeat;
+  if (verify_k > 0 && from_image) LOG(INFO) << "SCALESIM_B200_VERIFY walks the application's own initial events; skipped for a scenario image";
+  const bool keep = verify_k > 0 && !quiet && !FLAGS_diff_init && !FLAGS_diff_repeat && !from_image;
   clk::time_point t1 = clk::now();
   ssb_stats st;
   std::memset(&st, 0, sizeof(st));
@@ -439,7 +513,7 @@ void runner<App>::run() {
     // --diff_init: the committed events leave the device together with their sent-log entries while the loop runs;
     // the lines are printed from the same records, the store file grows on a writer thread
     for (size_t i = 0; i < states.size(); ++i) hist.state_lps.push_back(states[i]->id());
-    hist.pool = model::model_data_blob(cx);
+    if (!from_image) hist.pool = model::model_data_blob(cx);
     const std::string p = history_path(), dir = p.substr(0, p.find_last_of('/'));
     std::error_code ec;
     std::filesystem::create_directories(dir, ec);

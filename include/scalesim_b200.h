@@ -288,6 +288,70 @@ int ssb_phold_build_tables(int64_t seed, double lambda, double remote_ratio, int
 int64_t ssb_phold_init_events(int64_t num_lp, int64_t num_init_msg, const int64_t* latency, int64_t table_size,
                               int64_t offset, int64_t stride, ssb_event* out, int64_t cap);
 
+/* ---- scenario ingestion at scale (no device work except ssb_scenario_load) ----
+ * The reference reads its input as text, one getline + boost::split + atol per line and one shared_ptr object per
+ * event / state (traffic_sim.hpp:345-451); a 10 M-trip scenario is ~3 GB of CSV. Two pieces replace that:
+ *
+ * 1. ssb_traffic_read: the three TrafficSim readers natively — the files are mapped, cut into line-aligned pieces and
+ *    parsed by `threads` host threads (0 = all cores) into flat arrays. Field meaning exactly as the reference's:
+ *      partition file  traffic_reader::graph_read (traffic_sim.hpp:345-362): atol(line), line index = LP id
+ *      road file       traffic_reader::road_read  (:364-408): one line per LP, roads split on ';', fields on ',':
+ *                      state id = field 2 of the LAST road of the line, destination = field 3, speed = field 4,
+ *                      length = field 5 (0 becomes 1), lanes = field 6 (unused by the handler)
+ *      trip file       traffic_reader::trip_read  (:410-451): vehicle id = field 1, arrival = departure = field 3,
+ *                      route = fields 4.., source = -1
+ *    Numbers are read as C atol reads them (leading blanks, sign, digits, anything else ends the number). Lines end
+ *    at '\n' (std::getline). A road with fewer than 7 fields or a trip with fewer than 5 is skipped (the reference
+ *    indexes past the end of its token vector there). A file that cannot be opened is SSB_ERR_INVALID (the
+ *    reference silently simulates nothing, traffic_sim.hpp:348-352). ssb_traffic_free releases the arrays.
+ *
+ * 2. The scenario image ("SSBSCN01"): everything an engine needs to start — partition table, LP states as the
+ *    device's state words, model data slots, initial events as 32-byte device records — in one file whose sections
+ *    are page-aligned, so opening it is one mmap and loading it is a handful of host-to-device copies straight from
+ *    the mapping (no parse, no per-event object). ssb_traffic_compile writes one from the three CSV files;
+ *    ssb_scenario_save writes one from arrays the caller holds (the drop-in runner does, after the application's own
+ *    readers / generators ran once: SCALESIM_B200_SCENARIO_OUT); ssb_scenario_load puts an image into an engine of
+ *    any rank / world: partition numbers are reduced modulo `world`, the states and events of LPs this rank owns are
+ *    loaded (what runner::init does with the app's vectors, runner.hpp:98-147).
+ */
+typedef struct ssb_traffic_tables {
+  int64_t n_part;   int64_t* part;                                         /* partition file (n_part = 0: none given) */
+  int64_t n_states; int64_t* state_ids; int64_t* road_start;               /* road file: CSR, road_start[n_states + 1] */
+  int64_t n_roads;  int64_t* road_dst; int64_t* road_speed; int64_t* road_len;
+  int64_t n_trips;  int64_t* trip_id; int64_t* trip_dep; int64_t* route_start;   /* trip file: CSR, route_start[n_trips + 1] */
+  int64_t n_nodes;  int64_t* route_nodes;
+} ssb_traffic_tables;
+int ssb_traffic_read(const char* partition_file /* may be NULL */, const char* road_file /* may be NULL */,
+                     const char* trip_file /* may be NULL */, int threads, ssb_traffic_tables* out);
+void ssb_traffic_free(ssb_traffic_tables* t);
+/* the inverse, for feeding a generated scenario to the reference's own binary: files in the reference's format
+ * (road line: "R,{road id},{lp},{dst},{speed},{length},1" joined by ';'; trip line: "{i},{id},0,{departure},{nodes...}") */
+int ssb_traffic_write_csv(const ssb_traffic_tables* t, const char* partition_file /* may be NULL */,
+                          const char* road_file /* may be NULL */, const char* trip_file /* may be NULL */);
+
+#define SSB_SCENARIO_SLOTS 4
+typedef struct ssb_scenario {
+  int32_t model;                      /* ssb_model_id */
+  int32_t state_words;                /* 32-bit words per LP state (= ssb_state_words of an engine of that model) */
+  int64_t n_lp, finish_time;
+  int64_t n_part;   const int64_t* lp_to_part;     /* partition numbers as the application gave them (0: lp % world) */
+  int64_t n_states; const int64_t* state_lps; const uint32_t* states;      /* states[n_states * state_words] */
+  int64_t slot_bytes[SSB_SCENARIO_SLOTS]; const void* slot_data[SSB_SCENARIO_SLOTS];   /* ssb_set_model_data slots */
+  int64_t n_events; const ssb_raw_record* events;  /* initial events, every partition's */
+  void* mapping; int64_t mapping_bytes;            /* set by ssb_scenario_open (the pointers above point into it) */
+} ssb_scenario;
+int ssb_scenario_save(const char* path, const ssb_scenario* sc);
+int ssb_scenario_open(const char* path, ssb_scenario* sc);      /* read-only mapping; ssb_scenario_close unmaps */
+void ssb_scenario_close(ssb_scenario* sc);
+/* partition + model data + the states and events of this engine's rank; call it where ssb_set_partition would be */
+int ssb_scenario_load(ssb_engine* e, const ssb_scenario* sc);
+/* CSV -> image for TrafficSim: ssb_traffic_read + the packing of scalesim/models/traffic_model.hpp (state words, road
+ * table for junctions with more than two out-roads, route pool, one initial event per trip) + ssb_scenario_save */
+int ssb_traffic_compile(const char* partition_file /* may be NULL */, const char* road_file, const char* trip_file,
+                        int64_t finish_time, int threads, const char* image_path);
+/* the configuration an engine was created with */
+int ssb_get_config(ssb_engine* e, ssb_config* out);
+
 #ifdef __cplusplus
 }
 #endif

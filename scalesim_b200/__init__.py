@@ -29,10 +29,10 @@ from .capi import (  # noqa: F401
     records_to_lines,
     digest_records,
 )
-from . import dist, phold, traffic  # noqa: F401
+from . import dist, phold, scenario, traffic  # noqa: F401
 
 __all__ = [
     "Engine", "EngineError", "Config", "Stats", "EVENT_DTYPE", "RECORD_DTYPE", "RAW_RECORD_DTYPE", "FLAG_KERNEL_TIMING", "FLAG_HISTORY", "SENT_RECORD_DTYPE", "PACKED_RECORD_DTYPE", "events_to_raw", "packed_to_records", "raw_to_records",
     "MODEL_PHOLD", "MODEL_TRAFFIC", "MODEL_PHOLD_STATEFUL", "library_path", "load_library",
-    "records_to_lines", "digest_records", "dist", "phold", "traffic",
+    "records_to_lines", "digest_records", "dist", "phold", "scenario", "traffic",
 ]

@@ -200,6 +200,17 @@ def load_library() -> C.CDLL:
     lib.ssb_phold_build_tables.argtypes = [i64, C.c_double, C.c_double, i64, vp, vp]
     lib.ssb_phold_init_events.argtypes = [i64, i64, vp, i64, i64, i64, vp, i64]
     lib.ssb_phold_init_events.restype = i64
+    lib.ssb_traffic_read.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, vp]
+    lib.ssb_traffic_free.argtypes = [vp]
+    lib.ssb_traffic_free.restype = None
+    lib.ssb_traffic_write_csv.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
+    lib.ssb_scenario_save.argtypes = [C.c_char_p, vp]
+    lib.ssb_scenario_open.argtypes = [C.c_char_p, vp]
+    lib.ssb_scenario_close.argtypes = [vp]
+    lib.ssb_scenario_close.restype = None
+    lib.ssb_scenario_load.argtypes = [vp, vp]
+    lib.ssb_traffic_compile.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i64, i32, C.c_char_p]
+    lib.ssb_get_config.argtypes = [vp, C.POINTER(_Config)]
     if lib.ssb_abi_version() != ABI_VERSION:
         raise EngineError(-1, "libscalesim_b200.so ABI version mismatch")
     _lib = lib
@@ -279,6 +290,17 @@ class Engine:
         assert events.dtype == EVENT_DTYPE
         a = np.ascontiguousarray(events)
         self._check(self._lib.ssb_load_events(self._h, _ptr(a), a.size))
+
+    def load_scenario(self, image):
+        """Partition, model data and this rank's states and events from a scenario image
+        (``scalesim_b200.scenario.Image``): ssb_scenario_load."""
+        self._check(self._lib.ssb_scenario_load(self._h, C.byref(image.c)))
+
+    def config(self) -> Config:
+        """The configuration the engine was created with, read back through ssb_get_config."""
+        c = _Config()
+        self._check(self._lib.ssb_get_config(self._h, C.byref(c)))
+        return Config(**{n: getattr(c, n) for n, _ in _Config._fields_ if n != "abi_version"})
 
     def load_events_ptr(self, ptr: int, n: int):
         """Load ``n`` ssb_event records from a raw host pointer (e.g. a pinned torch tensor)."""

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/scalesim_b200.h"
+#include "ssb_host_internal.h"
 #include "ssb_kernels.cuh"
 
 // kernel launch: <<<>>> on the device; the developer-only host emulation (tools/emu) calls the kernel body once
@@ -666,9 +667,18 @@ template <class T> bool regrow(ssb_engine* e, T** p, size_t n) {
 }  // namespace
 
 // ======================================= C ABI =======================================
+void ssb_internal_set_error(const std::string& what) { g_create_error = what; }
+void ssb_internal_set_engine_error(ssb_engine* e, const std::string& what) { if (e) e->set_error(what); else g_create_error = what; }
+
 extern "C" {
 
 int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+
+int ssb_get_config(ssb_engine* e, ssb_config* out) {
+  if (!e || !out) return SSB_ERR_INVALID;
+  *out = e->cfg;
+  return SSB_OK;
+}
 
 const char* ssb_last_error(ssb_engine* e) { return e ? e->error.c_str() : g_create_error.c_str(); }
 

@@ -103,3 +103,48 @@ def test_dropin_repeat_without_store_fails_loudly(tmp_path):
     p = subprocess.run([path, "--diff_repeat", "--sim_id=1", f"--store_dir={tmp_path}/none", "100", "1600", "0.1", "1.0", "1", "50"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert p.returncode == 1 and "no history store" in p.stderr
+
+
+def test_phold_dropin_writes_and_starts_from_a_scenario_image(tmp_path):
+    """SCALESIM_B200_SCENARIO_OUT keeps what phold.hpp's generators produced as a scenario image; a second run with
+    SCALESIM_B200_SCENARIO starts from it (no init_events, no per-event objects) and prints the same reference lines."""
+    img = str(tmp_path / "phold.ssbscn")
+    args = [100, 1600, 0.1, 1.0, 1, 50]
+    lines, err = _run("PHOLD", args, {"SCALESIM_B200_SCENARIO_OUT": img})
+    assert sorted(lines) == golden_lines("phold_100_1600") and "Scenario image written" in err
+    lines, err = _run("PHOLD", args, {"SCALESIM_B200_SCENARIO": img, "SCALESIM_B200_WINDOW": "3"})
+    assert sorted(lines) == golden_lines("phold_100_1600")
+    assert "Total events num (this partition): 1600" in err and "Total states num (this partition): 100" in err
+    # an image of another application is refused
+    p = subprocess.run([os.path.join(APPS, "TrafficSim"), "x", "y", "z"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, SCALESIM_B200_SCENARIO=img), timeout=120)
+    assert p.returncode == 1 and "another application" in p.stderr
+
+
+def test_trafficsim_dropin_from_a_compiled_csv_image(tmp_path):
+    """The ring's CSV files compiled natively (ssb_traffic_compile) -> TrafficSim started from the image: the
+    reference's 38 lines; --diff_init from the image writes the store the reference writes, and --diff_repeat on it
+    prints the reference's 19 lines."""
+    from scalesim_b200 import scenario, store
+    g, gd = golden("ring"), golden("ring_diff")
+    rd, trip, part = write_ring_files(str(tmp_path))
+    part1 = str(tmp_path / "part1")
+    with open(part1, "w") as f:
+        f.write("0\n" * 10)
+    img = str(tmp_path / "ring.ssbscn")
+    scenario.compile_traffic_csv(rd, trip, img, partition_file=part1)
+    env = {"SCALESIM_B200_SCENARIO": img}
+    lines, err = _run("TrafficSim", ["-", "-", "-"], env)              # the file arguments are not read
+    assert sorted(lines) == g["lines"]
+    flags = ["--sim_id=5", f"--store_dir={tmp_path}/st"]
+    lines, err = _run("TrafficSim", flags + ["--diff_init", "-", "-", "-"], env)
+    assert sorted(lines) == gd["init_lines"]
+    hs = store.HistoryStore.load(f"{tmp_path}/st", 5, 0)
+    assert hs.event_keys().tolist() == sorted(gd["store"]["event"])
+    assert hs.cancel_keys().tolist() == sorted(gd["store"]["cancel"])
+    assert hs.state_keys().tolist() == sorted(gd["store"]["state"])
+    ae = str(tmp_path / "add_ev.csv")
+    with open(ae, "w") as f:
+        f.write("".join(l + "\n" for l in gd["ae_lines"]))
+    lines, err = _run("TrafficSim", flags + ["--diff_repeat", part1, rd, ae])
+    assert sorted(lines) == gd["repeat_union"]

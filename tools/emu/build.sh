@@ -6,6 +6,7 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(cd "$HERE/../.." && pwd)
 g++ -std=c++17 -O1 -g -DSSB_EMU -fPIC -shared -Wno-unknown-pragmas -I "$HERE" \
     -x c++ "$ROOT/scalesim_b200/csrc/ssb_engine.cu" -x c++ "$ROOT/scalesim_b200/csrc/phold_host.cc" \
+    -x c++ "$ROOT/scalesim_b200/csrc/scenario_host.cc" \
     -o "$HERE/libssb_emu.so" -ldl
 echo "built $HERE/libssb_emu.so"
 # the drop-in applications against the emulation (only where the reference tree exists): tools/emu/apps/{PHOLD,TrafficSim};
