@@ -32,6 +32,7 @@
 #ifndef SCALESIM_B200_SIMULATION_RUNNER_HPP_
 #define SCALESIM_B200_SIMULATION_RUNNER_HPP_
 
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -363,6 +364,7 @@ void runner<App>::run() {
     model::restore_model_data(cx, hist.pool);
     {
       std::vector<boost::shared_ptr<const what_if<App> > > wi;
+      std::vector<std::pair<uint64_t, uint32_t> > by_key;      // (key, index) of the recorded events, sorted; built on demand
       app_.init_what_if(wi, 0, 1);      // every query in one pass (same sharding contract as init_events)
       for (size_t i = 0; i < wi.size(); ++i) {
         long d = wi[i]->lp_id_;
@@ -381,8 +383,15 @@ void runner<App>::run() {
           // output is NOT cancelled — and an anti-message goes into the LP's inbox (eventq::delete_ev,
           // queue.hpp:227-241), which erases the event and rolls the LP back to its key
           const uint64_t key = ((uint64_t)wi[i]->time_ << 32) | (uint64_t)(uint32_t)wi[i]->delete_event_id_;
-          for (size_t k = 0; k < hist.rec.size(); ++k)
-            if (hist.rec[k].key == key && (long)hist.rec[k].dst == d) hist.sent[k].dst = 0xffffffffu;
+          if (by_key.empty() && !hist.rec.empty()) {      // first delete query: index the history once (key -> record)
+            by_key.resize(hist.rec.size());
+            for (size_t k = 0; k < by_key.size(); ++k) by_key[k] = std::make_pair(hist.rec[k].key, (uint32_t)k);
+            std::sort(by_key.begin(), by_key.end());
+          }
+          for (std::vector<std::pair<uint64_t, uint32_t> >::const_iterator it =
+                   std::lower_bound(by_key.begin(), by_key.end(), std::make_pair(key, (uint32_t)0));
+               it != by_key.end() && it->first == key; ++it)
+            if ((long)hist.rec[it->second].dst == d) hist.sent[it->second].dst = 0xffffffffu;
           ssb_event a;
           std::memset(&a, 0, sizeof(a));
           a.id = wi[i]->delete_event_id_; a.src = -1; a.dst = d; a.recv_time = a.send_time = wi[i]->time_; a.flags = 1;

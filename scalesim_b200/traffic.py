@@ -367,9 +367,14 @@ def make_repeat_engine(sc: Scenario, store, what_if, **kw) -> Engine:
         # (eventq::delete_ev, :227-236), which erases it and rolls the LP back to its key
         sent = sent.copy()
         keys = (deletes[:, 1].astype(np.uint64) << np.uint64(32)) | deletes[:, 2].astype(np.uint64)
-        for lp, key in zip(deletes[:, 0], keys):
-            hit = np.nonzero((store.rec["key"] == key) & (store.rec["dst"] == lp))[0]
-            sent["dst"][hit] = 0xFFFFFFFF
+        # one sort of the recorded keys, then a binary search per query (not a scan of the history per query)
+        order = np.argsort(store.rec["key"], kind="stable")
+        sorted_keys = store.rec["key"][order]
+        lo = np.searchsorted(sorted_keys, keys, side="left")
+        hi = np.searchsorted(sorted_keys, keys, side="right")
+        for lp, a, b in zip(deletes[:, 0], lo, hi):
+            hit = order[a:b]
+            sent["dst"][hit[store.rec["dst"][hit] == lp]] = 0xFFFFFFFF
     eng.load_history(store.rec, sent)
     part = sc.partition
     for (lp, t, *_), w in zip(state_changes, sc_words):
