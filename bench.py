@@ -591,6 +591,23 @@ def exact_diff_measure(env):
 
 
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# Input at scale: CSV in the reference's format -> native readers -> scenario image -> HBM, host wall
+# clock; the engine started from the image must commit what the engine fed through the array calls commits. A side
+# measurement: a failure is reported in the key, it does not take the bench line down.
+# ------------------------------------------------------------------------------------------------
+def ingest_measure(env):
+    try:
+        from scalesim_b200 import scenario
+        res = scenario.ingest_measure(env.args.traffic_grid, env.args.traffic_grid, env.args.ingest_trips,
+                                      bucket_ticks=env.args.traffic_bucket, device=env.local_rank)
+        if not (res.get("digest_equal") and res.get("read_equals_generator")):
+            res["error"] = "the engine started from the image and the array path disagree"
+        return res
+    except Exception as e:      # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -620,6 +637,9 @@ def main():
     ap.add_argument("--no-exact-diff", action="store_true", help="skip the exact-differential (config 5) measurement")
     ap.add_argument("--diff-trips", type=int, default=2_000_000)
     ap.add_argument("--diff-added", type=int, default=1000)
+    ap.add_argument("--no-ingest", action="store_true", help="skip the scenario-ingestion measurement (CSV -> image -> HBM)")
+    ap.add_argument("--ingest-only", action="store_true")
+    ap.add_argument("--ingest-trips", type=int, default=500_000)
     args = ap.parse_args()
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line and nothing else
@@ -654,6 +674,10 @@ def main():
 
     if args.exact_diff_only:
         print(json.dumps(exact_diff_measure(env)), flush=True)
+        return
+
+    if args.ingest_only:
+        print(json.dumps(ingest_measure(env)), flush=True)
         return
 
     which = args.workload if args.workload != "auto" else ("config2" if world == 1 else "config4")
@@ -696,6 +720,10 @@ def main():
     if world == 1 and not args.no_exact_diff and not args.no_traffic:
         exact_diff = exact_diff_measure(env)
 
+    ingest = None
+    if rank == 0 and world == 1 and not args.no_ingest and not args.no_traffic:
+        ingest = ingest_measure(env)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -716,6 +744,7 @@ def main():
             "gpu_launches": main_res["launches"],
             "clocks": main_res["clocks"], "roofline": main_res.get("roofline"), "e2e": main_res.get("e2e"),
             "cpu_baseline": cpu, "optimistic": optimistic, "weak_config2": weak, "traffic": traffic_res, "exact_diff": exact_diff,
+            "ingest": ingest,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -241,3 +241,69 @@ def phold_image(n_lp: int, n_init: int, remote_ratio: float, lam: float, tables=
     ids = np.arange(n_lp, dtype=np.int64)
     words = np.stack([(ids & 0xFFFFFFFF).astype(np.uint32), (ids >> 32).astype(np.uint32)], axis=1)
     return Image.of(MODEL_PHOLD, n_lp, phold.FINISH_TIME, ids, words, [lat, rem, params], ev)
+
+
+def ingest_measure(width: int = 1024, height: int = 1024, n_trips: int = 500_000, workdir: str | None = None,
+                   bucket_ticks: int = 11, device: int = 0, run: bool = True) -> dict:
+    """Scenario ingestion end to end, timed (host wall clock): a generated torus scenario written in the reference's
+    CSV format -> native readers -> scenario image -> engine (ssb_scenario_load), next to the array path
+    (``traffic.make_engine``) on the same scenario; with ``run`` both engines simulate and their committed digests must
+    be equal. Used by ``bench.py`` (key ``ingest``) and by tests/test_gpu_scenario.py."""
+    import shutil
+    import tempfile
+    import time
+
+    from . import traffic
+    from .capi import Config, Engine
+
+    own = workdir is None
+    d = tempfile.mkdtemp(prefix="ssb_ingest_") if own else workdir
+    out = {"workload": f"TrafficSim {width}x{height} torus grid, {n_trips} trips as CSV in the reference's format"}
+    try:
+        sc = traffic.synthetic_grid(width, height, n_trips, seed=1)
+        rd, trip, img = (os.path.join(d, n) for n in ("rd.csv", "trip.csv", "scenario.ssbscn"))
+        t = time.perf_counter()
+        write_traffic_csv(sc, rd, trip)
+        out["write_csv_s"] = round(time.perf_counter() - t, 4)
+        out["csv_bytes"] = os.path.getsize(rd) + os.path.getsize(trip)
+        t = time.perf_counter()
+        tabs = read_traffic_csv(rd, trip)
+        out["native_read_s"] = round(time.perf_counter() - t, 4)
+        out["native_read_gb_per_s"] = round(out["csv_bytes"] / 1e9 / max(out["native_read_s"], 1e-9), 3)
+        out["host_threads"] = os.cpu_count()
+        same = all(np.array_equal(tabs[k], getattr(sc, k)) for k in (
+            "state_ids", "road_start", "road_dst", "road_speed", "road_len", "trip_id", "trip_dep", "route_start", "route_nodes"))
+        out["read_equals_generator"] = bool(same)
+        del tabs
+        t = time.perf_counter()
+        compile_traffic_csv(rd, trip, img, finish_time=traffic.FINISH_TIME)
+        out["compile_to_image_s"] = round(time.perf_counter() - t, 4)
+        out["image_bytes"] = os.path.getsize(img)
+
+        kw = dict(max_events=int(n_trips * 1.5) + (1 << 16) + 4096 * 8, max_batch=max(1 << 14, n_trips // 2 + (1 << 14)))
+        t = time.perf_counter()
+        im = Image.open(img)
+        out["open_image_s"] = round(time.perf_counter() - t, 5)
+        eng = Engine(Config(model=MODEL_TRAFFIC, n_lp=im.n_lp, finish_time=im.finish_time, bucket_ticks=bucket_ticks,
+                            device=device, rounds_per_sync=8, **kw))
+        t = time.perf_counter()
+        eng.load_scenario(im)
+        out["load_image_s"] = round(time.perf_counter() - t, 4)      # mapping -> HBM: partition, tables, states, events
+        im.close()
+        digest_image = None
+        if run:
+            st = eng.run()
+            digest_image = eng.digest()
+            out["committed"] = st.committed
+        eng.close()
+        t = time.perf_counter()
+        eng2 = traffic.make_engine(sc, bucket_ticks=bucket_ticks, device=device, rounds_per_sync=8, **kw)
+        out["array_path_pack_and_load_s"] = round(time.perf_counter() - t, 4)   # numpy packing + per-array ABI calls
+        if run:
+            eng2.run()
+            out["digest_equal"] = bool(eng2.digest() == digest_image)
+        eng2.close()
+        return out
+    finally:
+        if own:
+            shutil.rmtree(d, ignore_errors=True)

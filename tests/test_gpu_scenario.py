@@ -108,3 +108,15 @@ def test_image_for_another_model_or_size_is_refused(phold_tables_01):
     with pytest.raises(ssb.EngineError, match="64 LPs"):
         eng.load_scenario(im)
     eng.close()
+
+
+def test_ingest_measure_small():
+    """What bench.py reports under the `ingest` key, at a small size: CSV -> native readers -> image -> engine commits
+    what the array path commits."""
+    res = scenario.ingest_measure(32, 32, 3000, bucket_ticks=11)
+    assert res["read_equals_generator"] and res["digest_equal"]
+    s = O.Sim.traffic_scenario(traffic.synthetic_grid(32, 32, 3000, seed=1))
+    s.run_closure(2)
+    assert res["committed"] == s.digest()[0]
+    for k in ("write_csv_s", "native_read_s", "compile_to_image_s", "open_image_s", "load_image_s", "array_path_pack_and_load_s"):
+        assert res[k] >= 0
