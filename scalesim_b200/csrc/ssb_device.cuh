@@ -303,8 +303,12 @@ __device__ __forceinline__ Ev* mb_data(const View& v, u32 owner, u32 par, u32 sr
 }
 
 // slot of position p in bucket b; the chunk must already exist
+// (after an event-pool overflow — E_POOL — a bucket's fill count can point past its chunk list or at a chunk that was
+// never allocated: such a position resolves into the sacrificial chunk 0, never outside the pool)
 __device__ __forceinline__ u32 slot_of(const View& v, u32 b, u32 p) {
-  u32 ch = v.chunk_tab[(size_t)b * v.maxc + (p >> v.ch_log)];
+  const u32 j = p >> v.ch_log;
+  u32 ch = j < v.maxc ? v.chunk_tab[(size_t)b * v.maxc + j] : 0u;
+  if (ch == NIL) ch = 0u;
   return (ch << v.ch_log) | (p & ((1u << v.ch_log) - 1u));
 }
 

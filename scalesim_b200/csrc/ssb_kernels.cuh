@@ -203,6 +203,10 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->gvt = gvt;
     u32 t = gvt == KEY_MAX ? 0xFFFFFFFFu : key_time(gvt);
     bool done = t >= v.finish_time;
+    // A device error (pool / batch / ring overflow, value out of range, ...) ends the run: the host reports it after
+    // the next synchronisation, and until then the rounds that are already enqueued (the unrolled body of the graph
+    // loop, rounds_per_sync on the stream path) commit, gather and scan nothing — the calendar may be inconsistent.
+    const bool halted = c->error != 0u;
     u32 fin_b = (v.finish_time + v.bucket_ticks - 1) / v.bucket_ticks;   // buckets [0, fin_b) hold times < finish
     if (fin_b > v.nb) fin_b = v.nb;
     u32 cur = done ? fin_b : t / v.bucket_ticks;
@@ -210,11 +214,11 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->cur_abs = cur;
     // commit list (a recorded history that was never re-executed is not committed: k_commit skips P_HISTORY)
     u32 nc = 0, tot = 0;
-    for (u32 b = c->commit_next; b < cur; ++b) {
+    for (u32 b = c->commit_next; b < cur && !halted; ++b) {
       u32 f = fillp[b];
       if (f) { v.commit[nc++] = make_uint4(b, f, tot, 0); tot += f; }
     }
-    c->commit_next = cur > c->commit_next ? cur : c->commit_next;
+    if (!halted) c->commit_next = cur > c->commit_next ? cur : c->commit_next;
     c->n_commit = nc;
     c->commit_total = tot;
     // snapshot ring: rounds whose window lies below GVT are dead (their snapshots can be reused)
@@ -222,7 +226,7 @@ __global__ void k_plan(View v, int use_global_gvt) {
     c->snap_tail = c->rq_tail == c->rq_head ? c->snap_head : c->rq_snap[c->rq_tail % RQ_LEN];
     u32 ng = 0, total = 0, ns = 0, stot = 0;
     u32 bound = cur;
-    if (!done) {
+    if (!done && !halted) {
       // scan list: what has been processed in the buckets from the window start on (before this round's gather)
       u32 shi = cur + v.window < fin_b ? cur + v.window : fin_b;
       if (c->hi_bound > shi) shi = c->hi_bound < fin_b ? c->hi_bound : fin_b;
@@ -400,10 +404,12 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(View v, typename M::D
     uint4 ce = v.commit[k];
     u32 b = ce.x;
     u32 nch = (ce.y + chs - 1) >> v.ch_log;
+    if (nch > v.maxc) nch = v.maxc;      // (only after an overflow; k_plan commits nothing once an error is set)
     for (u32 j = threadIdx.x; j < nch; j += blockDim.x) {
       u32* entry = &v.chunk_tab[(size_t)b * v.maxc + j];
       u32 ch = *entry;
       *entry = NIL;
+      if (ch == NIL || ch == 0u) continue;
       u32 pos = atomicAdd(&c->free_top, 1u);
       v.free_stack[pos] = ch;
     }
@@ -743,8 +749,18 @@ __device__ __forceinline__ Sorted load_sorted(const Sorted* p) {
 __device__ __forceinline__ Sorted* claim_entry(const View& v, u32 t) {
   const u32 f = t - 1u;
   const u32 p = atomicAdd(&v.fixpos[f], 1u);
-  if (p >= v.fixstart[f] + v.fixcnt[f]) { internal_error(v, 6, v.fixlp[f]); return nullptr; }
+  if (p >= v.fixstart[f] + v.fixcnt[f]) {
+    if (!(v.ctl->error & E_BATCH)) internal_error(v, 6, v.fixlp[f]);      // (a segment voided by E_BATCH takes no entries)
+    return nullptr;
+  }
   return v.sorted + p;
+}
+
+// entries of ticket f's segment. (A segment that did not fit the entry table — E_BATCH, k_fix_segs — has fixcnt 0
+// while claim_entry still counted the attempts in fixpos: it is empty, not `attempts` entries of someone else's data.)
+__device__ __forceinline__ u32 seg_len(const View& v, u32 f) {
+  const u32 claimed = v.fixpos[f] - v.fixstart[f], counted = v.fixcnt[f];
+  return claimed < counted ? claimed : counted;
 }
 
 __global__ void __launch_bounds__(256) k_fix_scatter(View v) {
@@ -909,7 +925,7 @@ __global__ void __launch_bounds__(kSortThreads) k_fix_sort(View v) {
   const u32 lane = threadIdx.x & 31u;
   const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (u32 f = wid; f < nf; f += nw) {
-    const u32 start = v.fixstart[f], n = v.fixpos[f] - start;
+    const u32 start = v.fixstart[f], n = seg_len(v, f);
     if (n < 2 || n > kWarpSortMax) continue;
     if (n <= 32) warp_sort_segment<1>(sorted + start, n, lane);
     else if (n <= 64) warp_sort_segment<2>(sorted + start, n, lane);
@@ -921,7 +937,7 @@ __global__ void __launch_bounds__(kSortThreads) k_fix_sort(View v) {
 #endif
   // long segments: one block each
   for (u32 f = blockIdx.x; f < nf; f += gridDim.x) {
-    const u32 start = v.fixstart[f], n = v.fixpos[f] - start;
+    const u32 start = v.fixstart[f], n = seg_len(v, f);
     if (n <= small_max) continue;
     if (n <= kSmemSortMax) {
       for (u32 i = threadIdx.x; i < n; i += blockDim.x) s_seg[i] = sorted[start + i];
@@ -1041,7 +1057,7 @@ __global__ void __launch_bounds__(256) k_fix_turn(View v, typename M::Data md) {
   u32 s_proc = 0, s_arr = 0, s_annih = 0, s_dup = 0, s_rb = 0;
   for (u32 f = wid; f < nf; f += nw) {
     const u32 lp = v.fixlp[f];
-    const u32 start = v.fixstart[f], n = v.fixpos[f] - start;
+    const u32 start = v.fixstart[f], n = seg_len(v, f);
     const u64 m = v.fixmin[f];
     const u32 n_und = v.fixund[f];
     const Sorted* seg = v.sorted + start;

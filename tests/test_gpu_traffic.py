@@ -113,3 +113,4 @@ def test_traffic_config3_full_size_count_and_digest():
     assert st.processed == st.committed and st.rollbacks == 0
     assert eng.digest() == want
     eng.close()
+

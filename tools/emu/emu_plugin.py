@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import scalesim_b200.capi as capi  # noqa: E402
 
-_EMU = os.path.join(ROOT, "tools", "emu", "libssb_emu.so")
+# EMU_LIB: another build of the emulation, e.g. one with -fsanitize=address (run python under LD_PRELOAD=libasan.so)
+_EMU = os.environ.get("EMU_LIB") or os.path.join(ROOT, "tools", "emu", "libssb_emu.so")
 capi.library_path = lambda: _EMU
 
 
