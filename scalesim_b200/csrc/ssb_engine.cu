@@ -1408,10 +1408,6 @@ int ssb_set_sync_interval(ssb_engine* e, int32_t windows) {
 int ssb_comm_export(ssb_engine* e, void* handle64) {
   if (!e || !handle64) return SSB_ERR_INVALID;
   if (e->cfg.world <= 1) { std::memset(handle64, 0, 64); return SSB_OK; }
-#ifdef SSB_EMU
-  e->set_error("the host emulation has no peer-memory exchange");
-  return SSB_ERR_COMM;
-#else
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1426,16 +1422,11 @@ int ssb_comm_export(ssb_engine* e, void* handle64) {
   CK(cudaIpcGetMemHandle(&h, e->mbox_block));
   std::memcpy(handle64, &h, 64);
   return SSB_OK;
-#endif
 }
 
 int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
   if (!e || !handles || world != e->cfg.world) return SSB_ERR_INVALID;
   if (world <= 1) return SSB_OK;
-#ifdef SSB_EMU
-  e->set_error("the host emulation has no peer-memory exchange");
-  return SSB_ERR_COMM;
-#else
   if (!e->mbox_block) { e->set_error("ssb_comm_export must be called first"); return SSB_ERR_INVALID; }
   cudaSetDevice(e->cfg.device);
   auto set_error = [&](const std::string& s) { e->set_error(s); };
@@ -1458,7 +1449,6 @@ int ssb_comm_import(ssb_engine* e, const void* handles, int32_t world) {
   e->v.p2p = 1;
   e->graph_dirty = true;
   return SSB_OK;
-#endif
 }
 
 }  // extern "C"

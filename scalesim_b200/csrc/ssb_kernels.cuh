@@ -142,6 +142,31 @@ __global__ void k_gvt(View v) {
   const u32 R = c->xround + 1u + (c->epoch << 20);      // stamp of the exchange round that is about to start (2^20 rounds per run, 4096 resets)
   const u64 lm = c->local_min;
   const u32 my_t = lm == KEY_MAX ? 0xFFFFFFFFu : key_time(lm);
+#ifdef SSB_EMU
+  // host emulation (one thread per kernel; the partitions are engines of one process, a host thread each —
+  // tools/emu/multi.py): the same protocol with the per-partition threads unrolled — publish to every partition
+  // first, then wait for each, so that no two partitions wait for each other's publication
+  for (u32 r = 0; r < v.world; ++r) {
+    if (r == v.rank) continue;
+    const u32 spar = c->xround & 1u;
+    *reinterpret_cast<volatile u32*>(mb_cnt(v, r, spar, v.rank, 0)) = c->send_count[r];
+    *reinterpret_cast<volatile u32*>(mb_cnt(v, r, spar, v.rank, 1)) = c->send_anti[r];
+    __threadfence_system();
+    *reinterpret_cast<volatile u64*>(mb_gvt(v, r, par, v.rank)) = ((u64)R << 32) | my_t;
+  }
+  for (u32 r = 0; r < v.world; ++r) {
+    u32 t = my_t;
+    if (r != v.rank) {
+      const volatile u64* mine = mb_gvt(v, v.rank, par, r);
+      u64 x = *mine;
+      for (u32 spin = 0; (u32)(x >> 32) != R && spin < (1u << 23); ++spin) { __nanosleep(20); x = *mine; }
+      if ((u32)(x >> 32) != R) { atomicOr(&c->error, E_COMM); t = 0xFFFFFFFFu; }
+      else t = (u32)x;
+      __threadfence_system();
+    }
+    s_t[r] = t;
+  }
+#else
   if (threadIdx.x < v.world) {
     const u32 r = threadIdx.x;
     u32 t = my_t;
@@ -162,6 +187,7 @@ __global__ void k_gvt(View v) {
     }
     s_t[r] = t;
   }
+#endif
   __syncthreads();
   if (threadIdx.x == 0) {
     u32 t = 0xFFFFFFFFu;
@@ -1244,7 +1270,7 @@ __device__ __forceinline__ void mbar_wait(u64*, u32) {}
 // the persistent grid gets the same number of equally large tiles (no tail wave).
 __global__ void __launch_bounds__(kRouteThreads) k_route(View v, int which, u32 peer, u32 filter) {
 #ifdef SSB_EMU
-  alignas(128) static unsigned char smem_route[1 << 20];
+  alignas(128) static thread_local unsigned char smem_route[1 << 20];      // (per host thread: tools/emu/multi.py runs one engine per thread)
 #else
   extern __shared__ __align__(128) unsigned char smem_route[];
 #endif

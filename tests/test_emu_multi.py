@@ -1,0 +1,47 @@
+"""CPU logic check of the MULTI-PARTITION path where there is no GPU: the kernel sources compiled for
+the host (tools/emu, a developer tool the product cannot load) with one emulated engine per partition, each on its own
+host thread, mailboxes exchanged by address — cross-partition events and anti-messages through k_route / the receive
+pass, GVT through k_gvt, sequence stamps. The union of the partitions' committed multisets must equal the oracle's for
+every world size (the invariant of §8e). It complements, and does not replace, the `-m gpu` tests on two B200s
+(tests/test_gpu_multi.py): races and NVLink visibility exist only there. Runs in a subprocess because the emulation is
+selected per process."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu_results():
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    subprocess.run(["sh", os.path.join(ROOT, "tools", "emu", "build.sh")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                   timeout=600)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu", "check_multi.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def test_phold_partitions_commit_the_oracles_multiset(emu_results):
+    for k in ("phold_w2_win1", "phold_w2_win3", "phold_w3_win2", "phold_w4_win1"):
+        r = emu_results[k]
+        assert r["equal"] and r["committed"] == 72351 and r["remote"] > 0, k
+    assert emu_results["phold_w2_win1"]["rollbacks"] == 0
+    assert emu_results["phold_w2_win3"]["rollbacks"] > 0 and emu_results["phold_w2_win3"]["antis"] > 0
+
+
+def test_state_mutating_model_across_partitions(emu_results):
+    r = emu_results["stateful_w3"]
+    assert r["equal"] and r["states_equal"] and r["rollbacks"] > 0
+
+
+def test_traffic_stripes_commit_the_oracles_multiset(emu_results):
+    for k in ("grid_w2_win1", "grid_w4_win3"):
+        assert emu_results[k]["equal"] and emu_results[k]["remote"] > 0, k
+    assert emu_results["grid_w4_win3"]["rollbacks"] > 0

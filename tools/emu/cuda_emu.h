@@ -9,13 +9,17 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <chrono>
+#include <thread>
 
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __shared__ static
+// (thread_local: several emulated engines — the partitions of a multi-GPU run — may execute kernels at the same time,
+// each on its own host thread: tools/emu/multi.py)
+#define __shared__ static thread_local
 #define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
 
@@ -46,8 +50,8 @@ inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline void __syncthreads() {}
 inline void __syncwarp() {}
 inline void __threadfence() {}
-inline void __threadfence_system() {}
-inline void __nanosleep(unsigned) {}
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }      // a spin on a peer partition's store: let its thread run
 
 typedef unsigned long long cudaGraphConditionalHandle;
 inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
@@ -87,3 +91,10 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   return cudaSuccess;
 }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+// "IPC" inside one process: the handle of a mailbox is its address (the partitions of an emulated multi-GPU run are
+// engines of the same process, one host thread each)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+constexpr unsigned cudaIpcMemLazyEnablePeerAccess = 1;
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -105,12 +105,106 @@ def one_traffic(rng):
     return ok, cfg, dict(committed=st.committed, rollbacks=st.rollbacks, antis=st.antis_sent, fix_turns=st.fix_turns, want=want[0])
 
 
+def one_diff(rng):
+    """--diff_init, then --diff_repeat with added trips (AE) and deleted events (DE) on a random network: the repeat
+    output must be the closure of the queries over the init output (tests/oracle_lib.repeat_closure), and — for AE only —
+    init + new == one full run over all trips (vehicles do not interact)."""
+    n_nodes = int(rng.choice([12, 100, 400]))
+    deg = int(rng.choice([1, 2, 4]))
+    n_trips = int(rng.choice([20, 500, 3000]))
+    n_add = int(rng.choice([1, 5, 60]))
+    seed = int(rng.integers(0, 1 << 30))
+    bucket = int(rng.choice([5, 11, 64, 400]))
+    window = int(rng.choice([1, 2, 8]))
+    rbucket = int(rng.choice([5, 11, 64, 400]))
+    rwindow = int(rng.choice([1, 2, 8]))
+    cfg = dict(kind="diff", n_nodes=n_nodes, deg=deg, n_trips=n_trips, n_add=n_add, seed=seed, bucket=bucket, window=window,
+               rbucket=rbucket, rwindow=rwindow)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("diff", cfg, flush=True)
+    both = _random_network(n_nodes, deg, n_trips + n_add, seed)
+    cut = int(both.route_start[n_trips])
+    sc = traffic.Scenario(both.n_lp, both.state_ids, both.road_start, both.road_dst, both.road_speed, both.road_len,
+                          both.trip_id[:n_trips], both.trip_dep[:n_trips], both.route_start[:n_trips + 1], both.route_nodes[:cut])
+    add = (both.trip_id[n_trips:], both.trip_dep[n_trips:], both.route_start[n_trips:] - cut, both.route_nodes[cut:])
+    big = dict(max_events=(both.route_nodes.size + 64) * 12 + (1 << 16), max_batch=both.route_nodes.size * 4 + (1 << 14))
+    st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=bucket, window_buckets=window, **big)
+    init_lines = sorted(ssb.records_to_lines(ssb.raw_to_records(rec)))
+    s = O.Sim.traffic_scenario(both)
+    s.run_closure(2)
+    full_lines = sorted(O.records_to_lines(s.committed()))
+    s1 = O.Sim.traffic_scenario(sc)
+    s1.run_closure(2)
+    ok = init_lines == sorted(O.records_to_lines(s1.committed()))
+    new_lines = sorted(set(full_lines) - set(init_lines))
+    eng = traffic.make_repeat_engine(sc, hs, add, bucket_ticks=rbucket, window_buckets=rwindow, keep_records=True,
+                                     max_committed=(both.route_nodes.size + 64) * 4, **big)
+    st2 = eng.run()
+    rep = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    ok = ok and sorted(set(rep) - set(init_lines)) == new_lines and len(set(rep)) == len(rep) and set(rep) <= set(full_lines)
+    ok = ok and rep == O.repeat_closure(init_lines, new_lines)
+    return ok, cfg, dict(init=len(init_lines), new=len(new_lines), repeat=len(rep), rollbacks=st2.rollbacks)
+
+
+def one_multi(rng):
+    """Several partitions (tools/emu/multi.py: one emulated engine per host thread, mailboxes exchanged by address):
+    PHOLD with lp % world, TrafficSim with a random partition table; the union of the partitions' committed multisets
+    must be the oracle's."""
+    import multi
+    world = int(rng.choice([2, 3, 4, 8]))
+    window = int(rng.choice([1, 2, 4, 16]))
+    if rng.random() < 0.6:
+        n_lp = int(rng.choice([world, 64, 300, 1500]))
+        n_init = int(rng.choice([5, 200, 3000, 12000]))
+        ratio = float(rng.choice([0.0, 0.1, 0.5, 1.0]))
+        lam = float(rng.choice([0.5, 1.0, 4.0, 30.0]))
+        stateful = bool(rng.random() < 0.3)
+        bucket = int(rng.choice([1000, 2500, 10000, 25000]))
+        cfg = dict(kind="multi-phold", world=world, n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, stateful=stateful, bucket=bucket, window=window)
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("multi", cfg, flush=True)
+        s = O.Sim.phold(n_lp, n_init, ratio, lam, stateful=stateful)
+        if stateful:
+            s.run_sequential()
+        else:
+            s.run_closure(2)
+        want = s.digest()
+        tb = tables(ratio, lam, 1)
+        got, st = multi.run_partitions(lambda r, w: phold.make_engine(
+            n_lp, n_init, ratio, lam, tables=tb, rank=r, world=w, bucket_ticks=bucket, window_buckets=window, stateful=stateful,
+            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world)
+        if got != want and stateful and sum(x.duplicates for x in st) > 0:
+            return None, cfg, dict(collision=True)
+    else:
+        n_nodes = int(rng.choice([8, 40, 300]))
+        deg = int(rng.choice([1, 2, 3, 9]))
+        n_trips = int(rng.choice([50, 2000, 6000]))
+        seed = int(rng.integers(0, 1 << 30))
+        bucket = int(rng.choice([5, 11, 64, 400]))
+        cfg = dict(kind="multi-traffic", world=world, n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, bucket=bucket, window=window)
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("multi", cfg, flush=True)
+        sc = _random_network(n_nodes, deg, n_trips, seed)
+        sc.partition = np.random.default_rng(seed).integers(0, 2 * world, n_nodes)      # reduced modulo world on load
+        s = O.Sim.traffic_scenario(sc)
+        s.run_closure(2)
+        want = s.digest()
+        got, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=bucket, window_buckets=window,
+                                                                        max_events=n_trips * 6 + (1 << 16), max_batch=n_trips * 2 + (1 << 14)), world)
+    return got == want, cfg, dict(committed=sum(x.committed for x in st), rollbacks=sum(x.rollbacks for x in st),
+                                  antis=sum(x.antis_sent for x in st), remote=sum(x.remote_sent for x in st), want=want[0])
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, n, bad, rb, cap, col = time.time(), 0, 0, 0, 0, 0
     while time.time() - t0 < budget:
-        kind = one_phold if rng.random() < 0.6 else one_traffic
+        r = rng.random()
+        kind = one_phold if r < 0.35 else (one_traffic if r < 0.55 else (one_diff if r < 0.75 else one_multi))
+        if os.environ.get("FUZZ_ONLY"):
+            kind = globals()["one_" + os.environ["FUZZ_ONLY"]]
         try:
             ok, cfg, info = kind(rng)
         except ssb.EngineError as e:
