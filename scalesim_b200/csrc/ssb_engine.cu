@@ -402,6 +402,9 @@ int ssb_engine::sync_ctl() {
 int ssb_engine::check_device_error() {
   u32 e = h_ctl->error;
   if (!e) return SSB_OK;
+#ifdef SSB_EMU
+  g_emu_peer_failed.store(1);      // (tools/emu/multi.py: the peer partitions stop waiting for this one)
+#endif
   std::string s = "device error:";
   if (e & E_POOL) s += " event pool exhausted (raise max_events)";
   if (e & E_RANGE) s += " value out of device record range / destination not owned";
@@ -713,6 +716,9 @@ void ssb_destroy(ssb_engine* e) {
 
 int ssb_create(const ssb_config* cfg, ssb_engine** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return SSB_ERR_INVALID; }
+#ifdef SSB_EMU
+  g_emu_peer_failed.store(0);
+#endif
   *out = nullptr;
   auto bad = [&](const char* m) { g_create_error = m; return SSB_ERR_INVALID; };
   if (cfg->abi_version != SSB_ABI_VERSION) return bad("abi_version mismatch");

@@ -159,7 +159,7 @@ __global__ void k_gvt(View v) {
     if (r != v.rank) {
       const volatile u64* mine = mb_gvt(v, v.rank, par, r);
       u64 x = *mine;
-      for (u32 spin = 0; (u32)(x >> 32) != R && spin < (1u << 23); ++spin) { __nanosleep(20); x = *mine; }
+      for (u32 spin = 0; (u32)(x >> 32) != R && spin < (1u << 27) && !(g_emu_peer_failed.load() && spin > 4096u); ++spin) { __nanosleep(20); x = *mine; }
       if ((u32)(x >> 32) != R) { atomicOr(&c->error, E_COMM); t = 0xFFFFFFFFu; }
       else t = (u32)x;
       __threadfence_system();

@@ -72,7 +72,8 @@ def make_engine(num_lp: int, num_init_msg: int, remote_ratio: float, lam: float,
                 bucket_ticks: int = LOOK_AHEAD, window_buckets: int = 1, keep_records: bool = False,
                 rank: int = 0, world: int = 1, device: int = 0, stateful: bool = False,
                 max_events: int | None = None, max_batch: int | None = None, max_committed: int | None = None,
-                finish_time: int = FINISH_TIME, rounds_per_sync: int = 4, load: bool = True, flags: int = 0) -> Engine:
+                finish_time: int = FINISH_TIME, rounds_per_sync: int = 4, load: bool = True, flags: int = 0,
+                max_snapshots: int = 1 << 16) -> Engine:
     """Build a PHOLD engine the way runner<phold>::init does (runner.hpp:79-176)."""
     lat, rem = tables if tables is not None else build_tables(remote_ratio, lam)
     per = (num_init_msg + world - 1) // world
@@ -85,7 +86,7 @@ def make_engine(num_lp: int, num_init_msg: int, remote_ratio: float, lam: float,
     cfg = Config(model=MODEL_PHOLD_STATEFUL if stateful else MODEL_PHOLD, n_lp=num_lp, finish_time=finish_time,
                  bucket_ticks=bucket_ticks, window_buckets=window_buckets, max_events=max_events,
                  max_batch=max_batch, max_committed=max_committed, rank=rank, world=world, device=device,
-                 rounds_per_sync=rounds_per_sync, flags=flags)
+                 rounds_per_sync=rounds_per_sync, flags=flags, max_snapshots=max_snapshots)
     eng = Engine(cfg)
     eng.set_partition(None)
     eng.set_model_data(0, lat)

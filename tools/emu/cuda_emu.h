@@ -91,6 +91,9 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   return cudaSuccess;
 }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+// Set when an emulated engine stops with a device error: its peer partitions (other engines of the process, waiting
+// for it at the GVT exchange) give up at once instead of spinning out their bound (k_gvt's SSB_EMU branch).
+inline std::atomic<int> g_emu_peer_failed{0};
 // "IPC" inside one process: the handle of a mailbox is its address (the partitions of an emulated multi-GPU run are
 // engines of the same process, one host thread each)
 struct cudaIpcMemHandle_t { char reserved[64]; };

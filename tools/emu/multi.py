@@ -39,9 +39,11 @@ def run_all(engines, call=lambda e: e.run()):
         t.start()
     for t in th:
         t.join()
-    for e in err:
-        if e is not None:
-            raise e
+    # a partition that stops with its own error (e.g. SSB_ERR_CAPACITY) leaves its peers waiting at the GVT exchange
+    # until they give up with SSB_ERR_COMM: report the cause, not the consequence
+    errs = [e for e in err if e is not None]
+    if errs:
+        raise next((e for e in errs if getattr(e, "status", None) != 6), errs[0])
     return out
 
 
