@@ -162,6 +162,9 @@ struct ssb_engine {
   bool graph_enabled = true;
   int build_graph();
   void destroy_graph();
+#ifdef SSB_EMU
+  int run_graph_emulated();
+#endif
 
   void set_error(const std::string& s) { error = s; }
 
@@ -274,9 +277,6 @@ int ssb_engine::init() {
   v.hmask = hcap - 1u;
   if (getenv("SSB_NO_GRAPH")) graph_enabled = false;
   if (const char* u = getenv("SSB_UNROLL")) { int x = atoi(u); if (x >= 1 && x <= 16) loop_unroll = x; }
-#ifdef SSB_EMU
-  graph_enabled = false;
-#endif
   if (const char* gs = getenv("SSB_GRID")) {
     int a = 0, b = 0, c2 = 0;
     if (sscanf(gs, "%d,%d,%d", &a, &b, &c2) == 3 && a > 0 && b > 0 && c2 > 0) { g_exec = a; g_commit = b; g_fix = c2; }
@@ -565,8 +565,40 @@ int ssb_engine::enqueue_round() {
 // because GVT and the barrier go through peer memory.
 // ------------------------------------------------------------------------------------------------
 #ifdef SSB_EMU
+// Host emulation: the graph below is interpreted — same nodes in the same order, the WHILE / IF conditions read from
+// the table cudaGraphSetConditional writes to (cuda_emu.h). The kernels run with use_graph = 1, so what they do only on
+// the graph path (loop condition and stall detection in k_plan, the IF condition set by the last block of k_exec,
+// several windows per synchronisation) is exercised where there is no GPU.
 void ssb_engine::destroy_graph() {}
-int ssb_engine::build_graph() { return SSB_OK; }
+int ssb_engine::build_graph() { graph_dirty = false; return SSB_OK; }
+int ssb_engine::run_graph_emulated() {
+  vg = v;
+  vg.use_graph = 1;
+  vg.sync = cfg.world > 1 ? (u32)sync_interval : 1u;
+  vg.h_loop = 1; vg.h_fix = 2;
+  const int subs = cfg.world > 1 ? sync_interval : 1;
+  g_emu_cond[1] = 1;                                  // cudaGraphCondAssignDefault, default value 1
+  while (g_emu_cond[1]) {                             // WHILE node
+    for (int rep = 0; rep < loop_unroll; ++rep) {     // its body: `unroll` rounds back to back
+      for (int j = 0; j < subs; ++j) {
+        View vj = vg;
+        vj.sub = (u32)j;
+        g_emu_cond[2] = 0;                            // this round's IF handle, default value 0
+        if (cfg.world > 1 && j == 0) {
+          SSB_LAUNCH(k_gvt, 1, 256, 0, stream, vj);
+          launch_route(vj, 2, 0, 0);
+        }
+        SSB_LAUNCH(k_plan, 1, 1024, 0, stream, vj, cfg.world > 1 ? 1 : 0);
+        if (j == 0) launch_commit(vj);
+        launch_exec(vj);
+        if (g_emu_cond[2]) launch_fix(vj, false);     // IF node
+        launch_route(vj, 1, 0, 0);
+        SSB_LAUNCH(k_post, n_sm * g_post, 256, 0, stream, vj);
+      }
+    }
+  }
+  return SSB_OK;
+}
 #else
 void ssb_engine::destroy_graph() {
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
@@ -928,6 +960,8 @@ int ssb_run(ssb_engine* e, ssb_stats* stats) {
   if (use_graph) {
 #ifndef SSB_EMU
     CK(cudaGraphLaunch(e->graph_exec, e->stream));
+#else
+    if ((rc = e->run_graph_emulated())) return rc;
 #endif
     if ((rc = e->sync_ctl())) return rc;
     e->rounds = e->h_ctl->round;
@@ -1109,7 +1143,11 @@ int ssb_run_drain_packed(ssb_engine* e, ssb_packed_record* out, int64_t cap, int
   auto set_error = [&](const std::string& s) { e->set_error(s); };
   int rc = e->model_ready();
   if (rc) return rc;
+#ifdef SSB_EMU
+  const bool use_graph = false;      // (the interpreted graph loop runs inside ssb_run: nothing to overlap with)
+#else
   const bool use_graph = use_graph_path(e);
+#endif
   if (!use_graph || e->log_drained != 0) {      // no device-side loop to overlap with: one after the other
     ssb_stats local;
     if ((rc = ssb_run(e, &local))) return rc;

@@ -45,3 +45,12 @@ def test_traffic_stripes_commit_the_oracles_multiset(emu_results):
     for k in ("grid_w2_win1", "grid_w4_win3"):
         assert emu_results[k]["equal"] and emu_results[k]["remote"] > 0, k
     assert emu_results["grid_w4_win3"]["rollbacks"] > 0
+
+
+def test_several_windows_per_synchronisation(emu_results):
+    """ssb_set_sync_interval on the interpreted graph loop: fewer exchanges than rounds, stragglers across partitions
+    repaired by rollbacks, same committed multiset."""
+    for k in ("grid_w2_sync2", "grid_w4_sync8", "phold_w3_sync4"):
+        r = emu_results[k]
+        assert r["equal"] and r["exchanges"] < r["rounds"] and r["rollbacks"] > 0, k
+    assert emu_results["phold_w2_stream"]["equal"]

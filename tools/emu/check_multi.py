@@ -49,6 +49,16 @@ def main():
         d, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=11, window_buckets=window), world)
         out[f"grid_w{world}_win{window}"] = dict(equal=d == o.digest(), remote=sum(x.remote_sent for x in st),
                                                  rollbacks=sum(x.rollbacks for x in st))
+    # several local windows per global synchronisation (ssb_set_sync_interval; graph loop): optimism across partitions
+    for world, k in ((2, 2), (4, 8)):
+        d, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=11), world, sync_interval=k)
+        out[f"grid_w{world}_sync{k}"] = dict(equal=d == o.digest(), rollbacks=sum(x.rollbacks for x in st),
+                                             rounds=st[0].rounds, exchanges=st[0].exchanges)
+    d, st = multi.run_partitions(lambda r, w: phold.make_engine(1000, 16000, 0.5, 1.0, tables=tables, rank=r, world=w), 3, sync_interval=4)
+    out["phold_w3_sync4"] = dict(equal=d == want, rollbacks=sum(s.rollbacks for s in st), rounds=st[0].rounds, exchanges=st[0].exchanges)
+    # the stream path (kernels launched round by round) instead of the graph loop
+    d, st = multi.run_partitions(lambda r, w: phold.make_engine(1000, 16000, 0.5, 1.0, tables=tables, rank=r, world=w, window_buckets=2), 2, graph=False)
+    out["phold_w2_stream"] = dict(equal=d == want, rollbacks=sum(s.rollbacks for s in st))
     print(json.dumps(out))
 
 

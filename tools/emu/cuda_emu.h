@@ -53,8 +53,11 @@ inline void __threadfence() {}
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }      // a spin on a peer partition's store: let its thread run
 
+// conditional handles of the interpreted graph (ssb_engine::build_graph / run_graph_emulated): small integers indexing
+// a per-thread table (one engine per host thread)
 typedef unsigned long long cudaGraphConditionalHandle;
-inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
+inline thread_local unsigned g_emu_cond[4] = {0, 0, 0, 0};
+inline void cudaGraphSetConditional(cudaGraphConditionalHandle h, unsigned value) { g_emu_cond[h & 3u] = value; }
 
 // ---- the slice of the runtime API that ssb_engine.cu uses: host memory, no streams ----
 typedef int cudaError_t;

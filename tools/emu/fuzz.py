@@ -154,6 +154,8 @@ def one_multi(rng):
     import multi
     world = int(rng.choice([2, 3, 4, 8]))
     window = int(rng.choice([1, 2, 4, 16]))
+    graph = bool(rng.random() < 0.6)
+    sync = int(rng.choice([1, 1, 2, 3, 8])) if graph else 1
     if rng.random() < 0.6:
         n_lp = int(rng.choice([world, 64, 300, 1500]))
         n_init = int(rng.choice([5, 200, 3000, 12000]))
@@ -161,7 +163,7 @@ def one_multi(rng):
         lam = float(rng.choice([0.5, 1.0, 4.0, 30.0]))
         stateful = bool(rng.random() < 0.3)
         bucket = int(rng.choice([1000, 2500, 10000, 25000]))
-        cfg = dict(kind="multi-phold", world=world, n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, stateful=stateful, bucket=bucket, window=window)
+        cfg = dict(kind="multi-phold", graph=graph, sync=sync, world=world, n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, stateful=stateful, bucket=bucket, window=window)
         if os.environ.get("FUZZ_VERBOSE"):
             print("multi", cfg, flush=True)
         s = O.Sim.phold(n_lp, n_init, ratio, lam, stateful=stateful)
@@ -173,7 +175,7 @@ def one_multi(rng):
         tb = tables(ratio, lam, 1)
         got, st = multi.run_partitions(lambda r, w: phold.make_engine(
             n_lp, n_init, ratio, lam, tables=tb, rank=r, world=w, bucket_ticks=bucket, window_buckets=window, stateful=stateful,
-            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world)
+            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world, graph=graph, sync_interval=sync)
         if got != want and stateful and sum(x.duplicates for x in st) > 0:
             return None, cfg, dict(collision=True)
     else:
@@ -182,7 +184,7 @@ def one_multi(rng):
         n_trips = int(rng.choice([50, 2000, 6000]))
         seed = int(rng.integers(0, 1 << 30))
         bucket = int(rng.choice([5, 11, 64, 400]))
-        cfg = dict(kind="multi-traffic", world=world, n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, bucket=bucket, window=window)
+        cfg = dict(kind="multi-traffic", graph=graph, sync=sync, world=world, n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, bucket=bucket, window=window)
         if os.environ.get("FUZZ_VERBOSE"):
             print("multi", cfg, flush=True)
         sc = _random_network(n_nodes, deg, n_trips, seed)
@@ -191,7 +193,8 @@ def one_multi(rng):
         s.run_closure(2)
         want = s.digest()
         got, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=bucket, window_buckets=window,
-                                                                        max_events=n_trips * 6 + (1 << 16), max_batch=n_trips * 2 + (1 << 14)), world)
+                                                                        max_events=n_trips * 6 + (1 << 16), max_batch=n_trips * 2 + (1 << 14)),
+                                     world, graph=graph, sync_interval=sync)
     return got == want, cfg, dict(committed=sum(x.committed for x in st), rollbacks=sum(x.rollbacks for x in st),
                                   antis=sum(x.antis_sent for x in st), remote=sum(x.remote_sent for x in st), want=want[0])
 

@@ -47,11 +47,20 @@ def run_all(engines, call=lambda e: e.run()):
     return out
 
 
-def run_partitions(make_engine, world, keep_engines=False):
-    """make_engine(rank, world) -> loaded Engine. Returns (digest of the union, stats per rank[, engines])."""
-    os.environ["SSB_NO_GRAPH"] = "1"
-    engines = [make_engine(r, world) for r in range(world)]
+def run_partitions(make_engine, world, keep_engines=False, graph=True, sync_interval=1):
+    """make_engine(rank, world) -> loaded Engine. graph: the interpreted graph loop (ssb_engine::run_graph_emulated) or
+    the stream path; sync_interval: local windows per global synchronisation (graph loop only, ssb_set_sync_interval).
+    Returns (digest of the union, stats per rank[, engines])."""
+    if not graph:
+        os.environ["SSB_NO_GRAPH"] = "1"
+    try:
+        engines = [make_engine(r, world) for r in range(world)]
+    finally:
+        os.environ.pop("SSB_NO_GRAPH", None)
     connect(engines)
+    if sync_interval > 1:
+        for e in engines:
+            e.set_sync_interval(sync_interval)
     stats = run_all(engines)
     digest = dist.combine_digests([e.digest() for e in engines])
     if keep_engines:
