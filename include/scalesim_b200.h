@@ -293,7 +293,8 @@ int64_t ssb_phold_init_events(int64_t num_lp, int64_t num_init_msg, const int64_
  * event / state (traffic_sim.hpp:345-451); a 10 M-trip scenario is ~3 GB of CSV. Two pieces replace that:
  *
  * 1. ssb_traffic_read: the three TrafficSim readers natively — the files are mapped, cut into line-aligned pieces and
- *    parsed by `threads` host threads (0 = all cores) into flat arrays. Field meaning exactly as the reference's:
+ *    parsed by `threads` host threads (0 = all cores; at least ~1 MiB of text per thread; a negative value forces
+ *    exactly that many pieces whatever the size) into flat arrays. Field meaning exactly as the reference's:
  *      partition file  traffic_reader::graph_read (traffic_sim.hpp:345-362): atol(line), line index = LP id
  *      road file       traffic_reader::road_read  (:364-408): one line per LP, roads split on ';', fields on ',':
  *                      state id = field 2 of the LAST road of the line, destination = field 3, speed = field 4,

@@ -85,6 +85,7 @@ void piece(const mapped_file& f, int t, int nt, size_t* begin, size_t* end) {
 }
 
 int thread_count(int asked, size_t bytes) {
+  if (asked < 0) return std::min(-asked, 256);        // exactly that many pieces whatever the size (tests of the cutting)
   int n = asked > 0 ? asked : (int)std::thread::hardware_concurrency();
   if (n < 1) n = 1;
   const size_t by_size = bytes / (1u << 20) + 1;      // at least ~1 MiB of text per thread

@@ -39,35 +39,44 @@ def _atol(s: str) -> int:
         sign = -1 if s[0] == "-" else 1
         i = 1
     j = i
-    while j < len(s) and s[j].isdigit():
+    while j < len(s) and "0" <= s[j] <= "9":      # ASCII digits only (str.isdigit also accepts other scripts' digits)
         j += 1
     return sign * int(s[i:j]) if j > i else 0
 
 
+def _lines(path: str) -> list:
+    """The lines std::getline yields: split at '\n' only (a '\r' stays in the line, where atol ignores it), the last
+    line counts with or without a final '\n'."""
+    with open(path, newline="", encoding="latin-1") as f:
+        text = f.read()
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    return lines
+
+
 def read_partition(path: str) -> np.ndarray:
     """traffic_reader::graph_read (traffic_sim.hpp:345-362): one partition number per line, line index = LP id."""
-    with open(path) as f:
-        return np.array([_atol(line) for line in f.read().splitlines()], dtype=np.int64)
+    return np.array([_atol(line) for line in _lines(path)], dtype=np.int64)
 
 
 def read_roads(path: str):
     """traffic_reader::road_read (traffic_sim.hpp:364-408), all partitions. One line per LP; roads split on ';',
     fields on ','; state id = field 2 of the last road; length 0 -> 1; lanes ignored by the handler."""
     state_ids, start, dst, speed, length = [], [0], [], [], []
-    with open(path) as f:
-        for line in f.read().splitlines():
-            sid = -1
-            for road in line.split(";"):
-                fld = road.split(",")
-                if len(fld) < 7:
-                    continue
-                sid = _atol(fld[2])
-                dst.append(_atol(fld[3]))
-                speed.append(_atol(fld[4]))
-                ln = _atol(fld[5])
-                length.append(ln if ln != 0 else 1)
-            state_ids.append(sid)
-            start.append(len(dst))
+    for line in _lines(path):
+        sid = -1
+        for road in line.split(";"):
+            fld = road.split(",")
+            if len(fld) < 7:
+                continue
+            sid = _atol(fld[2])
+            dst.append(_atol(fld[3]))
+            speed.append(_atol(fld[4]))
+            ln = _atol(fld[5])
+            length.append(ln if ln != 0 else 1)
+        state_ids.append(sid)
+        start.append(len(dst))
     return (np.array(state_ids, dtype=np.int64), np.array(start, dtype=np.int64), np.array(dst, dtype=np.int64),
             np.array(speed, dtype=np.int64), np.array(length, dtype=np.int64))
 
@@ -76,15 +85,14 @@ def read_trips(path: str):
     """traffic_reader::trip_read (traffic_sim.hpp:410-451): vehicle id = field 1, arrival = departure = field 3,
     route = fields 4.., source = -1 (field 2 ignored)."""
     tid, dep, start, nodes = [], [], [0], []
-    with open(path) as f:
-        for line in f.read().splitlines():
-            fld = line.split(",")
-            if len(fld) < 5:
-                continue
-            tid.append(_atol(fld[1]))
-            dep.append(_atol(fld[3]))
-            nodes.extend(_atol(x) for x in fld[4:])
-            start.append(len(nodes))
+    for line in _lines(path):
+        fld = line.split(",")
+        if len(fld) < 5:
+            continue
+        tid.append(_atol(fld[1]))
+        dep.append(_atol(fld[3]))
+        nodes.extend(_atol(x) for x in fld[4:])
+        start.append(len(nodes))
     return (np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
             np.array(nodes, dtype=np.int64))
 
@@ -111,25 +119,24 @@ def read_what_if(path: str) -> WhatIf:
     ``SC,{lp id},{time};{road};{road};...``                    state change: the LP's roads from ``time`` on (:473-521);
                                                                road = ``R,{id},{lp},{dst},{speed},{length},{lanes}``"""
     tid, dep, start, nodes, dels, scs = [], [], [0], [], [], []
-    with open(path) as f:
-        for line in f.read().splitlines():
-            fld = line.split(",")
-            if line[:2] == "AE":
-                tid.append(_atol(fld[1]))
-                dep.append(_atol(fld[3]))
-                nodes.extend(_atol(x) for x in fld[4:])
-                start.append(len(nodes))
-            elif line[:2] == "DE":
-                dels.append((_atol(fld[1]), _atol(fld[2]), _atol(fld[3])))
-            elif line[:2] == "RE":
-                dels.append((_atol(fld[4]), _atol(fld[5]), _atol(fld[1])))
-            elif line[:2] == "SC":
-                parts = line.split(";")
-                head = parts[0].split(",")
-                roads = [r.split(",") for r in parts[1:]]
-                ln = [_atol(r[5]) for r in roads]
-                scs.append((_atol(head[1]), _atol(head[2]), [_atol(r[3]) for r in roads], [_atol(r[4]) for r in roads],
-                            [x if x != 0 else 1 for x in ln]))
+    for line in _lines(path):
+        fld = line.split(",")
+        if line[:2] == "AE":
+            tid.append(_atol(fld[1]))
+            dep.append(_atol(fld[3]))
+            nodes.extend(_atol(x) for x in fld[4:])
+            start.append(len(nodes))
+        elif line[:2] == "DE":
+            dels.append((_atol(fld[1]), _atol(fld[2]), _atol(fld[3])))
+        elif line[:2] == "RE":
+            dels.append((_atol(fld[4]), _atol(fld[5]), _atol(fld[1])))
+        elif line[:2] == "SC":
+            parts = line.split(";")
+            head = parts[0].split(",")
+            roads = [r.split(",") for r in parts[1:]]
+            ln = [_atol(r[5]) for r in roads]
+            scs.append((_atol(head[1]), _atol(head[2]), [_atol(r[3]) for r in roads], [_atol(r[4]) for r in roads],
+                        [x if x != 0 else 1 for x in ln]))
     return WhatIf(np.array(tid, dtype=np.int64), np.array(dep, dtype=np.int64), np.array(start, dtype=np.int64),
                   np.array(nodes, dtype=np.int64), np.array(dels, dtype=np.int64).reshape(-1, 3), scs)
 

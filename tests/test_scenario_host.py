@@ -192,3 +192,35 @@ def test_written_csv_is_what_the_reference_binary_reads(tmp_path):
             lines = sorted(l for l in p.stdout.splitlines() if l.startswith("RE,"))
             break
     assert lines == g["lines"]
+
+
+def test_native_readers_equal_the_line_readers_on_arbitrary_text(tmp_path):
+    """Property test: on any text over the characters the formats use (and some they do not), the native readers and the
+    per-line restatement of the reference's readers yield the same arrays — same line splitting ('\\n' only, as
+    std::getline), same skipping of short lines, same atol reading."""
+    import re
+    from hypothesis import HealthCheck, assume, given, settings, strategies as st
+
+    text = st.text(alphabet="0123456789,,,,;;--+ \tRTPx.\r\n\n", max_size=400)
+    paths = [str(tmp_path / n) for n in ("a.txt",)]
+
+    @settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(text, st.integers(-9, -1))      # negative: exactly that many pieces, however small the file
+    def check(t, threads):
+        assume(not re.search(r"\d{17,}", t))                 # beyond int64 the reference's atol is undefined
+        with open(paths[0], "w", newline="", encoding="latin-1") as f:
+            f.write(t)
+        for kind in ("road", "trip", "part"):
+            if kind == "road":
+                nat = scenario.read_traffic_csv(road_csv=paths[0], threads=threads)
+                py = dict(zip(("state_ids", "road_start", "road_dst", "road_speed", "road_len"), traffic.read_roads(paths[0])))
+            elif kind == "trip":
+                nat = scenario.read_traffic_csv(trip_csv=paths[0], threads=threads)
+                py = dict(zip(("trip_id", "trip_dep", "route_start", "route_nodes"), traffic.read_trips(paths[0])))
+            else:
+                nat = scenario.read_traffic_csv(partition_file=paths[0], threads=threads)
+                py = dict(part=traffic.read_partition(paths[0]))
+            for k, v in py.items():
+                assert np.array_equal(nat[k], v), (kind, k, t)
+
+    check()

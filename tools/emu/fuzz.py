@@ -137,6 +137,23 @@ def one_diff(rng):
     s1.run_closure(2)
     ok = init_lines == sorted(O.records_to_lines(s1.committed()))
     new_lines = sorted(set(full_lines) - set(init_lines))
+    if rng.random() < 0.4 and len(init_lines) > 3:
+        # delete-event queries (DE, runner.hpp:246-276) on top of the added trips: random recorded events disappear
+        k = int(rng.choice([1, 3]))
+        picks = rng.choice(len(init_lines), size=k, replace=False)
+        dels = []
+        for j in picks:
+            i_, src_, send_, dst_, recv_ = O.parse_line(init_lines[int(j)])
+            dels.append((dst_, recv_, i_))
+        cfg["deletes"] = dels
+        wi = traffic.WhatIf(add[0], add[1], add[2], add[3], np.array(dels, dtype=np.int64).reshape(-1, 3))
+        eng = traffic.make_repeat_engine(sc, hs, wi, bucket_ticks=rbucket, window_buckets=rwindow, keep_records=True,
+                                         max_committed=(both.route_nodes.size + 64) * 4, **big)
+        st2 = eng.run()
+        rep = sorted(ssb.records_to_lines(eng.drain_committed()))
+        eng.close()
+        ok = ok and rep == O.repeat_closure(init_lines, new_lines, dels)
+        return ok, cfg, dict(init=len(init_lines), new=len(new_lines), repeat=len(rep), rollbacks=st2.rollbacks)
     eng = traffic.make_repeat_engine(sc, hs, add, bucket_ticks=rbucket, window_buckets=rwindow, keep_records=True,
                                      max_committed=(both.route_nodes.size + 64) * 4, **big)
     st2 = eng.run()
