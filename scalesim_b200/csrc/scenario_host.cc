@@ -241,7 +241,7 @@ template <bool store>
 inline int64_t trip_line(const char* lb, const char* le, int64_t* id, int64_t* dep, int64_t* nodes) {
   const char* p = skip_field(lb, le);                   // field 0
   if (p > le) return -1;
-  int64_t vid, ignored, t;
+  int64_t vid = 0, t = 0;
   if (store) p = field(p, le, &vid); else p = skip_field(p, le);      // field 1: vehicle id
   if (p > le) return -1;
   p = skip_field(p, le);                                // field 2: ignored
@@ -256,7 +256,6 @@ inline int64_t trip_line(const char* lb, const char* le, int64_t* id, int64_t* d
     n = 1;
     for (const char* q = p; q < le; ++q) n += *q == ',';
   }
-  (void)ignored;
   return n;
 }
 

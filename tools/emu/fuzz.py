@@ -216,13 +216,66 @@ def one_multi(rng):
                                   antis=sum(x.antis_sent for x in st), remote=sum(x.remote_sent for x in st), want=want[0])
 
 
+def one_multidiff(rng):
+    """--diff_init and --diff_repeat with the LPs split over several partitions (one history store per partition): the
+    union of the partitions' repeat outputs must be the closure of the added trips over the union of the init outputs."""
+    import multi
+    from scalesim_b200.store import HistoryStore
+    world = int(rng.choice([2, 3, 4]))
+    n_nodes = int(rng.choice([12, 100, 400]))
+    deg = int(rng.choice([1, 2, 4]))
+    n_trips = int(rng.choice([20, 500, 3000]))
+    n_add = int(rng.choice([1, 5, 60]))
+    seed = int(rng.integers(0, 1 << 30))
+    bucket = int(rng.choice([5, 11, 64]))
+    rbucket = int(rng.choice([5, 11, 64]))
+    rwindow = int(rng.choice([1, 2, 8]))
+    graph = bool(rng.random() < 0.5)
+    cfg = dict(kind="multidiff", world=world, n_nodes=n_nodes, deg=deg, n_trips=n_trips, n_add=n_add, seed=seed, bucket=bucket,
+               rbucket=rbucket, rwindow=rwindow, graph=graph)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("multidiff", cfg, flush=True)
+    both = _random_network(n_nodes, deg, n_trips + n_add, seed)
+    part = np.random.default_rng(seed).integers(0, world, n_nodes)
+    cut = int(both.route_start[n_trips])
+    sc = traffic.Scenario(both.n_lp, both.state_ids, both.road_start, both.road_dst, both.road_speed, both.road_len,
+                          both.trip_id[:n_trips], both.trip_dep[:n_trips], both.route_start[:n_trips + 1], both.route_nodes[:cut], part)
+    add = (both.trip_id[n_trips:], both.trip_dep[n_trips:], both.route_start[n_trips:] - cut, both.route_nodes[cut:])
+    big = dict(max_events=(both.route_nodes.size + 64) * 12 + (1 << 16), max_batch=both.route_nodes.size * 4 + (1 << 14))
+    _, _, engines = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=bucket, history=True, **big),
+                                         world, keep_engines=True, graph=graph)
+    stores, init_lines = [], []
+    for e in engines:
+        rec, sent = e.drain_history()
+        e.close()
+        stores.append(HistoryStore(rec, sent, None, sc.route_nodes))
+        init_lines += ssb.records_to_lines(ssb.raw_to_records(rec))
+    init_lines.sort()
+    s1 = O.Sim.traffic_scenario(sc)
+    s1.run_closure(2)
+    ok = init_lines == sorted(O.records_to_lines(s1.committed()))
+    s = O.Sim.traffic_scenario(both)
+    s.run_closure(2)
+    new_lines = sorted(set(O.records_to_lines(s.committed())) - set(init_lines))
+    _, st2, engines = multi.run_partitions(
+        lambda r, w: traffic.make_repeat_engine(sc, stores[r], add, rank=r, world=w, bucket_ticks=rbucket, window_buckets=rwindow,
+                                                keep_records=True, max_committed=(both.route_nodes.size + 64) * 4, **big),
+        world, keep_engines=True, graph=graph)
+    rep = []
+    for e in engines:
+        rep += ssb.records_to_lines(e.drain_committed())
+        e.close()
+    ok = ok and sorted(rep) == O.repeat_closure(init_lines, new_lines)
+    return ok, cfg, dict(init=len(init_lines), new=len(new_lines), repeat=len(rep), rollbacks=sum(x.rollbacks for x in st2))
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, n, bad, rb, cap, col = time.time(), 0, 0, 0, 0, 0
     while time.time() - t0 < budget:
         r = rng.random()
-        kind = one_phold if r < 0.35 else (one_traffic if r < 0.55 else (one_diff if r < 0.75 else one_multi))
+        kind = one_phold if r < 0.3 else (one_traffic if r < 0.5 else (one_diff if r < 0.7 else (one_multi if r < 0.9 else one_multidiff)))
         if os.environ.get("FUZZ_ONLY"):
             kind = globals()["one_" + os.environ["FUZZ_ONLY"]]
         try:
