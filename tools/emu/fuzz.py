@@ -318,6 +318,58 @@ def one_sc(rng):
     return ok, cfg, dict(init=len(init), full=len(full), new=len(new), repeat=len(lines), rollbacks=st2.rollbacks)
 
 
+def _run_lines(cmd, env=None, tries=4):
+    """stdout "RE," lines of a binary, sorted; the reference has an intermittent start-up crash: retry"""
+    import subprocess
+    for _ in range(tries):
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+        if p.returncode == 0:
+            return sorted(l for l in p.stdout.splitlines() if l.startswith("RE,"))
+    raise RuntimeError(f"{cmd[0]} failed: {p.stderr[-300:]}")
+
+
+def one_ref(rng):
+    """Three-way check on a random input: the UNMODIFIED reference binary (oracle/_ref, built from /root/reference where
+    that tree exists) == the oracle's restatement == the drop-in binary on the emulated kernels (tools/emu/apps), line
+    for line. Pins the oracle on the reference beyond the committed goldens."""
+    import tempfile
+    ref_dir, emu_dir = os.path.join(ROOT, "oracle", "_ref"), os.path.join(HERE, "apps")
+    window = str(int(rng.choice([1, 2, 5])))
+    if rng.random() < 0.5:
+        n_lp = int(rng.choice([1, 8, 50, 200]))
+        n_init = int(rng.choice([1, 40, 600, 2000]))
+        ratio = float(rng.choice([0.0, 0.1, 0.5, 1.0]))
+        lam = float(rng.choice([0.5, 1.0, 3.0]))
+        cfg = dict(kind="ref-phold", n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, window=window)
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("ref", cfg, flush=True)
+        args = [str(n_lp), str(n_init), str(ratio), str(lam), "0", "50"]
+        ref = _run_lines([os.path.join(ref_dir, "PHOLD")] + args, {"SCALESIM_NUM_THR": str(int(rng.choice([1, 2, 4])))})
+        emu = _run_lines([os.path.join(emu_dir, "PHOLD")] + args, {"SCALESIM_B200_WINDOW": window})
+        s = O.Sim.phold(n_lp, n_init, ratio, lam)
+        s.run_closure(2)
+    else:
+        n_nodes = int(rng.choice([4, 30, 150]))
+        deg = int(rng.choice([1, 2, 5]))
+        n_trips = int(rng.choice([1, 30, 400]))
+        seed = int(rng.integers(0, 1 << 30))
+        cfg = dict(kind="ref-traffic", n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, window=window)
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("ref", cfg, flush=True)
+        sc = _random_network(n_nodes, deg, n_trips, seed)
+        sc.partition = np.zeros(n_nodes, dtype=np.int64)
+        from scalesim_b200 import scenario
+        with tempfile.TemporaryDirectory() as td:
+            rd, trip, part = (os.path.join(td, n) for n in ("rd.csv", "trip.csv", "part"))
+            scenario.write_traffic_csv(sc, rd, trip, part)
+            ref = _run_lines([os.path.join(ref_dir, "TrafficSim"), part, rd, trip], {"SCALESIM_NUM_THR": str(int(rng.choice([2, 4])))})
+            emu = _run_lines([os.path.join(emu_dir, "TrafficSim"), part, rd, trip], {"SCALESIM_B200_WINDOW": window})
+        s = O.Sim.traffic_scenario(sc)
+        s.run_closure(2)
+    orc = sorted(O.records_to_lines(s.committed()))
+    return ref == orc == emu, cfg, dict(ref=len(ref), oracle=len(orc), emu=len(emu))
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
