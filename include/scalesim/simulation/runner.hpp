@@ -200,6 +200,8 @@ class runner {
     return (FLAGS_store_dir.empty() ? std::string(".") : FLAGS_store_dir) + "/" + FLAGS_sim_id + "/history" + std::to_string(rank_) + ".ssb";
   }
   void read_history(history& h);
+  void write_image(const char* path, const std::vector<long>& part, const std::vector<int64_t>& state_lps,
+                   const std::vector<uint32_t>& words, const std::vector<ssb_event>& pod, typename model::context& cx, long n_lp);
   void verify_twin(const ev_vec<App>& initial, const std::vector<ssb_record>& committed, long k);
 };
 
@@ -301,6 +303,38 @@ void runner<App>::read_history(history& h) {
   }
   int64_t total = -1;
   if (!f.read((char*)&total, 8) || total != (int64_t)h.rec.size()) bad("record count does not match the chunks");
+}
+
+// SCALESIM_B200_SCENARIO_OUT: what the application's readers / generators produced — partition table, packed states, model
+// data, initial events as device records — kept as a scenario image (ssb_scenario_save) for later runs
+template <class App>
+void runner<App>::write_image(const char* path, const std::vector<long>& part, const std::vector<int64_t>& state_lps,
+                              const std::vector<uint32_t>& words, const std::vector<ssb_event>& pod, typename model::context& cx,
+                              long n_lp) {
+  if (world_ != 1) { LOG(ERROR) << "SCALESIM_B200_SCENARIO_OUT needs a single partition (the image holds every partition's share)"; std::exit(1); }
+  std::vector<ssb_raw_record> raw(pod.size());
+  for (size_t i = 0; i < pod.size(); ++i) {
+    const ssb_event& e = pod[i];
+    if (e.recv_time < 0 || e.recv_time >= (1ll << 31) || e.send_time < 0 || e.send_time >= (1ll << 31) || e.id < 0 || e.id >= 0xffffffffll ||
+        e.dst < 0 || e.dst >= 0xffffffffll || e.src < -1 || e.src >= 0xffffffffll || e.p0 < 0 || e.p0 > 0xffffffffll || e.p1 < 0 || e.p1 > 0xffffffffll) {
+      LOG(ERROR) << "event " << e.id << " does not fit the device record (see the limits in scalesim_b200.h)"; std::exit(1);
+    }
+    ssb_raw_record& r = raw[i];
+    r.key = ((uint64_t)e.recv_time << 32) | (uint64_t)e.id;
+    r.dst = (uint32_t)e.dst; r.src = e.src < 0 ? 0xffffffffu : (uint32_t)e.src; r.send_time = (uint32_t)e.send_time;
+    r.p0 = (uint32_t)e.p0; r.p1 = (uint32_t)e.p1; r.tag = (uint32_t)(e.flags & 1);
+  }
+  std::vector<int64_t> part_raw(part.begin(), part.end());
+  ssb_scenario out;
+  std::memset(&out, 0, sizeof(out));
+  out.model = model::model_id(); out.state_words = model::state_words(); out.n_lp = n_lp; out.finish_time = App::finish_time();
+  out.n_part = (int64_t)part_raw.size(); out.lp_to_part = part_raw.data();
+  out.n_states = (int64_t)state_lps.size(); out.state_lps = state_lps.data(); out.states = words.data();
+  out.n_events = (int64_t)raw.size(); out.events = raw.data();
+  model::image_slots(cx, out);
+  int rc = ssb_scenario_save(path, &out);
+  if (rc) { LOG(ERROR) << "ssb_scenario_save failed (status " << rc << "): " << ssb_last_error(NULL); std::exit(1); }
+  LOG(INFO) << "Scenario image written: " << path;
 }
 
 template <class App>
@@ -449,10 +483,9 @@ void runner<App>::run() {
     if (FLAGS_diff_init) hist.pool = model::model_data_blob_of(img);
     ssb_scenario_close(&img);
   } else {
-  std::vector<int64_t> part64(part.begin(), part.end());
-  for (size_t i = 0; i < part64.size(); ++i) part64[i] %= world_;
-  if ((rc = ssb_set_partition(engine_, part64.data(), (int64_t)part64.size()))) fail("ssb_set_partition", rc);
-  {
+    std::vector<int64_t> part64(part.begin(), part.end());
+    for (size_t i = 0; i < part64.size(); ++i) part64[i] %= world_;
+    if ((rc = ssb_set_partition(engine_, part64.data(), (int64_t)part64.size()))) fail("ssb_set_partition", rc);
     const int sw = model::state_words();
     std::vector<int64_t> ids(states.size());
     std::vector<uint32_t> words(states.size() * (size_t)sw);
@@ -462,33 +495,7 @@ void runner<App>::run() {
     }
     if ((rc = model::upload_model_data(engine_, cx))) fail("ssb_set_model_data", rc);
     if ((rc = ssb_load_states(engine_, ids.data(), words.data(), (int64_t)ids.size()))) fail("ssb_load_states", rc);
-    if (image_out && *image_out && !FLAGS_diff_repeat) {
-      // keep what the application's readers / generators produced as a scenario image for later runs
-      if (world_ != 1) { LOG(ERROR) << "SCALESIM_B200_SCENARIO_OUT needs a single partition (the image holds every partition's share)"; std::exit(1); }
-      std::vector<ssb_raw_record> raw(pod.size());
-      for (size_t i = 0; i < pod.size(); ++i) {
-        const ssb_event& e = pod[i];
-        if (e.recv_time < 0 || e.recv_time >= (1ll << 31) || e.send_time < 0 || e.send_time >= (1ll << 31) || e.id < 0 || e.id >= 0xffffffffll ||
-            e.dst < 0 || e.dst >= 0xffffffffll || e.src < -1 || e.src >= 0xffffffffll || e.p0 < 0 || e.p0 > 0xffffffffll || e.p1 < 0 || e.p1 > 0xffffffffll) {
-          LOG(ERROR) << "event " << e.id << " does not fit the device record (see the limits in scalesim_b200.h)"; std::exit(1);
-        }
-        ssb_raw_record& r = raw[i];
-        r.key = ((uint64_t)e.recv_time << 32) | (uint64_t)e.id;
-        r.dst = (uint32_t)e.dst; r.src = e.src < 0 ? 0xffffffffu : (uint32_t)e.src; r.send_time = (uint32_t)e.send_time;
-        r.p0 = (uint32_t)e.p0; r.p1 = (uint32_t)e.p1; r.tag = (uint32_t)(e.flags & 1);
-      }
-      std::vector<int64_t> part_raw(part.begin(), part.end());
-      ssb_scenario out;
-      std::memset(&out, 0, sizeof(out));
-      out.model = model::model_id(); out.state_words = sw; out.n_lp = n_lp; out.finish_time = App::finish_time();
-      out.n_part = (int64_t)part_raw.size(); out.lp_to_part = part_raw.data();
-      out.n_states = (int64_t)ids.size(); out.state_lps = ids.data(); out.states = words.data();
-      out.n_events = (int64_t)raw.size(); out.events = raw.data();
-      model::image_slots(cx, out);
-      if ((rc = ssb_scenario_save(image_out, &out))) { LOG(ERROR) << "ssb_scenario_save failed (status " << rc << "): " << ssb_last_error(NULL); std::exit(1); }
-      LOG(INFO) << "Scenario image written: " << image_out;
-    }
-  }
+    if (image_out && *image_out && !FLAGS_diff_repeat) write_image(image_out, part, ids, words, pod, cx, n_lp);
   }
   if (FLAGS_diff_repeat &&
       (rc = ssb_load_history(engine_, hist.rec.data(), hist.sent.data(), (int64_t)hist.rec.size()))) fail("ssb_load_history", rc);
