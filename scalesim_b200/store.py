@@ -13,7 +13,8 @@ which is the logical content of all three reference stores:
     event  DB : one record per committed event,       key (dst, receive_time, id)            queue.hpp:179-189
     cancel DB : one record per event that produced    key (dst, receive_time, id)            queue.hpp:191-201
                 something (the produced event's send_time is the input's receive_time, same id — the app convention)
-    state  DB : the same keys as cancel + one (lp, -1, -1) initial version per LP             queue.hpp:304-323
+    state  DB : the same keys as cancel + one (lp, -1, -1) initial version per LP that        queue.hpp:304-323,
+                executed an event (only LPs the scheduler dequeued are stored)                 runner.hpp:573-583
 
 ``key60`` renders the reference's 60-byte LevelDB key (leveldb_store.hpp:336-368) so that stores can be compared
 record by record. The value bytes of the reference (Boost binary archives) are not reproduced (unpinned).
@@ -66,9 +67,18 @@ class HistoryStore:
     def cancel_keys(self) -> np.ndarray:
         return self._keys(self.sent["dst"] != NONE)
 
+    def active_lps(self) -> np.ndarray:
+        """LPs of this rank that executed a committed event. The reference stores / fossil-collects only LPs its
+        scheduler ever dequeued (runner::clear walks scheduler::active_lp, runner.hpp:573-583,
+        process_scheduler.hpp:55-67), so an LP no event ever reached has no record in any of its stores — not even its
+        initial state. (An LP reached only by events at or beyond finish_time is dequeued or not depending on the
+        reference's thread timing: its (lp, -1, -1) record is not deterministic there and is not produced here.)"""
+        return np.unique(self.rec["dst"].astype(np.int64))
+
     def state_keys(self) -> np.ndarray:
         k = self.cancel_keys()
-        init = np.stack([self.state_lps, np.full(self.state_lps.size, -1), np.full(self.state_lps.size, -1)], axis=1)
+        lps = np.intersect1d(self.state_lps, self.active_lps())
+        init = np.stack([lps, np.full(lps.size, -1), np.full(lps.size, -1)], axis=1)
         k = np.concatenate([init.astype(np.int64), k]) if init.size else k
         return k[np.lexsort((k[:, 2], k[:, 1], k[:, 0]))]
 

@@ -56,3 +56,29 @@ def write_ring_files(tmpdir):
     with open(part, "w") as f:
         f.write("".join(f"{p}\n" for p in sc.partition))
     return rd, trip, part
+
+
+def sparse_network(n_nodes, n_trips, seed):
+    """tests/golden/sparse_diff.json: random network in which some junctions are never visited; speeds 20..60 (no zero
+    speed: no hop reaches finish_time), short random walks"""
+    from scalesim_b200 import traffic
+    rng = np.random.default_rng(seed)
+    deg = rng.integers(1, 3, n_nodes)
+    road_start = np.zeros(n_nodes + 1, dtype=np.int64)
+    np.cumsum(deg, out=road_start[1:])
+    road_dst = rng.integers(0, n_nodes, road_start[-1])
+    road_speed = rng.integers(20, 61, road_start[-1])
+    road_len = rng.integers(100, 1200, road_start[-1])
+    dep, start, nodes = [], [0], []
+    for _ in range(n_trips):
+        cur = int(rng.integers(0, n_nodes))
+        route = [cur]
+        for _ in range(int(rng.integers(1, 6))):
+            cur = int(road_dst[road_start[cur] + rng.integers(0, deg[cur])])
+            route.append(cur)
+        dep.append(int(rng.integers(0, 3000)))
+        nodes.extend(route)
+        start.append(len(nodes))
+    a = lambda x: np.array(x, dtype=np.int64)
+    return traffic.Scenario(n_nodes, np.arange(n_nodes, dtype=np.int64), road_start, road_dst, road_speed, road_len,
+                            np.arange(n_trips, dtype=np.int64), a(dep), a(start), a(nodes), np.zeros(n_nodes, dtype=np.int64))

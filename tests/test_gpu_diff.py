@@ -223,3 +223,19 @@ def test_state_change_query_with_more_roads_than_fit_inline(tmp_path):
         eng.close()
         new = set(l for l in lines if l not in set(init_lines))
         assert sorted((set(init_lines) - superseded) | new) == full
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_store_of_a_network_with_unvisited_junctions_equals_reference(case):
+    """--diff_init on the networks of tests/golden/sparse_diff.json: the engine's history gives the reference's three
+    key sets — in particular no initial-state record for a junction no event ever reached (runner.hpp:573-583)."""
+    from fixtures import sparse_network
+    g = golden("sparse_diff")["cases"][case]
+    sc = sparse_network(g["n_nodes"], g["n_trips"], g["seed"])
+    sc.partition = None
+    for bucket, window in ((8, 1), (50, 3)):
+        st, rec, hs = traffic.run_diff_init(sc, bucket_ticks=bucket, window_buckets=window)
+        assert sorted(ssb.records_to_lines(ssb.raw_to_records(rec))) == g["init_lines"]
+        assert hs.event_keys().tolist() == sorted(g["store"]["event"])
+        assert hs.cancel_keys().tolist() == sorted(g["store"]["cancel"])
+        assert hs.state_keys().tolist() == sorted(g["store"]["state"])

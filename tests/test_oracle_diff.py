@@ -74,3 +74,39 @@ def test_history_store_keys_and_file_roundtrip(tmp_path):
     back = store.HistoryStore.load(str(tmp_path), 999, 0)
     assert back.rec.tobytes() == hs.rec.tobytes() and back.sent.tobytes() == hs.sent.tobytes()
     assert back.state_lps.tolist() == list(range(10))
+
+
+def _store_from_lines(lines, state_lps):
+    """HistoryStore of a run given by its result lines: the sent-log entry of an event is the line it produced (same id,
+    source = this event's LP, send time = this event's receive time — the app convention)."""
+    import scalesim_b200 as ssb
+    parsed = [O.parse_line(l) for l in lines]                       # id, src, send, dst, recv
+    produced = {(i, src, send): (dst, recv) for i, src, send, dst, recv in parsed if (src, send) != (dst, recv)}
+    rec = np.zeros(len(parsed), dtype=ssb.RAW_RECORD_DTYPE)
+    sent = np.zeros(len(parsed), dtype=ssb.SENT_RECORD_DTYPE)
+    for k, (i, src, send, dst, recv) in enumerate(parsed):
+        rec[k] = ((recv << 32) | i, dst, 0xFFFFFFFF if src < 0 else src, send, 0, 0, 0)
+        out = produced.get((i, dst, recv))
+        sent[k] = (out[0], i, out[1], 0) if out else (store.NONE, 0, 0, 0)
+    return store.HistoryStore(rec, sent, np.asarray(state_lps, dtype=np.int64))
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_store_has_no_records_for_lps_that_never_execute(case):
+    """tests/golden/sparse_diff.json (make_golden_sparse.py, unmodified reference): networks where some junctions are
+    never visited. The reference stores only LPs its scheduler ever dequeued (runner.hpp:573-583): an unvisited LP has
+    no (lp, -1, -1) initial-state record. Event / cancel / state key sets derived by store.py == the reference's."""
+    g = golden("sparse_diff")["cases"][case]
+    hs = _store_from_lines(g["init_lines"], np.arange(g["n_nodes"]))
+    assert hs.event_keys().tolist() == sorted(g["store"]["event"])
+    assert hs.cancel_keys().tolist() == sorted(g["store"]["cancel"])
+    assert hs.state_keys().tolist() == sorted(g["store"]["state"])
+    assert hs.active_lps().tolist() == g["visited_lps"] and len(g["visited_lps"]) < g["n_nodes"]
+
+
+def test_store_from_lines_reproduces_the_ring_store():
+    """the same derivation on the ring (every LP visited): the reference's 38 / 35 / 45 records"""
+    g = golden("ring_diff")
+    hs = _store_from_lines(g["init_lines"], np.arange(10))
+    assert (len(hs.event_keys()), len(hs.cancel_keys()), len(hs.state_keys())) == (38, 35, 45)
+    assert hs.state_keys().tolist() == sorted(g["store"]["state"])

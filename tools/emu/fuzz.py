@@ -318,13 +318,23 @@ def one_sc(rng):
     return ok, cfg, dict(init=len(init), full=len(full), new=len(new), repeat=len(lines), rollbacks=st2.rollbacks)
 
 
+class RefHang(Exception):
+    pass
+
+
 def _run_lines(cmd, env=None, tries=4):
     """stdout "RE," lines of a binary, sorted; the reference has an intermittent start-up crash: retry"""
     import subprocess
     for _ in range(tries):
-        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+        try:
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=float(os.environ.get("FUZZ_REF_TIMEOUT", "60")),
+                               env=dict(os.environ, **(env or {})))
+        except subprocess.TimeoutExpired:
+            raise RefHang(cmd[0])      # the reference itself sometimes never terminates (seen with --diff_init): not a finding here
         if p.returncode == 0:
             return sorted(l for l in p.stdout.splitlines() if l.startswith("RE,"))
+    if "oracle/_ref" in cmd[0]:
+        raise RefHang(cmd[0])      # ... or dies on every try (seen with --diff_init on some networks)
     raise RuntimeError(f"{cmd[0]} failed: {p.stderr[-300:]}")
 
 
@@ -370,10 +380,63 @@ def one_ref(rng):
     return ref == orc == emu, cfg, dict(ref=len(ref), oracle=len(orc), emu=len(emu))
 
 
+def _ref_store_keys(path):
+    """keys of one stand-in LevelDB file the reference wrote (oracle/shim/leveldb/db.h: [u64 klen][key][u64 vlen][value]...;
+    key = 60 bytes lp | time | id, leveldb_store.hpp:336-368)"""
+    import struct
+    b = open(os.path.join(path, "data.bin"), "rb").read()
+    o, out = 0, []
+    while o < len(b):
+        (a,) = struct.unpack_from("<Q", b, o); o += 8
+        k = b[o:o + a]; o += a
+        (v,) = struct.unpack_from("<Q", b, o); o += 8 + v
+        f = k.rstrip(b"\0").split(b"\0")
+        out.append([-int(x.split(b"-")[1]) if b"-" in x else int(x) for x in f])
+    return sorted(out)
+
+
+def one_refstore(rng):
+    """--diff_init on a random road network: the three stores the UNMODIFIED reference writes (event / cancel / state
+    key sets, for keys below finish_time) == the key sets derived from the history store the drop-in binary writes on
+    the emulated kernels; and both print the same lines."""
+    import subprocess
+    import tempfile
+    from scalesim_b200 import scenario, store
+    n_nodes = int(rng.choice([4, 30, 150]))
+    deg = int(rng.choice([1, 2, 5]))
+    n_trips = int(rng.choice([1, 30, 300]))
+    seed = int(rng.integers(0, 1 << 30))
+    window = str(int(rng.choice([1, 2, 5])))
+    cfg = dict(kind="refstore", n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, window=window)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("refstore", cfg, flush=True)
+    sc = _random_network(n_nodes, deg, n_trips, seed)
+    sc.partition = np.zeros(n_nodes, dtype=np.int64)
+    with tempfile.TemporaryDirectory() as td:
+        rd, trip, part = (os.path.join(td, n) for n in ("rd.csv", "trip.csv", "part"))
+        scenario.write_traffic_csv(sc, rd, trip, part)
+        st_ref, st_emu = os.path.join(td, "ref"), os.path.join(td, "emu")
+        os.makedirs(st_ref)
+        ref = _run_lines([os.path.join(ROOT, "oracle", "_ref", "TrafficSim"), "--sim_id=7", f"--store_dir={st_ref}", "--diff_init", part, rd, trip],
+                         {"SCALESIM_NUM_THR": "2"})
+        emu = _run_lines([os.path.join(HERE, "apps", "TrafficSim"), "--sim_id=7", f"--store_dir={st_emu}", "--diff_init", part, rd, trip],
+                         {"SCALESIM_B200_WINDOW": window})
+        fin = traffic.FINISH_TIME
+        keys = {db: [k for k in _ref_store_keys(os.path.join(st_ref, "7", db + "0")) if k[1] < fin] for db in ("event", "cancel", "state")}
+        hs = store.HistoryStore.load(st_emu, 7, 0)
+        # (lp, -1, -1) records of LPs reached only by events at or beyond finish_time depend on the reference's thread
+        # timing (dequeued before the loop ends or not): compared on the LPs that executed a committed event
+        live = set(int(x) for x in hs.active_lps())
+        ref_state = [k for k in keys["state"] if k[1] >= 0 or k[0] in live]
+        ok = ref == emu and hs.event_keys().tolist() == keys["event"] and hs.cancel_keys().tolist() == keys["cancel"] \
+            and hs.state_keys().tolist() == ref_state
+    return ok, cfg, dict(lines=len(ref), events=len(keys["event"]), cancels=len(keys["cancel"]), states=len(keys["state"]))
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    t0, n, bad, rb, cap, col = time.time(), 0, 0, 0, 0, 0
+    t0, n, bad, rb, cap, col, hang = time.time(), 0, 0, 0, 0, 0, 0
     while time.time() - t0 < budget:
         r = rng.random()
         kind = one_phold if r < 0.3 else (one_traffic if r < 0.5 else (one_diff if r < 0.7 else (one_multi if r < 0.85 else (one_multidiff if r < 0.93 else one_sc))))
@@ -381,6 +444,9 @@ def main():
             kind = globals()["one_" + os.environ["FUZZ_ONLY"]]
         try:
             ok, cfg, info = kind(rng)
+        except RefHang:
+            hang += 1
+            continue
         except ssb.EngineError as e:
             # a capacity overflow (pool / batch / snapshot ring too small for a hostile setting) must be a clean
             # SSB_ERR_CAPACITY — it counts as handled; anything else is a finding
@@ -396,7 +462,7 @@ def main():
         if not ok:
             bad += 1
             print("MISMATCH", kind.__name__, cfg, info, flush=True)
-    print(f"{n} runs ({rb} with rollbacks, {cap} clean capacity errors, {col} key collisions (R1)), {bad} mismatches, {time.time() - t0:.0f} s", flush=True)
+    print(f"{n} runs ({rb} with rollbacks, {cap} clean capacity errors, {col} key collisions (R1), {hang} runs the reference binary itself did not survive), {bad} mismatches, {time.time() - t0:.0f} s", flush=True)
     return 1 if bad else 0
 
 
