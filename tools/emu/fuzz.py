@@ -484,6 +484,47 @@ def one_refrepeat(rng):
     return ok, cfg, dict(init=len(emu_init), new=len(new), repeat=len(emu), ref_sizes=[len(r) for r in refs])
 
 
+def one_refphold(rng):
+    """PHOLD --diff_init then --diff_repeat with NUM_WHAT_IF added events (phold::init_what_if: id NUM_INIT_MSG + i at LP i,
+    time 1; phold.hpp:232-246) through the unmodified reference and the drop-in binary: equal init lines and store key
+    sets; every reference repeat run contained in the drop-in's output (= the closure), equal new lines."""
+    import tempfile
+    from scalesim_b200 import store
+    n_lp = int(rng.choice([4, 20, 100]))
+    n_init = int(rng.choice([n_lp, 4 * n_lp, 16 * n_lp]))
+    ratio = float(rng.choice([0.0, 0.1, 0.5]))
+    lam = float(rng.choice([0.5, 1.0, 3.0]))
+    n_wi = int(rng.choice([1, 3]))
+    window = str(int(rng.choice([1, 2, 5])))
+    cfg = dict(kind="refphold", n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, n_wi=n_wi, window=window)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("refphold", cfg, flush=True)
+    args = [str(n_lp), str(n_init), str(ratio), str(lam), str(n_wi), "50"]
+    with tempfile.TemporaryDirectory() as td:
+        st_ref, st_emu = os.path.join(td, "ref"), os.path.join(td, "emu")
+        os.makedirs(st_ref)
+        flags = lambda st: ["--sim_id=3", f"--store_dir={st}"]
+        ref_bin, emu_bin = os.path.join(ROOT, "oracle", "_ref", "PHOLD"), os.path.join(HERE, "apps", "PHOLD")
+        ref_init = _run_lines([ref_bin] + flags(st_ref) + ["--diff_init"] + args, {"SCALESIM_NUM_THR": "2"})
+        emu_init = _run_lines([emu_bin] + flags(st_emu) + ["--diff_init"] + args, {"SCALESIM_B200_WINDOW": window})
+        fin = phold.FINISH_TIME
+        keys = {db: [k for k in _ref_store_keys(os.path.join(st_ref, "3", db + "0")) if k[1] < fin] for db in ("event", "cancel", "state")}
+        hs = store.HistoryStore.load(st_emu, 3, 0)
+        live = set(int(x) for x in hs.active_lps())
+        ok = ref_init == emu_init and hs.event_keys().tolist() == keys["event"] and hs.cancel_keys().tolist() == keys["cancel"] \
+            and hs.state_keys().tolist() == [k for k in keys["state"] if k[1] >= 0 or k[0] in live]
+        refs = [_run_lines([ref_bin] + flags(st_ref) + ["--diff_repeat"] + args, {"SCALESIM_NUM_THR": str(t)}) for t in (2, 4)]
+        emu = _run_lines([emu_bin] + flags(st_emu) + ["--diff_repeat"] + args, {"SCALESIM_B200_WINDOW": window})
+    init = set(emu_init)
+    new = sorted(l for l in emu if l not in init)
+    ok = ok and emu == O.repeat_closure(emu_init, new)
+    if not set(range(n_wi)) <= live:
+        return ("skip" if ok else False), cfg, dict(reference_not_comparable="a what-if event reaches an LP without recorded state")
+    for r in refs:
+        ok = ok and set(r) <= set(emu) and sorted(l for l in r if l not in init) == new
+    return ok, cfg, dict(init=len(emu_init), new=len(new), repeat=len(emu), ref_sizes=[len(r) for r in refs])
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
