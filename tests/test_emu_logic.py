@@ -1,4 +1,5 @@
-"""CPU logic check of the MULTI-PARTITION path where there is no GPU: the kernel sources compiled for
+"""CPU logic checks on the emulated kernels (tools/emu) where there is no GPU. First the MULTI-PARTITION path
+(SURVEY.md §8e): the kernel sources compiled for
 the host (tools/emu, a developer tool the product cannot load) with one emulated engine per partition, each on its own
 host thread, mailboxes exchanged by address — cross-partition events and anti-messages through k_route / the receive
 pass, GVT through k_gvt, sequence stamps. The union of the partitions' committed multisets must equal the oracle's for
@@ -54,3 +55,17 @@ def test_several_windows_per_synchronisation(emu_results):
         r = emu_results[k]
         assert r["equal"] and r["exchanges"] < r["rounds"] and r["rollbacks"] > 0, k
     assert emu_results["phold_w2_stream"]["equal"]
+
+
+def test_device_parity_tests_pass_on_the_emulated_kernels(emu_results):
+    """The `-m gpu` files that fit a CPU budget — device KATs of logical_process_test.cc, TrafficSim, scenario images,
+    overflow behaviour, the drop-in binaries — run against the emulated kernels in a subprocess: a logic regression net
+    where there is no GPU (the same tests run on the B200 with `-m gpu`; only those runs are parity claims)."""
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tools", "emu"), SCALESIM_B200_APPS_DIR=os.path.join(ROOT, "tools", "emu", "apps"))
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_gpu_kat.py", "test_gpu_scenario.py", "test_gpu_zz_overflow.py",
+                                                       "test_gpu_dropin.py", "test_gpu_traffic.py")]
+    p = subprocess.run([sys.executable, "-m", "pytest", "-p", "emu_plugin", "-m", "gpu", "-q", "-x", "-k", "not full_size",
+                        "-p", "no:cacheprovider"] + files, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                       cwd=ROOT, timeout=1200)
+    tail = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
+    assert p.returncode == 0 and " passed" in tail and "failed" not in tail, p.stdout[-3000:]

@@ -1,5 +1,5 @@
 """Developer tool / CPU logic check: a few multi-partition runs on the host emulation (tools/emu/multi.py), printed as
-one JSON object. Run by tests/test_emu_multi.py in a subprocess (the emulation is selected per process).
+one JSON object. Run by tests/test_emu_logic.py in a subprocess (the emulation is selected per process).
 
     tools/emu/build.sh && python tools/emu/check_multi.py
 """
