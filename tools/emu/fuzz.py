@@ -69,6 +69,13 @@ def one_phold(rng):
     if ok and stateful:
         ids, words = s.final_states(n_lp)
         ok = bool(np.array_equal(eng.read_states(ids), words))
+    if ok and rng.random() < 0.3:
+        # the same engine again after ssb_reset (what bench.py does between steps): same result, same statistics
+        eng.reset()
+        eng.load_events(phold.init_events(n_lp, n_init, tables(ratio, lam, seed)[0]))
+        st_b = eng.run()
+        ok = eng.digest() == want and (st_b.committed, st_b.rollbacks, st_b.antis_sent) == (st.committed, st.rollbacks, st.antis_sent)
+        cfg["reset"] = True
     eng.close()
     if not ok and stateful and st.duplicates > 0:
         # Two DIFFERENT events with one key (receive time, id): the state-mutating test model makes an event's output
@@ -190,9 +197,24 @@ def one_multi(rng):
             s.run_closure(2)
         want = s.digest()
         tb = tables(ratio, lam, 1)
-        got, st = multi.run_partitions(lambda r, w: phold.make_engine(
+        got, st, engines = multi.run_partitions(lambda r, w: phold.make_engine(
             n_lp, n_init, ratio, lam, tables=tb, rank=r, world=w, bucket_ticks=bucket, window_buckets=window, stateful=stateful,
-            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world, graph=graph, sync_interval=sync)
+            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world, graph=graph, sync_interval=sync, keep_engines=True)
+        if got == want and rng.random() < 0.3:
+            # all partitions again after ssb_reset (bench.py between steps; the mailboxes are cleared too)
+            for e in engines:
+                e.reset()
+            if stateful:
+                for r, e in enumerate(engines):
+                    e.load_states(*phold.init_states(n_lp, r, world, True))
+            for r, e in enumerate(engines):
+                e.load_events(phold.init_events(n_lp, n_init, tb[0], r, world))
+            multi.run_all(engines)
+            from scalesim_b200 import dist
+            got = dist.combine_digests([e.digest() for e in engines])
+            cfg["reset"] = True
+        for e in engines:
+            e.close()
         if got != want and stateful and sum(x.duplicates for x in st) > 0:
             return None, cfg, dict(collision=True)
     else:
