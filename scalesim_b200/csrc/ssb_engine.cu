@@ -55,6 +55,16 @@ struct Nccl {
   static constexpr int kUint8 = 1, kUint32 = 3, kUint64 = 5, kMin = 3;
   bool load(std::string& why) {
     if (lib) return true;
+#ifdef SSB_EMU
+    // host emulation: the ranks are threads of one process (cuda_emu.h, emu_nccl)
+    (void)why;
+    lib = this;
+    GetUniqueId = [](UniqueId* id) { return emu_nccl::GetUniqueId(id); };
+    CommInitRank = [](Comm* c, int n, UniqueId id, int r) { return emu_nccl::CommInitRank(c, n, id, r); };
+    CommDestroy = emu_nccl::CommDestroy; AllReduce = emu_nccl::AllReduce; Send = emu_nccl::Send; Recv = emu_nccl::Recv;
+    GroupStart = emu_nccl::GroupStart; GroupEnd = emu_nccl::GroupEnd; GetErrorString = emu_nccl::GetErrorString;
+    return true;
+#endif
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
     if (!lib) { why = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }

@@ -57,6 +57,13 @@ def test_several_windows_per_synchronisation(emu_results):
     assert emu_results["phold_w2_stream"]["equal"]
 
 
+def test_nccl_exchange_mode(emu_results):
+    """the ncclSend / ncclRecv + all-reduce exchange (ssb_comm_init; --exchange nccl) over the emulation's in-process NCCL:
+    counts all-to-all, payload all-to-all, per-peer receive pass, GVT by all-reduce"""
+    for k in ("phold_w3_nccl", "grid_w4_nccl"):
+        assert emu_results[k]["equal"] and emu_results[k]["remote"] > 0 and emu_results[k]["rollbacks"] > 0, k
+
+
 def test_device_parity_tests_pass_on_the_emulated_kernels(emu_results):
     """The `-m gpu` files that fit a CPU budget — device KATs of logical_process_test.cc, TrafficSim, scenario images,
     overflow behaviour, the drop-in binaries — run against the emulated kernels in a subprocess: a logic regression net

@@ -59,6 +59,11 @@ def main():
     # the stream path (kernels launched round by round) instead of the graph loop
     d, st = multi.run_partitions(lambda r, w: phold.make_engine(1000, 16000, 0.5, 1.0, tables=tables, rank=r, world=w, window_buckets=2), 2, graph=False)
     out["phold_w2_stream"] = dict(equal=d == want, rollbacks=sum(s.rollbacks for s in st))
+    # the NCCL exchange mode (ncclSend / ncclRecv + all-reduce min; here the emulation's in-process NCCL)
+    d, st = multi.run_partitions(lambda r, w: phold.make_engine(1000, 16000, 0.5, 1.0, tables=tables, rank=r, world=w, window_buckets=3), 3, p2p=False)
+    out["phold_w3_nccl"] = dict(equal=d == want, rollbacks=sum(s.rollbacks for s in st), remote=sum(s.remote_sent for s in st))
+    d, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=11, window_buckets=2), 4, p2p=False)
+    out["grid_w4_nccl"] = dict(equal=d == o.digest(), rollbacks=sum(x.rollbacks for x in st), remote=sum(x.remote_sent for x in st))
     print(json.dumps(out))
 
 

@@ -11,7 +11,13 @@
 #include <cstring>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <thread>
+#include <utility>
+#include <vector>
 
 #define __global__
 #define __device__
@@ -104,3 +110,93 @@ constexpr unsigned cudaIpcMemLazyEnablePeerAccess = 1;
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h, &p, sizeof(p)); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+
+// ---- NCCL inside one process: the ranks are host threads (tools/emu/multi.py). Only what ssb_engine.cu calls: grouped
+// ncclSend / ncclRecv (eager: a send copies its payload into the world's queue, a receive waits for it), ncclAllReduce of
+// one u64 with min, the unique id (= the address of the world object). A rank that stopped with a device error releases
+// the waits of the others (g_emu_peer_failed). ----
+namespace emu_nccl {
+struct World {
+  std::mutex m;
+  std::condition_variable cv;
+  std::map<std::pair<int, int>, std::deque<std::vector<unsigned char>>> box;      // (src, dst) -> messages in order
+  std::vector<unsigned long long> vals;
+  int arrived = 0, generation = 0;
+  unsigned long long result = 0;
+};
+struct Comm { World* w; int rank, nranks; };
+struct Op { bool send; void* buf; size_t bytes; int peer; Comm* c; };
+inline thread_local std::vector<Op> g_ops;
+inline thread_local int g_depth = 0;
+inline size_t dtype_bytes(int t) { return t == 1 ? 1 : (t == 3 ? 4 : 8); }
+inline int run(const Op& o) {
+  World* w = o.c->w;
+  std::unique_lock<std::mutex> lk(w->m);
+  if (o.send) {
+    const unsigned char* p = (const unsigned char*)o.buf;
+    w->box[{o.c->rank, o.peer}].emplace_back(p, p + o.bytes);
+    w->cv.notify_all();
+    return 0;
+  }
+  auto& q = w->box[{o.peer, o.c->rank}];
+  while (q.empty()) {
+    if (g_emu_peer_failed.load()) return 1;
+    w->cv.wait_for(lk, std::chrono::milliseconds(20));
+  }
+  if (q.front().size() != o.bytes) return 2;
+  std::memcpy(o.buf, q.front().data(), o.bytes);
+  q.pop_front();
+  return 0;
+}
+inline int GetUniqueId(void* id128) { World* w = new World(); std::memset(id128, 0, 128); std::memcpy(id128, &w, sizeof(w)); return 0; }
+template <class Id> inline int CommInitRank(void** comm, int nranks, Id id, int rank) {
+  World* w; std::memcpy(&w, &id, sizeof(w));
+  { std::lock_guard<std::mutex> g(w->m); w->vals.resize((size_t)nranks); }
+  *comm = new Comm{w, rank, nranks};
+  return 0;
+}
+inline int CommDestroy(void* c) { delete (Comm*)c; return 0; }      // (the world object stays: other ranks may still hold it)
+inline int GroupStart() { ++g_depth; return 0; }
+inline int GroupEnd() {
+  if (--g_depth > 0) return 0;
+  int rc = 0;
+  for (const Op& o : g_ops) if (o.send) { int r = run(o); if (r && !rc) rc = r; }      // sends first: never blocks
+  for (const Op& o : g_ops) if (!o.send) { int r = run(o); if (r && !rc) rc = r; }
+  g_ops.clear();
+  return rc;
+}
+inline int Send(const void* buf, size_t count, int dtype, int peer, void* c, cudaStream_t) {
+  Op o{true, const_cast<void*>(buf), count * dtype_bytes(dtype), peer, (Comm*)c};
+  if (g_depth) { g_ops.push_back(o); return 0; }
+  return run(o);
+}
+inline int Recv(void* buf, size_t count, int dtype, int peer, void* c, cudaStream_t) {
+  Op o{false, buf, count * dtype_bytes(dtype), peer, (Comm*)c};
+  if (g_depth) { g_ops.push_back(o); return 0; }
+  return run(o);
+}
+// one u64, min (what the GVT reduction needs)
+inline int AllReduce(const void* in, void* out, size_t count, int, int, void* cc, cudaStream_t) {
+  if (count != 1) return 3;
+  Comm* c = (Comm*)cc;
+  World* w = c->w;
+  std::unique_lock<std::mutex> lk(w->m);
+  w->vals[(size_t)c->rank] = *(const unsigned long long*)in;
+  const int gen = w->generation;
+  if (++w->arrived == c->nranks) {
+    unsigned long long m = ~0ull;
+    for (unsigned long long v : w->vals) m = v < m ? v : m;
+    w->result = m; w->arrived = 0; ++w->generation;
+    w->cv.notify_all();
+  } else {
+    while (w->generation == gen) {
+      if (g_emu_peer_failed.load()) return 1;
+      w->cv.wait_for(lk, std::chrono::milliseconds(20));
+    }
+  }
+  *(unsigned long long*)out = w->result;
+  return 0;
+}
+inline const char* GetErrorString(int rc) { return rc == 1 ? "a peer rank stopped" : (rc == 2 ? "message size mismatch" : "emulated NCCL error"); }
+}  // namespace emu_nccl

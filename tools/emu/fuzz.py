@@ -178,7 +178,8 @@ def one_multi(rng):
     import multi
     world = int(rng.choice([2, 3, 4, 8]))
     window = int(rng.choice([1, 2, 4, 16]))
-    graph = bool(rng.random() < 0.6)
+    p2p = bool(rng.random() < 0.75)      # else the NCCL exchange mode (stream path; the emulation's in-process NCCL)
+    graph = p2p and bool(rng.random() < 0.6)
     sync = int(rng.choice([1, 1, 2, 3, 8])) if graph else 1
     if rng.random() < 0.6:
         n_lp = int(rng.choice([world, 64, 300, 1500]))
@@ -187,7 +188,7 @@ def one_multi(rng):
         lam = float(rng.choice([0.5, 1.0, 4.0, 30.0]))
         stateful = bool(rng.random() < 0.3)
         bucket = int(rng.choice([1000, 2500, 10000, 25000]))
-        cfg = dict(kind="multi-phold", graph=graph, sync=sync, world=world, n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, stateful=stateful, bucket=bucket, window=window)
+        cfg = dict(kind="multi-phold", p2p=p2p, graph=graph, sync=sync, world=world, n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, stateful=stateful, bucket=bucket, window=window)
         if os.environ.get("FUZZ_VERBOSE"):
             print("multi", cfg, flush=True)
         s = O.Sim.phold(n_lp, n_init, ratio, lam, stateful=stateful)
@@ -199,7 +200,7 @@ def one_multi(rng):
         tb = tables(ratio, lam, 1)
         got, st, engines = multi.run_partitions(lambda r, w: phold.make_engine(
             n_lp, n_init, ratio, lam, tables=tb, rank=r, world=w, bucket_ticks=bucket, window_buckets=window, stateful=stateful,
-            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world, graph=graph, sync_interval=sync, keep_engines=True)
+            max_events=int(n_init * 3) + (1 << 16), max_batch=n_init + (1 << 14)), world, graph=graph, sync_interval=sync, keep_engines=True, p2p=p2p)
         if got == want and rng.random() < 0.3:
             # all partitions again after ssb_reset (bench.py between steps; the mailboxes are cleared too)
             for e in engines:
@@ -223,7 +224,7 @@ def one_multi(rng):
         n_trips = int(rng.choice([50, 2000, 6000]))
         seed = int(rng.integers(0, 1 << 30))
         bucket = int(rng.choice([5, 11, 64, 400]))
-        cfg = dict(kind="multi-traffic", graph=graph, sync=sync, world=world, n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, bucket=bucket, window=window)
+        cfg = dict(kind="multi-traffic", p2p=p2p, graph=graph, sync=sync, world=world, n_nodes=n_nodes, deg=deg, n_trips=n_trips, seed=seed, bucket=bucket, window=window)
         if os.environ.get("FUZZ_VERBOSE"):
             print("multi", cfg, flush=True)
         sc = _random_network(n_nodes, deg, n_trips, seed)
@@ -233,7 +234,7 @@ def one_multi(rng):
         want = s.digest()
         got, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=bucket, window_buckets=window,
                                                                         max_events=n_trips * 6 + (1 << 16), max_batch=n_trips * 2 + (1 << 14)),
-                                     world, graph=graph, sync_interval=sync)
+                                     world, graph=graph, sync_interval=sync, p2p=p2p)
     return got == want, cfg, dict(committed=sum(x.committed for x in st), rollbacks=sum(x.rollbacks for x in st),
                                   antis=sum(x.antis_sent for x in st), remote=sum(x.remote_sent for x in st), want=want[0])
 

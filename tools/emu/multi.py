@@ -16,8 +16,15 @@ import emu_plugin  # noqa: F401,E402
 from scalesim_b200 import dist  # noqa: E402
 
 
-def connect(engines):
-    """ssb_comm_export on every engine, then ssb_comm_import of all handles on every engine."""
+def connect(engines, p2p=True):
+    """Peer-memory exchange: ssb_comm_export on every engine, then ssb_comm_import of all handles on every engine.
+    p2p=False: the NCCL exchange mode (ssb_comm_unique_id / ssb_comm_init) over the emulation's in-process NCCL."""
+    if not p2p:
+        from scalesim_b200 import Engine
+        uid = Engine.comm_unique_id()
+        for e in engines:
+            e.comm_init(uid)
+        return
     handles = b"".join(e.comm_export() for e in engines)
     for e in engines:
         e.comm_import(handles)
@@ -47,7 +54,7 @@ def run_all(engines, call=lambda e: e.run()):
     return out
 
 
-def run_partitions(make_engine, world, keep_engines=False, graph=True, sync_interval=1):
+def run_partitions(make_engine, world, keep_engines=False, graph=True, sync_interval=1, p2p=True):
     """make_engine(rank, world) -> loaded Engine. graph: the interpreted graph loop (ssb_engine::run_graph_emulated) or
     the stream path; sync_interval: local windows per global synchronisation (graph loop only, ssb_set_sync_interval).
     Returns (digest of the union, stats per rank[, engines])."""
@@ -57,7 +64,7 @@ def run_partitions(make_engine, world, keep_engines=False, graph=True, sync_inte
         engines = [make_engine(r, world) for r in range(world)]
     finally:
         os.environ.pop("SSB_NO_GRAPH", None)
-    connect(engines)
+    connect(engines, p2p)
     if sync_interval > 1:
         for e in engines:
             e.set_sync_interval(sync_interval)
