@@ -1,9 +1,13 @@
 // cuda_emu.h — DEVELOPER TOOL, never shipped and never loadable by the product (scalesim_b200/capi.py has no switch
 // for it): a sequential host emulation of the CUDA constructs the kernels in scalesim_b200/csrc use, so that their
-// LOGIC can be exercised with gdb / asan on a machine without a GPU (tools/emu/build.sh compiles ssb_engine.cu with
-// g++ -DSSB_EMU into tools/emu/libssb_emu.so). Every kernel runs as ONE block of ONE thread ("warp" of one lane):
-// grid-stride loops visit every element, atomics are plain read-modify-writes, barriers and fences are no-ops.
-// It finds logic errors, not races; parity claims are made on the B200 only.
+// LOGIC can be exercised with gdb / AddressSanitizer on a machine without a GPU (tools/emu/build.sh compiles
+// ssb_engine.cu with g++ -DSSB_EMU into tools/emu/libssb_emu.so). Every kernel runs as ONE block of ONE thread ("warp"
+// of one lane): grid-stride loops visit every element, atomics are plain read-modify-writes, barriers are no-ops.
+// The CUDA graph of the window loop is interpreted (ssb_engine::run_graph_emulated). Several partitions = several
+// engines of one process, one host thread each (tools/emu/multi.py): shared memory is thread_local, a mailbox's "IPC
+// handle" is its address, system fences are real fences, and the six NCCL calls of the NCCL exchange mode have an
+// in-process stand-in (emu_nccl below).
+// It finds logic errors and out-of-bounds accesses, not races; parity claims are made on the B200 only.
 #pragma once
 #include <algorithm>
 #include <cstdint>
