@@ -57,6 +57,11 @@ def test_several_windows_per_synchronisation(emu_results):
     assert emu_results["phold_w2_stream"]["equal"]
 
 
+def test_partitions_started_from_one_scenario_image(emu_results):
+    r = emu_results["grid_w4_from_image"]
+    assert r["equal"] and r["remote"] > 0
+
+
 def test_nccl_exchange_mode(emu_results):
     """the ncclSend / ncclRecv + all-reduce exchange (ssb_comm_init; --exchange nccl) over the emulation's in-process NCCL:
     counts all-to-all, payload all-to-all, per-peer receive pass, GVT by all-reduce"""

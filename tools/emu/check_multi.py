@@ -64,6 +64,18 @@ def main():
     out["phold_w3_nccl"] = dict(equal=d == want, rollbacks=sum(s.rollbacks for s in st), remote=sum(s.remote_sent for s in st))
     d, st = multi.run_partitions(lambda r, w: traffic.make_engine(sc, rank=r, world=w, bucket_ticks=11, window_buckets=2), 4, p2p=False)
     out["grid_w4_nccl"] = dict(equal=d == o.digest(), rollbacks=sum(x.rollbacks for x in st), remote=sum(x.remote_sent for x in st))
+    # every partition started from ONE scenario image (ssb_scenario_load keeps the rank's share)
+    import scalesim_b200 as ssb
+    from scalesim_b200 import scenario
+    im = scenario.traffic_image(sc)
+
+    def from_image(r, w):
+        e = ssb.Engine(ssb.Config(model=ssb.MODEL_TRAFFIC, n_lp=sc.n_lp, finish_time=traffic.FINISH_TIME, bucket_ticks=11, window_buckets=2,
+                                  max_events=sc.trip_id.size * 2 + (1 << 16), max_batch=sc.trip_id.size + (1 << 14), rank=r, world=w))
+        e.load_scenario(im)
+        return e
+    d, st = multi.run_partitions(from_image, 4)
+    out["grid_w4_from_image"] = dict(equal=d == o.digest(), remote=sum(x.remote_sent for x in st), rollbacks=sum(x.rollbacks for x in st))
     print(json.dumps(out))
 
 
