@@ -1,9 +1,11 @@
+"""Host-side scenario ingestion timing (profiles/r2_ingest_host.json): python tools/ingest_bench.py [n_trips]"""
 import os, sys, time, json
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from scalesim_b200 import traffic, scenario
 n_trips = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-d = '/tmp/ssb_ingest'; os.makedirs(d, exist_ok=True)
+import tempfile
+d = tempfile.mkdtemp(prefix='ssb_ingest_')
 t = time.time(); sc = traffic.synthetic_grid(1024, 1024, n_trips, seed=1); sc.partition = traffic.stripe_partition(1024, 1024, 8); gen = time.time() - t
 rd, trip, part, img = (os.path.join(d, n) for n in ('rd.csv', 'trip.csv', 'part', 'grid.ssbscn'))
 t = time.time(); scenario.write_traffic_csv(sc, rd, trip, part); wr = time.time() - t
