@@ -548,13 +548,55 @@ def one_refphold(rng):
     return ok, cfg, dict(init=len(emu_init), new=len(new), repeat=len(emu), ref_sizes=[len(r) for r in refs])
 
 
+def one_pholddiff(rng):
+    """PHOLD --diff_init / --diff_repeat through the C ABI: the history goes back as processed events
+    (ssb_load_history), random what-if events are injected (new ids, random LPs and times), and the repeat output must
+    be the closure of those events over the recorded output; init + new == one full run with the extra events."""
+    n_lp = int(rng.choice([1, 8, 100, 800]))
+    n_init = int(rng.choice([20, 400, 4000]))
+    ratio = float(rng.choice([0.0, 0.1, 0.5, 1.0]))
+    lam = float(rng.choice([0.5, 1.0, 4.0]))
+    n_wi = int(rng.choice([1, 3, 20]))
+    window, rwindow = int(rng.choice([1, 2, 8])), int(rng.choice([1, 2, 8]))
+    cfg = dict(kind="pholddiff", n_lp=n_lp, n_init=n_init, ratio=ratio, lam=lam, n_wi=n_wi, window=window, rwindow=rwindow)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("pholddiff", cfg, flush=True)
+    tb = tables(ratio, lam, 1)
+    kw = dict(tables=tb, max_committed=n_init * 12 + 4096, max_events=n_init * 24 + (1 << 16), max_batch=n_init * 4 + (1 << 14))
+    eng = phold.make_engine(n_lp, n_init, ratio, lam, flags=ssb.FLAG_HISTORY, window_buckets=window, **kw)
+    eng.run()
+    rec, sent = eng.drain_history()
+    eng.close()
+    init_lines = sorted(ssb.records_to_lines(ssb.raw_to_records(rec)))
+    ev = np.zeros(n_wi, dtype=ssb.EVENT_DTYPE)
+    ev["id"] = n_init + np.arange(n_wi)
+    ev["src"] = ev["dst"] = rng.integers(0, n_lp, n_wi)
+    ev["recv_time"] = ev["send_time"] = rng.integers(1, phold.FINISH_TIME, n_wi)
+    # one full run with the extra events: the definition of what the repeat run has to add
+    full = phold.make_engine(n_lp, n_init, ratio, lam, window_buckets=1, keep_records=True, **kw)
+    full.load_events(ev)
+    full.run()
+    full_lines = sorted(ssb.records_to_lines(full.drain_committed()))
+    full.close()
+    new_lines = sorted(set(full_lines) - set(init_lines))
+    ok = set(init_lines) <= set(full_lines)                      # PHOLD chains do not interact
+    eng = phold.make_engine(n_lp, n_init, ratio, lam, load=False, window_buckets=rwindow, **kw)
+    eng.load_history(rec, sent)
+    eng.load_events(ev)
+    st = eng.run()
+    rep = sorted(ssb.records_to_lines(eng.drain_committed()))
+    eng.close()
+    ok = ok and sorted(set(rep) - set(init_lines)) == new_lines and rep == O.repeat_closure(init_lines, new_lines)
+    return ok, cfg, dict(init=len(init_lines), new=len(new_lines), repeat=len(rep), rollbacks=st.rollbacks)
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     t0, n, bad, rb, cap, col, hang, skip = time.time(), 0, 0, 0, 0, 0, 0, 0
     while time.time() - t0 < budget:
         r = rng.random()
-        kind = one_phold if r < 0.3 else (one_traffic if r < 0.5 else (one_diff if r < 0.7 else (one_multi if r < 0.85 else (one_multidiff if r < 0.93 else one_sc))))
+        kind = one_phold if r < 0.3 else (one_traffic if r < 0.5 else (one_diff if r < 0.7 else (one_multi if r < 0.82 else (one_multidiff if r < 0.89 else (one_sc if r < 0.95 else one_pholddiff)))))
         if os.environ.get("FUZZ_ONLY"):
             kind = globals()["one_" + os.environ["FUZZ_ONLY"]]
         try:
